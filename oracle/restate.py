@@ -1,0 +1,89 @@
+"""TEST INFRASTRUCTURE ONLY: ctypes binding of oracle/_build/liboracle_enum.so (oracle/enum_restate.c, the plain-C
+restatement of /root/reference/src/vertexenumeration.cpp:263-364) plus the numpy restatement of the
+BifurcationStorage list order (/root/reference/src/indexedsequence.cpp:51-67 + bifurcationstorage.cpp:113-126).
+Never imported by sibelia_b200/.  PARITY PINNED against oracle/_ref (tests/test_oracle.py, tests/golden/).
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "_build", "liboracle_enum.so")
+INST_DTYPE = np.dtype([("bifId", "<u4"), ("chr", "<u4"), ("pos", "<u4")])
+_lib = None
+
+
+def build():
+    subprocess.check_call(["make", "-s", "-C", _HERE, "restate"])
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            build()
+        _lib = C.CDLL(LIB_PATH)
+        _lib.orc_enumerate.restype = C.c_uint64
+        _lib.orc_free.argtypes = [C.c_void_p]
+    return _lib
+
+
+def _take(ptr, n):
+    if n:
+        buf = (C.c_char * (n * INST_DTYPE.itemsize)).from_address(ptr.value)
+        out = np.frombuffer(buf, dtype=INST_DTYPE, count=n).copy()
+    else:
+        out = np.zeros(0, dtype=INST_DTYPE)
+    lib().orc_free(ptr)
+    return out
+
+
+def enumerate_bifurcations(chrs, k):
+    """-> (count, pos, neg): the reference's `bifurcationCount` and its two (chr,pos)-sorted instance vectors."""
+    L = lib()
+    chrs = [c if isinstance(c, (bytes, bytearray)) else (c.tobytes() if isinstance(c, np.ndarray) else c.encode())
+            for c in chrs]
+    n = len(chrs)
+    arr = (C.c_char_p * n)(*chrs)
+    lens = (C.c_uint64 * n)(*[len(c) for c in chrs])
+    pos, neg = C.c_void_p(), C.c_void_p()
+    npos, nneg = C.c_uint64(), C.c_uint64()
+    cnt = L.orc_enumerate(C.c_uint32(n), arr, lens, C.c_uint32(k), C.byref(pos), C.byref(npos),
+                          C.byref(neg), C.byref(nneg))
+    if cnt == 2 ** 64 - 1:
+        raise MemoryError("orc_enumerate")
+    return int(cnt), _take(pos, npos.value), _take(neg, nneg.value)
+
+
+def list_positions(count, pos, neg, lens):
+    """ListPositions(id) order for id in 0..count (inclusive: the storage holds maxId+1 lists,
+    bifurcationstorage.cpp:53-59) as CSR (off, gidx, strand).
+
+    IndexedSequence::Init walks strand 0 then strand 1, chromosomes ascending, positions ascending, and AddPoint
+    pushes to the FRONT of the per-id slist (bifurcationstorage.cpp:122), so each list is the reverse of that walk;
+    ListPositions emits the positive list and then the negative list (bifurcationstorage.h:59-72).
+    gidx = DNASequence::GlobalIndex of the instance's base element (dnasequence.cpp:269-272): elements are numbered
+    chr0 '$' chr1 '$' ... from 0; a negative-strand instance at rc-position p sits on element start+len-1-p."""
+    lens = np.asarray(lens, dtype=np.int64)
+    start = np.concatenate([[0], np.cumsum(lens + 1)[:-1]])
+    ids, gidx, strand = [], [], []
+    for s, inst in ((0, pos), (1, neg)):
+        if len(inst) == 0:
+            continue
+        c = inst["chr"].astype(np.int64)
+        p = inst["pos"].astype(np.int64)
+        g = start[c] + (p if s == 0 else lens[c] - 1 - p)
+        ids.append(inst["bifId"].astype(np.int64)[::-1])          # reverse insertion order
+        gidx.append(g[::-1])
+        strand.append(np.full(len(inst), s, dtype=np.uint8))
+    if not ids:
+        return np.zeros(count + 2, dtype=np.uint64), np.zeros(0, np.uint32), np.zeros(0, np.uint8)
+    ids = np.concatenate(ids)
+    gidx = np.concatenate(gidx)
+    strand = np.concatenate(strand)
+    order = np.lexsort((np.arange(len(ids)), strand, ids))       # stable: by id, then strand, then list order
+    off = np.zeros(count + 2, dtype=np.uint64)
+    np.cumsum(np.bincount(ids, minlength=count + 1), out=off[1:])
+    return off, gidx[order].astype(np.uint32), strand[order]
