@@ -1,0 +1,117 @@
+/* sibgpu.h -- C ABI of the B200-native de Bruijn-graph hot path of Sibelia.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no C++/torch types.  Every entry point names the
+ * reference interface it replaces (paths relative to the reference tree, /root/reference).  The C++ facade in
+ * sibelia_b200/csrc/facade/ (namespace SyntenyFinder, same class and method names as the reference) sits on top of
+ * this header; INTEGRATION.md shows the binding a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a sibgpu_status otherwise; sibgpu_last_error() gives the message
+ *     (the reference throws std::runtime_error, src/sibelia.cpp:351-365; the facade rethrows).
+ *   - input chromosomes must already be sanitised to upper-case ACGT: the reference replaces every other
+ *     character with DEFINITE_BASE[rand() % 4] on the HOST in row-major order (src/indexedsequence.cpp:31-37);
+ *     that step stays on the host (facade) because it consumes the process-wide glibc rand() stream.
+ *   - there is NO CPU fallback: without a CUDA device every compute entry point fails with SIBGPU_ERR_CUDA.
+ *   - one context per device; calls on one context are serialised by the caller (the reference is single-threaded).
+ */
+#ifndef SIBGPU_H_
+#define SIBGPU_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct sibgpu_ctx sibgpu_ctx;
+
+typedef enum sibgpu_status {
+	SIBGPU_OK = 0,
+	SIBGPU_ERR_CUDA = 1,          /* no device / CUDA runtime error / out of device memory */
+	SIBGPU_ERR_INVALID = 2,       /* bad argument (k == 0, NULL pointer, input too large for 32-bit positions, ...) */
+	SIBGPU_ERR_INPUT = 3,         /* a character outside ACGT reached the device (caller skipped sanitising) */
+	SIBGPU_ERR_INTERNAL = 4,      /* capacity fallback exhausted, fingerprint verification failed twice, ... */
+	SIBGPU_ERR_STATE = 5          /* staged call made out of order (e.g. download before enumerate) */
+} sibgpu_status;
+
+/* == IndexedSequence::BifurcationInstance (src/indexedsequence.h:57-68): vertex id, chromosome, position in that
+ *    strand's own coordinates (negative strand: position in the reverse complement of the chromosome). */
+typedef struct sibgpu_inst { uint32_t bifId, chr, pos; } sibgpu_inst;
+
+/* per-kernel device timing of the last enumerate on a context (CUDA events on the launching stream) */
+typedef struct sibgpu_kernel_stat {
+	const char *name;             /* kernel name, static storage */
+	uint32_t launches;            /* launches in the last run */
+	float ms;                     /* summed device time of those launches */
+	uint64_t algo_bytes;          /* algorithmic bytes those launches had to move */
+} sibgpu_kernel_stat;
+
+const char *sibgpu_last_error(void);
+const char *sibgpu_version(void);
+
+/* number of visible CUDA devices (0 if none / no driver); never fails */
+int sibgpu_device_count(void);
+
+int sibgpu_create(int device, sibgpu_ctx **out);
+void sibgpu_destroy(sibgpu_ctx *ctx);
+
+/* Frees any buffer handed out by this library (instance arrays, sequences, position maps). */
+void sibgpu_free(void *p);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * sibgpu_enumerate: replaces
+ *     size_t IndexedSequence::EnumerateBifurcationsSArrayInRAM(const std::vector<std::string>& data,
+ *            std::vector<BifurcationInstance>& positiveBif, std::vector<BifurcationInstance>& negativeBif)
+ *     src/indexedsequence.h:73, src/vertexenumeration.cpp:263-364   (and its file-backed twin :160-261, which returns
+ *     the same tables), called from IndexedSequence::Init, src/indexedsequence.cpp:40-47.
+ * Host buffers in, host buffers out; the host<->device copies are inside the call.
+ *   chr[i], len[i]   the nchr sanitised chromosomes (not NUL-terminated)
+ *   k                vertex size, k >= 1
+ *   *pos, *neg       library-allocated arrays sorted by (chr, pos) exactly like the reference's two vectors after
+ *                    vertexenumeration.cpp:361-362; release with sibgpu_free
+ *   *count           the reference's return value `bifurcationCount` (ids are 0 .. count-1; a vertex id is the
+ *                    lexicographic rank of its k-mer among all vertex k-mers)
+ */
+int sibgpu_enumerate(sibgpu_ctx *ctx, const char *const *chr, const uint64_t *len, uint32_t nchr, uint32_t k,
+	sibgpu_inst **pos, uint64_t *npos, sibgpu_inst **neg, uint64_t *nneg, uint32_t *count);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Staged form of the same operation, for callers that keep the genome resident in HBM across calls (one upload,
+ * several k: the reference builds five indexes per `-s loose` run, src/sibelia.cpp:242-289) and for bench.py's
+ * device-resident timing.  sibgpu_enumerate == upload + enumerate_resident + download.
+ */
+int sibgpu_upload(sibgpu_ctx *ctx, const char *const *chr, const uint64_t *len, uint32_t nchr);
+int sibgpu_enumerate_resident(sibgpu_ctx *ctx, uint32_t k, uint64_t *ninst_per_strand, uint32_t *count);
+int sibgpu_download(sibgpu_ctx *ctx, sibgpu_inst **pos, uint64_t *npos, sibgpu_inst **neg, uint64_t *nneg);
+
+/* Kernel statistics of the last enumerate on this context: fills at most cap entries, returns how many exist.
+ * Timing is only recorded when enabled with sibgpu_set_profiling(ctx, 1) (it inserts events between kernels). */
+int sibgpu_set_profiling(sibgpu_ctx *ctx, int enabled);
+int sibgpu_kernel_stats(sibgpu_ctx *ctx, sibgpu_kernel_stat *out, int cap);
+/* number of kernels this library launched during the last enumerate / simplify on this context */
+uint64_t sibgpu_last_launches(sibgpu_ctx *ctx);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * sibgpu_simplify: replaces one stage of
+ *     size_t BlockFinder::PerformGraphSimplifications(size_t k, size_t minBranchSize, size_t maxIterations,
+ *            ProgressCallBack f)                              src/blockfinder.h:45, src/blockfinder.cpp:78-98
+ * i.e. IndexedSequence(rawSeq_, originalPos_, k, tempDir_, true) + SimplifyGraph (blockfinder.cpp:16-51, which
+ * calls RemoveBulges, bulgeremoval.cpp:330-430, for every vertex id and sweep) + the copy-back of :85-95.
+ * State in/out is the reference's inter-stage state (src/blockfinder.h:52-54):
+ *   seq[i] / origpos[i] / len[i]   rawSeq_[i], originalPos_[i] and their common length.  On success the three
+ *                                  arrays are overwritten with library-allocated buffers of the new lengths
+ *                                  (release with sibgpu_free); the caller keeps ownership of the old ones.
+ *   progress(done, state, user)    optional; same protocol as BlockFinder::ProgressCallBack (blockfinder.h:39):
+ *                                  state 0 = start, 1 = run (<= 50 ticks), 2 = end
+ *   *bulges                        the return value (cumulative number of collapsed bulges)
+ */
+typedef void (*sibgpu_progress_fn)(size_t done, int state, void *user);
+int sibgpu_simplify(sibgpu_ctx *ctx, char **seq, uint32_t **origpos, uint64_t *len, uint32_t nchr,
+	uint32_t k, uint32_t min_branch_size, uint32_t max_iterations,
+	sibgpu_progress_fn progress, void *user, uint64_t *bulges);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SIBGPU_H_ */

@@ -1,0 +1,173 @@
+"""ctypes binding of libsibgpu.so (include/sibgpu.h).  Fails loudly when the library or a GPU is missing."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+INST_DTYPE = np.dtype([("bifId", "<u4"), ("chr", "<u4"), ("pos", "<u4")])
+
+# every symbol include/sibgpu.h declares (tests/test_abi.py cross-checks this list against the header)
+SYMBOLS = [
+    "sibgpu_last_error", "sibgpu_version", "sibgpu_device_count", "sibgpu_create", "sibgpu_destroy", "sibgpu_free",
+    "sibgpu_enumerate", "sibgpu_upload", "sibgpu_enumerate_resident", "sibgpu_download", "sibgpu_set_profiling",
+    "sibgpu_kernel_stats", "sibgpu_last_launches", "sibgpu_simplify",
+]
+
+
+class SibgpuError(RuntimeError):
+    def __init__(self, status, msg):
+        super().__init__("sibgpu status %d: %s" % (status, msg))
+        self.status = status
+
+
+class _KStat(C.Structure):
+    _fields_ = [("name", C.c_char_p), ("launches", C.c_uint32), ("ms", C.c_float), ("algo_bytes", C.c_uint64)]
+
+
+def lib_path():
+    return os.path.join(_HERE, "libsibgpu.so")
+
+
+def build(verbose=False):
+    """Compile libsibgpu.so for sm_100a in-tree (nvcc cross-compiles without a GPU)."""
+    cmd = ["make", "-C", _HERE, "-j8"] + ([] if verbose else ["-s"])
+    subprocess.check_call(cmd)
+    return lib_path()
+
+
+_lib = None
+
+
+def load():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(lib_path()):
+            raise ImportError("libsibgpu.so is not built: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                              "(there is no CPU fallback)")
+        L = C.CDLL(lib_path())
+        L.sibgpu_last_error.restype = C.c_char_p
+        L.sibgpu_version.restype = C.c_char_p
+        L.sibgpu_last_launches.restype = C.c_uint64
+        L.sibgpu_last_launches.argtypes = [C.c_void_p]
+        L.sibgpu_destroy.argtypes = [C.c_void_p]
+        L.sibgpu_destroy.restype = None
+        L.sibgpu_free.argtypes = [C.c_void_p]
+        L.sibgpu_free.restype = None
+        _lib = L
+    return _lib
+
+
+def device_count():
+    return load().sibgpu_device_count()
+
+
+def _check(rc):
+    if rc != 0:
+        raise SibgpuError(rc, load().sibgpu_last_error().decode())
+
+
+def _chr_args(chrs):
+    bufs = []
+    for c in chrs:
+        if isinstance(c, np.ndarray):
+            bufs.append(np.ascontiguousarray(c, dtype=np.uint8))
+        else:
+            bufs.append(np.frombuffer(bytes(c) if not isinstance(c, str) else c.encode(), dtype=np.uint8))
+    n = len(bufs)
+    ptrs = (C.c_void_p * max(n, 1))(*[b.ctypes.data if len(b) else None for b in bufs])
+    lens = (C.c_uint64 * max(n, 1))(*[len(b) for b in bufs])
+    return bufs, ptrs, lens, n
+
+
+def _take(ptr, n):
+    L = load()
+    if n:
+        buf = (C.c_char * (n * INST_DTYPE.itemsize)).from_address(ptr.value)
+        out = np.frombuffer(buf, dtype=INST_DTYPE, count=n).copy()
+    else:
+        out = np.zeros(0, dtype=INST_DTYPE)
+    if ptr.value:
+        L.sibgpu_free(ptr)
+    return out
+
+
+class Context:
+    """One sibgpu context (= one GPU)."""
+
+    def __init__(self, device=0):
+        L = load()
+        self._h = C.c_void_p()
+        _check(L.sibgpu_create(C.c_int(device), C.byref(self._h)))
+        self._keep = None
+
+    def close(self):
+        if self._h:
+            load().sibgpu_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- sibgpu_enumerate: host buffers in, host tables out
+    def enumerate(self, chrs, k):
+        L = load()
+        bufs, ptrs, lens, n = _chr_args(chrs)
+        pos, neg = C.c_void_p(), C.c_void_p()
+        npos, nneg, cnt = C.c_uint64(), C.c_uint64(), C.c_uint32()
+        _check(L.sibgpu_enumerate(self._h, ptrs, lens, C.c_uint32(n), C.c_uint32(k), C.byref(pos), C.byref(npos),
+                                  C.byref(neg), C.byref(nneg), C.byref(cnt)))
+        return cnt.value, _take(pos, npos.value), _take(neg, nneg.value)
+
+    # -- staged form
+    def upload(self, chrs):
+        bufs, ptrs, lens, n = _chr_args(chrs)
+        _check(load().sibgpu_upload(self._h, ptrs, lens, C.c_uint32(n)))
+
+    def enumerate_resident(self, k):
+        ninst, cnt = C.c_uint64(), C.c_uint32()
+        _check(load().sibgpu_enumerate_resident(self._h, C.c_uint32(k), C.byref(ninst), C.byref(cnt)))
+        return cnt.value, ninst.value
+
+    def download(self):
+        pos, neg = C.c_void_p(), C.c_void_p()
+        npos, nneg = C.c_uint64(), C.c_uint64()
+        _check(load().sibgpu_download(self._h, C.byref(pos), C.byref(npos), C.byref(neg), C.byref(nneg)))
+        return _take(pos, npos.value), _take(neg, nneg.value)
+
+    def set_profiling(self, on):
+        _check(load().sibgpu_set_profiling(self._h, C.c_int(1 if on else 0)))
+
+    def kernel_stats(self):
+        arr = (_KStat * 64)()
+        n = load().sibgpu_kernel_stats(self._h, arr, C.c_int(64))
+        return [dict(name=arr[i].name.decode(), launches=arr[i].launches, ms=arr[i].ms, algo_bytes=arr[i].algo_bytes)
+                for i in range(min(n, 64))]
+
+    def last_launches(self):
+        return int(load().sibgpu_last_launches(self._h))
+
+    # -- sibgpu_simplify: one PerformGraphSimplifications stage
+    def simplify(self, chrs, origpos, k, min_branch_size, max_iterations=4):
+        L = load()
+        bufs, _, lens, n = _chr_args(chrs)
+        seq = (C.c_void_p * max(n, 1))(*[b.ctypes.data for b in bufs])
+        ops = [np.ascontiguousarray(o, dtype=np.uint32) for o in origpos]
+        op = (C.c_void_p * max(n, 1))(*[o.ctypes.data for o in ops])
+        bulges = C.c_uint64()
+        _check(L.sibgpu_simplify(self._h, seq, op, lens, C.c_uint32(n), C.c_uint32(k), C.c_uint32(min_branch_size),
+                                 C.c_uint32(max_iterations), None, None, C.byref(bulges)))
+        new_chrs, new_op = [], []
+        for i in range(n):
+            m = lens[i]
+            sbuf = (C.c_char * m).from_address(seq[i]) if m else b""
+            new_chrs.append(bytes(sbuf))
+            obuf = (C.c_char * (4 * m)).from_address(op[i]) if m else b""
+            new_op.append(np.frombuffer(bytes(obuf), dtype=np.uint32).copy())
+            L.sibgpu_free(C.c_void_p(seq[i]))
+            L.sibgpu_free(C.c_void_p(op[i]))
+        return new_chrs, new_op, bulges.value

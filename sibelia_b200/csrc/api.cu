@@ -1,0 +1,260 @@
+// extern "C" surface of libsibgpu (include/sibgpu.h): context, upload/download, enumerate.
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+
+#include "context.h"
+
+namespace sibgpu {
+static thread_local std::string g_error;
+void set_error(const std::string &msg) { g_error = msg; }
+} // namespace sibgpu
+
+using namespace sibgpu;
+
+cudaEvent_t sibgpu_ctx::get_event()
+{
+	if(events_used == event_pool.size())
+	{
+		cudaEvent_t e;
+		cudaEventCreate(&e);
+		event_pool.push_back(e);
+	}
+	return event_pool[events_used++];
+}
+
+void sibgpu_ctx::prof_begin(const char *name, uint64_t bytes)
+{
+	Span s = {name, get_event(), get_event(), bytes};
+	cudaEventRecord(s.a, stream);
+	spans.push_back(s);
+}
+
+void sibgpu_ctx::prof_end() { cudaEventRecord(spans.back().b, stream); }
+
+void sibgpu_ctx::prof_reset()
+{
+	spans.clear();
+	events_used = 0;
+	stats.clear();
+}
+
+int sibgpu_ctx::prof_collect()
+{
+	SIB_CUDA(cudaStreamSynchronize(stream));
+	stats.clear();
+	for(const Span &s : spans)
+	{
+		float ms = 0.f;
+		SIB_CUDA(cudaEventElapsedTime(&ms, s.a, s.b));
+		size_t i = 0;
+		for(; i < stats.size() && strcmp(stats[i].name, s.name) != 0; i++);
+		if(i == stats.size()) stats.push_back(Stat{s.name, 0u, 0.f, 0ull});
+		stats[i].launches++;
+		stats[i].ms += ms;
+		stats[i].bytes += s.bytes;
+	}
+	return SIBGPU_OK;
+}
+
+extern "C" {
+
+const char *sibgpu_last_error(void) { return g_error.c_str(); }
+const char *sibgpu_version(void) { return "sibgpu 0.1 (sm_100a)"; }
+
+int sibgpu_device_count(void)
+{
+	int n = 0;
+	if(cudaGetDeviceCount(&n) != cudaSuccess)
+	{
+		cudaGetLastError();
+		return 0;
+	}
+	return n;
+}
+
+int sibgpu_create(int device, sibgpu_ctx **out)
+{
+	if(!out)
+	{
+		set_error("invalid: out == NULL");
+		return SIBGPU_ERR_INVALID;
+	}
+	*out = nullptr;
+	int n = 0;
+	SIB_CUDA(cudaGetDeviceCount(&n));
+	if(device < 0 || device >= n)
+	{
+		set_error("cuda: device " + std::to_string(device) + " not available (" + std::to_string(n) + " visible)");
+		return SIBGPU_ERR_CUDA;
+	}
+	SIB_CUDA(cudaSetDevice(device));
+	sibgpu_ctx *c = new sibgpu_ctx();
+	c->device = device;
+	cudaDeviceProp prop;
+	SIB_CUDA(cudaGetDeviceProperties(&prop, device));
+	c->sm_count = prop.multiProcessorCount;
+	SIB_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+	SIB_CUDA(cudaMallocHost(&c->h_scalars, 64 * sizeof(uint64_t)));
+	if(const char *e = getenv("SIBGPU_PART_RECORDS"))
+	{
+		uint64_t v = strtoull(e, nullptr, 10);
+		if(v >= 1024) c->part_target = v;
+	}
+	*out = c;
+	return SIBGPU_OK;
+}
+
+void sibgpu_destroy(sibgpu_ctx *c)
+{
+	if(!c) return;
+	cudaSetDevice(c->device);
+	DevBuf *bufs[] = {&c->d_text, &c->d_packed, &c->d_chr_start, &c->d_chr_len, &c->d_hist, &c->d_partoff, &c->d_cursor,
+		&c->d_records, &c->d_table, &c->d_partcnt, &c->d_keyoff, &c->d_ckeys, &c->d_vkeys, &c->d_vkeys_alt, &c->d_cubtmp,
+		&c->d_map, &c->d_filter, &c->d_hitmask, &c->d_tilecnt, &c->d_tileoff, &c->d_pos, &c->d_negtmp, &c->d_neg,
+		&c->d_chrinst, &c->d_scalars, &c->d_fp, &c->d_rep, &c->d_order};
+	for(DevBuf *b : bufs) b->release();
+	for(cudaEvent_t e : c->event_pool) cudaEventDestroy(e);
+	if(c->h_scalars) cudaFreeHost(c->h_scalars);
+	if(c->stream) cudaStreamDestroy(c->stream);
+	delete c;
+}
+
+void sibgpu_free(void *p) { free(p); }
+
+int sibgpu_upload(sibgpu_ctx *c, const char *const *chr, const uint64_t *len, uint32_t nchr)
+{
+	if(!c || (nchr && (!chr || !len)))
+	{
+		set_error("invalid: NULL argument");
+		return SIBGPU_ERR_INVALID;
+	}
+	SIB_CUDA(cudaSetDevice(c->device));
+	c->have_text = false;
+	c->have_result = false;
+	uint64_t N = 0;
+	for(uint32_t i = 0; i < nchr; i++) N += len[i];
+	const uint64_t M = N + nchr + 1;
+	// positions are 32-bit like the reference's Pos/Size (src/common.h:50-52: MAX_INPUT_SIZE = 1 << 30)
+	if(M >= (1ull << 31))
+	{
+		set_error("invalid: input of " + std::to_string(N) + " bases exceeds the 32-bit position range");
+		return SIBGPU_ERR_INVALID;
+	}
+	c->h_chr_start.resize(nchr);
+	c->h_chr_len.resize(nchr);
+	uint64_t at = 1;
+	for(uint32_t i = 0; i < nchr; i++)
+	{
+		c->h_chr_start[i] = (uint32_t)at;
+		c->h_chr_len[i] = (uint32_t)len[i];
+		at += len[i] + 1;
+	}
+	const size_t nwords = (size_t)((M + 15) / 16) + 8;
+	SIB_TRY(c->d_text.ensure(nwords * 16));
+	SIB_TRY(c->d_chr_start.ensure(sizeof(uint32_t) * (nchr + 1)));
+	SIB_TRY(c->d_chr_len.ensure(sizeof(uint32_t) * (nchr + 1)));
+	// text = '$' chr0 '$' chr1 '$' ... '$' (the DNASequence layout, src/dnasequence.cpp:75-103), '$'-padded
+	SIB_CUDA(cudaMemsetAsync(c->d_text.p, '$', nwords * 16, c->stream));
+	for(uint32_t i = 0; i < nchr; i++)
+	{
+		if(len[i])
+		{
+			SIB_CUDA(cudaMemcpyAsync(c->d_text.as<char>() + c->h_chr_start[i], chr[i], len[i], cudaMemcpyHostToDevice, c->stream));
+		}
+	}
+	if(nchr)
+	{
+		SIB_CUDA(cudaMemcpyAsync(c->d_chr_start.p, c->h_chr_start.data(), sizeof(uint32_t) * nchr, cudaMemcpyHostToDevice, c->stream));
+		SIB_CUDA(cudaMemcpyAsync(c->d_chr_len.p, c->h_chr_len.data(), sizeof(uint32_t) * nchr, cudaMemcpyHostToDevice, c->stream));
+	}
+	SIB_CUDA(cudaStreamSynchronize(c->stream));
+	c->nchr = nchr;
+	c->N = N;
+	c->M = M;
+	c->have_text = true;
+	return SIBGPU_OK;
+}
+
+int sibgpu_enumerate_resident(sibgpu_ctx *c, uint32_t k, uint64_t *ninst, uint32_t *count)
+{
+	if(!c || k == 0)
+	{
+		set_error("invalid: NULL context or k == 0");
+		return SIBGPU_ERR_INVALID;
+	}
+	if(!c->have_text)
+	{
+		set_error("state: sibgpu_upload must precede sibgpu_enumerate_resident");
+		return SIBGPU_ERR_STATE;
+	}
+	SIB_TRY(enumerate_resident(c, k));
+	if(ninst) *ninst = c->n_inst;
+	if(count) *count = c->n_vertices;
+	return SIBGPU_OK;
+}
+
+int sibgpu_download(sibgpu_ctx *c, sibgpu_inst **pos, uint64_t *npos, sibgpu_inst **neg, uint64_t *nneg)
+{
+	if(!c || !pos || !neg || !npos || !nneg)
+	{
+		set_error("invalid: NULL argument");
+		return SIBGPU_ERR_INVALID;
+	}
+	if(!c->have_result)
+	{
+		set_error("state: no enumeration result to download");
+		return SIBGPU_ERR_STATE;
+	}
+	SIB_CUDA(cudaSetDevice(c->device));
+	const uint64_t n = c->n_inst;
+	*pos = static_cast<sibgpu_inst*>(malloc(sizeof(sibgpu_inst) * (n + 1)));
+	*neg = static_cast<sibgpu_inst*>(malloc(sizeof(sibgpu_inst) * (n + 1)));
+	if(!*pos || !*neg)
+	{
+		set_error("invalid: host allocation failed");
+		return SIBGPU_ERR_INVALID;
+	}
+	if(n)
+	{
+		SIB_CUDA(cudaMemcpyAsync(*pos, c->d_pos.p, sizeof(sibgpu_inst) * n, cudaMemcpyDeviceToHost, c->stream));
+		SIB_CUDA(cudaMemcpyAsync(*neg, c->d_neg.p, sizeof(sibgpu_inst) * n, cudaMemcpyDeviceToHost, c->stream));
+		SIB_CUDA(cudaStreamSynchronize(c->stream));
+	}
+	*npos = n;
+	*nneg = n;
+	return SIBGPU_OK;
+}
+
+int sibgpu_enumerate(sibgpu_ctx *c, const char *const *chr, const uint64_t *len, uint32_t nchr, uint32_t k,
+	sibgpu_inst **pos, uint64_t *npos, sibgpu_inst **neg, uint64_t *nneg, uint32_t *count)
+{
+	SIB_TRY(sibgpu_upload(c, chr, len, nchr));
+	SIB_TRY(sibgpu_enumerate_resident(c, k, nullptr, count));
+	return sibgpu_download(c, pos, npos, neg, nneg);
+}
+
+int sibgpu_set_profiling(sibgpu_ctx *c, int enabled)
+{
+	if(!c) return SIBGPU_ERR_INVALID;
+	c->profiling = enabled != 0;
+	return SIBGPU_OK;
+}
+
+int sibgpu_kernel_stats(sibgpu_ctx *c, sibgpu_kernel_stat *out, int cap)
+{
+	if(!c) return 0;
+	int n = (int)c->stats.size();
+	for(int i = 0; i < n && i < cap; i++)
+	{
+		out[i].name = c->stats[i].name;
+		out[i].launches = c->stats[i].launches;
+		out[i].ms = c->stats[i].ms;
+		out[i].algo_bytes = c->stats[i].bytes;
+	}
+	return n;
+}
+
+uint64_t sibgpu_last_launches(sibgpu_ctx *c) { return c ? c->total_launches : 0; }
+
+}

@@ -1,0 +1,69 @@
+// libsibgpu context: device buffers, stream, per-kernel timing.
+#pragma once
+#include <map>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+
+struct sibgpu_ctx {
+	int device = 0;
+	int sm_count = 148;
+	cudaStream_t stream = nullptr;
+
+	// resident input (sibgpu_upload)
+	bool have_text = false;
+	std::vector<uint32_t> h_chr_start, h_chr_len;     // text coordinates of every chromosome
+	uint32_t nchr = 0;
+	uint64_t M = 0;                                    // text length: N + nchr + 1  ('$' chr0 '$' chr1 ... '$')
+	uint64_t N = 0;                                    // total bases
+	sibgpu::DevBuf d_text, d_packed, d_chr_start, d_chr_len;
+
+	// enumeration workspace
+	sibgpu::DevBuf d_hist, d_partoff, d_cursor, d_records, d_table, d_partcnt, d_keyoff, d_ckeys, d_vkeys, d_vkeys_alt,
+		d_cubtmp, d_map, d_filter, d_hitmask, d_tilecnt, d_tileoff, d_pos, d_negtmp, d_neg, d_chrinst, d_scalars,
+		d_fp, d_rep, d_order;
+	void *h_scalars = nullptr;                         // pinned, 64 x u64
+
+	// last result
+	bool have_result = false;
+	uint64_t n_inst = 0;                               // instances per strand
+	uint32_t n_vertices = 0;
+	uint32_t last_k = 0;
+
+	// tunables (env SIBGPU_PART_RECORDS)
+	uint64_t part_target = 1u << 20;
+
+	// profiling
+	bool profiling = false;
+	struct Span { const char *name; cudaEvent_t a, b; uint64_t bytes; };
+	std::vector<Span> spans;
+	std::vector<cudaEvent_t> event_pool;
+	size_t events_used = 0;
+	struct Stat { const char *name; uint32_t launches; float ms; uint64_t bytes; };
+	std::vector<Stat> stats;
+	uint64_t total_launches = 0;
+
+	cudaEvent_t get_event();
+	void prof_begin(const char *name, uint64_t bytes);
+	void prof_end();
+	void prof_reset();
+	int prof_collect();
+};
+
+namespace sibgpu {
+struct ProfScope {
+	sibgpu_ctx *c;
+	ProfScope(sibgpu_ctx *ctx, const char *name, uint64_t bytes, uint32_t launches = 1) : c(ctx)
+	{
+		c->total_launches += launches;
+		if(c->profiling) c->prof_begin(name, bytes);
+	}
+	~ProfScope()
+	{
+		if(c->profiling) c->prof_end();
+	}
+};
+
+int enumerate_resident(sibgpu_ctx *ctx, uint32_t k);
+} // namespace sibgpu

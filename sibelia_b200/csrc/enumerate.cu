@@ -1,0 +1,981 @@
+// Bifurcation (vertex) enumeration on the GPU -- replaces IndexedSequence::EnumerateBifurcationsSArrayInRAM
+// (/root/reference/src/vertexenumeration.cpp:263-364).  The reference sorts every suffix of both strands
+// (libdivsufsort + Kasai LCP) to find the classes of equal k-mers; here the classes are found by hashing:
+//
+//   K0 k_pack         ASCII text -> 2-bit packed words (+ legality check)                 1 B/base read, .25 written
+//   K1 k_scan_hist    rolling canonical k-mer keys of every position -> histogram over P hash partitions
+//   K2 k_scatter      same scan, records (key, context) counting-sorted per CTA in shared memory and written to
+//                     their partition in coalesced runs
+//   K3 k_insert       one partition at a time (sized so its open-addressing table stays resident in the 126 MB L2):
+//                     claim the slot of the key (CAS), OR the occurrence's predecessor/successor symbols into it
+//   K4 k_table_scan   apply the reference's predicate (vertexenumeration.cpp:67-70,330,348) to every class,
+//                     append the bifurcation k-mers, reset the table
+//   K5 k_expand / cub sort / k_build_map    vertex id = lexicographic rank among {w, revcomp(w)} (:350)
+//   K6 k_mark, K7 k_emit   second scan of the packed text: positions whose canonical key is a vertex, compacted in
+//                     text order -> the two (chr,pos)-sorted instance tables (:361-362)
+//
+// Both strands are handled with ONE record per text position: the record carries the canonical key
+// min(w, revcomp(w)) and the neighbour symbols re-expressed in the canonical orientation, so the class of w and the
+// class of revcomp(w) (which the reference enumerates separately and symmetrically) are decided once.
+#include <cub/cub.cuh>
+
+#include "context.h"
+
+namespace sibgpu {
+
+// ---------------------------------------------------------------------------------------------------------------
+// layout constants
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int TILE_THREADS = 256;
+constexpr int POS_PER_THREAD = 16;                     // one packed 32-bit word
+constexpr int TILE_POS = TILE_THREADS * POS_PER_THREAD; // 4096 text positions per tile
+constexpr int MAX_PARTS = 1024;
+constexpr uint64_t EMPTY64 = ~0ull;
+
+// occurrence context, 8 bits:  [7] forward k-mer is the canonical one  [6] palindrome  [5:3] prev  [2:0] next
+// (prev/next are symbols 0..3 = ACGT, 4 = chromosome end '#', already in canonical orientation)
+// table payload (stored inverted so that one 0xFF memset initialises keys and payloads):
+//   bits 0-4 prev-symbol set, bits 5-9 next-symbol set, bit 10 "seen more than once"
+constexpr uint32_t PAY_MULTI = 1u << 10;
+
+struct TextDesc {
+	const uint32_t *packed;        // 16 bases per word, first base in the top bit pair
+	const uint32_t *chr_start;     // text index of the first base of every chromosome
+	const uint32_t *chr_len;
+	uint32_t nchr;
+	uint32_t M;                    // text length
+	uint32_t nwords;               // valid words in packed[]
+};
+
+struct Rec16 { uint64_t a, b; };
+
+// MODE 0: k <= 28, record = key << 7 | ctx[6:0] in one 64-bit word
+// MODE 1: k <= 32, record = {key, ctx}
+// MODE 2: k  > 32, record = {fingerprint a, fingerprint b << 8 | ctx}, read from the per-position array d_fp
+template<int MODE> struct RecT { typedef Rec16 type; };
+template<> struct RecT<0> { typedef uint64_t type; };
+
+__device__ __forceinline__ uint64_t rec_hash(uint64_t a, uint64_t b_fp)
+{
+	return mix64(a ^ (b_fp * 0x9E3779B97F4A7C15ull));
+}
+
+__device__ __forceinline__ uint32_t payload_bits(uint32_t ctx)
+{
+	uint32_t p = (ctx >> 3) & 7u, n = ctx & 7u;
+	uint32_t bits = (1u << p) | (32u << n);
+	if(ctx & 64u)                                       // palindrome: the same text position is also an occurrence
+	{                                                   // on the other strand, with swapped complemented neighbours
+		bits |= (1u << comp_sym(n)) | (32u << comp_sym(p)) | PAY_MULTI;
+	}
+	return bits;
+}
+
+// The reference's predicate in closed form (vertexenumeration.cpp:67-70,330,343,348)
+__device__ __forceinline__ bool is_bifurcation(uint32_t pay)
+{
+	uint32_t P = pay & 31u, Nn = (pay >> 5) & 31u;
+	bool sep = ((P | Nn) & 16u) != 0;
+	if(pay & PAY_MULTI) return __popc(P) > 1 || __popc(Nn) > 1 || sep;
+	return sep;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// K0: pack
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_pack(const uint4 *__restrict__ text, uint32_t *__restrict__ packed,
+	uint32_t nwords, uint32_t *__restrict__ err)
+{
+	uint32_t bad = 0;
+	for(uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < nwords; i += gridDim.x * blockDim.x)
+	{
+		uint4 v = __ldg(text + i);
+		bad |= ~(legal_bytes(v.x) & legal_bytes(v.y) & legal_bytes(v.z) & legal_bytes(v.w)) & 0x80808080u;
+		packed[i] = (encode4(v.x) << 24) | (encode4(v.y) << 16) | (encode4(v.z) << 8) | encode4(v.w);
+	}
+	if(__any_sync(0xffffffffu, bad != 0) && (threadIdx.x & 31) == 0) atomicOr(err, 1u);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// per-thread scan of 16 consecutive text positions
+// ---------------------------------------------------------------------------------------------------------------
+// Stages the packed words of a tile (one back-halo word, 256 own, 4 forward-halo) into shared memory.
+__device__ __forceinline__ void stage_tile(const TextDesc &t, uint32_t tile, uint32_t *sw)
+{
+	int64_t base = (int64_t)tile * TILE_THREADS - 1;
+	for(int j = threadIdx.x; j < TILE_THREADS + 5; j += TILE_THREADS)
+	{
+		int64_t w = base + j;
+		sw[j] = (w >= 0 && w < (int64_t)t.nwords) ? __ldg(t.packed + w) : 0u;
+	}
+}
+
+// chromosome cursor of a thread: [cs, ce) is the chromosome containing (or preceding) the current position
+struct ChrCursor {
+	uint32_t cs, ce, nc;
+	__device__ __forceinline__ void init(const TextDesc &t, uint32_t p)
+	{
+		uint32_t lo = 0, hi = t.nchr;                  // number of chromosomes starting at or before p
+		while(lo < hi)
+		{
+			uint32_t mid = (lo + hi) >> 1;
+			if(__ldg(t.chr_start + mid) <= p) lo = mid + 1; else hi = mid;
+		}
+		nc = lo;
+		if(lo == 0) { cs = 0; ce = 0; }
+		else { cs = __ldg(t.chr_start + lo - 1); ce = cs + __ldg(t.chr_len + lo - 1); }
+	}
+	__device__ __forceinline__ void advance(const TextDesc &t, uint32_t p)
+	{
+		while(nc < t.nchr && p >= __ldg(t.chr_start + nc))
+		{
+			cs = __ldg(t.chr_start + nc);
+			ce = cs + __ldg(t.chr_len + nc);
+			nc++;
+		}
+	}
+};
+
+// Calls f(i, a, b, ctx) for every valid k-mer start among the thread's 16 positions (exact modes, k <= 32).
+//   a   = canonical key min(w, revcomp(w));  ctx as documented above (bit 7 = forward is canonical)
+template<class F>
+__device__ __forceinline__ void scan16_exact(const TextDesc &t, const uint32_t *sw, uint32_t tile, uint32_t k, F f_emit)
+{
+	const uint32_t tid = threadIdx.x;
+	const uint32_t p0 = tile * TILE_POS + tid * POS_PER_THREAD;
+	if(p0 >= t.M) return;
+	const uint32_t wm1 = sw[tid], w0 = sw[tid + 1], w1 = sw[tid + 2], w2 = sw[tid + 3], w3 = sw[tid + 4];
+	const uint64_t hi = ((uint64_t)w0 << 32) | w1, lo = ((uint64_t)w2 << 32) | w3;
+	const uint32_t kk = 2 * k;
+	const uint64_t mask = kk == 64 ? ~0ull : ((1ull << kk) - 1);
+	uint64_t f = hi >> (64 - kk);
+	uint64_t stream = kk == 64 ? lo : ((hi << kk) | (lo >> (64 - kk)));   // bases p0+k, p0+k+1, ...
+	uint64_t r = revcomp_key(f, k);
+	uint32_t prevc = wm1 & 3u;
+	ChrCursor cur;
+	cur.init(t, p0);
+#pragma unroll
+	for(int i = 0; i < POS_PER_THREAD; i++)
+	{
+		const uint32_t p = p0 + i;
+		const uint32_t nextc = (uint32_t)(stream >> 62);
+		cur.advance(t, p);
+		if(p >= cur.cs && p + k <= cur.ce)
+		{
+			const uint32_t ps = p == cur.cs ? 4u : prevc;
+			const uint32_t ns = p + k == cur.ce ? 4u : nextc;
+			const bool fw = f <= r;
+			const uint64_t canon = fw ? f : r;
+			uint32_t ctx = fw ? ((ps << 3) | ns) : ((comp_sym(ns) << 3) | comp_sym(ps));
+			ctx |= (f == r ? 64u : 0u) | (fw ? 128u : 0u);
+			f_emit(i, canon, (uint64_t)0, ctx);
+		}
+		prevc = (uint32_t)(f >> (kk - 2)) & 3u;
+		f = ((f << 2) | nextc) & mask;
+		r = (r >> 2) | ((uint64_t)(3u - nextc) << (kk - 2));
+		stream <<= 2;
+	}
+}
+
+// MODE 2: the per-position canonical fingerprints were precomputed by k_fingerprint (fingerprint.cu)
+template<class F>
+__device__ __forceinline__ void scan16_fp(const TextDesc &t, const Rec16 *__restrict__ fp, uint32_t tile, F f_emit)
+{
+	const uint32_t p0 = tile * TILE_POS + threadIdx.x * POS_PER_THREAD;
+#pragma unroll
+	for(int i = 0; i < POS_PER_THREAD; i++)
+	{
+		const uint32_t p = p0 + i;
+		if(p < t.M)
+		{
+			Rec16 v = fp[p];
+			if(v.a != EMPTY64) f_emit(i, v.a, v.b >> 8, (uint32_t)(v.b & 255u));
+		}
+	}
+}
+
+template<int MODE, class F>
+__device__ __forceinline__ void scan16(const TextDesc &t, const Rec16 *fp, const uint32_t *sw, uint32_t tile, uint32_t k,
+	F f_emit)
+{
+	if(MODE == 2) scan16_fp(t, fp, tile, f_emit);
+	else scan16_exact(t, sw, tile, k, f_emit);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// K1: scan + partition histogram
+// ---------------------------------------------------------------------------------------------------------------
+template<int MODE>
+__global__ void __launch_bounds__(TILE_THREADS) k_scan_hist(TextDesc t, const Rec16 *__restrict__ fp, uint32_t k,
+	uint32_t ntiles, uint32_t P, uint32_t *__restrict__ ghist)
+{
+	__shared__ uint32_t sw[TILE_THREADS + 5];
+	__shared__ uint32_t shist[MAX_PARTS];
+	for(uint32_t b = threadIdx.x; b < P; b += TILE_THREADS) shist[b] = 0;
+	for(uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x)
+	{
+		__syncthreads();
+		if(MODE != 2) stage_tile(t, tile, sw);
+		__syncthreads();
+		scan16<MODE>(t, fp, sw, tile, k, [&](int, uint64_t a, uint64_t b, uint32_t) {
+			uint32_t bin = __umulhi((uint32_t)(rec_hash(a, b) >> 32), P);
+			atomicAdd(&shist[bin], 1u);
+		});
+	}
+	__syncthreads();
+	for(uint32_t b = threadIdx.x; b < P; b += TILE_THREADS)
+	{
+		uint32_t c = shist[b];
+		if(c) atomicAdd(&ghist[b], c);
+	}
+}
+
+// exclusive scan of the P partition counts (one CTA); also publishes the largest partition
+__global__ void __launch_bounds__(MAX_PARTS) k_part_offsets(const uint32_t *__restrict__ hist, uint32_t P,
+	uint64_t *__restrict__ partoff, unsigned long long *__restrict__ cursor, uint64_t *__restrict__ scalars)
+{
+	typedef cub::BlockScan<uint64_t, MAX_PARTS> Scan;
+	typedef cub::BlockReduce<uint32_t, MAX_PARTS> Red;
+	__shared__ union { typename Scan::TempStorage s; typename Red::TempStorage r; } tmp;
+	uint32_t c = threadIdx.x < P ? hist[threadIdx.x] : 0u;
+	uint64_t off, total;
+	Scan(tmp.s).ExclusiveSum((uint64_t)c, off, total);
+	__syncthreads();
+	uint32_t mx = Red(tmp.r).Reduce(c, cub::Max());
+	if(threadIdx.x < P) { partoff[threadIdx.x] = off; cursor[threadIdx.x] = off; }
+	if(threadIdx.x == 0) { partoff[P] = total; scalars[0] = total; scalars[1] = mx; }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// K2: scan + scatter into hash partitions
+// ---------------------------------------------------------------------------------------------------------------
+template<int MODE> struct ScatterSmem {
+	uint32_t sw[TILE_THREADS + 5];
+	uint32_t cnt[MAX_PARTS];           // per-bin count of this tile, then exclusive local offset
+	unsigned long long gbase[MAX_PARTS]; // global index of the bin's run minus its local offset
+	uint32_t total;
+	uint64_t a[TILE_POS];
+	uint16_t bin_of[TILE_POS];         // bin of the record at each sorted local index
+};
+template<> struct ScatterSmem<1> : ScatterSmem<0> { uint64_t b[TILE_POS]; };
+template<> struct ScatterSmem<2> : ScatterSmem<1> {};
+
+template<int MODE>
+__global__ void __launch_bounds__(TILE_THREADS) k_scatter(TextDesc t, const Rec16 *__restrict__ fp, uint32_t k,
+	uint32_t ntiles, uint32_t P, unsigned long long *__restrict__ cursor, typename RecT<MODE>::type *__restrict__ out)
+{
+	extern __shared__ __align__(16) unsigned char smem_raw[];
+	ScatterSmem<MODE> &s = *reinterpret_cast<ScatterSmem<MODE>*>(smem_raw);
+	typedef cub::BlockScan<uint32_t, TILE_THREADS> Scan;
+	__shared__ typename Scan::TempStorage scan_tmp;
+	constexpr int BINS_PER_THREAD = MAX_PARTS / TILE_THREADS;
+
+	for(uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x)
+	{
+		for(uint32_t b = threadIdx.x; b < P; b += TILE_THREADS) s.cnt[b] = 0;
+		if(MODE != 2) stage_tile(t, tile, s.sw);
+		__syncthreads();
+
+		uint64_t ra[POS_PER_THREAD], rb[POS_PER_THREAD];
+		uint32_t binrank[POS_PER_THREAD];
+		uint32_t valid = 0;
+		scan16<MODE>(t, fp, s.sw, tile, k, [&](int i, uint64_t a, uint64_t b, uint32_t ctx) {
+			uint32_t bin = __umulhi((uint32_t)(rec_hash(a, b) >> 32), P);
+			uint32_t rank = atomicAdd(&s.cnt[bin], 1u);
+			binrank[i] = (bin << 16) | rank;             // rank < 4096, bin < 1024
+			valid |= 1u << i;
+			if(MODE == 0) { ra[i] = (a << 7) | (ctx & 127u); }
+			else { ra[i] = a; rb[i] = (b << 8) | ctx; }
+		});
+		__syncthreads();
+
+		// exclusive scan over the bins (4 per thread) + reservation of the global runs
+		uint32_t c[BINS_PER_THREAD], o[BINS_PER_THREAD], sum = 0;
+#pragma unroll
+		for(int j = 0; j < BINS_PER_THREAD; j++)
+		{
+			uint32_t b = threadIdx.x * BINS_PER_THREAD + j;
+			c[j] = b < P ? s.cnt[b] : 0u;
+			sum += c[j];
+		}
+		uint32_t excl, total;
+		Scan(scan_tmp).ExclusiveSum(sum, excl, total);
+#pragma unroll
+		for(int j = 0; j < BINS_PER_THREAD; j++)
+		{
+			uint32_t b = threadIdx.x * BINS_PER_THREAD + j;
+			o[j] = excl;
+			excl += c[j];
+			if(b < P)
+			{
+				unsigned long long g = c[j] ? atomicAdd(&cursor[b], (unsigned long long)c[j]) : 0ull;
+				s.cnt[b] = o[j];
+				s.gbase[b] = g - o[j];
+			}
+		}
+		if(threadIdx.x == 0) s.total = total;
+		__syncthreads();
+
+		// place the records in bin order in shared memory
+#pragma unroll
+		for(int i = 0; i < POS_PER_THREAD; i++)
+		{
+			if(valid & (1u << i))
+			{
+				uint32_t bin = binrank[i] >> 16, rank = binrank[i] & 0xFFFFu;
+				uint32_t l = s.cnt[bin] + rank;
+				s.a[l] = ra[i];
+				if(MODE != 0) static_cast<ScatterSmem<1>&>(s).b[l] = rb[i];
+				s.bin_of[l] = (uint16_t)bin;
+			}
+		}
+		__syncthreads();
+
+		// coalesced copy-out: consecutive l of the same bin go to consecutive global slots
+		const uint32_t n = s.total;
+		for(uint32_t l = threadIdx.x; l < n; l += TILE_THREADS)
+		{
+			unsigned long long g = s.gbase[s.bin_of[l]] + l;
+			if(MODE == 0) { reinterpret_cast<uint64_t*>(out)[g] = s.a[l]; }
+			else
+			{
+				Rec16 v; v.a = s.a[l]; v.b = static_cast<ScatterSmem<1>&>(s).b[l];
+				reinterpret_cast<ulonglong2*>(out)[g] = make_ulonglong2(v.a, v.b);
+			}
+		}
+		__syncthreads();
+	}
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// K3: insert one partition into the L2-resident table.   K4: predicate + reset.
+// ---------------------------------------------------------------------------------------------------------------
+struct Slot8 { unsigned long long key; uint32_t pay; uint32_t pad; };             // 16 B
+struct Slot16 { unsigned long long a, b; uint32_t pay; uint32_t pad[3]; };        // 32 B
+
+template<int MODE>
+__global__ void __launch_bounds__(256) k_insert(const typename RecT<MODE>::type *__restrict__ recs, uint64_t n,
+	void *__restrict__ table, uint32_t T)
+{
+	for(uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
+	{
+		if(MODE == 0)
+		{
+			Slot8 *tab = static_cast<Slot8*>(table);
+			const uint64_t rec = reinterpret_cast<const uint64_t*>(recs)[i];
+			const unsigned long long key = rec >> 7;
+			const uint32_t ctx = (uint32_t)rec & 127u;
+			uint32_t slot = __umulhi((uint32_t)rec_hash(key, 0), T);
+			uint32_t bits = payload_bits(ctx);
+			for(;;)
+			{
+				// plain peek first: in related genomes most keys are already present, which saves the CAS
+				unsigned long long old = __ldcg(&tab[slot].key);
+				if(old == EMPTY64) old = atomicCAS(&tab[slot].key, EMPTY64, key);
+				if(old == EMPTY64 || old == key)
+				{
+					if(old == key) bits |= PAY_MULTI;
+					atomicAnd(&tab[slot].pay, ~bits);
+					break;
+				}
+				slot = slot + 1 == T ? 0 : slot + 1;
+			}
+		}
+		else
+		{
+			Slot16 *tab = static_cast<Slot16*>(table);
+			const ulonglong2 rec = reinterpret_cast<const ulonglong2*>(recs)[i];
+			const unsigned long long a = rec.x, b = rec.y >> 8;    // b < 2^56, never the "unclaimed" sentinel
+			const uint32_t ctx = (uint32_t)rec.y & 127u;
+			uint32_t slot = __umulhi((uint32_t)rec_hash(a, b), T);
+			uint32_t bits = payload_bits(ctx);
+			for(;;)
+			{
+				unsigned long long oa = __ldcg(&tab[slot].a);
+				if(oa == EMPTY64) oa = atomicCAS(&tab[slot].a, EMPTY64, a);
+				if(oa == EMPTY64 || oa == a)
+				{
+					// second word: claimed by whoever CASes it first; a different b means another class
+					unsigned long long ob = atomicCAS(&tab[slot].b, EMPTY64, b);
+					if(ob == EMPTY64 || ob == b)
+					{
+						if(ob == b) bits |= PAY_MULTI;
+						atomicAnd(&tab[slot].pay, ~bits);
+						break;
+					}
+				}
+				slot = slot + 1 == T ? 0 : slot + 1;
+			}
+		}
+	}
+}
+
+// Appends the canonical keys of the partition's bifurcation classes to `out` (the partition's own, now dead, record
+// region) and resets the table for the next partition.
+template<int MODE>
+__global__ void __launch_bounds__(256) k_table_scan(void *__restrict__ table, uint32_t T,
+	typename RecT<MODE>::type *__restrict__ out, uint32_t *__restrict__ counter)
+{
+	const uint32_t lane_id = threadIdx.x & 31u;
+	for(uint32_t wbase = (blockIdx.x * blockDim.x + threadIdx.x) & ~31u; wbase < T; wbase += gridDim.x * blockDim.x)
+	{
+		const uint32_t sidx = wbase + lane_id;            // wbase is warp-uniform: the ballots below are convergent
+		bool bif = false;
+		unsigned long long a = 0, b = 0;
+		if(sidx < T)
+		{
+			if(MODE == 0)
+			{
+				Slot8 *tab = static_cast<Slot8*>(table);
+				a = tab[sidx].key;
+				if(a != EMPTY64)
+				{
+					bif = is_bifurcation(~tab[sidx].pay);
+					tab[sidx].key = EMPTY64;
+					tab[sidx].pay = ~0u;
+				}
+			}
+			else
+			{
+				Slot16 *tab = static_cast<Slot16*>(table);
+				a = tab[sidx].a;
+				if(a != EMPTY64)
+				{
+					b = tab[sidx].b;
+					bif = is_bifurcation(~tab[sidx].pay);
+					tab[sidx].a = EMPTY64;
+					tab[sidx].b = EMPTY64;
+					tab[sidx].pay = ~0u;
+				}
+			}
+		}
+		// warp-aggregated append
+		const uint32_t m = __ballot_sync(0xffffffffu, bif);
+		if(m)
+		{
+			const uint32_t lane = threadIdx.x & 31u;
+			uint32_t base = 0;
+			if(lane == (uint32_t)(__ffs(m) - 1)) base = atomicAdd(counter, (uint32_t)__popc(m));
+			base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
+			if(bif)
+			{
+				uint32_t idx = base + __popc(m & ((1u << lane) - 1));
+				if(MODE == 0) reinterpret_cast<uint64_t*>(out)[idx] = a;
+				else reinterpret_cast<ulonglong2*>(out)[idx] = make_ulonglong2(a, b);
+			}
+		}
+	}
+}
+
+// exclusive scan of the per-partition vertex-class counts (one CTA)
+__global__ void __launch_bounds__(MAX_PARTS) k_key_offsets(const uint32_t *__restrict__ cnt, uint32_t P,
+	uint64_t *__restrict__ keyoff, uint64_t *__restrict__ scalars)
+{
+	typedef cub::BlockScan<uint64_t, MAX_PARTS> Scan;
+	__shared__ typename Scan::TempStorage tmp;
+	uint32_t c = threadIdx.x < P ? cnt[threadIdx.x] : 0u;
+	uint64_t off, total;
+	Scan(tmp).ExclusiveSum((uint64_t)c, off, total);
+	if(threadIdx.x < P) keyoff[threadIdx.x] = off;
+	if(threadIdx.x == 0) { keyoff[P] = total; scalars[2] = total; }
+}
+
+// gathers the per-partition key lists into one array; blockIdx.y = partition
+template<int MODE>
+__global__ void __launch_bounds__(256) k_gather_keys(const typename RecT<MODE>::type *__restrict__ recs,
+	const uint64_t *__restrict__ partoff, const uint32_t *__restrict__ cnt, const uint64_t *__restrict__ keyoff,
+	typename RecT<MODE>::type *__restrict__ ckeys)
+{
+	const uint32_t p = blockIdx.y;
+	const uint32_t n = cnt[p];
+	const typename RecT<MODE>::type *src = recs + partoff[p];
+	typename RecT<MODE>::type *dst = ckeys + keyoff[p];
+	for(uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) dst[i] = src[i];
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// K5: vertex ids (exact modes): the vertex k-mers are {c, revcomp(c)}; id = rank in the sorted array
+// ---------------------------------------------------------------------------------------------------------------
+template<int MODE>
+__global__ void __launch_bounds__(256) k_expand(const typename RecT<MODE>::type *__restrict__ ckeys, uint64_t n, uint32_t k,
+	uint64_t *__restrict__ vkeys, uint32_t *__restrict__ npal)
+{
+	uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+	if(i >= n) return;
+	uint64_t c = MODE == 0 ? reinterpret_cast<const uint64_t*>(ckeys)[i] : reinterpret_cast<const Rec16*>(ckeys)[i].a;
+	uint64_t r = revcomp_key(c, k);
+	vkeys[2 * i] = c;
+	vkeys[2 * i + 1] = r == c ? EMPTY64 : r;           // sentinel sorts last (k = 32: revcomp of all-T is 0 != c)
+	if(r == c) atomicAdd(npal, 1u);
+}
+
+__device__ __forceinline__ uint32_t lower_bound_u64(const uint64_t *__restrict__ v, uint32_t n, uint64_t x)
+{
+	uint32_t lo = 0, hi = n;
+	while(lo < hi)
+	{
+		uint32_t mid = (lo + hi) >> 1;
+		if(__ldg(v + mid) < x) lo = mid + 1; else hi = mid;
+	}
+	return lo;
+}
+
+// vertex map: canonical key -> (id of the canonical k-mer, id of its reverse complement); 32-byte slots
+struct MapSlot { unsigned long long a, b; uint32_t idc, idr; uint32_t pad[2]; };
+
+__device__ __forceinline__ void map_insert(MapSlot *map, uint32_t Tm, uint32_t *filter, uint32_t fshift,
+	unsigned long long a, unsigned long long b, uint32_t idc, uint32_t idr)
+{
+	uint64_t h = rec_hash(a, b);
+	uint32_t slot = __umulhi((uint32_t)h, Tm);
+	for(;;)
+	{
+		unsigned long long old = atomicCAS(&map[slot].a, EMPTY64, a);
+		if(old == EMPTY64) break;                      // canonical keys are distinct: no equal-key case
+		slot = slot + 1 == Tm ? 0 : slot + 1;
+	}
+	map[slot].b = b;
+	map[slot].idc = idc;
+	map[slot].idr = idr;
+	uint32_t bit = (uint32_t)(h >> fshift);
+	atomicOr(&filter[bit >> 5], 1u << (bit & 31u));
+}
+
+template<int MODE>
+__global__ void __launch_bounds__(256) k_build_map(const typename RecT<MODE>::type *__restrict__ ckeys, uint64_t n, uint32_t k,
+	const uint64_t *__restrict__ vsorted, uint32_t V, MapSlot *__restrict__ map, uint32_t Tm,
+	uint32_t *__restrict__ filter, uint32_t fshift)
+{
+	uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+	if(i >= n) return;
+	uint64_t c = MODE == 0 ? reinterpret_cast<const uint64_t*>(ckeys)[i] : reinterpret_cast<const Rec16*>(ckeys)[i].a;
+	uint32_t idc = lower_bound_u64(vsorted, V, c);
+	uint32_t idr = lower_bound_u64(vsorted, V, revcomp_key(c, k));
+	map_insert(map, Tm, filter, fshift, c, 0ull, idc, idr);
+}
+
+__device__ __forceinline__ bool map_lookup(const MapSlot *__restrict__ map, uint32_t Tm, const uint32_t *__restrict__ filter,
+	uint32_t fshift, unsigned long long a, unsigned long long b, uint32_t &idc, uint32_t &idr)
+{
+	uint64_t h = rec_hash(a, b);
+	uint32_t bit = (uint32_t)(h >> fshift);
+	if(!((__ldg(filter + (bit >> 5)) >> (bit & 31u)) & 1u)) return false;
+	uint32_t slot = __umulhi((uint32_t)h, Tm);
+	for(;;)
+	{
+		const ulonglong2 kv = __ldg(reinterpret_cast<const ulonglong2*>(&map[slot]));
+		if(kv.x == EMPTY64) return false;
+		if(kv.x == a && kv.y == b)
+		{
+			const uint2 ids = __ldg(reinterpret_cast<const uint2*>(&map[slot].idc));
+			idc = ids.x;
+			idr = ids.y;
+			return true;
+		}
+		slot = slot + 1 == Tm ? 0 : slot + 1;
+	}
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// K6: mark vertex positions.   K7: emit the instance tables in text order.
+// ---------------------------------------------------------------------------------------------------------------
+template<int MODE>
+__global__ void __launch_bounds__(TILE_THREADS) k_mark(TextDesc t, const Rec16 *__restrict__ fp, uint32_t k, uint32_t ntiles,
+	const MapSlot *__restrict__ map, uint32_t Tm, const uint32_t *__restrict__ filter, uint32_t fshift,
+	uint16_t *__restrict__ hitmask, uint64_t *__restrict__ tilecnt)
+{
+	__shared__ uint32_t sw[TILE_THREADS + 5];
+	typedef cub::BlockReduce<uint32_t, TILE_THREADS> Red;
+	__shared__ typename Red::TempStorage red_tmp;
+	for(uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x)
+	{
+		__syncthreads();
+		if(MODE != 2) stage_tile(t, tile, sw);
+		__syncthreads();
+		uint32_t mask = 0;
+		scan16<MODE>(t, fp, sw, tile, k, [&](int i, uint64_t a, uint64_t b, uint32_t) {
+			uint32_t idc, idr;
+			if(map_lookup(map, Tm, filter, fshift, a, b, idc, idr)) mask |= 1u << i;
+		});
+		hitmask[(uint64_t)tile * TILE_THREADS + threadIdx.x] = (uint16_t)mask;
+		uint32_t total = Red(red_tmp).Sum((uint32_t)__popc(mask));
+		if(threadIdx.x == 0) tilecnt[tile] = total;
+	}
+}
+
+// forward key of the k-mer starting at text position p (k <= 32), straight from the packed words
+__device__ __forceinline__ uint64_t key_at(const TextDesc &t, uint32_t p, uint32_t k)
+{
+	const uint32_t w = p >> 4, sh = 2 * (p & 15u);
+	uint64_t x0 = ((uint64_t)__ldg(t.packed + w) << 32) | __ldg(t.packed + w + 1);
+	uint64_t x1 = ((uint64_t)__ldg(t.packed + w + 2) << 32);
+	uint64_t x = sh ? ((x0 << sh) | (x1 >> (64 - sh))) : x0;
+	return x >> (64 - 2 * k);
+}
+
+template<int MODE>
+__global__ void __launch_bounds__(TILE_THREADS) k_emit(TextDesc t, const Rec16 *__restrict__ fp, uint32_t k, uint32_t ntiles,
+	const MapSlot *__restrict__ map, uint32_t Tm, const uint32_t *__restrict__ filter, uint32_t fshift,
+	const uint16_t *__restrict__ hitmask, const uint64_t *__restrict__ tileoff,
+	sibgpu_inst *__restrict__ pos_out, sibgpu_inst *__restrict__ neg_tmp)
+{
+	typedef cub::BlockScan<uint32_t, TILE_THREADS> Scan;
+	__shared__ typename Scan::TempStorage scan_tmp;
+	for(uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x)
+	{
+		uint32_t mask = hitmask[(uint64_t)tile * TILE_THREADS + threadIdx.x];
+		uint32_t rank;
+		__syncthreads();
+		Scan(scan_tmp).ExclusiveSum((uint32_t)__popc(mask), rank);
+		uint64_t o = tileoff[tile] + rank;
+		const uint32_t p0 = tile * TILE_POS + threadIdx.x * POS_PER_THREAD;
+		while(mask)
+		{
+			const uint32_t i = __ffs(mask) - 1;
+			mask &= mask - 1;
+			const uint32_t p = p0 + i;
+			unsigned long long a, b = 0;
+			bool fw;
+			if(MODE == 2)
+			{
+				Rec16 v = fp[p];
+				a = v.a; b = v.b >> 8; fw = (v.b & 128u) != 0;
+			}
+			else
+			{
+				uint64_t f = key_at(t, p, k), r = revcomp_key(f, k);
+				fw = f <= r;
+				a = fw ? f : r;
+			}
+			uint32_t idc = 0, idr = 0;
+			map_lookup(map, Tm, filter, fshift, a, b, idc, idr);
+			ChrCursor cur;
+			cur.init(t, p);
+			const uint32_t c = cur.nc - 1, ppos = p - cur.cs, len = cur.ce - cur.cs;
+			sibgpu_inst ip = {fw ? idc : idr, c, ppos};
+			sibgpu_inst in = {fw ? idr : idc, c, len - ppos - k};
+			pos_out[o] = ip;
+			neg_tmp[o] = in;
+			o++;
+		}
+	}
+}
+
+// chrinst[c] = first index in the (text-ordered) negative table whose chr >= c, for c in 0..nchr
+__global__ void __launch_bounds__(256) k_chr_bounds(const sibgpu_inst *__restrict__ neg_tmp, uint64_t n, uint32_t nchr,
+	uint64_t *__restrict__ chrinst)
+{
+	uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+	if(c > nchr) return;
+	uint64_t lo = 0, hi = n;
+	while(lo < hi)
+	{
+		uint64_t mid = (lo + hi) >> 1;
+		if(neg_tmp[mid].chr < c) lo = mid + 1; else hi = mid;
+	}
+	chrinst[c] = lo;
+}
+
+// The negative-strand table is sorted by (chr, position in the reverse complement): within a chromosome that is
+// descending text order, so every chromosome's run is reversed.
+__global__ void __launch_bounds__(256) k_reverse_neg(const sibgpu_inst *__restrict__ neg_tmp, uint64_t n,
+	const uint64_t *__restrict__ chrinst, sibgpu_inst *__restrict__ neg_out)
+{
+	uint64_t j = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+	if(j >= n) return;
+	sibgpu_inst v = neg_tmp[j];
+	neg_out[chrinst[v.chr] + chrinst[v.chr + 1] - 1 - j] = v;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// host orchestration
+// ---------------------------------------------------------------------------------------------------------------
+int fingerprint_positions(sibgpu_ctx *ctx, const TextDesc &t, uint32_t k, uint32_t attempt);            // fingerprint.cu
+int rank_fingerprint_vertices(sibgpu_ctx *ctx, const TextDesc &t, uint32_t k, uint64_t Vc, uint32_t ntiles,
+	uint32_t Tm, uint32_t fshift, uint32_t *V_out, bool *collision);                                        // fingerprint.cu
+
+static inline uint32_t grid_for(uint64_t work_items, int threads, int sm_count, int waves = 8)
+{
+	uint64_t blocks = (work_items + threads - 1) / threads;
+	uint64_t cap = (uint64_t)sm_count * waves;
+	if(blocks < 1) blocks = 1;
+	return (uint32_t)(blocks < cap ? blocks : cap);
+}
+
+template<int MODE>
+static int enumerate_mode(sibgpu_ctx *ctx, uint32_t k, uint64_t nrec)
+{
+	typedef typename RecT<MODE>::type Rec;
+	cudaStream_t st = ctx->stream;
+	const int sms = ctx->sm_count;
+	uint64_t *hs = static_cast<uint64_t*>(ctx->h_scalars);
+	uint64_t *ds = ctx->d_scalars.as<uint64_t>();
+
+	TextDesc t;
+	t.packed = ctx->d_packed.as<uint32_t>();
+	t.chr_start = ctx->d_chr_start.as<uint32_t>();
+	t.chr_len = ctx->d_chr_len.as<uint32_t>();
+	t.nchr = ctx->nchr;
+	t.M = (uint32_t)ctx->M;
+	t.nwords = (uint32_t)((ctx->M + 15) / 16) + 8;
+	const uint32_t ntiles = (uint32_t)((ctx->M + TILE_POS - 1) / TILE_POS);
+	const Rec16 *fp = ctx->d_fp.as<Rec16>();
+
+	for(uint32_t attempt = 0; ; attempt++)
+	{
+		if(MODE == 2) SIB_TRY(fingerprint_positions(ctx, t, k, attempt));
+
+		// ---- partition plan
+		uint64_t P64 = (nrec + ctx->part_target - 1) / ctx->part_target;
+		const uint32_t P = (uint32_t)(P64 < 1 ? 1 : (P64 > MAX_PARTS ? MAX_PARTS : P64));
+		SIB_TRY(ctx->d_hist.ensure(sizeof(uint32_t) * MAX_PARTS));
+		SIB_TRY(ctx->d_partoff.ensure(sizeof(uint64_t) * (MAX_PARTS + 1)));
+		SIB_TRY(ctx->d_cursor.ensure(sizeof(uint64_t) * MAX_PARTS));
+		SIB_TRY(ctx->d_partcnt.ensure(sizeof(uint32_t) * MAX_PARTS));
+		SIB_TRY(ctx->d_keyoff.ensure(sizeof(uint64_t) * (MAX_PARTS + 1)));
+		SIB_TRY(ctx->d_records.ensure(sizeof(Rec) * nrec));
+		SIB_CUDA(cudaMemsetAsync(ctx->d_hist.p, 0, sizeof(uint32_t) * MAX_PARTS, st));
+		SIB_CUDA(cudaMemsetAsync(ctx->d_partcnt.p, 0, sizeof(uint32_t) * MAX_PARTS, st));
+
+		const uint32_t scan_grid = ntiles < (uint32_t)sms * 8 ? ntiles : (uint32_t)sms * 8;
+		{
+			ProfScope ps(ctx, "k_scan_hist", MODE == 2 ? ctx->M * 16 : ctx->M / 4);
+			k_scan_hist<MODE><<<scan_grid, TILE_THREADS, 0, st>>>(t, fp, k, ntiles, P, ctx->d_hist.as<uint32_t>());
+		}
+		{
+			ProfScope ps(ctx, "k_part_offsets", 0);
+			k_part_offsets<<<1, MAX_PARTS, 0, st>>>(ctx->d_hist.as<uint32_t>(), P, ctx->d_partoff.as<uint64_t>(),
+				ctx->d_cursor.as<unsigned long long>(), ds);
+		}
+		SIB_CUDA(cudaMemcpyAsync(hs, ds, sizeof(uint64_t) * 2, cudaMemcpyDeviceToHost, st));
+		SIB_CUDA(cudaStreamSynchronize(st));
+		if(hs[0] != nrec)
+		{
+			set_error("internal: scan kernel counted " + std::to_string(hs[0]) + " k-mers, expected " + std::to_string(nrec));
+			return SIBGPU_ERR_INTERNAL;
+		}
+		const uint64_t maxpart = hs[1];
+		std::vector<uint64_t> h_partoff(P + 1);
+		SIB_CUDA(cudaMemcpyAsync(h_partoff.data(), ctx->d_partoff.p, sizeof(uint64_t) * (P + 1), cudaMemcpyDeviceToHost, st));
+
+		// ---- scatter
+		{
+			size_t smem = sizeof(ScatterSmem<MODE>);
+			SIB_CUDA(cudaFuncSetAttribute(k_scatter<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+			const uint32_t g = ntiles < (uint32_t)sms * 4 ? ntiles : (uint32_t)sms * 4;
+			ProfScope ps(ctx, "k_scatter", (MODE == 2 ? ctx->M * 16 : ctx->M / 4) + nrec * sizeof(Rec));
+			k_scatter<MODE><<<g, TILE_THREADS, smem, st>>>(t, fp, k, ntiles, P, ctx->d_cursor.as<unsigned long long>(),
+				ctx->d_records.as<Rec>());
+		}
+		SIB_CUDA(cudaStreamSynchronize(st));
+
+		// ---- per-partition L2-resident grouping
+		uint64_t T64 = 2 * maxpart + 1024;
+		if(T64 > 0xFFFFFF00ull)
+		{
+			set_error("internal: hash partition of " + std::to_string(maxpart) + " records does not fit a 32-bit table");
+			return SIBGPU_ERR_INTERNAL;
+		}
+		const uint32_t T = (uint32_t)T64;
+		const size_t slot_bytes = MODE == 0 ? sizeof(Slot8) : sizeof(Slot16);
+		SIB_TRY(ctx->d_table.ensure(slot_bytes * T));
+		SIB_CUDA(cudaMemsetAsync(ctx->d_table.p, 0xFF, slot_bytes * T, st));
+		for(uint32_t p = 0; p < P; p++)
+		{
+			const uint64_t n = h_partoff[p + 1] - h_partoff[p];
+			if(n == 0) continue;
+			Rec *part = ctx->d_records.as<Rec>() + h_partoff[p];
+			{
+				ProfScope ps(ctx, "k_insert", n * sizeof(Rec));
+				k_insert<MODE><<<grid_for(n, 256, sms, 8), 256, 0, st>>>(part, n, ctx->d_table.p, T);
+			}
+			{
+				ProfScope ps(ctx, "k_table_scan", (uint64_t)T * slot_bytes);
+				k_table_scan<MODE><<<grid_for(T, 256, sms, 8), 256, 0, st>>>(ctx->d_table.p, T, part,
+					ctx->d_partcnt.as<uint32_t>() + p);
+			}
+		}
+		{
+			ProfScope ps(ctx, "k_key_offsets", 0);
+			k_key_offsets<<<1, MAX_PARTS, 0, st>>>(ctx->d_partcnt.as<uint32_t>(), P, ctx->d_keyoff.as<uint64_t>(), ds);
+		}
+		SIB_CUDA(cudaMemcpyAsync(hs + 2, ds + 2, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+		SIB_CUDA(cudaStreamSynchronize(st));
+		const uint64_t Vc = hs[2];                         // canonical vertex classes
+		if(Vc == 0)
+		{
+			ctx->n_inst = 0;
+			ctx->n_vertices = 0;
+			return SIBGPU_OK;
+		}
+		if(2 * Vc > 0xFFFFFFF0ull)
+		{
+			set_error("invalid: more than 2^32 vertices");
+			return SIBGPU_ERR_INVALID;
+		}
+		SIB_TRY(ctx->d_ckeys.ensure(sizeof(Rec) * Vc));
+		{
+			ProfScope ps(ctx, "k_gather_keys", 2 * Vc * sizeof(Rec));
+			dim3 g(8, P);
+			k_gather_keys<MODE><<<g, 256, 0, st>>>(ctx->d_records.as<Rec>(), ctx->d_partoff.as<uint64_t>(),
+				ctx->d_partcnt.as<uint32_t>(), ctx->d_keyoff.as<uint64_t>(), ctx->d_ckeys.as<Rec>());
+		}
+
+		// ---- vertex ids + vertex map
+		uint64_t Tm64 = 2 * Vc + 64;
+		const uint32_t Tm = (uint32_t)Tm64;
+		uint32_t fbits_log = 16;
+		while((1ull << fbits_log) < 32 * Vc && fbits_log < 32) fbits_log++;
+		const uint32_t fshift = 64 - fbits_log;
+		SIB_TRY(ctx->d_map.ensure(sizeof(MapSlot) * (size_t)Tm));
+		SIB_TRY(ctx->d_filter.ensure((1ull << fbits_log) / 8));
+		SIB_CUDA(cudaMemsetAsync(ctx->d_map.p, 0xFF, sizeof(MapSlot) * (size_t)Tm, st));
+		SIB_CUDA(cudaMemsetAsync(ctx->d_filter.p, 0, (1ull << fbits_log) / 8, st));
+		uint32_t V = 0;
+		if(MODE != 2)
+		{
+			SIB_TRY(ctx->d_vkeys.ensure(sizeof(uint64_t) * 2 * Vc));
+			SIB_TRY(ctx->d_vkeys_alt.ensure(sizeof(uint64_t) * 2 * Vc));
+			SIB_CUDA(cudaMemsetAsync(ds + 3, 0, sizeof(uint64_t), st));
+			{
+				ProfScope ps(ctx, "k_expand", Vc * (sizeof(Rec) + 16));
+				k_expand<MODE><<<(uint32_t)((Vc + 255) / 256), 256, 0, st>>>(ctx->d_ckeys.as<Rec>(), Vc, k,
+					ctx->d_vkeys.as<uint64_t>(), reinterpret_cast<uint32_t*>(ds + 3));
+			}
+			size_t tmp_bytes = 0;
+			cub::DoubleBuffer<uint64_t> dbuf(ctx->d_vkeys.as<uint64_t>(), ctx->d_vkeys_alt.as<uint64_t>());
+			SIB_CUDA(cub::DeviceRadixSort::SortKeys(nullptr, tmp_bytes, dbuf, (int)(2 * Vc), 0, 64, st));
+			SIB_TRY(ctx->d_cubtmp.ensure(tmp_bytes));
+			{
+				ProfScope ps(ctx, "cub_sort_vertex_keys", 2 * Vc * 8 * 2, 8);
+				SIB_CUDA(cub::DeviceRadixSort::SortKeys(ctx->d_cubtmp.p, tmp_bytes, dbuf, (int)(2 * Vc), 0, 64, st));
+			}
+			SIB_CUDA(cudaMemcpyAsync(hs + 3, ds + 3, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+			SIB_CUDA(cudaStreamSynchronize(st));
+			const uint32_t npal = (uint32_t)(hs[3] & 0xFFFFFFFFu);
+			V = (uint32_t)(2 * Vc - npal);
+			{
+				ProfScope ps(ctx, "k_build_map", Vc * (sizeof(Rec) + sizeof(MapSlot)));
+				k_build_map<MODE><<<(uint32_t)((Vc + 255) / 256), 256, 0, st>>>(ctx->d_ckeys.as<Rec>(), Vc, k, dbuf.Current(), V,
+					ctx->d_map.as<MapSlot>(), Tm, ctx->d_filter.as<uint32_t>(), fshift);
+			}
+		}
+		else
+		{
+			bool collision = false;
+			SIB_TRY(rank_fingerprint_vertices(ctx, t, k, Vc, ntiles, Tm, fshift, &V, &collision));
+			if(collision)
+			{
+				if(attempt >= 2)
+				{
+					set_error("internal: fingerprint verification failed three times");
+					return SIBGPU_ERR_INTERNAL;
+				}
+				continue;                                  // re-run with another fingerprint base
+			}
+		}
+
+		// ---- instance tables
+		SIB_TRY(ctx->d_hitmask.ensure(sizeof(uint16_t) * (size_t)ntiles * TILE_THREADS));
+		SIB_TRY(ctx->d_tilecnt.ensure(sizeof(uint64_t) * ntiles));
+		SIB_TRY(ctx->d_tileoff.ensure(sizeof(uint64_t) * (ntiles + 1)));
+		{
+			ProfScope ps(ctx, "k_mark", (MODE == 2 ? ctx->M * 16 : ctx->M / 4) + ctx->M / 8);
+			k_mark<MODE><<<scan_grid, TILE_THREADS, 0, st>>>(t, fp, k, ntiles, ctx->d_map.as<MapSlot>(), Tm,
+				ctx->d_filter.as<uint32_t>(), fshift, ctx->d_hitmask.as<uint16_t>(), ctx->d_tilecnt.as<uint64_t>());
+		}
+		{
+			size_t tmp_bytes = 0;
+			const uint64_t *in = ctx->d_tilecnt.as<uint64_t>();
+			SIB_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, in, ctx->d_tileoff.as<uint64_t>(), (int)ntiles, st));
+			SIB_TRY(ctx->d_cubtmp.ensure(tmp_bytes));
+			ProfScope ps(ctx, "cub_scan_tile_counts", ntiles * 12ull, 2);
+			SIB_CUDA(cub::DeviceScan::ExclusiveSum(ctx->d_cubtmp.p, tmp_bytes, in, ctx->d_tileoff.as<uint64_t>(), (int)ntiles, st));
+		}
+		uint64_t last_off = 0;
+		uint64_t last_cnt = 0;
+		SIB_CUDA(cudaMemcpyAsync(&last_off, ctx->d_tileoff.as<uint64_t>() + (ntiles - 1), 8, cudaMemcpyDeviceToHost, st));
+		SIB_CUDA(cudaMemcpyAsync(&last_cnt, ctx->d_tilecnt.as<uint64_t>() + (ntiles - 1), 8, cudaMemcpyDeviceToHost, st));
+		SIB_CUDA(cudaStreamSynchronize(st));
+		const uint64_t I = last_off + last_cnt;
+		SIB_TRY(ctx->d_pos.ensure(sizeof(sibgpu_inst) * (I + 1)));
+		SIB_TRY(ctx->d_negtmp.ensure(sizeof(sibgpu_inst) * (I + 1)));
+		SIB_TRY(ctx->d_neg.ensure(sizeof(sibgpu_inst) * (I + 1)));
+		SIB_TRY(ctx->d_chrinst.ensure(sizeof(uint64_t) * (ctx->nchr + 2)));
+		if(I)
+		{
+			{
+				ProfScope ps(ctx, "k_emit", ctx->M / 8 + I * 24);
+				k_emit<MODE><<<scan_grid, TILE_THREADS, 0, st>>>(t, fp, k, ntiles, ctx->d_map.as<MapSlot>(), Tm,
+					ctx->d_filter.as<uint32_t>(), fshift, ctx->d_hitmask.as<uint16_t>(), ctx->d_tileoff.as<uint64_t>(),
+					ctx->d_pos.as<sibgpu_inst>(), ctx->d_negtmp.as<sibgpu_inst>());
+			}
+			{
+				ProfScope ps(ctx, "k_chr_bounds", 0);
+				k_chr_bounds<<<(ctx->nchr + 1 + 255) / 256, 256, 0, st>>>(ctx->d_negtmp.as<sibgpu_inst>(), I, ctx->nchr,
+					ctx->d_chrinst.as<uint64_t>());
+			}
+			{
+				ProfScope ps(ctx, "k_reverse_neg", I * 24);
+				k_reverse_neg<<<(uint32_t)((I + 255) / 256), 256, 0, st>>>(ctx->d_negtmp.as<sibgpu_inst>(), I,
+					ctx->d_chrinst.as<uint64_t>(), ctx->d_neg.as<sibgpu_inst>());
+			}
+		}
+		SIB_CUDA(cudaStreamSynchronize(st));
+		ctx->n_inst = I;
+		ctx->n_vertices = V;
+		return SIBGPU_OK;
+	}
+}
+
+int enumerate_resident(sibgpu_ctx *ctx, uint32_t k)
+{
+	cudaStream_t st = ctx->stream;
+	ctx->have_result = false;
+	ctx->prof_reset();
+	ctx->total_launches = 0;
+	SIB_CUDA(cudaSetDevice(ctx->device));
+
+	// K0: pack (+ legality)
+	const uint32_t nwords = (uint32_t)((ctx->M + 15) / 16) + 8;
+	SIB_TRY(ctx->d_packed.ensure(sizeof(uint32_t) * (size_t)nwords));
+	SIB_TRY(ctx->d_scalars.ensure(sizeof(uint64_t) * 64));
+	SIB_CUDA(cudaMemsetAsync(ctx->d_scalars.p, 0, sizeof(uint64_t) * 64, st));
+	uint32_t *d_err = reinterpret_cast<uint32_t*>(ctx->d_scalars.as<uint64_t>() + 8);
+	{
+		ProfScope ps(ctx, "k_pack", ctx->M + ctx->M / 4);
+		k_pack<<<grid_for(nwords, 256, ctx->sm_count, 8), 256, 0, st>>>(ctx->d_text.as<uint4>(), ctx->d_packed.as<uint32_t>(),
+			nwords, d_err);
+	}
+	uint64_t *hs = static_cast<uint64_t*>(ctx->h_scalars);
+	SIB_CUDA(cudaMemcpyAsync(hs + 8, ctx->d_scalars.as<uint64_t>() + 8, 8, cudaMemcpyDeviceToHost, st));
+	SIB_CUDA(cudaStreamSynchronize(st));
+	if(hs[8] & 1u)
+	{
+		set_error("input: a character outside ACGT reached the device; sanitise first (indexedsequence.cpp:31-37)");
+		return SIBGPU_ERR_INPUT;
+	}
+
+	uint64_t nrec = 0;
+	for(uint32_t c = 0; c < ctx->nchr; c++)
+	{
+		if(ctx->h_chr_len[c] >= k) nrec += ctx->h_chr_len[c] - k + 1;
+	}
+	ctx->last_k = k;
+	int rc = SIBGPU_OK;
+	if(nrec == 0)
+	{
+		ctx->n_inst = 0;
+		ctx->n_vertices = 0;
+	}
+	else if(k <= 28) rc = enumerate_mode<0>(ctx, k, nrec);
+	else if(k <= 32) rc = enumerate_mode<1>(ctx, k, nrec);
+	else rc = enumerate_mode<2>(ctx, k, nrec);
+	if(rc != SIBGPU_OK) return rc;
+	SIB_CUDA(cudaGetLastError());
+	ctx->have_result = true;
+	if(ctx->profiling) SIB_TRY(ctx->prof_collect());
+	return SIBGPU_OK;
+}
+
+} // namespace sibgpu

@@ -1,0 +1,113 @@
+"""GPU parity: sibgpu_enumerate (through the C ABI) against the oracle and the committed golden fixtures."""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+import helpers
+from oracle import restate
+from sibelia_b200 import synth
+from test_oracle import GOLDEN_FILES, load_golden
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("path", GOLDEN_FILES, ids=[os.path.basename(p)[:-4] for p in GOLDEN_FILES])
+def test_golden(ctx, path):
+    chrs, k, z = load_golden(path)
+    got = ctx.enumerate(chrs, k)
+    helpers.assert_tables_equal(got, (int(z["count"]), z["pos"], z["neg"]), "golden")
+
+
+def test_random_tiny(ctx):
+    rng = np.random.default_rng(2024)
+    for it in range(300):
+        chrs, k = helpers.random_case(rng, max_rec=5, max_len=60, kmax=12)
+        helpers.assert_tables_equal(ctx.enumerate(chrs, k), restate.enumerate_bifurcations(chrs, k), "case %d k=%d" % (it, k))
+
+
+def test_edge_cases(ctx):
+    A = lambda s: np.frombuffer(s, dtype=np.uint8)
+    cases = [
+        ([A(b"")], 3), ([A(b""), A(b"")], 2), ([A(b"AC")], 3), ([A(b"ACG")], 3), ([A(b"A" * 100)], 5),
+        ([A(b"ACGT" * 30)], 4), ([A(b"ACGT" * 30), A(b"")], 4), ([A(b"AT" * 40)], 6), ([A(b"T" * 64)], 32),
+        ([A(b"T" * 64), A(b"A" * 64)], 32), ([A(b"ACGTTGCA" * 8)], 8), ([A(b"G")], 1), ([A(b"GATTACA")], 7),
+    ]
+    for chrs, k in cases:
+        helpers.assert_tables_equal(ctx.enumerate(chrs, k), restate.enumerate_bifurcations(chrs, k), "edge k=%d" % k)
+
+
+def test_zero_chromosomes(ctx):
+    count, pos, neg = ctx.enumerate([], 5)
+    assert count == 0 and len(pos) == 0 and len(neg) == 0
+
+
+@pytest.mark.parametrize("k", [2, 11, 15, 16, 17, 25, 28, 29, 31, 32])
+def test_strains_exact_k(ctx, k):
+    st = helpers.strain_case(4, 60_000, seed=77)
+    helpers.assert_tables_equal(ctx.enumerate(st, k), restate.enumerate_bifurcations(st, k), "strains k=%d" % k)
+
+
+def test_many_small_chromosomes(ctx):
+    rng = np.random.default_rng(5)
+    base = synth.random_genome(3000, 9)
+    chrs = []
+    for i in range(200):
+        o = int(rng.integers(0, 2500))
+        L = int(rng.integers(0, 400))
+        piece = base[o:o + L]
+        chrs.append(synth.revcomp(piece) if rng.random() < 0.4 else piece.copy())
+    for k in (5, 25, 30):
+        helpers.assert_tables_equal(ctx.enumerate(chrs, k), restate.enumerate_bifurcations(chrs, k), "many k=%d" % k)
+
+
+def test_multi_partition_path(built):
+    """Force many hash partitions (SIBGPU_PART_RECORDS) so the scatter / per-partition tables are exercised."""
+    import sibelia_b200 as sb
+    os.environ["SIBGPU_PART_RECORDS"] = "4096"
+    try:
+        c = sb.Context(0)
+    finally:
+        del os.environ["SIBGPU_PART_RECORDS"]
+    st = helpers.strain_case(4, 100_000, seed=99)
+    for k in (25, 31):
+        helpers.assert_tables_equal(c.enumerate(st, k), restate.enumerate_bifurcations(st, k), "parts k=%d" % k)
+    c.close()
+
+
+def test_rejects_unsanitised_input(ctx):
+    import sibelia_b200 as sb
+    with pytest.raises(sb.SibgpuError) as e:
+        ctx.enumerate([np.frombuffer(b"ACGTNNACGT" * 10, dtype=np.uint8)], 5)
+    assert e.value.status == 3
+
+
+def test_staged_api_reuses_upload(ctx):
+    st = helpers.strain_case(3, 40_000, seed=5)
+    ctx.upload(st)
+    for k in (20, 25):
+        count, ninst = ctx.enumerate_resident(k)
+        pos, neg = ctx.download()
+        want = restate.enumerate_bifurcations(st, k)
+        helpers.assert_tables_equal((count, pos, neg), want, "staged k=%d" % k)
+        assert ninst == len(pos)
+
+
+def test_large_random_properties(ctx):
+    """BASELINE configs[1] shape at reduced length (16 Mb random single contig): a random genome has almost no
+    repeated 25-mers, so the vertices are the two chromosome-end k-mers plus rare repeats; size-independent
+    invariants: strand symmetry, sortedness, id range."""
+    g = synth.random_genome(16_000_000, 12345)
+    count, pos, neg = ctx.enumerate([g], 25)
+    assert len(pos) == len(neg)
+    assert count >= 4
+    key = pos["chr"].astype(np.int64) << 32 | pos["pos"]
+    assert np.all(np.diff(key) > 0)
+    keyn = neg["chr"].astype(np.int64) << 32 | neg["pos"]
+    assert np.all(np.diff(keyn) > 0)
+    assert pos["bifId"].max() < count and neg["bifId"].max() < count
+    # every + instance at p has its - twin at len - p - k
+    assert np.array_equal(np.sort(len(g) - pos["pos"].astype(np.int64) - 25), neg["pos"].astype(np.int64))
+    want = restate.enumerate_bifurcations([g[:2_000_000]], 25)
+    helpers.assert_tables_equal(ctx.enumerate([g[:2_000_000]], 25), want, "2 Mb prefix")
