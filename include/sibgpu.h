@@ -91,6 +91,9 @@ int sibgpu_set_profiling(sibgpu_ctx *ctx, int enabled);
 int sibgpu_kernel_stats(sibgpu_ctx *ctx, sibgpu_kernel_stat *out, int cap);
 /* number of kernels this library launched during the last enumerate / simplify on this context */
 uint64_t sibgpu_last_launches(sibgpu_ctx *ctx);
+/* device time of the last sibgpu_enumerate_resident / device part of sibgpu_simplify on this context: milliseconds
+ * between two CUDA events recorded on the library's stream around the whole operation */
+float sibgpu_last_device_ms(sibgpu_ctx *ctx);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * sibgpu_simplify: replaces one stage of

@@ -12,7 +12,7 @@ INST_DTYPE = np.dtype([("bifId", "<u4"), ("chr", "<u4"), ("pos", "<u4")])
 SYMBOLS = [
     "sibgpu_last_error", "sibgpu_version", "sibgpu_device_count", "sibgpu_create", "sibgpu_destroy", "sibgpu_free",
     "sibgpu_enumerate", "sibgpu_upload", "sibgpu_enumerate_resident", "sibgpu_download", "sibgpu_set_profiling",
-    "sibgpu_kernel_stats", "sibgpu_last_launches", "sibgpu_simplify",
+    "sibgpu_kernel_stats", "sibgpu_last_launches", "sibgpu_last_device_ms", "sibgpu_simplify",
 ]
 
 
@@ -51,6 +51,8 @@ def load():
         L.sibgpu_version.restype = C.c_char_p
         L.sibgpu_last_launches.restype = C.c_uint64
         L.sibgpu_last_launches.argtypes = [C.c_void_p]
+        L.sibgpu_last_device_ms.restype = C.c_float
+        L.sibgpu_last_device_ms.argtypes = [C.c_void_p]
         L.sibgpu_destroy.argtypes = [C.c_void_p]
         L.sibgpu_destroy.restype = None
         L.sibgpu_free.argtypes = [C.c_void_p]
@@ -147,6 +149,9 @@ class Context:
         n = load().sibgpu_kernel_stats(self._h, arr, C.c_int(64))
         return [dict(name=arr[i].name.decode(), launches=arr[i].launches, ms=arr[i].ms, algo_bytes=arr[i].algo_bytes)
                 for i in range(min(n, 64))]
+
+    def last_device_ms(self):
+        return float(load().sibgpu_last_device_ms(self._h))
 
     def last_launches(self):
         return int(load().sibgpu_last_launches(self._h))

@@ -96,6 +96,8 @@ int sibgpu_create(int device, sibgpu_ctx **out)
 	c->sm_count = prop.multiProcessorCount;
 	SIB_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
 	SIB_CUDA(cudaMallocHost(&c->h_scalars, 64 * sizeof(uint64_t)));
+	SIB_CUDA(cudaEventCreate(&c->ev_begin));
+	SIB_CUDA(cudaEventCreate(&c->ev_end));
 	if(const char *e = getenv("SIBGPU_PART_RECORDS"))
 	{
 		uint64_t v = strtoull(e, nullptr, 10);
@@ -116,6 +118,8 @@ void sibgpu_destroy(sibgpu_ctx *c)
 	for(DevBuf *b : bufs) b->release();
 	for(cudaEvent_t e : c->event_pool) cudaEventDestroy(e);
 	if(c->h_scalars) cudaFreeHost(c->h_scalars);
+	if(c->ev_begin) cudaEventDestroy(c->ev_begin);
+	if(c->ev_end) cudaEventDestroy(c->ev_end);
 	if(c->stream) cudaStreamDestroy(c->stream);
 	delete c;
 }
@@ -188,7 +192,12 @@ int sibgpu_enumerate_resident(sibgpu_ctx *c, uint32_t k, uint64_t *ninst, uint32
 		set_error("state: sibgpu_upload must precede sibgpu_enumerate_resident");
 		return SIBGPU_ERR_STATE;
 	}
+	SIB_CUDA(cudaSetDevice(c->device));
+	SIB_CUDA(cudaEventRecord(c->ev_begin, c->stream));
 	SIB_TRY(enumerate_resident(c, k));
+	SIB_CUDA(cudaEventRecord(c->ev_end, c->stream));
+	SIB_CUDA(cudaEventSynchronize(c->ev_end));
+	SIB_CUDA(cudaEventElapsedTime(&c->last_ms, c->ev_begin, c->ev_end));
 	if(ninst) *ninst = c->n_inst;
 	if(count) *count = c->n_vertices;
 	return SIBGPU_OK;
@@ -256,5 +265,6 @@ int sibgpu_kernel_stats(sibgpu_ctx *c, sibgpu_kernel_stat *out, int cap)
 }
 
 uint64_t sibgpu_last_launches(sibgpu_ctx *c) { return c ? c->total_launches : 0; }
+float sibgpu_last_device_ms(sibgpu_ctx *c) { return c ? c->last_ms : 0.f; }
 
 }

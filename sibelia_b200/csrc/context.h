@@ -43,6 +43,8 @@ struct sibgpu_ctx {
 	struct Stat { const char *name; uint32_t launches; float ms; uint64_t bytes; };
 	std::vector<Stat> stats;
 	uint64_t total_launches = 0;
+	cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
+	float last_ms = 0.f;
 
 	cudaEvent_t get_event();
 	void prof_begin(const char *name, uint64_t bytes);
