@@ -32,7 +32,7 @@ struct sibgpu_ctx {
 	uint32_t last_k = 0;
 
 	// tunables (env SIBGPU_PART_RECORDS)
-	uint64_t part_target = 1u << 20;
+	uint64_t part_target = 1u << 22;
 
 	// profiling
 	bool profiling = false;

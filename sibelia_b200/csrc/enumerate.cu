@@ -467,6 +467,65 @@ __global__ void __launch_bounds__(256) k_table_scan(void *__restrict__ table, ui
 	}
 }
 
+// Compact variant for k <= 26: key (<= 52 bits) and the 11 payload bits share ONE 64-bit slot, so an occurrence costs a
+// single atomic: CAS when it creates the class, a fire-and-forget OR when the class exists.
+constexpr uint32_t COMPACT_MAX_K = 26;
+__global__ void __launch_bounds__(256) k_insert_compact(const uint64_t *__restrict__ recs, uint64_t n,
+	unsigned long long *__restrict__ tab, uint32_t T)
+{
+	for(uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
+	{
+		const uint64_t rec = __ldcs(recs + i);
+		const unsigned long long key = rec >> 7;
+		const unsigned long long bits = payload_bits((uint32_t)rec & 127u);
+		uint32_t slot = __umulhi((uint32_t)rec_hash(key, 0), T);
+		for(;;)
+		{
+			unsigned long long cur = __ldcg(&tab[slot]);
+			if(cur == EMPTY64)
+			{
+				cur = atomicCAS(&tab[slot], EMPTY64, (key << 11) | bits);
+				if(cur == EMPTY64) break;
+			}
+			if((cur >> 11) == key)
+			{
+				atomicOr(&tab[slot], bits | PAY_MULTI);
+				break;
+			}
+			slot = slot + 1 == T ? 0 : slot + 1;
+		}
+	}
+}
+
+__global__ void __launch_bounds__(256) k_table_scan_compact(unsigned long long *__restrict__ tab, uint32_t T,
+	uint64_t *__restrict__ out, uint32_t *__restrict__ counter)
+{
+	const uint32_t lane_id = threadIdx.x & 31u;
+	for(uint32_t wbase = (blockIdx.x * blockDim.x + threadIdx.x) & ~31u; wbase < T; wbase += gridDim.x * blockDim.x)
+	{
+		const uint32_t sidx = wbase + lane_id;
+		bool bif = false;
+		unsigned long long w = EMPTY64;
+		if(sidx < T)
+		{
+			w = tab[sidx];
+			if(w != EMPTY64)
+			{
+				bif = is_bifurcation((uint32_t)w & 2047u);
+				tab[sidx] = EMPTY64;
+			}
+		}
+		const uint32_t m = __ballot_sync(0xffffffffu, bif);
+		if(m)
+		{
+			uint32_t base = 0;
+			if(lane_id == (uint32_t)(__ffs(m) - 1)) base = atomicAdd(counter, (uint32_t)__popc(m));
+			base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
+			if(bif) out[base + __popc(m & ((1u << lane_id) - 1))] = w >> 11;
+		}
+	}
+}
+
 // exclusive scan of the per-partition vertex-class counts (one CTA)
 __global__ void __launch_bounds__(MAX_PARTS) k_key_offsets(const uint32_t *__restrict__ cnt, uint32_t P,
 	uint64_t *__restrict__ keyoff, uint64_t *__restrict__ scalars)
@@ -777,7 +836,8 @@ static int enumerate_mode(sibgpu_ctx *ctx, uint32_t k, uint64_t nrec)
 			return SIBGPU_ERR_INTERNAL;
 		}
 		const uint32_t T = (uint32_t)T64;
-		const size_t slot_bytes = MODE == 0 ? sizeof(Slot8) : sizeof(Slot16);
+		const bool compact = MODE == 0 && k <= COMPACT_MAX_K;
+		const size_t slot_bytes = compact ? 8 : (MODE == 0 ? sizeof(Slot8) : sizeof(Slot16));
 		SIB_TRY(ctx->d_table.ensure(slot_bytes * T));
 		SIB_CUDA(cudaMemsetAsync(ctx->d_table.p, 0xFF, slot_bytes * T, st));
 		for(uint32_t p = 0; p < P; p++)
@@ -787,11 +847,15 @@ static int enumerate_mode(sibgpu_ctx *ctx, uint32_t k, uint64_t nrec)
 			Rec *part = ctx->d_records.as<Rec>() + h_partoff[p];
 			{
 				ProfScope ps(ctx, "k_insert", n * sizeof(Rec));
-				k_insert<MODE><<<grid_for(n, 256, sms, 8), 256, 0, st>>>(part, n, ctx->d_table.p, T);
+				if(compact) k_insert_compact<<<grid_for(n, 256, sms, 8), 256, 0, st>>>(reinterpret_cast<const uint64_t*>(part), n,
+					ctx->d_table.as<unsigned long long>(), T);
+				else k_insert<MODE><<<grid_for(n, 256, sms, 8), 256, 0, st>>>(part, n, ctx->d_table.p, T);
 			}
 			{
 				ProfScope ps(ctx, "k_table_scan", (uint64_t)T * slot_bytes);
-				k_table_scan<MODE><<<grid_for(T, 256, sms, 8), 256, 0, st>>>(ctx->d_table.p, T, part,
+				if(compact) k_table_scan_compact<<<grid_for(T, 256, sms, 8), 256, 0, st>>>(ctx->d_table.as<unsigned long long>(), T,
+					reinterpret_cast<uint64_t*>(part), ctx->d_partcnt.as<uint32_t>() + p);
+				else k_table_scan<MODE><<<grid_for(T, 256, sms, 8), 256, 0, st>>>(ctx->d_table.p, T, part,
 					ctx->d_partcnt.as<uint32_t>() + p);
 			}
 		}
