@@ -19,66 +19,9 @@
 // class of revcomp(w) (which the reference enumerates separately and symmetrically) are decided once.
 #include <cub/cub.cuh>
 
-#include "context.h"
+#include "enum_common.cuh"
 
 namespace sibgpu {
-
-// ---------------------------------------------------------------------------------------------------------------
-// layout constants
-// ---------------------------------------------------------------------------------------------------------------
-constexpr int TILE_THREADS = 256;
-constexpr int POS_PER_THREAD = 16;                     // one packed 32-bit word
-constexpr int TILE_POS = TILE_THREADS * POS_PER_THREAD; // 4096 text positions per tile
-constexpr int MAX_PARTS = 1024;
-constexpr uint64_t EMPTY64 = ~0ull;
-
-// occurrence context, 8 bits:  [7] forward k-mer is the canonical one  [6] palindrome  [5:3] prev  [2:0] next
-// (prev/next are symbols 0..3 = ACGT, 4 = chromosome end '#', already in canonical orientation)
-// table payload (stored inverted so that one 0xFF memset initialises keys and payloads):
-//   bits 0-4 prev-symbol set, bits 5-9 next-symbol set, bit 10 "seen more than once"
-constexpr uint32_t PAY_MULTI = 1u << 10;
-
-struct TextDesc {
-	const uint32_t *packed;        // 16 bases per word, first base in the top bit pair
-	const uint32_t *chr_start;     // text index of the first base of every chromosome
-	const uint32_t *chr_len;
-	uint32_t nchr;
-	uint32_t M;                    // text length
-	uint32_t nwords;               // valid words in packed[]
-};
-
-struct Rec16 { uint64_t a, b; };
-
-// MODE 0: k <= 28, record = key << 7 | ctx[6:0] in one 64-bit word
-// MODE 1: k <= 32, record = {key, ctx}
-// MODE 2: k  > 32, record = {fingerprint a, fingerprint b << 8 | ctx}, read from the per-position array d_fp
-template<int MODE> struct RecT { typedef Rec16 type; };
-template<> struct RecT<0> { typedef uint64_t type; };
-
-__device__ __forceinline__ uint64_t rec_hash(uint64_t a, uint64_t b_fp)
-{
-	return mix64(a ^ (b_fp * 0x9E3779B97F4A7C15ull));
-}
-
-__device__ __forceinline__ uint32_t payload_bits(uint32_t ctx)
-{
-	uint32_t p = (ctx >> 3) & 7u, n = ctx & 7u;
-	uint32_t bits = (1u << p) | (32u << n);
-	if(ctx & 64u)                                       // palindrome: the same text position is also an occurrence
-	{                                                   // on the other strand, with swapped complemented neighbours
-		bits |= (1u << comp_sym(n)) | (32u << comp_sym(p)) | PAY_MULTI;
-	}
-	return bits;
-}
-
-// The reference's predicate in closed form (vertexenumeration.cpp:67-70,330,343,348)
-__device__ __forceinline__ bool is_bifurcation(uint32_t pay)
-{
-	uint32_t P = pay & 31u, Nn = (pay >> 5) & 31u;
-	bool sep = ((P | Nn) & 16u) != 0;
-	if(pay & PAY_MULTI) return __popc(P) > 1 || __popc(Nn) > 1 || sep;
-	return sep;
-}
 
 // ---------------------------------------------------------------------------------------------------------------
 // K0: pack
@@ -109,32 +52,6 @@ __device__ __forceinline__ void stage_tile(const TextDesc &t, uint32_t tile, uin
 		sw[j] = (w >= 0 && w < (int64_t)t.nwords) ? __ldg(t.packed + w) : 0u;
 	}
 }
-
-// chromosome cursor of a thread: [cs, ce) is the chromosome containing (or preceding) the current position
-struct ChrCursor {
-	uint32_t cs, ce, nc;
-	__device__ __forceinline__ void init(const TextDesc &t, uint32_t p)
-	{
-		uint32_t lo = 0, hi = t.nchr;                  // number of chromosomes starting at or before p
-		while(lo < hi)
-		{
-			uint32_t mid = (lo + hi) >> 1;
-			if(__ldg(t.chr_start + mid) <= p) lo = mid + 1; else hi = mid;
-		}
-		nc = lo;
-		if(lo == 0) { cs = 0; ce = 0; }
-		else { cs = __ldg(t.chr_start + lo - 1); ce = cs + __ldg(t.chr_len + lo - 1); }
-	}
-	__device__ __forceinline__ void advance(const TextDesc &t, uint32_t p)
-	{
-		while(nc < t.nchr && p >= __ldg(t.chr_start + nc))
-		{
-			cs = __ldg(t.chr_start + nc);
-			ce = cs + __ldg(t.chr_len + nc);
-			nc++;
-		}
-	}
-};
 
 // Calls f(i, a, b, ctx) for every valid k-mer start among the thread's 16 positions (exact modes, k <= 32).
 //   a   = canonical key min(w, revcomp(w));  ctx as documented above (bit 7 = forward is canonical)
@@ -580,10 +497,9 @@ __device__ __forceinline__ uint32_t lower_bound_u64(const uint64_t *__restrict__
 }
 
 // vertex map: canonical key -> (id of the canonical k-mer, id of its reverse complement); 32-byte slots
-struct MapSlot { unsigned long long a, b; uint32_t idc, idr; uint32_t pad[2]; };
 
 __device__ __forceinline__ void map_insert(MapSlot *map, uint32_t Tm, uint32_t *filter, uint32_t fshift,
-	unsigned long long a, unsigned long long b, uint32_t idc, uint32_t idr)
+	unsigned long long a, unsigned long long b, uint32_t idc, uint32_t idr, uint32_t cls)
 {
 	uint64_t h = rec_hash(a, b);
 	uint32_t slot = __umulhi((uint32_t)h, Tm);
@@ -596,6 +512,7 @@ __device__ __forceinline__ void map_insert(MapSlot *map, uint32_t Tm, uint32_t *
 	map[slot].b = b;
 	map[slot].idc = idc;
 	map[slot].idr = idr;
+	map[slot].cls = cls;
 	uint32_t bit = (uint32_t)(h >> fshift);
 	atomicOr(&filter[bit >> 5], 1u << (bit & 31u));
 }
@@ -607,14 +524,21 @@ __global__ void __launch_bounds__(256) k_build_map(const typename RecT<MODE>::ty
 {
 	uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
 	if(i >= n) return;
+	if(MODE == 2)
+	{
+		// fingerprint classes: ids are assigned after the lexicographic ranking (fingerprint.cu)
+		Rec16 v = reinterpret_cast<const Rec16*>(ckeys)[i];
+		map_insert(map, Tm, filter, fshift, v.a, v.b, 0u, 0u, (uint32_t)i);
+		return;
+	}
 	uint64_t c = MODE == 0 ? reinterpret_cast<const uint64_t*>(ckeys)[i] : reinterpret_cast<const Rec16*>(ckeys)[i].a;
 	uint32_t idc = lower_bound_u64(vsorted, V, c);
 	uint32_t idr = lower_bound_u64(vsorted, V, revcomp_key(c, k));
-	map_insert(map, Tm, filter, fshift, c, 0ull, idc, idr);
+	map_insert(map, Tm, filter, fshift, c, 0ull, idc, idr, (uint32_t)i);
 }
 
 __device__ __forceinline__ bool map_lookup(const MapSlot *__restrict__ map, uint32_t Tm, const uint32_t *__restrict__ filter,
-	uint32_t fshift, unsigned long long a, unsigned long long b, uint32_t &idc, uint32_t &idr)
+	uint32_t fshift, unsigned long long a, unsigned long long b, uint32_t &idc, uint32_t &idr, uint32_t &cls)
 {
 	uint64_t h = rec_hash(a, b);
 	uint32_t bit = (uint32_t)(h >> fshift);
@@ -629,6 +553,7 @@ __device__ __forceinline__ bool map_lookup(const MapSlot *__restrict__ map, uint
 			const uint2 ids = __ldg(reinterpret_cast<const uint2*>(&map[slot].idc));
 			idc = ids.x;
 			idr = ids.y;
+			cls = __ldg(&map[slot].cls);
 			return true;
 		}
 		slot = slot + 1 == Tm ? 0 : slot + 1;
@@ -641,7 +566,7 @@ __device__ __forceinline__ bool map_lookup(const MapSlot *__restrict__ map, uint
 template<int MODE>
 __global__ void __launch_bounds__(TILE_THREADS) k_mark(TextDesc t, const Rec16 *__restrict__ fp, uint32_t k, uint32_t ntiles,
 	const MapSlot *__restrict__ map, uint32_t Tm, const uint32_t *__restrict__ filter, uint32_t fshift,
-	uint16_t *__restrict__ hitmask, uint64_t *__restrict__ tilecnt)
+	uint16_t *__restrict__ hitmask, uint64_t *__restrict__ tilecnt, unsigned long long *__restrict__ rep)
 {
 	__shared__ uint32_t sw[TILE_THREADS + 5];
 	typedef cub::BlockReduce<uint32_t, TILE_THREADS> Red;
@@ -652,9 +577,18 @@ __global__ void __launch_bounds__(TILE_THREADS) k_mark(TextDesc t, const Rec16 *
 		if(MODE != 2) stage_tile(t, tile, sw);
 		__syncthreads();
 		uint32_t mask = 0;
-		scan16<MODE>(t, fp, sw, tile, k, [&](int i, uint64_t a, uint64_t b, uint32_t) {
-			uint32_t idc, idr;
-			if(map_lookup(map, Tm, filter, fshift, a, b, idc, idr)) mask |= 1u << i;
+		scan16<MODE>(t, fp, sw, tile, k, [&](int i, uint64_t a, uint64_t b, uint32_t ctx) {
+			uint32_t idc, idr, cls;
+			if(map_lookup(map, Tm, filter, fshift, a, b, idc, idr, cls))
+			{
+				mask |= 1u << i;
+				if(MODE == 2)
+				{
+					// representative occurrence of the class = its smallest text position (+ palindrome / forward flags)
+					const uint32_t p = tile * TILE_POS + threadIdx.x * POS_PER_THREAD + i;
+					atomicMin(&rep[cls], ((unsigned long long)p << 2) | ((ctx >> 5) & 2u) | ((ctx >> 7) & 1u));
+				}
+			}
 		});
 		hitmask[(uint64_t)tile * TILE_THREADS + threadIdx.x] = (uint16_t)mask;
 		uint32_t total = Red(red_tmp).Sum((uint32_t)__popc(mask));
@@ -662,21 +596,12 @@ __global__ void __launch_bounds__(TILE_THREADS) k_mark(TextDesc t, const Rec16 *
 	}
 }
 
-// forward key of the k-mer starting at text position p (k <= 32), straight from the packed words
-__device__ __forceinline__ uint64_t key_at(const TextDesc &t, uint32_t p, uint32_t k)
-{
-	const uint32_t w = p >> 4, sh = 2 * (p & 15u);
-	uint64_t x0 = ((uint64_t)__ldg(t.packed + w) << 32) | __ldg(t.packed + w + 1);
-	uint64_t x1 = ((uint64_t)__ldg(t.packed + w + 2) << 32);
-	uint64_t x = sh ? ((x0 << sh) | (x1 >> (64 - sh))) : x0;
-	return x >> (64 - 2 * k);
-}
-
 template<int MODE>
 __global__ void __launch_bounds__(TILE_THREADS) k_emit(TextDesc t, const Rec16 *__restrict__ fp, uint32_t k, uint32_t ntiles,
 	const MapSlot *__restrict__ map, uint32_t Tm, const uint32_t *__restrict__ filter, uint32_t fshift,
 	const uint16_t *__restrict__ hitmask, const uint64_t *__restrict__ tileoff,
-	sibgpu_inst *__restrict__ pos_out, sibgpu_inst *__restrict__ neg_tmp)
+	sibgpu_inst *__restrict__ pos_out, sibgpu_inst *__restrict__ neg_tmp,
+	const unsigned long long *__restrict__ rep, uint32_t *__restrict__ collision)
 {
 	typedef cub::BlockScan<uint32_t, TILE_THREADS> Scan;
 	__shared__ typename Scan::TempStorage scan_tmp;
@@ -706,8 +631,21 @@ __global__ void __launch_bounds__(TILE_THREADS) k_emit(TextDesc t, const Rec16 *
 				fw = f <= r;
 				a = fw ? f : r;
 			}
-			uint32_t idc = 0, idr = 0;
-			map_lookup(map, Tm, filter, fshift, a, b, idc, idr);
+			uint32_t idc = 0, idr = 0, cls = 0;
+			map_lookup(map, Tm, filter, fshift, a, b, idc, idr, cls);
+			if(MODE == 2)
+			{
+				// exactness: the k-mer here must spell the same string as the class representative; a fingerprint
+				// collision that could change the result always surfaces here
+				const unsigned long long R = rep[cls];
+				const uint32_t rp = (uint32_t)(R >> 2), rfw = (uint32_t)R & 1u;
+				bool same = true;
+				for(uint32_t m = 0; m * 32 < k && same; m++)
+				{
+					same = vstr_chunk(t, p, fw ? 1u : 0u, m, k) == vstr_chunk(t, rp, rfw, m, k);
+				}
+				if(!same) atomicOr(collision, 1u);
+			}
 			ChrCursor cur;
 			cur.init(t, p);
 			const uint32_t c = cur.nc - 1, ppos = p - cur.cs, len = cur.ce - cur.cs;
@@ -750,8 +688,7 @@ __global__ void __launch_bounds__(256) k_reverse_neg(const sibgpu_inst *__restri
 // host orchestration
 // ---------------------------------------------------------------------------------------------------------------
 int fingerprint_positions(sibgpu_ctx *ctx, const TextDesc &t, uint32_t k, uint32_t attempt);            // fingerprint.cu
-int rank_fingerprint_vertices(sibgpu_ctx *ctx, const TextDesc &t, uint32_t k, uint64_t Vc, uint32_t ntiles,
-	uint32_t Tm, uint32_t fshift, uint32_t *V_out, bool *collision);                                        // fingerprint.cu
+int rank_fingerprint_vertices(sibgpu_ctx *ctx, const TextDesc &t, uint32_t k, uint64_t Vc, uint32_t Tm, uint32_t *V_out);   // fingerprint.cu
 
 static inline uint32_t grid_for(uint64_t work_items, int threads, int sm_count, int waves = 8)
 {
@@ -778,11 +715,11 @@ static int enumerate_mode(sibgpu_ctx *ctx, uint32_t k, uint64_t nrec)
 	t.M = (uint32_t)ctx->M;
 	t.nwords = (uint32_t)((ctx->M + 15) / 16) + 8;
 	const uint32_t ntiles = (uint32_t)((ctx->M + TILE_POS - 1) / TILE_POS);
-	const Rec16 *fp = ctx->d_fp.as<Rec16>();
 
 	for(uint32_t attempt = 0; ; attempt++)
 	{
 		if(MODE == 2) SIB_TRY(fingerprint_positions(ctx, t, k, attempt));
+		const Rec16 *fp = ctx->d_fp.as<Rec16>();
 
 		// ---- partition plan
 		uint64_t P64 = (nrec + ctx->part_target - 1) / ctx->part_target;
@@ -926,17 +863,12 @@ static int enumerate_mode(sibgpu_ctx *ctx, uint32_t k, uint64_t nrec)
 		}
 		else
 		{
-			bool collision = false;
-			SIB_TRY(rank_fingerprint_vertices(ctx, t, k, Vc, ntiles, Tm, fshift, &V, &collision));
-			if(collision)
-			{
-				if(attempt >= 2)
-				{
-					set_error("internal: fingerprint verification failed three times");
-					return SIBGPU_ERR_INTERNAL;
-				}
-				continue;                                  // re-run with another fingerprint base
-			}
+			// classes only; the ids follow once every class has a representative occurrence (after k_mark)
+			SIB_TRY(ctx->d_rep.ensure(sizeof(uint64_t) * Vc));
+			SIB_CUDA(cudaMemsetAsync(ctx->d_rep.p, 0xFF, sizeof(uint64_t) * Vc, st));
+			ProfScope ps(ctx, "k_build_map", Vc * (sizeof(Rec) + sizeof(MapSlot)));
+			k_build_map<MODE><<<(uint32_t)((Vc + 255) / 256), 256, 0, st>>>(ctx->d_ckeys.as<Rec>(), Vc, k, nullptr, 0,
+				ctx->d_map.as<MapSlot>(), Tm, ctx->d_filter.as<uint32_t>(), fshift);
 		}
 
 		// ---- instance tables
@@ -946,8 +878,10 @@ static int enumerate_mode(sibgpu_ctx *ctx, uint32_t k, uint64_t nrec)
 		{
 			ProfScope ps(ctx, "k_mark", (MODE == 2 ? ctx->M * 16 : ctx->M / 4) + ctx->M / 8);
 			k_mark<MODE><<<scan_grid, TILE_THREADS, 0, st>>>(t, fp, k, ntiles, ctx->d_map.as<MapSlot>(), Tm,
-				ctx->d_filter.as<uint32_t>(), fshift, ctx->d_hitmask.as<uint16_t>(), ctx->d_tilecnt.as<uint64_t>());
+				ctx->d_filter.as<uint32_t>(), fshift, ctx->d_hitmask.as<uint16_t>(), ctx->d_tilecnt.as<uint64_t>(),
+				ctx->d_rep.as<unsigned long long>());
 		}
+		if(MODE == 2) SIB_TRY(rank_fingerprint_vertices(ctx, t, k, Vc, Tm, &V));
 		{
 			size_t tmp_bytes = 0;
 			const uint64_t *in = ctx->d_tilecnt.as<uint64_t>();
@@ -972,7 +906,8 @@ static int enumerate_mode(sibgpu_ctx *ctx, uint32_t k, uint64_t nrec)
 				ProfScope ps(ctx, "k_emit", ctx->M / 8 + I * 24);
 				k_emit<MODE><<<scan_grid, TILE_THREADS, 0, st>>>(t, fp, k, ntiles, ctx->d_map.as<MapSlot>(), Tm,
 					ctx->d_filter.as<uint32_t>(), fshift, ctx->d_hitmask.as<uint16_t>(), ctx->d_tileoff.as<uint64_t>(),
-					ctx->d_pos.as<sibgpu_inst>(), ctx->d_negtmp.as<sibgpu_inst>());
+					ctx->d_pos.as<sibgpu_inst>(), ctx->d_negtmp.as<sibgpu_inst>(), ctx->d_rep.as<unsigned long long>(),
+					reinterpret_cast<uint32_t*>(ds + 9));
 			}
 			{
 				ProfScope ps(ctx, "k_chr_bounds", 0);
@@ -983,6 +918,22 @@ static int enumerate_mode(sibgpu_ctx *ctx, uint32_t k, uint64_t nrec)
 				ProfScope ps(ctx, "k_reverse_neg", I * 24);
 				k_reverse_neg<<<(uint32_t)((I + 255) / 256), 256, 0, st>>>(ctx->d_negtmp.as<sibgpu_inst>(), I,
 					ctx->d_chrinst.as<uint64_t>(), ctx->d_neg.as<sibgpu_inst>());
+			}
+		}
+		if(MODE == 2)
+		{
+			SIB_CUDA(cudaMemcpyAsync(hs + 9, ds + 9, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+			SIB_CUDA(cudaStreamSynchronize(st));
+			if(hs[9] & 1u)
+			{
+				// two different k-mers shared a fingerprint inside a vertex class: start over with other bases
+				if(attempt >= 2)
+				{
+					set_error("internal: fingerprint verification failed three times");
+					return SIBGPU_ERR_INTERNAL;
+				}
+				SIB_CUDA(cudaMemsetAsync(ds + 9, 0, sizeof(uint64_t), st));
+				continue;
 			}
 		}
 		SIB_CUDA(cudaStreamSynchronize(st));

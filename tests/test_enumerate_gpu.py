@@ -49,6 +49,32 @@ def test_strains_exact_k(ctx, k):
     helpers.assert_tables_equal(ctx.enumerate(st, k), restate.enumerate_bifurcations(st, k), "strains k=%d" % k)
 
 
+@pytest.mark.parametrize("k", [33, 34, 48, 63, 64, 65, 100, 128, 1000, 5000])
+def test_strains_fingerprint_k(ctx, k):
+    """k > 32 goes through the fingerprint path (+ string ranking and per-instance verification)."""
+    st = helpers.strain_case(4, 60_000, seed=78)
+    helpers.assert_tables_equal(ctx.enumerate(st, k), restate.enumerate_bifurcations(st, k), "strains k=%d" % k)
+
+
+def test_long_palindromes(ctx):
+    """Even k > 32 with k-mers equal to their own reverse complement (one vertex id, instances on both strands)."""
+    rng = np.random.default_rng(3)
+    w = synth.random_genome(40, 1)
+    pal = np.concatenate([w, synth.revcomp(w)])                      # an 80-mer that is its own reverse complement
+    x, y, z = (synth.random_genome(300, s) for s in (2, 3, 4))
+    chrs = [np.concatenate([x, pal, y]), np.concatenate([z, pal, x[:100]]), synth.revcomp(np.concatenate([y, pal]))]
+    for k in (34, 40, 60, 80):
+        helpers.assert_tables_equal(ctx.enumerate(chrs, k), restate.enumerate_bifurcations(chrs, k), "pal k=%d" % k)
+    for k in (8, 20, 32):
+        helpers.assert_tables_equal(ctx.enumerate(chrs, k), restate.enumerate_bifurcations(chrs, k), "pal k=%d" % k)
+
+
+def test_k_longer_than_everything(ctx):
+    st = helpers.strain_case(2, 3000, seed=1)
+    count, pos, neg = ctx.enumerate(st, 4000)
+    assert count == 0 and len(pos) == 0 and len(neg) == 0
+
+
 def test_many_small_chromosomes(ctx):
     rng = np.random.default_rng(5)
     base = synth.random_genome(3000, 9)
@@ -58,7 +84,7 @@ def test_many_small_chromosomes(ctx):
         L = int(rng.integers(0, 400))
         piece = base[o:o + L]
         chrs.append(synth.revcomp(piece) if rng.random() < 0.4 else piece.copy())
-    for k in (5, 25, 30):
+    for k in (5, 25, 30, 40, 150):
         helpers.assert_tables_equal(ctx.enumerate(chrs, k), restate.enumerate_bifurcations(chrs, k), "many k=%d" % k)
 
 
