@@ -114,6 +114,11 @@ int sibgpu_simplify(sibgpu_ctx *ctx, char **seq, uint32_t **origpos, uint64_t *l
 	uint32_t k, uint32_t min_branch_size, uint32_t max_iterations,
 	sibgpu_progress_fn progress, void *user, uint64_t *bulges);
 
+/* Test hook (host only, no GPU needed): iteration order of the reference's boost::unordered_map<size_t, BranchData>
+ * (Boost 1.54, src/bulgeremoval.cpp:168,203-215) after inserting n distinct keys in the given order, as restated in
+ * sibelia_b200/csrc/boost_order.h.  out receives the n keys in begin()..end() order. */
+void sibgpu_debug_unordered_order(const uint64_t *keys, uint64_t n, uint64_t *out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -108,3 +108,11 @@ def simplify(chrs, origpos, k, D, iters=4):
         new_chrs.append(_take(C.c_void_p(seq[i]), m, np.dtype("u1")).tobytes())
         new_op.append(_take(C.c_void_p(op[i]), m, np.dtype("<u4")))
     return new_chrs, new_op, bulges.value, sec.value
+
+
+def boost_order(keys):
+    """Iteration order of the vendored boost::unordered_map<size_t,int> after inserting distinct keys in order."""
+    keys = np.ascontiguousarray(keys, dtype=np.uint64)
+    out = np.zeros(len(keys), dtype=np.uint64)
+    lib().ref_boost_order(C.c_void_p(keys.ctypes.data), C.c_uint64(len(keys)), C.c_void_p(out.ctypes.data))
+    return out

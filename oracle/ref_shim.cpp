@@ -151,6 +151,22 @@ int ref_index(uint32_t nchr, const char* const* chr, const uint64_t* len, uint32
 	}
 }
 
+// Iteration order of the vendored boost::unordered_map<size_t, ...> (Boost 1.54) after inserting the given DISTINCT
+// keys with operator[] in the given order -- the container AnyBulges relies on (src/bulgeremoval.cpp:168,203-215).
+void ref_boost_order(const uint64_t* keys, uint64_t n, uint64_t* out)
+{
+	boost::unordered_map<size_t, int> m;
+	for(uint64_t i = 0; i < n; i++)
+	{
+		m[static_cast<size_t>(keys[i])] = static_cast<int>(i);
+	}
+	uint64_t j = 0;
+	for(boost::unordered_map<size_t, int>::iterator it = m.begin(); it != m.end(); ++it)
+	{
+		out[j++] = it->first;
+	}
+}
+
 // One stage of BlockFinder::PerformGraphSimplifications(k, D, iters) (src/blockfinder.cpp:78-98) seeded with an
 // arbitrary inter-stage state (rawSeq_, originalPos_).  seq/origpos are replaced by malloc'ed outputs.
 int ref_simplify(uint32_t nchr, char** seq, uint32_t** origpos, uint64_t* len,

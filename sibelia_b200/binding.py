@@ -12,7 +12,7 @@ INST_DTYPE = np.dtype([("bifId", "<u4"), ("chr", "<u4"), ("pos", "<u4")])
 SYMBOLS = [
     "sibgpu_last_error", "sibgpu_version", "sibgpu_device_count", "sibgpu_create", "sibgpu_destroy", "sibgpu_free",
     "sibgpu_enumerate", "sibgpu_upload", "sibgpu_enumerate_resident", "sibgpu_download", "sibgpu_set_profiling",
-    "sibgpu_kernel_stats", "sibgpu_last_launches", "sibgpu_last_device_ms", "sibgpu_simplify",
+    "sibgpu_kernel_stats", "sibgpu_last_launches", "sibgpu_last_device_ms", "sibgpu_simplify", "sibgpu_debug_unordered_order",
 ]
 
 
@@ -176,3 +176,12 @@ class Context:
             L.sibgpu_free(C.c_void_p(seq[i]))
             L.sibgpu_free(C.c_void_p(op[i]))
         return new_chrs, new_op, bulges.value
+
+
+def debug_unordered_order(keys):
+    keys = np.ascontiguousarray(keys, dtype=np.uint64)
+    out = np.zeros(len(keys), dtype=np.uint64)
+    f = load().sibgpu_debug_unordered_order
+    f.restype = None
+    f(C.c_void_p(keys.ctypes.data), C.c_uint64(len(keys)), C.c_void_p(out.ctypes.data))
+    return out
