@@ -1,0 +1,79 @@
+"""GPU end-to-end parity (BASELINE.json configs[0]): the reference CLI with its two hot-path seams served by
+libsibgpu.so (oracle/_ref/Sibelia_gpu = the reference's own translation units minus vertexenumeration.cpp /
+blockfinder.cpp / bulgeremoval.cpp / libdivsufsort, plus sibelia_b200/csrc/facade/*_gpu.cpp) must write byte-identical
+blocks_coords.txt / genomes_permutations.txt / coverage_report.txt to the unmodified reference CLI (oracle/_ref/Sibelia).
+Both binaries are built in the authoring container by `make -C oracle sibelia sibelia_gpu data` and travel to the box."""
+import hashlib
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import helpers
+from sibelia_b200 import synth
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF_BIN = os.path.join(ROOT, "oracle", "_ref", "Sibelia")
+GPU_BIN = os.path.join(ROOT, "oracle", "_ref", "Sibelia_gpu")
+DATA = os.path.join(ROOT, "oracle", "_ref", "data")
+FILES = ["blocks_coords.txt", "genomes_permutations.txt", "coverage_report.txt"]
+have = os.path.exists(REF_BIN) and os.path.exists(GPU_BIN)
+
+
+def write_fasta(path, chrs, names=None):
+    with open(path, "wb") as f:
+        for i, c in enumerate(chrs):
+            f.write((">%s\n" % (names[i] if names else "strain%d" % i)).encode())
+            b = bytes(c)
+            for o in range(0, len(b), 80):
+                f.write(b[o:o + 80] + b"\n")
+
+
+def run(binary, args, outdir):
+    os.makedirs(outdir, exist_ok=True)
+    subprocess.run([binary] + args + ["-o", outdir], check=True, stdout=subprocess.PIPE, stderr=subprocess.STDOUT,
+                   timeout=1500)
+    return {f: open(os.path.join(outdir, f), "rb").read() for f in FILES}
+
+
+def compare(args, tmp_path):
+    want = run(REF_BIN, args, str(tmp_path / "ref"))
+    got = run(GPU_BIN, args, str(tmp_path / "gpu"))
+    for f in FILES:
+        assert got[f] == want[f], "%s differs (%d vs %d bytes)" % (f, len(got[f]), len(want[f]))
+    return got
+
+
+@pytest.mark.skipif(not have, reason="oracle/_ref/Sibelia{,_gpu} did not travel")
+@pytest.mark.parametrize("params", ["loose", "fine"])
+def test_synthetic_strains(tmp_path, params):
+    chrs = helpers.strain_case(3, 150_000, p_sub=0.01, inv_len=20_000, seed=31)
+    fa = str(tmp_path / "in.fasta")
+    write_fasta(fa, chrs)
+    got = compare(["-s", params, "-m", "2000", fa], tmp_path)
+    assert got["blocks_coords.txt"].count(b"Block #") >= 2
+
+
+@pytest.mark.skipif(not have, reason="oracle/_ref/Sibelia{,_gpu} did not travel")
+def test_non_acgt_input_consumes_rand_like_the_reference(tmp_path):
+    """Ns are replaced with rand() % 4 on the host in the reference's order (indexedsequence.cpp:31-37); --inram keeps
+    the temp-file names from consuming rand() in the reference."""
+    rng = np.random.default_rng(5)
+    chrs = [c.copy() for c in helpers.strain_case(3, 60_000, p_sub=0.01, inv_len=5_000, seed=32)]
+    for c in chrs:
+        for o in rng.integers(0, len(c) - 50, 30):
+            c[o:o + int(rng.integers(1, 40))] = ord("N")
+    fa = str(tmp_path / "in.fasta")
+    write_fasta(fa, chrs)
+    compare(["-s", "loose", "-m", "1000", "-r", fa], tmp_path)
+
+
+@pytest.mark.skipif(not (have and os.path.exists(os.path.join(DATA, "Helicobacter_pylori.fasta"))),
+                    reason="reference example genome did not travel")
+def test_helicobacter_pylori_loose(tmp_path):
+    """BASELINE configs[0]; digests pinned in BASELINE.md section 4 / SURVEY.md section 8(c)."""
+    got = compare(["-s", "loose", os.path.join(DATA, "Helicobacter_pylori.fasta")], tmp_path)
+    assert hashlib.md5(got["blocks_coords.txt"]).hexdigest() == "9cf97c63809c08c961a5f30036e3dc28"
+    assert hashlib.md5(got["genomes_permutations.txt"]).hexdigest() == "a1d4765580a36622839e9065873304d4"
