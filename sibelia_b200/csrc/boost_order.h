@@ -14,7 +14,7 @@
 //                  whose bucket is occupied is linked right after the bucket's predecessor node
 //                                                                          .../detail/unique.hpp:302-333
 //   * rehash:      nodes are re-threaded in current list order with the same two rules     .../unique.hpp:591-618
-// Differentially tested against the vendored header itself (tests/test_boost_order.py through oracle/_ref).
+// Differentially tested against the vendored header itself (tests/test_boost_order.py).
 #pragma once
 #include <cstddef>
 #include <cstdint>
