@@ -114,6 +114,31 @@ int sibgpu_simplify(sibgpu_ctx *ctx, char **seq, uint32_t **origpos, uint64_t *l
 	uint32_t k, uint32_t min_branch_size, uint32_t max_iterations,
 	sibgpu_progress_fn progress, void *user, uint64_t *bulges);
 
+/* ---------------------------------------------------------------------------------------------------------------
+ * Sharded enumeration over `world` GPUs of one box, ONE PROCESS PER GPU (k <= 32).  The concatenated genome is split
+ * into `world` contiguous text ranges; records are bucketed by hash prefix so that partition p belongs to rank
+ * p / (nparts_total / world); the caller moves them with one all-to-all (NCCL) between two device buffers it owns,
+ * and all-gathers the (few) vertex keys so every rank can compute the global lexicographic ids.
+ *
+ *   sibgpu_dist_upload   every rank passes the whole input, only the bytes of its own range (+ halo) are copied
+ *   sibgpu_dist_scan     -> nparts_total, hist[nparts_total] (records of this rank per partition), nrec_local
+ *   sibgpu_dist_scatter  fills send_dev (nrec_local records of sibgpu_dist_record_bytes, ordered by partition)
+ *   [all_gather hist -> counts[world][nparts_total]; all_to_all records: to rank r go this rank's partitions of r]
+ *   sibgpu_dist_group    recv_dev = for each source rank in order, its records of my partitions in partition order
+ *                        -> nkeys_local canonical vertex keys; sibgpu_dist_keys copies them to a device buffer
+ *   [all_gather keys -> allkeys_dev, nkeys_total]
+ *   sibgpu_dist_finish   global ids, instances of the own text range; sibgpu_download then returns the LOCAL tables,
+ *                        both in text order (the caller concatenates ranks in order and reverses the negative table
+ *                        inside each chromosome, vertexenumeration.cpp:361-362 -- see binding.assemble_tables).
+ */
+int sibgpu_dist_upload(sibgpu_ctx *ctx, const char *const *chr, const uint64_t *len, uint32_t nchr, uint32_t rank, uint32_t world);
+int sibgpu_dist_scan(sibgpu_ctx *ctx, uint32_t k, uint32_t *nparts_total, uint32_t *hist, uint64_t *nrec_local);
+uint32_t sibgpu_dist_record_bytes(sibgpu_ctx *ctx);
+int sibgpu_dist_scatter(sibgpu_ctx *ctx, void *send_dev);
+int sibgpu_dist_group(sibgpu_ctx *ctx, const void *recv_dev, const uint32_t *counts, uint64_t *nkeys_local);
+int sibgpu_dist_keys(sibgpu_ctx *ctx, void *keys_dev);
+int sibgpu_dist_finish(sibgpu_ctx *ctx, const void *allkeys_dev, uint64_t nkeys_total, uint64_t *ninst_local, uint32_t *count);
+
 /* Test hook (host only, no GPU needed): iteration order of the reference's boost::unordered_map<size_t, BranchData>
  * (Boost 1.54, src/bulgeremoval.cpp:168,203-215) after inserting n distinct keys in the given order, as restated in
  * sibelia_b200/csrc/boost_order.h.  out receives the n keys in begin()..end() order. */

@@ -12,7 +12,8 @@ INST_DTYPE = np.dtype([("bifId", "<u4"), ("chr", "<u4"), ("pos", "<u4")])
 SYMBOLS = [
     "sibgpu_last_error", "sibgpu_version", "sibgpu_device_count", "sibgpu_create", "sibgpu_destroy", "sibgpu_free",
     "sibgpu_enumerate", "sibgpu_upload", "sibgpu_enumerate_resident", "sibgpu_download", "sibgpu_set_profiling",
-    "sibgpu_kernel_stats", "sibgpu_last_launches", "sibgpu_last_device_ms", "sibgpu_simplify", "sibgpu_debug_unordered_order",
+    "sibgpu_kernel_stats", "sibgpu_last_launches", "sibgpu_last_device_ms", "sibgpu_simplify", "sibgpu_debug_unordered_order", "sibgpu_dist_upload", "sibgpu_dist_scan", "sibgpu_dist_record_bytes",
+    "sibgpu_dist_scatter", "sibgpu_dist_group", "sibgpu_dist_keys", "sibgpu_dist_finish",
 ]
 
 
@@ -155,6 +156,39 @@ class Context:
 
     def last_launches(self):
         return int(load().sibgpu_last_launches(self._h))
+
+    # -- sharded enumeration phases (see sibelia_b200/distributed.py for the orchestration)
+    def dist_upload(self, chrs, rank, world):
+        bufs, ptrs, lens, n = _chr_args(chrs)
+        _check(load().sibgpu_dist_upload(self._h, ptrs, lens, C.c_uint32(n), C.c_uint32(rank), C.c_uint32(world)))
+
+    def dist_scan(self, k):
+        hist = np.zeros(1024, dtype=np.uint32)
+        nparts, nrec = C.c_uint32(), C.c_uint64()
+        _check(load().sibgpu_dist_scan(self._h, C.c_uint32(k), C.byref(nparts), C.c_void_p(hist.ctypes.data), C.byref(nrec)))
+        return nparts.value, hist[:nparts.value].copy(), nrec.value
+
+    def dist_record_bytes(self):
+        f = load().sibgpu_dist_record_bytes
+        f.restype = C.c_uint32
+        return int(f(self._h))
+
+    def dist_scatter(self, send_ptr):
+        _check(load().sibgpu_dist_scatter(self._h, C.c_void_p(send_ptr)))
+
+    def dist_group(self, recv_ptr, counts):
+        counts = np.ascontiguousarray(counts, dtype=np.uint32)
+        nkeys = C.c_uint64()
+        _check(load().sibgpu_dist_group(self._h, C.c_void_p(recv_ptr), C.c_void_p(counts.ctypes.data), C.byref(nkeys)))
+        return nkeys.value
+
+    def dist_keys(self, keys_ptr):
+        _check(load().sibgpu_dist_keys(self._h, C.c_void_p(keys_ptr)))
+
+    def dist_finish(self, allkeys_ptr, nkeys_total):
+        ninst, cnt = C.c_uint64(), C.c_uint32()
+        _check(load().sibgpu_dist_finish(self._h, C.c_void_p(allkeys_ptr), C.c_uint64(nkeys_total), C.byref(ninst), C.byref(cnt)))
+        return cnt.value, ninst.value
 
     # -- sibgpu_simplify: one PerformGraphSimplifications stage
     def simplify(self, chrs, origpos, k, min_branch_size, max_iterations=4):

@@ -136,6 +136,8 @@ int sibgpu_upload(sibgpu_ctx *c, const char *const *chr, const uint64_t *len, ui
 	SIB_CUDA(cudaSetDevice(c->device));
 	c->have_text = false;
 	c->have_result = false;
+	c->dist_result = false;
+	c->dist_world = 1;
 	uint64_t N = 0;
 	for(uint32_t i = 0; i < nchr; i++) N += len[i];
 	const uint64_t M = N + nchr + 1;
@@ -227,7 +229,7 @@ int sibgpu_download(sibgpu_ctx *c, sibgpu_inst **pos, uint64_t *npos, sibgpu_ins
 	if(n)
 	{
 		SIB_CUDA(cudaMemcpyAsync(*pos, c->d_pos.p, sizeof(sibgpu_inst) * n, cudaMemcpyDeviceToHost, c->stream));
-		SIB_CUDA(cudaMemcpyAsync(*neg, c->d_neg.p, sizeof(sibgpu_inst) * n, cudaMemcpyDeviceToHost, c->stream));
+		SIB_CUDA(cudaMemcpyAsync(*neg, c->dist_result ? c->d_negtmp.p : c->d_neg.p, sizeof(sibgpu_inst) * n, cudaMemcpyDeviceToHost, c->stream));
 		SIB_CUDA(cudaStreamSynchronize(c->stream));
 	}
 	*npos = n;
@@ -241,6 +243,145 @@ int sibgpu_enumerate(sibgpu_ctx *c, const char *const *chr, const uint64_t *len,
 	SIB_TRY(sibgpu_upload(c, chr, len, nchr));
 	SIB_TRY(sibgpu_enumerate_resident(c, k, nullptr, count));
 	return sibgpu_download(c, pos, npos, neg, nneg);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// sharded enumeration (one process per GPU)
+// ---------------------------------------------------------------------------------------------------------------
+int sibgpu_dist_upload(sibgpu_ctx *c, const char *const *chr, const uint64_t *len, uint32_t nchr, uint32_t rank, uint32_t world)
+{
+	if(!c || (nchr && (!chr || !len)) || world == 0 || rank >= world || world > 64)
+	{
+		set_error("invalid: NULL argument or bad rank/world");
+		return SIBGPU_ERR_INVALID;
+	}
+	SIB_CUDA(cudaSetDevice(c->device));
+	c->have_text = false;
+	c->have_result = false;
+	uint64_t N = 0;
+	for(uint32_t i = 0; i < nchr; i++) N += len[i];
+	const uint64_t M = N + nchr + 1;
+	if(M >= (1ull << 31))
+	{
+		set_error("invalid: input of " + std::to_string(N) + " bases exceeds the 32-bit position range");
+		return SIBGPU_ERR_INVALID;
+	}
+	c->h_chr_start.resize(nchr);
+	c->h_chr_len.resize(nchr);
+	uint64_t at = 1;
+	for(uint32_t i = 0; i < nchr; i++)
+	{
+		c->h_chr_start[i] = (uint32_t)at;
+		c->h_chr_len[i] = (uint32_t)len[i];
+		at += len[i] + 1;
+	}
+	const size_t nwords = (size_t)((M + 15) / 16) + 8;
+	const uint64_t tile_pos = 4096;
+	const uint64_t ntiles = (M + tile_pos - 1) / tile_pos;
+	c->dist_rank = rank;
+	c->dist_world = world;
+	c->dist_tile_lo = (uint32_t)(ntiles * rank / world);
+	c->dist_tile_hi = (uint32_t)(ntiles * (rank + 1) / world);
+	// bytes this rank reads: its tiles, one word of back halo, k + 1 <= 33 bases and the staged words of forward halo
+	uint64_t b_lo = (uint64_t)c->dist_tile_lo * tile_pos, b_hi = (uint64_t)c->dist_tile_hi * tile_pos + 128;
+	b_lo = b_lo >= 16 ? b_lo - 16 : 0;
+	if(b_hi > nwords * 16) b_hi = nwords * 16;
+	if(c->dist_tile_hi == c->dist_tile_lo) b_hi = b_lo;
+	c->dist_byte_lo = b_lo;
+	c->dist_byte_hi = b_hi;
+	SIB_TRY(c->d_text.ensure(nwords * 16));
+	SIB_TRY(c->d_chr_start.ensure(sizeof(uint32_t) * (nchr + 1)));
+	SIB_TRY(c->d_chr_len.ensure(sizeof(uint32_t) * (nchr + 1)));
+	if(b_hi > b_lo) SIB_CUDA(cudaMemsetAsync(c->d_text.as<char>() + b_lo, '$', b_hi - b_lo, c->stream));
+	for(uint32_t i = 0; i < nchr; i++)
+	{
+		const uint64_t s = c->h_chr_start[i], e = s + len[i];
+		const uint64_t lo = s > b_lo ? s : b_lo, hi = e < b_hi ? e : b_hi;
+		if(hi > lo)
+		{
+			SIB_CUDA(cudaMemcpyAsync(c->d_text.as<char>() + lo, chr[i] + (lo - s), hi - lo, cudaMemcpyHostToDevice, c->stream));
+		}
+	}
+	if(nchr)
+	{
+		SIB_CUDA(cudaMemcpyAsync(c->d_chr_start.p, c->h_chr_start.data(), sizeof(uint32_t) * nchr, cudaMemcpyHostToDevice, c->stream));
+		SIB_CUDA(cudaMemcpyAsync(c->d_chr_len.p, c->h_chr_len.data(), sizeof(uint32_t) * nchr, cudaMemcpyHostToDevice, c->stream));
+	}
+	SIB_CUDA(cudaStreamSynchronize(c->stream));
+	c->nchr = nchr;
+	c->N = N;
+	c->M = M;
+	c->have_text = true;
+	c->dist_result = false;
+	return SIBGPU_OK;
+}
+
+int sibgpu_dist_scan(sibgpu_ctx *c, uint32_t k, uint32_t *nparts_total, uint32_t *hist, uint64_t *nrec_local)
+{
+	if(!c || !hist || !nparts_total || k == 0 || k > 32)
+	{
+		set_error("invalid: the sharded path supports 1 <= k <= 32");
+		return SIBGPU_ERR_INVALID;
+	}
+	if(!c->have_text)
+	{
+		set_error("state: sibgpu_dist_upload must come first");
+		return SIBGPU_ERR_STATE;
+	}
+	SIB_CUDA(cudaEventRecord(c->ev_begin, c->stream));
+	SIB_TRY(dist_scan(c, k, hist));
+	*nparts_total = c->dist_P_total;
+	if(nrec_local) *nrec_local = c->dist_nrec_local;
+	return SIBGPU_OK;
+}
+
+uint32_t sibgpu_dist_record_bytes(sibgpu_ctx *c) { return c && c->last_k > 28 ? 16u : 8u; }
+
+int sibgpu_dist_scatter(sibgpu_ctx *c, void *send_dev)
+{
+	if(!c || (!send_dev && c->dist_nrec_local))
+	{
+		set_error("invalid: NULL argument");
+		return SIBGPU_ERR_INVALID;
+	}
+	return dist_scatter(c, send_dev);
+}
+
+int sibgpu_dist_group(sibgpu_ctx *c, const void *recv_dev, const uint32_t *counts, uint64_t *nkeys_local)
+{
+	if(!c || !counts || !nkeys_local)
+	{
+		set_error("invalid: NULL argument");
+		return SIBGPU_ERR_INVALID;
+	}
+	return dist_group(c, recv_dev, counts, nkeys_local);
+}
+
+int sibgpu_dist_keys(sibgpu_ctx *c, void *keys_dev)
+{
+	if(!c) return SIBGPU_ERR_INVALID;
+	if(c->dist_nkeys_local)
+	{
+		SIB_CUDA(cudaMemcpyAsync(keys_dev, c->d_ckeys.p, c->dist_nkeys_local * sibgpu_dist_record_bytes(c), cudaMemcpyDeviceToDevice, c->stream));
+		SIB_CUDA(cudaStreamSynchronize(c->stream));
+	}
+	return SIBGPU_OK;
+}
+
+int sibgpu_dist_finish(sibgpu_ctx *c, const void *allkeys_dev, uint64_t nkeys_total, uint64_t *ninst_local, uint32_t *count)
+{
+	if(!c)
+	{
+		set_error("invalid: NULL argument");
+		return SIBGPU_ERR_INVALID;
+	}
+	SIB_TRY(dist_finish(c, allkeys_dev, nkeys_total));
+	SIB_CUDA(cudaEventRecord(c->ev_end, c->stream));
+	SIB_CUDA(cudaEventSynchronize(c->ev_end));
+	SIB_CUDA(cudaEventElapsedTime(&c->last_ms, c->ev_begin, c->ev_end));
+	if(ninst_local) *ninst_local = c->n_inst;
+	if(count) *count = c->n_vertices;
+	return SIBGPU_OK;
 }
 
 int sibgpu_set_profiling(sibgpu_ctx *c, int enabled)

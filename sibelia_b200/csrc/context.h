@@ -6,6 +6,19 @@
 
 #include "common.cuh"
 
+namespace sibgpu {
+// device-side description of the concatenated text '$' chr0 '$' chr1 ... '$'
+struct TextDesc {
+	const uint32_t *packed;        // 16 bases per word, first base in the top bit pair
+	const uint32_t *chr_start;     // text index of the first base of every chromosome
+	const uint32_t *chr_len;
+	uint32_t nchr;
+	uint32_t M;                    // text length
+	uint32_t nwords;               // valid words in packed[]
+	uint32_t tile0;                // first 4096-position tile of this rank's text range (0 on a single GPU)
+};
+}
+
 struct sibgpu_ctx {
 	int device = 0;
 	int sm_count = 148;
@@ -30,6 +43,12 @@ struct sibgpu_ctx {
 	uint64_t n_inst = 0;                               // instances per strand
 	uint32_t n_vertices = 0;
 	uint32_t last_k = 0;
+
+	// sharded mode (sibgpu_dist_*)
+	uint32_t dist_rank = 0, dist_world = 1, dist_tile_lo = 0, dist_tile_hi = 0, dist_P_local = 0, dist_P_total = 0;
+	uint64_t dist_byte_lo = 0, dist_byte_hi = 0, dist_nrec_local = 0, dist_nkeys_local = 0;
+	bool dist_result = false;
+	sibgpu::TextDesc dist_text = {};
 
 	// tunables (env SIBGPU_PART_RECORDS)
 	uint64_t part_target = 1u << 22;
@@ -68,4 +87,8 @@ struct ProfScope {
 };
 
 int enumerate_resident(sibgpu_ctx *ctx, uint32_t k);
+int dist_scan(sibgpu_ctx *ctx, uint32_t k, uint32_t *hist_out);
+int dist_scatter(sibgpu_ctx *ctx, void *send_dev);
+int dist_group(sibgpu_ctx *ctx, const void *recv_dev, const uint32_t *counts, uint64_t *nkeys_local);
+int dist_finish(sibgpu_ctx *ctx, const void *allkeys_dev, uint64_t nkeys_total);
 } // namespace sibgpu

@@ -1,0 +1,252 @@
+// Sharded enumeration over `world` GPUs, one process per GPU (included at the end of enumerate.cu).
+//
+// The concatenated text is split into `world` contiguous tile ranges; every rank scans only its range.  Records are
+// partitioned by the SAME hash function on every rank into P_total = world * P_local partitions; partition p belongs
+// to rank p / P_local, so after one all-to-all (done by the caller with NCCL on the send/recv device buffers handed
+// in here) every rank holds ALL occurrences of the k-mer classes it owns and decides them locally.  The (few) vertex
+// keys are then all-gathered so that every rank can compute the global lexicographic ids and emit the instances of its
+// own text range.  k <= 32 only (the k > 32 ranking needs the whole text on every rank).
+//
+//   dist_scan     pack own range, histogram over P_total partitions          -> counts (host)
+//   dist_scatter  records of the own range, ordered by partition             -> send buffer
+//   [caller: all_gather(counts), all_to_all(records)]
+//   dist_group    per owned partition: insert the world segments, predicate  -> local canonical vertex keys
+//   [caller: all_gather(keys)]
+//   dist_finish   global ids + map, mark/emit over the own range             -> local instance tables (text order)
+
+template<int MODE>
+static int dist_scan_mode(sibgpu_ctx *ctx, uint32_t k, uint32_t *hist_out)
+{
+	cudaStream_t st = ctx->stream;
+	TextDesc t = ctx->dist_text;
+	const uint32_t ntiles = ctx->dist_tile_hi - ctx->dist_tile_lo;
+	SIB_TRY(ctx->d_hist.ensure(sizeof(uint32_t) * MAX_PARTS));
+	SIB_CUDA(cudaMemsetAsync(ctx->d_hist.p, 0, sizeof(uint32_t) * MAX_PARTS, st));
+	if(ntiles)
+	{
+		const uint32_t g = ntiles < (uint32_t)ctx->sm_count * 8 ? ntiles : (uint32_t)ctx->sm_count * 8;
+		ProfScope ps(ctx, "k_scan_hist", (uint64_t)ntiles * TILE_POS / 4);
+		k_scan_hist<MODE><<<g, TILE_THREADS, 0, st>>>(t, nullptr, k, ntiles, ctx->dist_P_total, ctx->d_hist.as<uint32_t>());
+	}
+	SIB_CUDA(cudaMemcpyAsync(hist_out, ctx->d_hist.p, sizeof(uint32_t) * ctx->dist_P_total, cudaMemcpyDeviceToHost, st));
+	SIB_CUDA(cudaStreamSynchronize(st));
+	return SIBGPU_OK;
+}
+
+template<int MODE>
+static int dist_scatter_mode(sibgpu_ctx *ctx, uint32_t k, void *send_dev)
+{
+	typedef typename RecT<MODE>::type Rec;
+	cudaStream_t st = ctx->stream;
+	TextDesc t = ctx->dist_text;
+	const uint32_t ntiles = ctx->dist_tile_hi - ctx->dist_tile_lo;
+	SIB_TRY(ctx->d_partoff.ensure(sizeof(uint64_t) * (MAX_PARTS + 1)));
+	SIB_TRY(ctx->d_cursor.ensure(sizeof(uint64_t) * MAX_PARTS));
+	k_part_offsets<<<1, MAX_PARTS, 0, st>>>(ctx->d_hist.as<uint32_t>(), ctx->dist_P_total, ctx->d_partoff.as<uint64_t>(),
+		ctx->d_cursor.as<unsigned long long>(), ctx->d_scalars.as<uint64_t>());
+	ctx->total_launches++;
+	if(ntiles)
+	{
+		size_t smem = sizeof(ScatterSmem<MODE>);
+		SIB_CUDA(cudaFuncSetAttribute(k_scatter<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+		const uint32_t g = ntiles < (uint32_t)ctx->sm_count * 4 ? ntiles : (uint32_t)ctx->sm_count * 4;
+		ProfScope ps(ctx, "k_scatter", (uint64_t)ntiles * TILE_POS / 4 + ctx->dist_nrec_local * sizeof(Rec));
+		k_scatter<MODE><<<g, TILE_THREADS, smem, st>>>(t, nullptr, k, ntiles, ctx->dist_P_total,
+			ctx->d_cursor.as<unsigned long long>(), static_cast<Rec*>(send_dev));
+	}
+	SIB_CUDA(cudaStreamSynchronize(st));
+	return SIBGPU_OK;
+}
+
+template<int MODE>
+static int dist_group_mode(sibgpu_ctx *ctx, uint32_t k, const void *recv_dev, const uint32_t *counts, uint64_t *nkeys_local)
+{
+	typedef typename RecT<MODE>::type Rec;
+	cudaStream_t st = ctx->stream;
+	const int sms = ctx->sm_count;
+	const uint32_t W = ctx->dist_world, PL = ctx->dist_P_local, PT = ctx->dist_P_total, b0 = ctx->dist_rank * PL;
+	uint64_t *hs = static_cast<uint64_t*>(ctx->h_scalars);
+	uint64_t *ds = ctx->d_scalars.as<uint64_t>();
+	// layout of the receive buffer: for every source rank s, its records of my partitions in partition order
+	std::vector<uint64_t> src_off(W + 1, 0), stage_off(PL + 1, 0);
+	uint64_t maxpart = 0;
+	for(uint32_t s = 0; s < W; s++)
+	{
+		uint64_t sum = 0;
+		for(uint32_t p = 0; p < PL; p++) sum += counts[(size_t)s * PT + b0 + p];
+		src_off[s + 1] = src_off[s] + sum;
+	}
+	for(uint32_t p = 0; p < PL; p++)
+	{
+		uint64_t sum = 0;
+		for(uint32_t s = 0; s < W; s++) sum += counts[(size_t)s * PT + b0 + p];
+		stage_off[p + 1] = stage_off[p] + sum;
+		if(sum > maxpart) maxpart = sum;
+	}
+	const uint64_t recv_total = src_off[W];
+	*nkeys_local = 0;
+	ctx->dist_nkeys_local = 0;
+	if(recv_total == 0) return SIBGPU_OK;
+	const uint64_t T64 = 2 * maxpart + 1024;
+	if(T64 > 0xFFFFFF00ull)
+	{
+		set_error("internal: hash partition does not fit a 32-bit table");
+		return SIBGPU_ERR_INTERNAL;
+	}
+	const uint32_t T = (uint32_t)T64;
+	const bool compact = MODE == 0 && k <= COMPACT_MAX_K;
+	const size_t slot_bytes = compact ? 8 : (MODE == 0 ? sizeof(Slot8) : sizeof(Slot16));
+	SIB_TRY(ctx->d_table.ensure(slot_bytes * T));
+	SIB_CUDA(cudaMemsetAsync(ctx->d_table.p, 0xFF, slot_bytes * T, st));
+	SIB_TRY(ctx->d_records.ensure(sizeof(Rec) * recv_total));          // staging area of the vertex keys, per partition
+	SIB_TRY(ctx->d_partcnt.ensure(sizeof(uint32_t) * MAX_PARTS));
+	SIB_TRY(ctx->d_keyoff.ensure(sizeof(uint64_t) * (MAX_PARTS + 1)));
+	SIB_TRY(ctx->d_partoff.ensure(sizeof(uint64_t) * (MAX_PARTS + 1)));
+	SIB_CUDA(cudaMemsetAsync(ctx->d_partcnt.p, 0, sizeof(uint32_t) * MAX_PARTS, st));
+	SIB_CUDA(cudaMemcpyAsync(ctx->d_partoff.p, stage_off.data(), sizeof(uint64_t) * (PL + 1), cudaMemcpyHostToDevice, st));
+	const Rec *recv = static_cast<const Rec*>(recv_dev);
+	std::vector<uint64_t> seg_cursor(src_off.begin(), src_off.end() - 1);
+	for(uint32_t p = 0; p < PL; p++)
+	{
+		if(stage_off[p + 1] == stage_off[p]) continue;
+		for(uint32_t s = 0; s < W; s++)
+		{
+			const uint64_t n = counts[(size_t)s * PT + b0 + p];
+			if(n == 0) continue;
+			const Rec *seg = recv + seg_cursor[s];
+			seg_cursor[s] += n;
+			ProfScope ps(ctx, "k_insert", n * sizeof(Rec));
+			if(compact) k_insert_compact<<<grid_for(n, 256, sms, 8), 256, 0, st>>>(reinterpret_cast<const uint64_t*>(seg), n,
+				ctx->d_table.as<unsigned long long>(), T);
+			else k_insert<MODE><<<grid_for(n, 256, sms, 8), 256, 0, st>>>(seg, n, ctx->d_table.p, T);
+		}
+		Rec *out = ctx->d_records.as<Rec>() + stage_off[p];
+		ProfScope ps(ctx, "k_table_scan", (uint64_t)T * slot_bytes);
+		if(compact) k_table_scan_compact<<<grid_for(T, 256, sms, 8), 256, 0, st>>>(ctx->d_table.as<unsigned long long>(), T,
+			reinterpret_cast<uint64_t*>(out), ctx->d_partcnt.as<uint32_t>() + p);
+		else k_table_scan<MODE><<<grid_for(T, 256, sms, 8), 256, 0, st>>>(ctx->d_table.p, T, out, ctx->d_partcnt.as<uint32_t>() + p);
+	}
+	k_key_offsets<<<1, MAX_PARTS, 0, st>>>(ctx->d_partcnt.as<uint32_t>(), PL, ctx->d_keyoff.as<uint64_t>(), ds);
+	ctx->total_launches++;
+	SIB_CUDA(cudaMemcpyAsync(hs + 2, ds + 2, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+	SIB_CUDA(cudaStreamSynchronize(st));
+	const uint64_t Vc = hs[2];
+	if(Vc)
+	{
+		SIB_TRY(ctx->d_ckeys.ensure(sizeof(Rec) * Vc));
+		ProfScope ps(ctx, "k_gather_keys", 2 * Vc * sizeof(Rec));
+		dim3 g(8, PL);
+		k_gather_keys<MODE><<<g, 256, 0, st>>>(ctx->d_records.as<Rec>(), ctx->d_partoff.as<uint64_t>(),
+			ctx->d_partcnt.as<uint32_t>(), ctx->d_keyoff.as<uint64_t>(), ctx->d_ckeys.as<Rec>());
+		SIB_CUDA(cudaStreamSynchronize(st));
+	}
+	ctx->dist_nkeys_local = Vc;
+	*nkeys_local = Vc;
+	return SIBGPU_OK;
+}
+
+template<int MODE>
+static int dist_finish_mode(sibgpu_ctx *ctx, uint32_t k, const void *allkeys_dev, uint64_t nkeys_total)
+{
+	typedef typename RecT<MODE>::type Rec;
+	const uint32_t ntiles = ctx->dist_tile_hi - ctx->dist_tile_lo;
+	ctx->n_inst = 0;
+	ctx->n_vertices = 0;
+	if(nkeys_total == 0) return SIBGPU_OK;
+	if(2 * nkeys_total > 0xFFFFFFF0ull)
+	{
+		set_error("invalid: more than 2^32 vertices");
+		return SIBGPU_ERR_INVALID;
+	}
+	if(ntiles == 0)
+	{
+		// nothing to emit here, but the vertex count is still a global quantity: rank the keys
+		ctx->dist_text.tile0 = 0;
+	}
+	bool collision = false;
+	return ids_and_tables<MODE>(ctx, ctx->dist_text, k, static_cast<const Rec*>(allkeys_dev), nkeys_total,
+		ntiles ? ntiles : 0, nullptr, false, &collision);
+}
+
+int dist_scan(sibgpu_ctx *ctx, uint32_t k, uint32_t *hist_out)
+{
+	cudaStream_t st = ctx->stream;
+	SIB_CUDA(cudaSetDevice(ctx->device));
+	ctx->have_result = false;
+	ctx->prof_reset();
+	ctx->total_launches = 0;
+	// K0 over the words of the own range (+ halo)
+	const uint64_t w_lo = ctx->dist_byte_lo / 16, w_hi = (ctx->dist_byte_hi + 15) / 16;
+	const uint32_t nwords_all = (uint32_t)((ctx->M + 15) / 16) + 8;
+	SIB_TRY(ctx->d_packed.ensure(sizeof(uint32_t) * (size_t)nwords_all));
+	SIB_TRY(ctx->d_scalars.ensure(sizeof(uint64_t) * 64));
+	SIB_CUDA(cudaMemsetAsync(ctx->d_scalars.p, 0, sizeof(uint64_t) * 64, st));
+	uint32_t *d_err = reinterpret_cast<uint32_t*>(ctx->d_scalars.as<uint64_t>() + 8);
+	if(w_hi > w_lo)
+	{
+		ProfScope ps(ctx, "k_pack", (w_hi - w_lo) * 20);
+		k_pack<<<grid_for(w_hi - w_lo, 256, ctx->sm_count, 8), 256, 0, st>>>(ctx->d_text.as<uint4>() + w_lo,
+			ctx->d_packed.as<uint32_t>() + w_lo, (uint32_t)(w_hi - w_lo), d_err);
+	}
+	uint64_t *hs = static_cast<uint64_t*>(ctx->h_scalars);
+	SIB_CUDA(cudaMemcpyAsync(hs + 8, ctx->d_scalars.as<uint64_t>() + 8, 8, cudaMemcpyDeviceToHost, st));
+	SIB_CUDA(cudaStreamSynchronize(st));
+	if(hs[8] & 1u)
+	{
+		set_error("input: a character outside ACGT reached the device; sanitise first (indexedsequence.cpp:31-37)");
+		return SIBGPU_ERR_INPUT;
+	}
+	uint64_t nrec = 0;
+	for(uint32_t c = 0; c < ctx->nchr; c++)
+	{
+		if(ctx->h_chr_len[c] >= k) nrec += ctx->h_chr_len[c] - k + 1;
+	}
+	const uint32_t W = ctx->dist_world;
+	uint64_t per_rank = (nrec + W - 1) / W;
+	uint64_t PL = (per_rank + ctx->part_target - 1) / ctx->part_target;
+	if(PL < 1) PL = 1;
+	if(PL > MAX_PARTS / W) PL = MAX_PARTS / W;
+	ctx->dist_P_local = (uint32_t)PL;
+	ctx->dist_P_total = (uint32_t)PL * W;
+	ctx->last_k = k;
+	TextDesc &t = ctx->dist_text;
+	t.packed = ctx->d_packed.as<uint32_t>();
+	t.chr_start = ctx->d_chr_start.as<uint32_t>();
+	t.chr_len = ctx->d_chr_len.as<uint32_t>();
+	t.nchr = ctx->nchr;
+	t.M = (uint32_t)ctx->M;
+	t.nwords = nwords_all;
+	t.tile0 = ctx->dist_tile_lo;
+	int rc = k <= 28 ? dist_scan_mode<0>(ctx, k, hist_out) : dist_scan_mode<1>(ctx, k, hist_out);
+	if(rc != SIBGPU_OK) return rc;
+	uint64_t local = 0;
+	for(uint32_t p = 0; p < ctx->dist_P_total; p++) local += hist_out[p];
+	ctx->dist_nrec_local = local;
+	return SIBGPU_OK;
+}
+
+int dist_scatter(sibgpu_ctx *ctx, void *send_dev)
+{
+	SIB_CUDA(cudaSetDevice(ctx->device));
+	return ctx->last_k <= 28 ? dist_scatter_mode<0>(ctx, ctx->last_k, send_dev) : dist_scatter_mode<1>(ctx, ctx->last_k, send_dev);
+}
+
+int dist_group(sibgpu_ctx *ctx, const void *recv_dev, const uint32_t *counts, uint64_t *nkeys_local)
+{
+	SIB_CUDA(cudaSetDevice(ctx->device));
+	return ctx->last_k <= 28 ? dist_group_mode<0>(ctx, ctx->last_k, recv_dev, counts, nkeys_local)
+		: dist_group_mode<1>(ctx, ctx->last_k, recv_dev, counts, nkeys_local);
+}
+
+int dist_finish(sibgpu_ctx *ctx, const void *allkeys_dev, uint64_t nkeys_total)
+{
+	SIB_CUDA(cudaSetDevice(ctx->device));
+	int rc = ctx->last_k <= 28 ? dist_finish_mode<0>(ctx, ctx->last_k, allkeys_dev, nkeys_total)
+		: dist_finish_mode<1>(ctx, ctx->last_k, allkeys_dev, nkeys_total);
+	if(rc != SIBGPU_OK) return rc;
+	SIB_CUDA(cudaGetLastError());
+	ctx->have_result = true;
+	ctx->dist_result = true;
+	if(ctx->profiling) SIB_TRY(ctx->prof_collect());
+	return SIBGPU_OK;
+}

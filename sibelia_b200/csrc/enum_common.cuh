@@ -19,14 +19,6 @@ constexpr uint64_t EMPTY64 = ~0ull;
 //   bits 0-4 prev-symbol set, bits 5-9 next-symbol set, bit 10 "seen more than once"
 constexpr uint32_t PAY_MULTI = 1u << 10;
 
-struct TextDesc {
-	const uint32_t *packed;        // 16 bases per word, first base in the top bit pair
-	const uint32_t *chr_start;     // text index of the first base of every chromosome
-	const uint32_t *chr_len;
-	uint32_t nchr;
-	uint32_t M;                    // text length
-	uint32_t nwords;               // valid words in packed[]
-};
 
 struct Rec16 { uint64_t a, b; };
 

@@ -132,9 +132,9 @@ __global__ void __launch_bounds__(TILE_THREADS) k_scan_hist(TextDesc t, const Re
 	for(uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x)
 	{
 		__syncthreads();
-		if(MODE != 2) stage_tile(t, tile, sw);
+		if(MODE != 2) stage_tile(t, t.tile0 + tile, sw);
 		__syncthreads();
-		scan16<MODE>(t, fp, sw, tile, k, [&](int, uint64_t a, uint64_t b, uint32_t) {
+		scan16<MODE>(t, fp, sw, t.tile0 + tile, k, [&](int, uint64_t a, uint64_t b, uint32_t) {
 			uint32_t bin = __umulhi((uint32_t)(rec_hash(a, b) >> 32), P);
 			atomicAdd(&shist[bin], 1u);
 		});
@@ -190,13 +190,13 @@ __global__ void __launch_bounds__(TILE_THREADS) k_scatter(TextDesc t, const Rec1
 	for(uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x)
 	{
 		for(uint32_t b = threadIdx.x; b < P; b += TILE_THREADS) s.cnt[b] = 0;
-		if(MODE != 2) stage_tile(t, tile, s.sw);
+		if(MODE != 2) stage_tile(t, t.tile0 + tile, s.sw);
 		__syncthreads();
 
 		uint64_t ra[POS_PER_THREAD], rb[POS_PER_THREAD];
 		uint32_t binrank[POS_PER_THREAD];
 		uint32_t valid = 0;
-		scan16<MODE>(t, fp, s.sw, tile, k, [&](int i, uint64_t a, uint64_t b, uint32_t ctx) {
+		scan16<MODE>(t, fp, s.sw, t.tile0 + tile, k, [&](int i, uint64_t a, uint64_t b, uint32_t ctx) {
 			uint32_t bin = __umulhi((uint32_t)(rec_hash(a, b) >> 32), P);
 			uint32_t rank = atomicAdd(&s.cnt[bin], 1u);
 			binrank[i] = (bin << 16) | rank;             // rank < 4096, bin < 1024
@@ -574,10 +574,10 @@ __global__ void __launch_bounds__(TILE_THREADS) k_mark(TextDesc t, const Rec16 *
 	for(uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x)
 	{
 		__syncthreads();
-		if(MODE != 2) stage_tile(t, tile, sw);
+		if(MODE != 2) stage_tile(t, t.tile0 + tile, sw);
 		__syncthreads();
 		uint32_t mask = 0;
-		scan16<MODE>(t, fp, sw, tile, k, [&](int i, uint64_t a, uint64_t b, uint32_t ctx) {
+		scan16<MODE>(t, fp, sw, t.tile0 + tile, k, [&](int i, uint64_t a, uint64_t b, uint32_t ctx) {
 			uint32_t idc, idr, cls;
 			if(map_lookup(map, Tm, filter, fshift, a, b, idc, idr, cls))
 			{
@@ -585,7 +585,7 @@ __global__ void __launch_bounds__(TILE_THREADS) k_mark(TextDesc t, const Rec16 *
 				if(MODE == 2)
 				{
 					// representative occurrence of the class = its smallest text position (+ palindrome / forward flags)
-					const uint32_t p = tile * TILE_POS + threadIdx.x * POS_PER_THREAD + i;
+					const uint32_t p = (t.tile0 + tile) * TILE_POS + threadIdx.x * POS_PER_THREAD + i;
 					atomicMin(&rep[cls], ((unsigned long long)p << 2) | ((ctx >> 5) & 2u) | ((ctx >> 7) & 1u));
 				}
 			}
@@ -612,7 +612,7 @@ __global__ void __launch_bounds__(TILE_THREADS) k_emit(TextDesc t, const Rec16 *
 		__syncthreads();
 		Scan(scan_tmp).ExclusiveSum((uint32_t)__popc(mask), rank);
 		uint64_t o = tileoff[tile] + rank;
-		const uint32_t p0 = tile * TILE_POS + threadIdx.x * POS_PER_THREAD;
+		const uint32_t p0 = (t.tile0 + tile) * TILE_POS + threadIdx.x * POS_PER_THREAD;
 		while(mask)
 		{
 			const uint32_t i = __ffs(mask) - 1;
@@ -698,6 +698,146 @@ static inline uint32_t grid_for(uint64_t work_items, int threads, int sm_count, 
 	return (uint32_t)(blocks < cap ? blocks : cap);
 }
 
+// Vertex ids, vertex map and the two instance tables for the text tiles [t.tile0, t.tile0 + ntiles), given the
+// canonical keys of ALL vertex classes (`ckeys`, Vc of them).  Shared by the single-GPU path and the sharded path.
+template<int MODE>
+static int ids_and_tables(sibgpu_ctx *ctx, const TextDesc &t, uint32_t k, const typename RecT<MODE>::type *ckeys_in, uint64_t Vc,
+	uint32_t ntiles, const Rec16 *fp, bool reverse_neg, bool *collision)
+{
+	typedef typename RecT<MODE>::type Rec;
+	cudaStream_t st = ctx->stream;
+	const int sms = ctx->sm_count;
+	uint64_t *hs = static_cast<uint64_t*>(ctx->h_scalars);
+	uint64_t *ds = ctx->d_scalars.as<uint64_t>();
+	const uint32_t scan_grid = ntiles < (uint32_t)sms * 8 ? ntiles : (uint32_t)sms * 8;
+	Rec *ckeys = const_cast<Rec*>(ckeys_in);
+	*collision = false;
+	// ---- vertex ids + vertex map
+	uint64_t Tm64 = 2 * Vc + 64;
+	const uint32_t Tm = (uint32_t)Tm64;
+	uint32_t fbits_log = 16;
+	while((1ull << fbits_log) < 32 * Vc && fbits_log < 32) fbits_log++;
+	const uint32_t fshift = 64 - fbits_log;
+	SIB_TRY(ctx->d_map.ensure(sizeof(MapSlot) * (size_t)Tm));
+	SIB_TRY(ctx->d_filter.ensure((1ull << fbits_log) / 8));
+	SIB_CUDA(cudaMemsetAsync(ctx->d_map.p, 0xFF, sizeof(MapSlot) * (size_t)Tm, st));
+	SIB_CUDA(cudaMemsetAsync(ctx->d_filter.p, 0, (1ull << fbits_log) / 8, st));
+	uint32_t V = 0;
+	if(MODE != 2)
+	{
+		SIB_TRY(ctx->d_vkeys.ensure(sizeof(uint64_t) * 2 * Vc));
+		SIB_TRY(ctx->d_vkeys_alt.ensure(sizeof(uint64_t) * 2 * Vc));
+		SIB_CUDA(cudaMemsetAsync(ds + 3, 0, sizeof(uint64_t), st));
+		{
+			ProfScope ps(ctx, "k_expand", Vc * (sizeof(Rec) + 16));
+			k_expand<MODE><<<(uint32_t)((Vc + 255) / 256), 256, 0, st>>>(ckeys, Vc, k,
+				ctx->d_vkeys.as<uint64_t>(), reinterpret_cast<uint32_t*>(ds + 3));
+		}
+		size_t tmp_bytes = 0;
+		cub::DoubleBuffer<uint64_t> dbuf(ctx->d_vkeys.as<uint64_t>(), ctx->d_vkeys_alt.as<uint64_t>());
+		SIB_CUDA(cub::DeviceRadixSort::SortKeys(nullptr, tmp_bytes, dbuf, (int)(2 * Vc), 0, 64, st));
+		SIB_TRY(ctx->d_cubtmp.ensure(tmp_bytes));
+		{
+			ProfScope ps(ctx, "cub_sort_vertex_keys", 2 * Vc * 8 * 2, 8);
+			SIB_CUDA(cub::DeviceRadixSort::SortKeys(ctx->d_cubtmp.p, tmp_bytes, dbuf, (int)(2 * Vc), 0, 64, st));
+		}
+		SIB_CUDA(cudaMemcpyAsync(hs + 3, ds + 3, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+		SIB_CUDA(cudaStreamSynchronize(st));
+		const uint32_t npal = (uint32_t)(hs[3] & 0xFFFFFFFFu);
+		V = (uint32_t)(2 * Vc - npal);
+		{
+			ProfScope ps(ctx, "k_build_map", Vc * (sizeof(Rec) + sizeof(MapSlot)));
+			k_build_map<MODE><<<(uint32_t)((Vc + 255) / 256), 256, 0, st>>>(ckeys, Vc, k, dbuf.Current(), V,
+				ctx->d_map.as<MapSlot>(), Tm, ctx->d_filter.as<uint32_t>(), fshift);
+		}
+	}
+	else
+	{
+		// classes only; the ids follow once every class has a representative occurrence (after k_mark)
+		SIB_TRY(ctx->d_rep.ensure(sizeof(uint64_t) * Vc));
+		SIB_CUDA(cudaMemsetAsync(ctx->d_rep.p, 0xFF, sizeof(uint64_t) * Vc, st));
+		ProfScope ps(ctx, "k_build_map", Vc * (sizeof(Rec) + sizeof(MapSlot)));
+		k_build_map<MODE><<<(uint32_t)((Vc + 255) / 256), 256, 0, st>>>(ckeys, Vc, k, nullptr, 0,
+			ctx->d_map.as<MapSlot>(), Tm, ctx->d_filter.as<uint32_t>(), fshift);
+	}
+
+	if(ntiles == 0)
+	{
+		// a rank without text (tiny input, many ranks) still reports the global vertex count
+		SIB_CUDA(cudaStreamSynchronize(st));
+		ctx->n_inst = 0;
+		ctx->n_vertices = V;
+		return SIBGPU_OK;
+	}
+	// ---- instance tables
+	SIB_TRY(ctx->d_hitmask.ensure(sizeof(uint16_t) * (size_t)ntiles * TILE_THREADS));
+	SIB_TRY(ctx->d_tilecnt.ensure(sizeof(uint64_t) * ntiles));
+	SIB_TRY(ctx->d_tileoff.ensure(sizeof(uint64_t) * (ntiles + 1)));
+	{
+		ProfScope ps(ctx, "k_mark", (MODE == 2 ? ctx->M * 16 : ctx->M / 4) + ctx->M / 8);
+		k_mark<MODE><<<scan_grid, TILE_THREADS, 0, st>>>(t, fp, k, ntiles, ctx->d_map.as<MapSlot>(), Tm,
+			ctx->d_filter.as<uint32_t>(), fshift, ctx->d_hitmask.as<uint16_t>(), ctx->d_tilecnt.as<uint64_t>(),
+			ctx->d_rep.as<unsigned long long>());
+	}
+	if(MODE == 2) SIB_TRY(rank_fingerprint_vertices(ctx, t, k, Vc, Tm, &V));
+	{
+		size_t tmp_bytes = 0;
+		const uint64_t *in = ctx->d_tilecnt.as<uint64_t>();
+		SIB_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, in, ctx->d_tileoff.as<uint64_t>(), (int)ntiles, st));
+		SIB_TRY(ctx->d_cubtmp.ensure(tmp_bytes));
+		ProfScope ps(ctx, "cub_scan_tile_counts", ntiles * 12ull, 2);
+		SIB_CUDA(cub::DeviceScan::ExclusiveSum(ctx->d_cubtmp.p, tmp_bytes, in, ctx->d_tileoff.as<uint64_t>(), (int)ntiles, st));
+	}
+	uint64_t last_off = 0;
+	uint64_t last_cnt = 0;
+	SIB_CUDA(cudaMemcpyAsync(&last_off, ctx->d_tileoff.as<uint64_t>() + (ntiles - 1), 8, cudaMemcpyDeviceToHost, st));
+	SIB_CUDA(cudaMemcpyAsync(&last_cnt, ctx->d_tilecnt.as<uint64_t>() + (ntiles - 1), 8, cudaMemcpyDeviceToHost, st));
+	SIB_CUDA(cudaStreamSynchronize(st));
+	const uint64_t I = last_off + last_cnt;
+	SIB_TRY(ctx->d_pos.ensure(sizeof(sibgpu_inst) * (I + 1)));
+	SIB_TRY(ctx->d_negtmp.ensure(sizeof(sibgpu_inst) * (I + 1)));
+	SIB_TRY(ctx->d_neg.ensure(sizeof(sibgpu_inst) * (I + 1)));
+	SIB_TRY(ctx->d_chrinst.ensure(sizeof(uint64_t) * (ctx->nchr + 2)));
+	if(I)
+	{
+		{
+			ProfScope ps(ctx, "k_emit", ctx->M / 8 + I * 24);
+			k_emit<MODE><<<scan_grid, TILE_THREADS, 0, st>>>(t, fp, k, ntiles, ctx->d_map.as<MapSlot>(), Tm,
+				ctx->d_filter.as<uint32_t>(), fshift, ctx->d_hitmask.as<uint16_t>(), ctx->d_tileoff.as<uint64_t>(),
+				ctx->d_pos.as<sibgpu_inst>(), ctx->d_negtmp.as<sibgpu_inst>(), ctx->d_rep.as<unsigned long long>(),
+				reinterpret_cast<uint32_t*>(ds + 9));
+		}
+		if(reverse_neg)
+		{
+			ProfScope ps(ctx, "k_chr_bounds", 0);
+			k_chr_bounds<<<(ctx->nchr + 1 + 255) / 256, 256, 0, st>>>(ctx->d_negtmp.as<sibgpu_inst>(), I, ctx->nchr,
+				ctx->d_chrinst.as<uint64_t>());
+		}
+		if(reverse_neg)
+		{
+			ProfScope ps(ctx, "k_reverse_neg", I * 24);
+			k_reverse_neg<<<(uint32_t)((I + 255) / 256), 256, 0, st>>>(ctx->d_negtmp.as<sibgpu_inst>(), I,
+				ctx->d_chrinst.as<uint64_t>(), ctx->d_neg.as<sibgpu_inst>());
+		}
+	}
+	if(MODE == 2)
+	{
+		SIB_CUDA(cudaMemcpyAsync(hs + 9, ds + 9, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+		SIB_CUDA(cudaStreamSynchronize(st));
+		if(hs[9] & 1u)
+		{
+			// two different k-mers shared a fingerprint inside a vertex class: the caller starts over with other bases
+			SIB_CUDA(cudaMemsetAsync(ds + 9, 0, sizeof(uint64_t), st));
+			*collision = true;
+			return SIBGPU_OK;
+		}
+	}
+	SIB_CUDA(cudaStreamSynchronize(st));
+	ctx->n_inst = I;
+	ctx->n_vertices = V;
+	return SIBGPU_OK;
+}
+
 template<int MODE>
 static int enumerate_mode(sibgpu_ctx *ctx, uint32_t k, uint64_t nrec)
 {
@@ -714,6 +854,7 @@ static int enumerate_mode(sibgpu_ctx *ctx, uint32_t k, uint64_t nrec)
 	t.nchr = ctx->nchr;
 	t.M = (uint32_t)ctx->M;
 	t.nwords = (uint32_t)((ctx->M + 15) / 16) + 8;
+	t.tile0 = 0;
 	const uint32_t ntiles = (uint32_t)((ctx->M + TILE_POS - 1) / TILE_POS);
 
 	for(uint32_t attempt = 0; ; attempt++)
@@ -822,123 +963,17 @@ static int enumerate_mode(sibgpu_ctx *ctx, uint32_t k, uint64_t nrec)
 				ctx->d_partcnt.as<uint32_t>(), ctx->d_keyoff.as<uint64_t>(), ctx->d_ckeys.as<Rec>());
 		}
 
-		// ---- vertex ids + vertex map
-		uint64_t Tm64 = 2 * Vc + 64;
-		const uint32_t Tm = (uint32_t)Tm64;
-		uint32_t fbits_log = 16;
-		while((1ull << fbits_log) < 32 * Vc && fbits_log < 32) fbits_log++;
-		const uint32_t fshift = 64 - fbits_log;
-		SIB_TRY(ctx->d_map.ensure(sizeof(MapSlot) * (size_t)Tm));
-		SIB_TRY(ctx->d_filter.ensure((1ull << fbits_log) / 8));
-		SIB_CUDA(cudaMemsetAsync(ctx->d_map.p, 0xFF, sizeof(MapSlot) * (size_t)Tm, st));
-		SIB_CUDA(cudaMemsetAsync(ctx->d_filter.p, 0, (1ull << fbits_log) / 8, st));
-		uint32_t V = 0;
-		if(MODE != 2)
+		bool collision = false;
+		SIB_TRY(ids_and_tables<MODE>(ctx, t, k, ctx->d_ckeys.as<Rec>(), Vc, ntiles, fp, true, &collision));
+		if(collision)
 		{
-			SIB_TRY(ctx->d_vkeys.ensure(sizeof(uint64_t) * 2 * Vc));
-			SIB_TRY(ctx->d_vkeys_alt.ensure(sizeof(uint64_t) * 2 * Vc));
-			SIB_CUDA(cudaMemsetAsync(ds + 3, 0, sizeof(uint64_t), st));
+			if(attempt >= 2)
 			{
-				ProfScope ps(ctx, "k_expand", Vc * (sizeof(Rec) + 16));
-				k_expand<MODE><<<(uint32_t)((Vc + 255) / 256), 256, 0, st>>>(ctx->d_ckeys.as<Rec>(), Vc, k,
-					ctx->d_vkeys.as<uint64_t>(), reinterpret_cast<uint32_t*>(ds + 3));
+				set_error("internal: fingerprint verification failed three times");
+				return SIBGPU_ERR_INTERNAL;
 			}
-			size_t tmp_bytes = 0;
-			cub::DoubleBuffer<uint64_t> dbuf(ctx->d_vkeys.as<uint64_t>(), ctx->d_vkeys_alt.as<uint64_t>());
-			SIB_CUDA(cub::DeviceRadixSort::SortKeys(nullptr, tmp_bytes, dbuf, (int)(2 * Vc), 0, 64, st));
-			SIB_TRY(ctx->d_cubtmp.ensure(tmp_bytes));
-			{
-				ProfScope ps(ctx, "cub_sort_vertex_keys", 2 * Vc * 8 * 2, 8);
-				SIB_CUDA(cub::DeviceRadixSort::SortKeys(ctx->d_cubtmp.p, tmp_bytes, dbuf, (int)(2 * Vc), 0, 64, st));
-			}
-			SIB_CUDA(cudaMemcpyAsync(hs + 3, ds + 3, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
-			SIB_CUDA(cudaStreamSynchronize(st));
-			const uint32_t npal = (uint32_t)(hs[3] & 0xFFFFFFFFu);
-			V = (uint32_t)(2 * Vc - npal);
-			{
-				ProfScope ps(ctx, "k_build_map", Vc * (sizeof(Rec) + sizeof(MapSlot)));
-				k_build_map<MODE><<<(uint32_t)((Vc + 255) / 256), 256, 0, st>>>(ctx->d_ckeys.as<Rec>(), Vc, k, dbuf.Current(), V,
-					ctx->d_map.as<MapSlot>(), Tm, ctx->d_filter.as<uint32_t>(), fshift);
-			}
+			continue;
 		}
-		else
-		{
-			// classes only; the ids follow once every class has a representative occurrence (after k_mark)
-			SIB_TRY(ctx->d_rep.ensure(sizeof(uint64_t) * Vc));
-			SIB_CUDA(cudaMemsetAsync(ctx->d_rep.p, 0xFF, sizeof(uint64_t) * Vc, st));
-			ProfScope ps(ctx, "k_build_map", Vc * (sizeof(Rec) + sizeof(MapSlot)));
-			k_build_map<MODE><<<(uint32_t)((Vc + 255) / 256), 256, 0, st>>>(ctx->d_ckeys.as<Rec>(), Vc, k, nullptr, 0,
-				ctx->d_map.as<MapSlot>(), Tm, ctx->d_filter.as<uint32_t>(), fshift);
-		}
-
-		// ---- instance tables
-		SIB_TRY(ctx->d_hitmask.ensure(sizeof(uint16_t) * (size_t)ntiles * TILE_THREADS));
-		SIB_TRY(ctx->d_tilecnt.ensure(sizeof(uint64_t) * ntiles));
-		SIB_TRY(ctx->d_tileoff.ensure(sizeof(uint64_t) * (ntiles + 1)));
-		{
-			ProfScope ps(ctx, "k_mark", (MODE == 2 ? ctx->M * 16 : ctx->M / 4) + ctx->M / 8);
-			k_mark<MODE><<<scan_grid, TILE_THREADS, 0, st>>>(t, fp, k, ntiles, ctx->d_map.as<MapSlot>(), Tm,
-				ctx->d_filter.as<uint32_t>(), fshift, ctx->d_hitmask.as<uint16_t>(), ctx->d_tilecnt.as<uint64_t>(),
-				ctx->d_rep.as<unsigned long long>());
-		}
-		if(MODE == 2) SIB_TRY(rank_fingerprint_vertices(ctx, t, k, Vc, Tm, &V));
-		{
-			size_t tmp_bytes = 0;
-			const uint64_t *in = ctx->d_tilecnt.as<uint64_t>();
-			SIB_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, in, ctx->d_tileoff.as<uint64_t>(), (int)ntiles, st));
-			SIB_TRY(ctx->d_cubtmp.ensure(tmp_bytes));
-			ProfScope ps(ctx, "cub_scan_tile_counts", ntiles * 12ull, 2);
-			SIB_CUDA(cub::DeviceScan::ExclusiveSum(ctx->d_cubtmp.p, tmp_bytes, in, ctx->d_tileoff.as<uint64_t>(), (int)ntiles, st));
-		}
-		uint64_t last_off = 0;
-		uint64_t last_cnt = 0;
-		SIB_CUDA(cudaMemcpyAsync(&last_off, ctx->d_tileoff.as<uint64_t>() + (ntiles - 1), 8, cudaMemcpyDeviceToHost, st));
-		SIB_CUDA(cudaMemcpyAsync(&last_cnt, ctx->d_tilecnt.as<uint64_t>() + (ntiles - 1), 8, cudaMemcpyDeviceToHost, st));
-		SIB_CUDA(cudaStreamSynchronize(st));
-		const uint64_t I = last_off + last_cnt;
-		SIB_TRY(ctx->d_pos.ensure(sizeof(sibgpu_inst) * (I + 1)));
-		SIB_TRY(ctx->d_negtmp.ensure(sizeof(sibgpu_inst) * (I + 1)));
-		SIB_TRY(ctx->d_neg.ensure(sizeof(sibgpu_inst) * (I + 1)));
-		SIB_TRY(ctx->d_chrinst.ensure(sizeof(uint64_t) * (ctx->nchr + 2)));
-		if(I)
-		{
-			{
-				ProfScope ps(ctx, "k_emit", ctx->M / 8 + I * 24);
-				k_emit<MODE><<<scan_grid, TILE_THREADS, 0, st>>>(t, fp, k, ntiles, ctx->d_map.as<MapSlot>(), Tm,
-					ctx->d_filter.as<uint32_t>(), fshift, ctx->d_hitmask.as<uint16_t>(), ctx->d_tileoff.as<uint64_t>(),
-					ctx->d_pos.as<sibgpu_inst>(), ctx->d_negtmp.as<sibgpu_inst>(), ctx->d_rep.as<unsigned long long>(),
-					reinterpret_cast<uint32_t*>(ds + 9));
-			}
-			{
-				ProfScope ps(ctx, "k_chr_bounds", 0);
-				k_chr_bounds<<<(ctx->nchr + 1 + 255) / 256, 256, 0, st>>>(ctx->d_negtmp.as<sibgpu_inst>(), I, ctx->nchr,
-					ctx->d_chrinst.as<uint64_t>());
-			}
-			{
-				ProfScope ps(ctx, "k_reverse_neg", I * 24);
-				k_reverse_neg<<<(uint32_t)((I + 255) / 256), 256, 0, st>>>(ctx->d_negtmp.as<sibgpu_inst>(), I,
-					ctx->d_chrinst.as<uint64_t>(), ctx->d_neg.as<sibgpu_inst>());
-			}
-		}
-		if(MODE == 2)
-		{
-			SIB_CUDA(cudaMemcpyAsync(hs + 9, ds + 9, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
-			SIB_CUDA(cudaStreamSynchronize(st));
-			if(hs[9] & 1u)
-			{
-				// two different k-mers shared a fingerprint inside a vertex class: start over with other bases
-				if(attempt >= 2)
-				{
-					set_error("internal: fingerprint verification failed three times");
-					return SIBGPU_ERR_INTERNAL;
-				}
-				SIB_CUDA(cudaMemsetAsync(ds + 9, 0, sizeof(uint64_t), st));
-				continue;
-			}
-		}
-		SIB_CUDA(cudaStreamSynchronize(st));
-		ctx->n_inst = I;
-		ctx->n_vertices = V;
 		return SIBGPU_OK;
 	}
 }
@@ -992,5 +1027,7 @@ int enumerate_resident(sibgpu_ctx *ctx, uint32_t k)
 	if(ctx->profiling) SIB_TRY(ctx->prof_collect());
 	return SIBGPU_OK;
 }
+
+#include "dist_impl.cuh"
 
 } // namespace sibgpu

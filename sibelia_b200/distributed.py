@@ -1,0 +1,113 @@
+"""Sharded bifurcation enumeration over several GPUs, one process per GPU (torch.distributed is only the plumbing).
+
+    count, pos_part, negtext_part = enumerate_sharded(GpuShard(ctx), chrs, k)      # on every rank
+    count, pos, neg = gather_tables(count, pos_part, negtext_part)                  # full tables on rank 0
+
+The compute phases live in libsibgpu (sibgpu_dist_*, include/sibgpu.h); this module moves the two variable-size
+payloads between ranks: ONE all-to-all of the k-mer records (bucketed by hash prefix = owner rank) and one all-gather
+of the vertex keys.  With the NCCL backend the collectives run on the device buffers the kernels wrote (NVLink /
+NVSwitch); with gloo (CPU tests, or two ranks sharing one GPU) the same tensors are staged through host memory.
+"""
+import numpy as np
+import torch
+import torch.distributed as dist
+
+
+class GpuShard:
+    """Backend of enumerate_sharded that runs the phases on this rank's GPU through the C ABI."""
+
+    def __init__(self, ctx, device=None):
+        self.ctx = ctx
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+
+    def upload(self, chrs, rank, world):
+        self.ctx.dist_upload(chrs, rank, world)
+
+    def scan(self, k):
+        nparts, hist, self.nrec = self.ctx.dist_scan(k)
+        self.words = self.ctx.dist_record_bytes() // 8
+        return nparts, hist
+
+    def scatter(self):
+        send = torch.empty(max(self.nrec * self.words, 1), dtype=torch.int64, device=self.device)
+        torch.cuda.synchronize(self.device)
+        self.ctx.dist_scatter(send.data_ptr())
+        return send[:self.nrec * self.words]
+
+    def group(self, recv, counts):
+        torch.cuda.synchronize(self.device)
+        recv = recv.contiguous()
+        n = self.ctx.dist_group(recv.data_ptr() if recv.numel() else 0, counts)
+        keys = torch.empty(max(n * self.words, 1), dtype=torch.int64, device=self.device)
+        torch.cuda.synchronize(self.device)
+        self.ctx.dist_keys(keys.data_ptr())
+        return keys[:n * self.words]
+
+    def finish(self, allkeys):
+        torch.cuda.synchronize(self.device)
+        allkeys = allkeys.contiguous()
+        count, ninst = self.ctx.dist_finish(allkeys.data_ptr() if allkeys.numel() else 0, allkeys.numel() // self.words)
+        pos, negtext = self.ctx.download()
+        return count, pos, negtext
+
+
+def _comm(t, group):
+    """Tensor as the process group wants it: device tensors for NCCL, host tensors for gloo."""
+    return t if dist.get_backend(group) == "nccl" else t.cpu()
+
+
+def enumerate_sharded(shard, chrs, k, group=None):
+    """Runs the sharded enumeration on every rank of `group`; returns (global vertex count, this rank's positive table,
+    this rank's negative table in TEXT order).  `shard` is a backend with upload/scan/scatter/group/finish."""
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    shard.upload(chrs, rank, world)
+    nparts, hist = shard.scan(k)
+    words = shard.words
+    send = shard.scatter()
+    dev = send.device
+    # --- partition counts of every rank
+    h = _comm(torch.from_numpy(hist.astype(np.int64)).to(dev), group)
+    allh = torch.empty(world * nparts, dtype=torch.int64, device=h.device)
+    dist.all_gather_into_tensor(allh, h, group=group)
+    counts = allh.cpu().numpy().reshape(world, nparts)
+    pl = nparts // world
+    in_splits = [int(counts[rank, r * pl:(r + 1) * pl].sum()) * words for r in range(world)]
+    out_splits = [int(counts[s, rank * pl:(rank + 1) * pl].sum()) * words for s in range(world)]
+    # --- THE exchange: every record goes to the rank that owns its hash partition
+    s_c = _comm(send, group)
+    recv = torch.empty(sum(out_splits), dtype=torch.int64, device=s_c.device)
+    dist.all_to_all_single(recv, s_c, out_splits, in_splits, group=group)
+    keys = shard.group(recv.to(dev), counts.astype(np.uint32))
+    # --- vertex keys of all ranks (variable sizes: pad to the maximum)
+    nk = _comm(torch.tensor([keys.numel()], dtype=torch.int64, device=dev), group)
+    all_nk = torch.empty(world, dtype=torch.int64, device=nk.device)
+    dist.all_gather_into_tensor(all_nk, nk, group=group)
+    all_nk = [int(x) for x in all_nk.cpu()]
+    mx = max(max(all_nk), 1)
+    padded = torch.zeros(mx, dtype=torch.int64, device=dev)
+    padded[:keys.numel()] = keys
+    p_c = _comm(padded, group)
+    gathered = torch.empty(world * mx, dtype=torch.int64, device=p_c.device)
+    dist.all_gather_into_tensor(gathered, p_c, group=group)
+    allkeys = torch.cat([gathered[s * mx:s * mx + all_nk[s]] for s in range(world)]).to(dev)
+    return shard.finish(allkeys)
+
+
+def assemble_tables(pos_parts, negtext_parts):
+    """Ranks in order -> the reference's two tables: positive = concatenation (text order = (chr,pos) order);
+    negative = sorted by (chr, position in the reverse complement) (vertexenumeration.cpp:361-362)."""
+    pos = np.concatenate(pos_parts) if pos_parts else np.zeros(0)
+    neg = np.concatenate(negtext_parts) if negtext_parts else np.zeros(0)
+    order = np.lexsort((neg["pos"], neg["chr"]))
+    return pos, neg[order]
+
+
+def gather_tables(count, pos_part, negtext_part, group=None):
+    """Collects the per-rank tables on rank 0 (returns (count, pos, neg) there, (count, None, None) elsewhere)."""
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    objs = [None] * world if rank == 0 else None
+    dist.gather_object((pos_part, negtext_part), objs, dst=0, group=group)
+    if rank != 0:
+        return count, None, None
+    pos, neg = assemble_tables([o[0] for o in objs], [o[1] for o in objs])
+    return count, pos, neg

@@ -1,0 +1,137 @@
+"""Test double for sibelia_b200.distributed: the per-rank phases of the sharded enumeration restated in numpy, so the
+orchestration (splits, all-to-all layout, key all-gather, assembly) can run under gloo on CPU with world_size > 1.
+It follows the same contract as GpuShard: same tile split, records ordered by partition, partition p owned by rank
+p // (nparts / world).  k <= 28."""
+import numpy as np
+import torch
+
+TILE = 4096
+M64 = np.uint64(0xFFFFFFFFFFFFFFFF)
+
+
+def mix64(x):
+    x = x.astype(np.uint64)
+    with np.errstate(over="ignore"):
+        x ^= x >> np.uint64(33)
+        x *= np.uint64(0xff51afd7ed558ccd)
+        x ^= x >> np.uint64(33)
+        x *= np.uint64(0xc4ceb9fe1a85ec53)
+        x ^= x >> np.uint64(33)
+    return x
+
+
+def comp_sym(s):
+    return np.where(s == 4, 4, 3 - s)
+
+
+class NumpyShard:
+    words = 1
+
+    def __init__(self, nparts_local=3):
+        self.pl = nparts_local
+
+    def upload(self, chrs, rank, world):
+        self.chrs = [np.asarray(c, dtype=np.uint8) for c in chrs]
+        self.rank, self.world = rank, world
+        lens = np.array([len(c) for c in self.chrs], dtype=np.int64)
+        self.lens = lens
+        self.start = 1 + np.concatenate([[0], np.cumsum(lens + 1)[:-1]]) if len(lens) else np.zeros(0, np.int64)
+        self.M = int(lens.sum() + len(lens) + 1)
+        ntiles = (self.M + TILE - 1) // TILE
+        self.lo = (ntiles * rank // world) * TILE
+        self.hi = (ntiles * (rank + 1) // world) * TILE
+
+    def _occurrences(self, k):
+        code = np.zeros(256, dtype=np.int64)
+        for i, ch in enumerate(b"ACGT"):
+            code[ch] = i
+        P, C, KEY, RKEY, PREV, NEXT = [], [], [], [], [], []
+        for c, (s, L) in enumerate(zip(self.start, self.lens)):
+            if L < k:
+                continue
+            cs = code[self.chrs[c]]
+            n = L - k + 1
+            pos = np.arange(n)
+            tp = s + pos
+            sel = (tp >= self.lo) & (tp < self.hi)
+            if not sel.any():
+                continue
+            pos = pos[sel]
+            f = np.zeros(len(pos), dtype=np.uint64)
+            r = np.zeros(len(pos), dtype=np.uint64)
+            for j in range(k):
+                f = (f << np.uint64(2)) | cs[pos + j].astype(np.uint64)
+                r = (r << np.uint64(2)) | (3 - cs[pos + k - 1 - j]).astype(np.uint64)
+            prev = np.where(pos == 0, 4, cs[np.maximum(pos - 1, 0)])
+            nxt = np.where(pos + k == L, 4, cs[np.minimum(pos + k, L - 1)])
+            P.append(pos); C.append(np.full(len(pos), c)); KEY.append(f); RKEY.append(r); PREV.append(prev); NEXT.append(nxt)
+        if not P:
+            z = np.zeros(0, dtype=np.int64)
+            return z, z, z.astype(np.uint64), z.astype(np.uint64), z, z
+        return tuple(np.concatenate(x) for x in (P, C, KEY, RKEY, PREV, NEXT))
+
+    def scan(self, k):
+        self.k = k
+        pos, chr_, f, r, prev, nxt = self._occurrences(k)
+        fw = f <= r
+        canon = np.where(fw, f, r)
+        cp = np.where(fw, prev, comp_sym(nxt))
+        cn = np.where(fw, nxt, comp_sym(prev))
+        ctx = (np.where(f == r, 64, 0) | (cp << 3) | cn).astype(np.uint64)
+        rec = (canon << np.uint64(7)) | ctx
+        nparts = self.pl * self.world
+        part = ((mix64(canon) >> np.uint64(32)) * np.uint64(nparts) >> np.uint64(32)).astype(np.int64)
+        order = np.argsort(part, kind="stable")
+        self.send = rec[order]
+        hist = np.bincount(part, minlength=nparts).astype(np.uint32)
+        self.occ = (pos, chr_, f, r)
+        return nparts, hist
+
+    def scatter(self):
+        return torch.from_numpy(self.send.view(np.int64).copy())
+
+    def group(self, recv, counts):
+        rec = recv.numpy().view(np.uint64)
+        key = rec >> np.uint64(7)
+        ctx = (rec & np.uint64(127)).astype(np.int64)
+        p, n, pal = (ctx >> 3) & 7, ctx & 7, (ctx & 64) != 0
+        bits = (1 << p) | (32 << n)
+        bits = np.where(pal, bits | (1 << comp_sym(n)) | (32 << comp_sym(p)), bits)
+        uk, inv, cnt = np.unique(key, return_inverse=True, return_counts=True)
+        pay = np.zeros(len(uk), dtype=np.int64)
+        np.bitwise_or.at(pay, inv, bits)
+        multi = (cnt > 1)
+        np.logical_or.at(multi, inv, pal)
+        P, N = pay & 31, (pay >> 5) & 31
+        pop = lambda x: np.array([bin(int(v)).count("1") for v in x])
+        sep = ((P | N) & 16) != 0
+        bif = np.where(multi, (pop(P) > 1) | (pop(N) > 1) | sep, sep)
+        return torch.from_numpy(uk[bif].view(np.int64).copy())
+
+    def _rc(self, key):
+        k = self.k
+        out = np.zeros(len(key), dtype=np.uint64)
+        x = key.copy()
+        for _ in range(k):
+            out = (out << np.uint64(2)) | (np.uint64(3) - (x & np.uint64(3)))
+            x >>= np.uint64(2)
+        return out
+
+    def finish(self, allkeys):
+        ck = allkeys.numpy().view(np.uint64)
+        inst = np.dtype([("bifId", "<u4"), ("chr", "<u4"), ("pos", "<u4")])
+        if len(ck) == 0:
+            return 0, np.zeros(0, inst), np.zeros(0, inst)
+        v = np.unique(np.concatenate([ck, self._rc(ck)]))
+        pos, chr_, f, r = self.occ
+        canon = np.minimum(f, r)
+        hit = np.isin(canon, ck)
+        pos, chr_, f, r = pos[hit], chr_[hit], f[hit], r[hit]
+        tp = self.start[chr_] + pos
+        o = np.argsort(tp, kind="stable")
+        pos, chr_, f, r = pos[o], chr_[o], f[o], r[o]
+        P = np.zeros(len(pos), inst)
+        P["bifId"], P["chr"], P["pos"] = np.searchsorted(v, f), chr_, pos
+        Nt = np.zeros(len(pos), inst)
+        Nt["bifId"], Nt["chr"], Nt["pos"] = np.searchsorted(v, r), chr_, self.lens[chr_] - pos - self.k
+        return len(v), P, Nt

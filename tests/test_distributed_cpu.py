@@ -1,0 +1,57 @@
+"""CPU, world_size 2 and 3 over gloo: the sharded-enumeration orchestration (sibelia_b200/distributed.py: partition
+counts, all-to-all splits and layout, vertex-key all-gather, assembly of the per-rank tables) with the numpy test
+double standing in for the GPU phases; the assembled result must equal the oracle."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+import helpers
+from oracle import restate
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, k, seed, q):
+    sys.path.insert(0, HERE)
+    sys.path.insert(0, os.path.dirname(HERE))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from sibelia_b200 import distributed as D
+    from fake_shard import NumpyShard
+    chrs = helpers.strain_case(3, 9_000, p_sub=0.02, inv_len=700, seed=seed)
+    count, pos_part, neg_part = D.enumerate_sharded(NumpyShard(), chrs, k)
+    count, pos, neg = D.gather_tables(count, pos_part, neg_part)
+    if rank == 0:
+        q.put((count, pos, neg))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,k,seed", [(2, 12, 1), (2, 25, 2), (3, 17, 3)])
+def test_sharded_orchestration_matches_oracle(world, k, seed):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, k, seed, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = q.get(timeout=240)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    chrs = helpers.strain_case(3, 9_000, p_sub=0.02, inv_len=700, seed=seed)
+    helpers.assert_tables_equal(got, restate.enumerate_bifurcations(chrs, k), "world=%d k=%d" % (world, k))
