@@ -7,8 +7,10 @@ A "step" is one construction of the de Bruijn-graph index of one synthetic genom
 (pack -> scan/histogram -> scatter -> L2-resident hash grouping -> vertex ranking -> instance tables), the GPU
 replacement of IndexedSequence's EnumerateBifurcationsSArrayInRAM (/root/reference/src/vertexenumeration.cpp:263-364).
 Workload at N=1 is BASELINE.json configs[1]: 100 MB random-ACGT single contig, numpy default_rng(12345), k=25.
-With N>1 ranks (torchrun) every rank indexes its own 100 MB contig (seed 12345+rank): weak scaling, no data-path
-collective; `value` = bases all ranks indexed / max-over-ranks device time.
+With N>1 ranks (torchrun, one process per GPU) the workload is ONE genome of N such contigs (seed 12345+c), sharded by
+contiguous text range over the ranks (weak scaling: 100 Mbases per GPU): scan/scatter locally, one NCCL all-to-all of
+the k-mer records bucketed by hash prefix, per-rank grouping, all-gather of the vertex keys, local instance tables
+(sibelia_b200/distributed.py); `value` = total bases / max-over-ranks step time.
 
 One JSON line is printed by rank 0 (see the task contract): value = device-resident throughput, e2e = the same
 metric through sibgpu_enumerate with pinned HOST buffers (H2D + D2H inside the timed region), roofline = dominant
@@ -167,37 +169,87 @@ def main():
         torch.cuda.synchronize()
 
     N = int(args.mbases * 1_000_000)
-    g = genome(args.mbases, 12345 + rank)
-    host = torch.empty(N, dtype=torch.uint8, pin_memory=True)
-    host.numpy()[:] = g
-    hview = host.numpy()
     ctx = sb.Context(local_rank)
-    ctx.upload([hview])
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 
     def l2_flush():
         flush.fill_(1)
         torch.cuda.synchronize()
 
-    # ---- device-resident arm: inputs already in HBM
-    ctx.set_profiling(True)
-    for _ in range(args.warmup):
-        count, ninst = ctx.enumerate_resident(args.k)
-    sampler = ClockSampler(local_rank)
-    barrier()
-    sampler.start()
-    dev_ms, launches, kstats = 0.0, 0, {}
-    wall0 = time.perf_counter()
-    for _ in range(args.steps):
-        l2_flush()
-        count, ninst = ctx.enumerate_resident(args.k)
-        dev_ms += ctx.last_device_ms()
-        launches += ctx.last_launches()
+    kstats = {}
+
+    def add_stats():
         for s in ctx.kernel_stats():
             a = kstats.setdefault(s["name"], {"launches": 0, "ms": 0.0, "algo_bytes": 0})
             a["launches"] += s["launches"]
             a["ms"] += s["ms"]
             a["algo_bytes"] += s["algo_bytes"]
+
+    if world == 1:
+        g = genome(args.mbases, 12345)
+        host = torch.empty(N, dtype=torch.uint8, pin_memory=True)
+        host.numpy()[:] = g
+        hview = [host.numpy()]
+        ctx.upload(hview)
+
+        def step_resident():
+            count, ninst = ctx.enumerate_resident(args.k)
+            return count, ninst, ctx.last_device_ms()
+
+        def step_e2e():
+            c2, pos, neg = ctx.enumerate(hview, args.k)
+            return pos.nbytes + neg.nbytes + 64
+        h2d = N + 8
+    else:
+        from sibelia_b200 import distributed as D
+        hosts = []
+        for c in range(world):
+            h = torch.empty(N, dtype=torch.uint8, pin_memory=(c == rank))
+            h.numpy()[:] = genome(args.mbases, 12345 + c)
+            hosts.append(h)
+        hview = [h.numpy() for h in hosts]
+        g = hview[0]
+        shard = D.GpuShard(ctx)
+
+        class Resident(D.GpuShard):
+            """the shard's text is already in HBM: skip the upload phase of enumerate_sharded"""
+            def upload(self, chrs, rank, world):
+                pass
+        resident = Resident(ctx)
+        ctx.dist_upload(hview, rank, world)
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+        def step_resident():
+            torch.cuda.synchronize()
+            ev0.record()
+            count, pos, neg = D.enumerate_sharded(resident, hview, args.k)
+            torch.cuda.synchronize()
+            ev1.record()
+            ev1.synchronize()
+            return count, len(pos), ev0.elapsed_time(ev1)
+
+        def step_e2e():
+            count, pos, neg = D.enumerate_sharded(shard, hview, args.k)
+            return pos.nbytes + neg.nbytes + 64
+        h2d = N + 8
+
+    # ---- device-resident arm: inputs already in HBM
+    ctx.set_profiling(True)
+    for _ in range(args.warmup):
+        count, ninst, _ms = step_resident()
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    dev_ms, launches = 0.0, 0
+    wall0 = time.perf_counter()
+    for _ in range(args.steps):
+        l2_flush()
+        if world > 1:
+            dist.barrier()
+        count, ninst, ms = step_resident()
+        dev_ms += ms
+        launches += ctx.last_launches()
+        add_stats()
     barrier()
     wall = time.perf_counter() - wall0
     clocks = sampler.stop()
@@ -208,16 +260,15 @@ def main():
     ms_per_step = float(t.item()) / args.steps
     value = world * N / 1e6 / (ms_per_step / 1e3)
 
-    # ---- end-to-end arm: pinned host buffers in, host tables out, through sibgpu_enumerate
+    # ---- end-to-end arm: pinned host buffers in, host tables out, through the public API
     for _ in range(2):
-        ctx.enumerate([hview], args.k)
+        step_e2e()
     barrier()
     t0 = time.perf_counter()
     d2h = 0
     for _ in range(args.steps):
-        c2, pos, neg = ctx.enumerate([hview], args.k)
-        d2h = pos.nbytes + neg.nbytes + 64
-    torch.cuda.synchronize()
+        d2h = step_e2e()
+    barrier()
     e2e_s = (time.perf_counter() - t0) / args.steps
     te = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
     if world > 1:
@@ -271,14 +322,17 @@ def main():
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u64", "data": "synthetic",
-        "config": {"workload": "synthetic %g MB random-ACGT single contig per GPU, numpy default_rng(12345+rank), k=%d "
-                               "(BASELINE configs[1])" % (args.mbases, args.k),
+        "config": {"workload": ("synthetic %g MB random-ACGT single contig, numpy default_rng(12345), k=%d (BASELINE configs[1])"
+                                % (args.mbases, args.k)) if world == 1 else
+                               ("one synthetic genome of %d random-ACGT contigs x %g MB (default_rng(12345+c)), k=%d, sharded by "
+                                "text range over %d GPUs with one NCCL all-to-all of k-mer records" % (world, args.mbases, args.k, world)),
                    "k": args.k, "bases_per_gpu": N, "vertices": int(count), "instances_per_strand": int(ninst),
                    "l2": "256 MB L2 flush between timed iterations (outside the event-timed region)",
-                   "timing": "CUDA events on the library stream around each whole step; wall %.1f ms/step incl. flush" % (
-                       wall / args.steps * 1e3)},
+                   "timing": ("CUDA events on the library stream around each whole step" if world == 1 else
+                              "CUDA events around each whole sharded step (device-synchronised on both sides)")
+                             + "; wall %.1f ms/step incl. flush" % (wall / args.steps * 1e3)},
         "clocks": clocks,
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": N + 8, "d2h_bytes_per_step": int(d2h),
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "ms_per_step": float(te.item()) * 1e3},
         "gpu_launches": int(launches),
         "roofline": roofline,
