@@ -103,6 +103,12 @@ int sibgpu_create(int device, sibgpu_ctx **out)
 		uint64_t v = strtoull(e, nullptr, 10);
 		if(v >= 1024) c->part_target = v;
 	}
+	if(const char *e = getenv("SIBGPU_INSERT_VARIANT")) c->insert_variant = atoi(e);
+	if(const char *e = getenv("SIBGPU_TABLE_FACTOR"))
+	{
+		int v = atoi(e);
+		if(v >= 2 && v <= 16) c->table_factor = v;
+	}
 	*out = c;
 	return SIBGPU_OK;
 }

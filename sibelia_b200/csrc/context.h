@@ -52,6 +52,8 @@ struct sibgpu_ctx {
 
 	// tunables (env SIBGPU_PART_RECORDS)
 	uint64_t part_target = 1u << 22;
+	int insert_variant = 1;                            // 1 = CAS first, one record per thread (env SIBGPU_INSERT_VARIANT, dev)
+	int table_factor = 2;                              // slots per record of the largest partition (env SIBGPU_TABLE_FACTOR)
 
 	// profiling
 	bool profiling = false;

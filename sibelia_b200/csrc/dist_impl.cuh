@@ -87,7 +87,7 @@ static int dist_group_mode(sibgpu_ctx *ctx, uint32_t k, const void *recv_dev, co
 	*nkeys_local = 0;
 	ctx->dist_nkeys_local = 0;
 	if(recv_total == 0) return SIBGPU_OK;
-	const uint64_t T64 = 2 * maxpart + 1024;
+	const uint64_t T64 = (uint64_t)ctx->table_factor * maxpart + 1024;
 	if(T64 > 0xFFFFFF00ull)
 	{
 		set_error("internal: hash partition does not fit a 32-bit table");
@@ -116,7 +116,7 @@ static int dist_group_mode(sibgpu_ctx *ctx, uint32_t k, const void *recv_dev, co
 			const Rec *seg = recv + seg_cursor[s];
 			seg_cursor[s] += n;
 			ProfScope ps(ctx, "k_insert", n * sizeof(Rec));
-			if(compact) k_insert_compact<<<grid_for(n, 256, sms, 8), 256, 0, st>>>(reinterpret_cast<const uint64_t*>(seg), n,
+			if(compact) launch_insert_compact(ctx->insert_variant, sms, st, reinterpret_cast<const uint64_t*>(seg), n,
 				ctx->d_table.as<unsigned long long>(), T);
 			else k_insert<MODE><<<grid_for(n, 256, sms, 8), 256, 0, st>>>(seg, n, ctx->d_table.p, T);
 		}

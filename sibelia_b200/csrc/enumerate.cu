@@ -286,9 +286,8 @@ __global__ void __launch_bounds__(256) k_insert(const typename RecT<MODE>::type 
 			uint32_t bits = payload_bits(ctx);
 			for(;;)
 			{
-				// plain peek first: in related genomes most keys are already present, which saves the CAS
-				unsigned long long old = __ldcg(&tab[slot].key);
-				if(old == EMPTY64) old = atomicCAS(&tab[slot].key, EMPTY64, key);
+				// CAS first (no peek): measured 1.7x faster than load-then-CAS on B200 (tools/ubench/atomics.cu)
+				unsigned long long old = atomicCAS(&tab[slot].key, EMPTY64, key);
 				if(old == EMPTY64 || old == key)
 				{
 					if(old == key) bits |= PAY_MULTI;
@@ -308,8 +307,7 @@ __global__ void __launch_bounds__(256) k_insert(const typename RecT<MODE>::type 
 			uint32_t bits = payload_bits(ctx);
 			for(;;)
 			{
-				unsigned long long oa = __ldcg(&tab[slot].a);
-				if(oa == EMPTY64) oa = atomicCAS(&tab[slot].a, EMPTY64, a);
+				unsigned long long oa = atomicCAS(&tab[slot].a, EMPTY64, a);
 				if(oa == EMPTY64 || oa == a)
 				{
 					// second word: claimed by whoever CASes it first; a different b means another class
@@ -387,30 +385,82 @@ __global__ void __launch_bounds__(256) k_table_scan(void *__restrict__ table, ui
 // Compact variant for k <= 26: key (<= 52 bits) and the 11 payload bits share ONE 64-bit slot, so an occurrence costs a
 // single atomic: CAS when it creates the class, a fire-and-forget OR when the class exists.
 constexpr uint32_t COMPACT_MAX_K = 26;
+constexpr int INSERT_ILP = 4;                          // records in flight per thread
+// VARIANT 0: peek, then CAS   1: CAS first   (x ILP = 1 or INSERT_ILP)
+template<int VARIANT, int ILP>
 __global__ void __launch_bounds__(256) k_insert_compact(const uint64_t *__restrict__ recs, uint64_t n,
 	unsigned long long *__restrict__ tab, uint32_t T)
 {
-	for(uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
+	const uint64_t chunk = (uint64_t)blockDim.x * ILP;
+	for(uint64_t base = blockIdx.x * chunk; base < n; base += (uint64_t)gridDim.x * chunk)
 	{
-		const uint64_t rec = __ldcs(recs + i);
-		const unsigned long long key = rec >> 7;
-		const unsigned long long bits = payload_bits((uint32_t)rec & 127u);
-		uint32_t slot = __umulhi((uint32_t)rec_hash(key, 0), T);
-		for(;;)
+		unsigned long long word[ILP], old[ILP];
+		uint32_t slot[ILP];
+		bool live[ILP];
+#pragma unroll
+		for(int j = 0; j < ILP; j++)
 		{
-			unsigned long long cur = __ldcg(&tab[slot]);
-			if(cur == EMPTY64)
-			{
-				cur = atomicCAS(&tab[slot], EMPTY64, (key << 11) | bits);
-				if(cur == EMPTY64) break;
-			}
-			if((cur >> 11) == key)
-			{
-				atomicOr(&tab[slot], bits | PAY_MULTI);
-				break;
-			}
-			slot = slot + 1 == T ? 0 : slot + 1;
+			const uint64_t i = base + (uint64_t)j * blockDim.x + threadIdx.x;      // coalesced per j
+			live[j] = i < n;
+			const uint64_t rec = live[j] ? __ldcs(recs + i) : 0ull;
+			const unsigned long long key = rec >> 7;
+			word[j] = (key << 11) | payload_bits((uint32_t)rec & 127u);
+			slot[j] = __umulhi((uint32_t)rec_hash(key, 0), T);
 		}
+		if(VARIANT == 0)
+		{
+#pragma unroll
+			for(int j = 0; j < ILP; j++) old[j] = live[j] ? __ldcg(&tab[slot[j]]) : 0ull;
+#pragma unroll
+			for(int j = 0; j < ILP; j++)
+			{
+				if(live[j] && old[j] == EMPTY64) old[j] = atomicCAS(&tab[slot[j]], EMPTY64, word[j]);
+			}
+		}
+		else
+		{
+#pragma unroll
+			for(int j = 0; j < ILP; j++)
+			{
+				if(live[j]) old[j] = atomicCAS(&tab[slot[j]], EMPTY64, word[j]);
+			}
+		}
+#pragma unroll
+		for(int j = 0; j < ILP; j++)
+		{
+			if(!live[j]) continue;
+			for(;;)
+			{
+				if(old[j] == EMPTY64) break;                                         // created
+				if((old[j] >> 11) == (word[j] >> 11))
+				{
+					atomicOr(&tab[slot[j]], (word[j] & 2047ull) | PAY_MULTI);        // existing class: OR the context in
+					break;
+				}
+				slot[j] = slot[j] + 1 == T ? 0 : slot[j] + 1;
+				if(VARIANT == 0)
+				{
+					old[j] = __ldcg(&tab[slot[j]]);
+					if(old[j] == EMPTY64) old[j] = atomicCAS(&tab[slot[j]], EMPTY64, word[j]);
+				}
+				else old[j] = atomicCAS(&tab[slot[j]], EMPTY64, word[j]);
+			}
+		}
+	}
+}
+
+static void launch_insert_compact(int variant, int sms, cudaStream_t st, const uint64_t *recs, uint64_t n, unsigned long long *tab, uint32_t T)
+{
+	auto grid = [&](int ilp) {
+		uint64_t blocks = ((n + ilp - 1) / ilp + 255) / 256, cap = (uint64_t)sms * 8;
+		return (uint32_t)(blocks < 1 ? 1 : (blocks < cap ? blocks : cap));
+	};
+	switch(variant)
+	{
+	case 0: k_insert_compact<0, 1><<<grid(1), 256, 0, st>>>(recs, n, tab, T); break;
+	case 1: k_insert_compact<1, 1><<<grid(1), 256, 0, st>>>(recs, n, tab, T); break;
+	case 2: k_insert_compact<1, INSERT_ILP><<<grid(INSERT_ILP), 256, 0, st>>>(recs, n, tab, T); break;
+	default: k_insert_compact<0, INSERT_ILP><<<grid(INSERT_ILP), 256, 0, st>>>(recs, n, tab, T); break;
 	}
 }
 
@@ -907,7 +957,7 @@ static int enumerate_mode(sibgpu_ctx *ctx, uint32_t k, uint64_t nrec)
 		SIB_CUDA(cudaStreamSynchronize(st));
 
 		// ---- per-partition L2-resident grouping
-		uint64_t T64 = 2 * maxpart + 1024;
+		uint64_t T64 = (uint64_t)ctx->table_factor * maxpart + 1024;
 		if(T64 > 0xFFFFFF00ull)
 		{
 			set_error("internal: hash partition of " + std::to_string(maxpart) + " records does not fit a 32-bit table");
@@ -925,7 +975,7 @@ static int enumerate_mode(sibgpu_ctx *ctx, uint32_t k, uint64_t nrec)
 			Rec *part = ctx->d_records.as<Rec>() + h_partoff[p];
 			{
 				ProfScope ps(ctx, "k_insert", n * sizeof(Rec));
-				if(compact) k_insert_compact<<<grid_for(n, 256, sms, 8), 256, 0, st>>>(reinterpret_cast<const uint64_t*>(part), n,
+				if(compact) launch_insert_compact(ctx->insert_variant, sms, st, reinterpret_cast<const uint64_t*>(part), n,
 					ctx->d_table.as<unsigned long long>(), T);
 				else k_insert<MODE><<<grid_for(n, 256, sms, 8), 256, 0, st>>>(part, n, ctx->d_table.p, T);
 			}
