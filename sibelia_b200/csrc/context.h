@@ -35,7 +35,7 @@ struct sibgpu_ctx {
 	// enumeration workspace
 	sibgpu::DevBuf d_hist, d_partoff, d_cursor, d_records, d_table, d_partcnt, d_keyoff, d_ckeys, d_vkeys, d_vkeys_alt,
 		d_cubtmp, d_map, d_filter, d_hitmask, d_tilecnt, d_tileoff, d_pos, d_negtmp, d_neg, d_chrinst, d_scalars,
-		d_fp, d_rep, d_order;
+		d_fp, d_rep, d_order, d_s_ch, d_s_m0, d_s_m1, d_s_off, d_s_inst, d_s_flag;
 	void *h_scalars = nullptr;                         // pinned, 64 x u64
 
 	// last result

@@ -15,695 +15,19 @@
 // the two info bits), per-vertex instance lists keep the reference's slist semantics (push-front, lazy erase,
 // Cleanup), and the bulge groups of a vertex are visited in Boost 1.54 unordered_map order (boost_order.h).
 #include <algorithm>
+#include <chrono>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <iterator>
 #include <string>
 
-#include "boost_order.h"
 #include "context.h"
+#include "simplifier.h"
 
 namespace sibgpu {
 
-namespace {
-
-const uint32_t NO_BIF = 0xFFFFFFFFu;                   // BifurcationStorage::NO_BIFURCATION, bifurcationstorage.cpp:12
-const char SEP = '$';                                  // DNASequence::SEPARATION_CHAR, dnasequence.cpp:33
-const char EMPTY = ' ';                                // bulgeremoval.cpp:13
-const uint32_t POS_MASK = (1u << 29) - 1;              // StrandIterator::PositionMask, stranditerator.cpp:19-27
-
-inline char complement(char c)                          // DNASequence::complementary_, dnasequence.cpp:11-29
-{
-	switch(c)
-	{
-	case 'A': return 'T';
-	case 'T': return 'A';
-	case 'C': return 'G';
-	case 'G': return 'C';
-	case 'a': return 't';
-	case 't': return 'a';
-	case 'c': return 'g';
-	case 'g': return 'c';
-	}
-	return c;
-}
-
-// DNASequence::StrandIterator over the element arrays: e = element, d = 0 positive / 1 negative strand
-struct It {
-	int32_t e;
-	uint8_t d;
-};
-
-struct VisitData {                                      // blockfinder.h:18-24
-	size_t kmerId, distance;
-};
-
-struct BifurcationMark {                                // bulgeremoval.cpp:20-37
-	size_t bifId, distance;
-	bool operator<(const BifurcationMark &o) const
-	{
-		if(bifId != o.bifId) return bifId < o.bifId;
-		return distance < o.distance;
-	}
-};
-
-class Simplifier {
-public:
-	// ---- sequence (DNASequence, dnasequence.cpp:75-103): element 0 is the leading '$'
-	std::vector<char> ch;
-	std::vector<uint32_t> opos;
-	std::vector<int32_t> nxt, prv;
-	std::vector<uint32_t> mark[2];                      // vertex id whose k-mer starts here on that strand, or NO_BIF
-	std::vector<int32_t> node_of[2];                    // instance-list node of that mark
-	std::vector<int32_t> chr_first_sep;                 // the '$' in front of chromosome c (chr c = elements after it
-	int32_t last_sep = 0;                               //   up to the next '$')
-	size_t live = 0;
-
-	// ---- BifurcationStorage::bifurcationPos_ (bifurcationstorage.h:17-121): per strand and id an slist of nodes
-	std::vector<int32_t> n_elem, n_next, n_prev;
-	std::vector<uint8_t> n_valid, n_strand;
-	std::vector<uint32_t> n_id;
-	std::vector<int32_t> head[2];
-	std::vector<uint32_t> lsize[2];
-	std::vector<int32_t> to_clear;
-	uint32_t max_id = 0;
-
-	// ---- snapshot bookkeeping
-	std::vector<uint8_t> dirty;
-	size_t k = 0, D = 0;
-
-	// =========================================================== iterators
-	inline void inc(It &it) const { it.e = it.d == 0 ? nxt[it.e] : prv[it.e]; }
-	inline char deref(It it) const { return it.d == 0 ? ch[it.e] : complement(ch[it.e]); }
-	inline bool at_valid(It it) const { return ch[it.e] != SEP; }
-	inline It advance(It it, size_t n) const
-	{
-		for(size_t i = 0; i < n; i++) inc(it);
-		return it;
-	}
-	inline It invert(It it) const                       // StrandIterator::Invert, stranditerator.cpp:193-201
-	{
-		It r;
-		if(it.d == 0) { r.e = prv[it.e]; r.d = 1; }
-		else { r.e = nxt[it.e]; r.d = 0; }
-		return r;
-	}
-	inline bool proper_kmer(It it, size_t n) const      // ProperKMer, dnasequence.h:154-165
-	{
-		for(size_t i = 0; i < n; i++, inc(it))
-		{
-			if(!at_valid(it)) return false;
-		}
-		return true;
-	}
-
-	// =========================================================== BifurcationStorage
-	inline uint32_t get_bif(It it) const { return mark[it.d][it.e]; }           // GetBifurcation, .cpp:157-162
-
-	void add_point(It it, size_t bif)                   // AddPoint, bifurcationstorage.cpp:113-126 (push-front)
-	{
-		if(mark[it.d][it.e] != NO_BIF || bif == NO_BIF) return;
-		const uint32_t id = (uint32_t)bif;
-		const int32_t n = (int32_t)n_elem.size();
-		n_elem.push_back(it.e);
-		n_strand.push_back(it.d);
-		n_id.push_back(id);
-		n_valid.push_back(1);
-		n_prev.push_back(-1);
-		n_next.push_back(head[it.d][id]);
-		if(head[it.d][id] >= 0) n_prev[head[it.d][id]] = n;
-		head[it.d][id] = n;
-		lsize[it.d][id]++;
-		mark[it.d][it.e] = id;
-		node_of[it.d][it.e] = n;
-		dirty[id] = 1;
-	}
-
-	void erase_point(It it)                              // ErasePoint, .cpp:144-155: lazy, the node stays until Cleanup
-	{
-		const uint32_t id = mark[it.d][it.e];
-		if(id == NO_BIF) return;
-		const int32_t n = node_of[it.d][it.e];
-		mark[it.d][it.e] = NO_BIF;
-		node_of[it.d][it.e] = -1;
-		n_valid[n] = 0;
-		to_clear.push_back(n);
-		dirty[id] = 1;
-	}
-
-	void cleanup()                                       // Cleanup, .cpp:33-41
-	{
-		for(size_t i = 0; i < to_clear.size(); i++)
-		{
-			const int32_t n = to_clear[i];
-			const uint8_t s = n_strand[n];
-			const uint32_t id = n_id[n];
-			if(n_prev[n] >= 0) n_next[n_prev[n]] = n_next[n]; else head[s][id] = n_next[n];
-			if(n_next[n] >= 0) n_prev[n_next[n]] = n_prev[n];
-			lsize[s][id]--;
-		}
-		to_clear.clear();
-	}
-
-	inline size_t count_bifurcations(size_t id) const { return (size_t)lsize[0][id] + lsize[1][id]; }   // .cpp:71-75
-
-	void list_positions(size_t id, std::vector<int32_t> &out) const   // ListPositions, bifurcationstorage.h:59-72
-	{
-		out.clear();
-		for(int s = 0; s < 2; s++)
-		{
-			for(int32_t n = head[s][id]; n >= 0; n = n_next[n]) out.push_back(n);
-		}
-	}
-	inline It node_it(int32_t n) const                   // IteratorProxy::operator*
-	{
-		It it;
-		it.e = n_elem[n];
-		it.d = n_strand[n];
-		return it;
-	}
-
-	// =========================================================== construction
-	void build(uint32_t nchr, char *const *seq, uint32_t *const *origpos, const uint64_t *len, size_t k_, size_t D_,
-		uint32_t count, const sibgpu_inst *pos, uint64_t npos, const sibgpu_inst *neg, uint64_t nneg)
-	{
-		k = k_;
-		D = D_;
-		max_id = count;
-		size_t total = 1;
-		for(uint32_t c = 0; c < nchr; c++) total += len[c] + 1;
-		ch.resize(total);
-		opos.resize(total);
-		nxt.resize(total);
-		prv.resize(total);
-		for(int s = 0; s < 2; s++)
-		{
-			mark[s].assign(total, NO_BIF);
-			node_of[s].assign(total, -1);
-			head[s].assign((size_t)count + 1, -1);
-			lsize[s].assign((size_t)count + 1, 0);
-		}
-		dirty.assign((size_t)count + 1, 0);
-		chr_first_sep.resize(nchr);
-		size_t at = 0;
-		ch[at] = SEP;
-		opos[at] = 0;
-		at++;
-		std::vector<size_t> start(nchr);
-		for(uint32_t c = 0; c < nchr; c++)
-		{
-			chr_first_sep[c] = (int32_t)(at - 1);
-			start[c] = at;
-			memcpy(&ch[at], seq[c], len[c]);
-			for(uint64_t i = 0; i < len[c]; i++) opos[at + i] = origpos[c][i] & POS_MASK;
-			at += len[c];
-			ch[at] = SEP;
-			opos[at] = (uint32_t)len[c] & POS_MASK;        // dnasequence.cpp:96-97
-			at++;
-		}
-		for(size_t i = 0; i < total; i++)
-		{
-			nxt[i] = (int32_t)i + 1;
-			prv[i] = (int32_t)i - 1;
-		}
-		nxt[total - 1] = -1;
-		last_sep = (int32_t)total - 1;
-		live = total;
-		// IndexedSequence::Init, indexedsequence.cpp:51-67: strand 0 then strand 1, chromosomes and positions ascending
-		n_elem.reserve(npos + nneg);
-		for(uint64_t i = 0; i < npos; i++)
-		{
-			It it;
-			it.e = (int32_t)(start[pos[i].chr] + pos[i].pos);
-			it.d = 0;
-			add_point(it, pos[i].bifId);
-		}
-		for(uint64_t i = 0; i < nneg; i++)
-		{
-			It it;
-			it.e = (int32_t)(start[neg[i].chr] + len[neg[i].chr] - 1 - neg[i].pos);
-			it.d = 1;
-			add_point(it, neg[i].bifId);
-		}
-		std::fill(dirty.begin(), dirty.end(), 0);
-	}
-
-	// Renumbers the elements in sequence order so that element index == flat position again (start of a sweep).
-	void compact()
-	{
-		const size_t total = live;
-		std::vector<int32_t> newidx(ch.size(), -1);
-		std::vector<char> ch2(total);
-		std::vector<uint32_t> op2(total), m0(total), m1(total);
-		std::vector<int32_t> no0(total), no1(total);
-		size_t j = 0;
-		for(int32_t e = 0; e >= 0; e = nxt[e], j++)
-		{
-			newidx[e] = (int32_t)j;
-			ch2[j] = ch[e];
-			op2[j] = opos[e];
-			m0[j] = mark[0][e];
-			m1[j] = mark[1][e];
-			no0[j] = node_of[0][e];
-			no1[j] = node_of[1][e];
-		}
-		for(size_t n = 0; n < n_elem.size(); n++)
-		{
-			if(n_valid[n]) n_elem[n] = newidx[n_elem[n]];
-		}
-		for(size_t c = 0; c < chr_first_sep.size(); c++) chr_first_sep[c] = newidx[chr_first_sep[c]];
-		last_sep = newidx[last_sep];
-		ch.swap(ch2);
-		opos.swap(op2);
-		mark[0].swap(m0);
-		mark[1].swap(m1);
-		node_of[0].swap(no0);
-		node_of[1].swap(no1);
-		nxt.resize(total);
-		prv.resize(total);
-		for(size_t i = 0; i < total; i++)
-		{
-			nxt[i] = (int32_t)i + 1;
-			prv[i] = (int32_t)i - 1;
-		}
-		nxt[total - 1] = -1;
-	}
-
-	// Drops the list nodes that Cleanup already unlinked (keeps node indices small between sweeps).
-	void compact_nodes()
-	{
-		std::vector<int32_t> remap(n_elem.size(), -1);
-		size_t j = 0;
-		for(size_t n = 0; n < n_elem.size(); n++)
-		{
-			if(n_valid[n]) remap[n] = (int32_t)j++;
-		}
-		std::vector<int32_t> e2(j), nx2(j), pv2(j);
-		std::vector<uint8_t> s2(j), v2(j, 1);
-		std::vector<uint32_t> id2(j);
-		for(size_t n = 0; n < n_elem.size(); n++)
-		{
-			if(!n_valid[n]) continue;
-			const int32_t m = remap[n];
-			e2[m] = n_elem[n];
-			s2[m] = n_strand[n];
-			id2[m] = n_id[n];
-			nx2[m] = n_next[n] >= 0 ? remap[n_next[n]] : -1;
-			pv2[m] = n_prev[n] >= 0 ? remap[n_prev[n]] : -1;
-			node_of[s2[m]][e2[m]] = m;
-		}
-		for(int s = 0; s < 2; s++)
-		{
-			for(size_t id = 0; id < head[s].size(); id++)
-			{
-				if(head[s][id] >= 0) head[s][id] = remap[head[s][id]];
-			}
-		}
-		n_elem.swap(e2);
-		n_next.swap(nx2);
-		n_prev.swap(pv2);
-		n_strand.swap(s2);
-		n_valid.swap(v2);
-		n_id.swap(id2);
-	}
-
-	// =========================================================== DNASequence::Replace
-	int32_t new_element(char c)
-	{
-		const int32_t e = (int32_t)ch.size();
-		ch.push_back(c);
-		opos.push_back(0);
-		nxt.push_back(-1);
-		prv.push_back(-1);
-		for(int s = 0; s < 2; s++)
-		{
-			mark[s].push_back(NO_BIF);
-			node_of[s].push_back(-1);
-		}
-		return e;
-	}
-
-	// ReplaceDirect, dnasequence.cpp:189-230.  `target` is the first (positive order) element of the target branch.
-	void replace_direct(It source, size_t sdist, int32_t target, size_t tdist)
-	{
-		const int32_t save = target;
-		const size_t first_pos = opos[save];
-		int32_t after = save;
-		for(size_t i = 0; i < tdist; i++) after = nxt[after];
-		const size_t last_pos = opos[after];
-		const size_t common = std::min(sdist, tdist);
-		for(size_t i = 0; i < common; i++)
-		{
-			ch[target] = deref(source);
-			target = nxt[target];
-			inc(source);
-		}
-		if(sdist < tdist)
-		{
-			// erase the surplus elements [target, target + tdist - sdist)
-			int32_t e = target;
-			const int32_t before = prv[target];
-			for(size_t i = 0; i < tdist - sdist; i++) e = nxt[e];
-			nxt[before] = e;
-			prv[e] = before;
-			live -= tdist - sdist;
-		}
-		else if(sdist != tdist)
-		{
-			// insert the rest of the source in front of `target`
-			std::string buf;
-			for(size_t i = 0; i < sdist - tdist; i++, inc(source)) buf.push_back(deref(source));
-			int32_t before = prv[target];
-			for(size_t i = 0; i < buf.size(); i++)
-			{
-				const int32_t e = new_element(buf[i]);
-				nxt[before] = e;
-				prv[e] = before;
-				before = e;
-			}
-			nxt[before] = target;
-			prv[target] = before;
-			live += sdist - tdist;
-		}
-		// original positions of the new branch: sequential double accumulation (:221-227)
-		double acc = static_cast<double>(first_pos);
-		const double ssize = double(tdist) / sdist;
-		int32_t e = save;
-		for(size_t step = 0; step < sdist; step++, e = nxt[e], acc += ssize)
-		{
-			const size_t p = std::min(last_pos, size_t(acc));
-			opos[e] = static_cast<uint32_t>(p) & POS_MASK;   // SetOriginalPosition also clears both info bits; the
-		}                                                    // branch carries no marks at this point
-	}
-
-	void replace(It source, size_t sdist, It target, size_t tdist)    // Replace, dnasequence.cpp:232-252
-	{
-		if(target.d == 0)
-		{
-			replace_direct(source, sdist, target.e, tdist);
-		}
-		else
-		{
-			source = invert(advance(source, sdist));
-			const int32_t begin = invert(advance(target, tdist)).e;
-			replace_direct(source, sdist, begin, tdist);
-		}
-	}
-
-	// =========================================================== bulgeremoval.cpp
-	size_t max_bifurcation_multiplicity(It it, size_t distance) const   // :39-53
-	{
-		size_t ret = 0;
-		for(size_t i = 0; i + 1 < distance; i++)
-		{
-			inc(it);
-			const uint32_t b = get_bif(it);
-			if(b != NO_BIF) ret = std::max(ret, count_bifurcations(b));
-		}
-		return ret;
-	}
-
-	void erase_bifurcations(const std::vector<int32_t> &start_kmer, VisitData target,
-		std::vector<std::pair<size_t, size_t> > &look_forward, std::vector<std::pair<size_t, size_t> > &look_back)   // :55-95
-	{
-		look_back.clear();
-		look_forward.clear();
-		const It t0 = node_it(start_kmer[target.kmerId]);
-		It amer = invert(advance(t0, k));
-		It bmer = advance(t0, target.distance);
-		for(size_t i = 0; i < k; i++, inc(amer), inc(bmer))
-		{
-			uint32_t b = get_bif(amer);
-			if(b != NO_BIF)
-			{
-				erase_point(amer);
-				look_back.push_back(std::make_pair(i, (size_t)b));
-			}
-			b = get_bif(bmer);
-			if(b != NO_BIF)
-			{
-				erase_point(bmer);
-				look_forward.push_back(std::make_pair(i, (size_t)b));
-			}
-		}
-		amer = t0;
-		bmer = invert(advance(amer, k + target.distance));
-		for(size_t i = 0; i < k + target.distance; i++, inc(amer), inc(bmer))
-		{
-			if(i > 0) erase_point(amer);
-			erase_point(bmer);
-		}
-	}
-
-	bool overlap(const std::vector<int32_t> &start_kmer, VisitData source, VisitData target) const   // :97-120
-	{
-		std::vector<int32_t> occur;
-		It it = node_it(start_kmer[source.kmerId]);
-		for(size_t i = 0; i < source.distance + k; i++, inc(it)) occur.push_back(it.e);
-		it = node_it(start_kmer[target.kmerId]);
-		std::sort(occur.begin(), occur.end());
-		for(size_t i = 0; i < target.distance + k; i++, inc(it))
-		{
-			if(std::binary_search(occur.begin(), occur.end(), it.e)) return true;
-		}
-		return false;
-	}
-
-	void fill_visit(It kmer, std::vector<BifurcationMark> &visit) const   // :122-146
-	{
-		visit.clear();
-		const uint32_t start = get_bif(kmer);
-		inc(kmer);
-		for(size_t step = 1; step < D && at_valid(kmer); inc(kmer), step++)
-		{
-			const uint32_t b = get_bif(kmer);
-			if(b == start) break;
-			if(b != NO_BIF)
-			{
-				BifurcationMark m;
-				m.bifId = b;
-				m.distance = step;
-				visit.push_back(m);
-			}
-		}
-		std::sort(visit.begin(), visit.end());
-	}
-
-	struct BranchData {
-		char end_char;
-		std::vector<size_t> branch_ids;
-	};
-
-	// AnyBulges, :158-218.  The visit map is boost::unordered_map<size_t, BranchData>: lookups through `slot_of`,
-	// iteration order through BoostUnorderedOrder.
-	std::vector<int32_t> slot_of;                        // vertex id -> index into `branches` (-1 = absent), kept sparse
-	std::vector<BranchData> branches;
-	std::vector<uint32_t> touched;
-	BoostUnorderedOrder order;
-
-	bool any_bulges(const std::vector<int32_t> &start_kmer, const std::vector<char> &end_char,
-		std::vector<std::vector<size_t> > &bulges)
-	{
-		bulges.clear();
-		branches.clear();
-		touched.clear();
-		order.clear();
-		for(size_t i = 0; i < start_kmer.size(); i++)
-		{
-			if(end_char[i] == EMPTY) continue;
-			It kmer = node_it(start_kmer[i]);
-			const uint32_t start = get_bif(kmer);
-			inc(kmer);
-			for(size_t step = 1; step < D && at_valid(kmer); inc(kmer), step++)
-			{
-				const uint32_t b = get_bif(kmer);
-				if(b == start) break;
-				if(b != NO_BIF)
-				{
-					const int32_t s = slot_of[b];
-					if(s < 0)
-					{
-						slot_of[b] = (int32_t)branches.size();
-						touched.push_back(b);
-						order.insert_new(b, (int)branches.size());
-						BranchData bd;
-						bd.end_char = end_char[i];
-						bd.branch_ids.push_back(i);
-						branches.push_back(bd);
-					}
-					else if(branches[s].end_char != end_char[i])
-					{
-						branches[s].branch_ids.push_back(i);
-						break;
-					}
-				}
-			}
-		}
-		std::vector<int> ord;
-		order.order(std::back_inserter(ord));
-		for(size_t i = 0; i < ord.size(); i++)
-		{
-			if(branches[ord[i]].branch_ids.size() > 1) bulges.push_back(branches[ord[i]].branch_ids);
-		}
-		for(size_t i = 0; i < touched.size(); i++) slot_of[touched[i]] = -1;
-		return !bulges.empty();
-	}
-
-	void update_bifurcations(const std::vector<int32_t> &start_kmer, VisitData source, VisitData target,
-		const std::vector<std::pair<size_t, size_t> > &look_forward, const std::vector<std::pair<size_t, size_t> > &look_back)   // :238-282
-	{
-		size_t anear = 0, bnear = 0;
-		const It t0 = node_it(start_kmer[target.kmerId]);
-		const It s0 = node_it(start_kmer[source.kmerId]);
-		It amer = invert(advance(t0, k));
-		It bmer = advance(t0, source.distance);
-		for(size_t i = 0; i < k; i++, inc(amer), inc(bmer))
-		{
-			if(anear < look_back.size() && i == look_back[anear].first) add_point(amer, look_back[anear++].second);
-			if(bnear < look_forward.size() && i == look_forward[bnear].first) add_point(bmer, look_forward[bnear++].second);
-		}
-		amer = t0;
-		bmer = invert(advance(t0, source.distance + k));
-		It src_a = s0;
-		It src_b = invert(advance(s0, source.distance + k));
-		for(size_t i = 0; i < source.distance + 1; i++, inc(amer), inc(bmer), inc(src_a), inc(src_b))
-		{
-			uint32_t b = get_bif(src_a);
-			if(b != NO_BIF) add_point(amer, b);
-			b = get_bif(src_b);
-			if(b != NO_BIF) add_point(bmer, b);
-		}
-	}
-
-	// Everything a collapse touched, in terms of the vertices whose detection walks could see it: the elements of the
-	// rewritten region plus a margin of `reach` elements on both sides; the vertex of every mark found there is dirty.
-	void mark_dirty_around(It t0, size_t new_distance)
-	{
-		const size_t reach = std::max(D, k + 1) + 1;
-		// the region spans offsets [0, new_distance + 2k) from the target's start in its strand direction
-		It lo = t0, hi = t0;
-		if(t0.d == 1)
-		{
-			// walk in positive order: the region lies towards smaller positive positions for a negative-strand target
-			It x = t0;
-			for(size_t i = 0; i < new_distance + 2 * k; i++)
-			{
-				if(prv[x.e] < 0) break;
-				x.e = prv[x.e];
-			}
-			lo = x;
-			hi = t0;
-		}
-		else
-		{
-			It x = t0;
-			for(size_t i = 0; i < new_distance + 2 * k; i++)
-			{
-				if(nxt[x.e] < 0) break;
-				x.e = nxt[x.e];
-			}
-			lo = t0;
-			hi = x;
-		}
-		int32_t a = lo.e, b = hi.e;
-		for(size_t i = 0; i < reach && prv[a] >= 0; i++) a = prv[a];
-		for(size_t i = 0; i < reach && nxt[b] >= 0; i++) b = nxt[b];
-		for(int32_t e = a; ; e = nxt[e])
-		{
-			if(mark[0][e] != NO_BIF) dirty[mark[0][e]] = 1;
-			if(mark[1][e] != NO_BIF) dirty[mark[1][e]] = 1;
-			if(e == b) break;
-		}
-	}
-
-	void collapse_bulge_greedily(std::vector<int32_t> &start_kmer, VisitData source, VisitData target)   // :284-327
-	{
-		std::vector<std::pair<size_t, size_t> > look_forward, look_back;
-		const It t0 = node_it(start_kmer[target.kmerId]);
-		// before anything moves: the vertices that can currently see the target region
-		mark_dirty_around(t0, target.distance);
-		erase_bifurcations(start_kmer, target, look_forward, look_back);
-		const It source_it = node_it(start_kmer[source.kmerId]);
-		replace(advance(source_it, k), source.distance, advance(t0, k), target.distance);
-		update_bifurcations(start_kmer, source, target, look_forward, look_back);
-		mark_dirty_around(t0, source.distance);
-		collapses++;
-	}
-
-	size_t collapses = 0;
-
-	size_t remove_bulges(size_t bif_id)                  // RemoveBulges, :330-430
-	{
-		size_t ret = 0;
-		std::vector<int32_t> start_kmer;
-		list_positions(bif_id, start_kmer);
-		if(start_kmer.size() < 2) return ret;
-		std::vector<char> end_char(start_kmer.size(), EMPTY);
-		for(size_t i = 0; i < start_kmer.size(); i++)
-		{
-			const It it = node_it(start_kmer[i]);
-			if(proper_kmer(it, k + 1)) end_char[i] = deref(advance(it, k));
-		}
-		std::vector<std::vector<size_t> > bulges;
-		if(!any_bulges(start_kmer, end_char, bulges)) return ret;
-		std::vector<BifurcationMark> visit;
-		for(size_t num_bulge = 0; num_bulge < bulges.size(); ++num_bulge)
-		{
-			for(size_t id_i = 0; id_i < bulges[num_bulge].size(); ++id_i)
-			{
-				const size_t kmer_i = bulges[num_bulge][id_i];
-				if(!n_valid[start_kmer[kmer_i]]) continue;
-				fill_visit(node_it(start_kmer[kmer_i]), visit);
-				for(size_t id_j = id_i + 1; id_j < bulges[num_bulge].size(); ++id_j)
-				{
-					const size_t kmer_j = bulges[num_bulge][id_j];
-					if(!n_valid[start_kmer[kmer_j]] || end_char[kmer_i] == end_char[kmer_j]) continue;
-					It kmer = node_it(start_kmer[kmer_j]);
-					inc(kmer);
-					for(size_t step = 1; at_valid(kmer) && step < D; inc(kmer), step++)
-					{
-						const uint32_t now_bif = get_bif(kmer);
-						if(now_bif == NO_BIF) continue;
-						if(now_bif == bif_id) break;
-						BifurcationMark probe;
-						probe.bifId = now_bif;
-						probe.distance = 0;
-						std::vector<BifurcationMark>::iterator vt = std::lower_bound(visit.begin(), visit.end(), probe);
-						if(vt != visit.end() && vt->bifId == now_bif)
-						{
-							VisitData jdata, idata;
-							jdata.kmerId = kmer_j;
-							jdata.distance = step;
-							idata.kmerId = kmer_i;
-							idata.distance = vt->distance;
-							if(overlap(start_kmer, idata, jdata) || now_bif == bif_id) break;
-							++ret;
-							const size_t imlp = max_bifurcation_multiplicity(node_it(start_kmer[kmer_i]), idata.distance);
-							const size_t jmlp = max_bifurcation_multiplicity(node_it(start_kmer[kmer_j]), jdata.distance);
-							const bool iless = imlp > jmlp || (imlp == jmlp && idata.kmerId < jdata.kmerId);
-							if(iless)
-							{
-								end_char[jdata.kmerId] = end_char[idata.kmerId];
-								collapse_bulge_greedily(start_kmer, idata, jdata);
-							}
-							else
-							{
-								end_char[idata.kmerId] = end_char[jdata.kmerId];
-								collapse_bulge_greedily(start_kmer, jdata, idata);
-								fill_visit(node_it(start_kmer[kmer_i]), visit);
-							}
-							break;
-						}
-					}
-				}
-			}
-		}
-		cleanup();
-		return ret;
-	}
-};
-
-} // namespace
+using namespace simp;
 
 // ---------------------------------------------------------------------------------------------------------------
 // K8: bulge detection for every vertex against the sweep snapshot.
@@ -795,6 +119,17 @@ extern "C" int sibgpu_simplify(sibgpu_ctx *ctx, char **seq, uint32_t **origpos, 
 		set_error("invalid: NULL argument or k == 0");
 		return SIBGPU_ERR_INVALID;
 	}
+	const bool trace = getenv("SIBGPU_TRACE") != nullptr;
+	auto now = []() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+	double t_mark = now();
+	auto lap = [&](const char *what) {
+		if(trace)
+		{
+			const double t = now();
+			fprintf(stderr, "[sibgpu_simplify] %-28s %8.2f ms\n", what, (t - t_mark) * 1e3);
+			t_mark = t;
+		}
+	};
 	// ---- IndexedSequence(rawSeq_, originalPos_, k, tempDir_, true): the vertex tables come from the GPU enumerator
 	sibgpu_inst *pos = nullptr, *neg = nullptr;
 	uint64_t npos = 0, nneg = 0;
@@ -802,16 +137,18 @@ extern "C" int sibgpu_simplify(sibgpu_ctx *ctx, char **seq, uint32_t **origpos, 
 	SIB_TRY(sibgpu_enumerate(ctx, seq, len, nchr, k, &pos, &npos, &neg, &nneg, &count));
 	uint64_t launches = ctx->total_launches;
 	float device_ms = ctx->last_ms;
+	lap("enumerate (host buffers)");
 	Simplifier S;
 	S.build(nchr, seq, origpos, len, k, min_branch_size, count, pos, npos, neg, nneg);
 	free(pos);
 	free(neg);
 	S.slot_of.assign((size_t)count + 1, -1);
+	lap("build host state");
 
 	// ---- SimplifyGraph, blockfinder.cpp:16-51
 	cudaStream_t st = ctx->stream;
-	DevBuf d_ch, d_m0, d_m1, d_off, d_inst, d_flag;
-	auto release = [&]() { d_ch.release(); d_m0.release(); d_m1.release(); d_off.release(); d_inst.release(); d_flag.release(); };
+	DevBuf &d_ch = ctx->d_s_ch, &d_m0 = ctx->d_s_m0, &d_m1 = ctx->d_s_m1, &d_off = ctx->d_s_off, &d_inst = ctx->d_s_inst, &d_flag = ctx->d_s_flag;
+	auto release = [&]() {};   // the buffers live in the context (grow-only): no cudaMalloc/cudaFree per stage
 	const size_t PROGRESS_STRIDE = 50;
 	size_t cnt = 0, total_bulges = 0, iterations = 0, total_progress = 0;
 	if(progress) progress(total_progress, 0, user);
@@ -830,6 +167,7 @@ extern "C" int sibgpu_simplify(sibgpu_ctx *ctx, char **seq, uint32_t **origpos, 
 			S.compact();
 			S.compact_nodes();
 		}
+		lap("renumber");
 		std::fill(S.dirty.begin(), S.dirty.end(), 0);
 		const size_t total = S.ch.size();
 		inst_elem.clear();
@@ -875,22 +213,57 @@ extern "C" int sibgpu_simplify(sibgpu_ctx *ctx, char **seq, uint32_t **origpos, 
 			launches++;
 			return SIBGPU_OK;
 		};
+		lap("instance CSR");
 		rc = dev();
 		if(rc != SIBGPU_OK)
 		{
 			release();
 			return rc;
 		}
+		lap("upload + k_bulge_detect");
+		size_t n_flag = 0, n_calls = 0;
+		const size_t collapses_before = S.collapses;
 		// ---- the reference's sweep, skipping the vertices whose negative outcome is already known
 		for(size_t id = 0; id <= max_id; id++)
 		{
-			if(flag[id] || S.dirty[id]) total_bulges += S.remove_bulges(id);
+			n_flag += flag[id];
+			if(flag[id] || S.dirty[id])
+			{
+				n_calls++;
+				total_bulges += S.remove_bulges(id);
+			}
 			if(++cnt >= threshold && progress)
 			{
 				cnt = 0;
 				total_progress = std::min(total_progress + 1, PROGRESS_STRIDE);
 				progress(total_progress, 1, user);
 			}
+		}
+		if(trace)
+		{
+			fprintf(stderr, "[sibgpu_simplify] sweep %zu: %zu vertices, %zu flagged by the GPU, %zu exact calls, %zu collapses\n",
+				iterations, max_id + 1, n_flag, n_calls, S.collapses - collapses_before);
+		}
+		lap("ordered host commit");
+		if(S.collapses == collapses_before)
+		{
+			// Nothing changed in this sweep, so every further sweep of the reference (it keeps sweeping while the
+			// CUMULATIVE count is positive, blockfinder.cpp:29-43) finds the same state and changes nothing: only its
+			// progress ticks remain.
+			while(total_bulges > 0 && iterations < max_iterations)
+			{
+				iterations++;
+				for(size_t id = 0; id <= max_id; id++)
+				{
+					if(++cnt >= threshold && progress)
+					{
+						cnt = 0;
+						total_progress = std::min(total_progress + 1, PROGRESS_STRIDE);
+						progress(total_progress, 1, user);
+					}
+				}
+			}
+			break;
 		}
 	}
 	while(total_bulges > 0 && iterations < max_iterations);
@@ -921,6 +294,7 @@ extern "C" int sibgpu_simplify(sibgpu_ctx *ctx, char **seq, uint32_t **origpos, 
 		origpos[c] = out_pos;
 		len[c] = n;
 	}
+	lap("copy-back");
 	*bulges = total_bulges;
 	return SIBGPU_OK;
 }
