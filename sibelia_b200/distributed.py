@@ -8,9 +8,14 @@ payloads between ranks: ONE all-to-all of the k-mer records (bucketed by hash pr
 of the vertex keys.  With the NCCL backend the collectives run on the device buffers the kernels wrote (NVLink /
 NVSwitch); with gloo (CPU tests, or two ranks sharing one GPU) the same tensors are staged through host memory.
 """
+import os
+import time
+
 import numpy as np
 import torch
 import torch.distributed as dist
+
+_TRACE = os.environ.get("SIBGPU_TRACE_DIST") is not None
 
 
 class GpuShard:
@@ -60,10 +65,21 @@ def enumerate_sharded(shard, chrs, k, group=None):
     """Runs the sharded enumeration on every rank of `group`; returns (global vertex count, this rank's positive table,
     this rank's negative table in TEXT order).  `shard` is a backend with upload/scan/scatter/group/finish."""
     rank, world = dist.get_rank(group), dist.get_world_size(group)
+    marks = []
+
+    def lap(what):
+        if _TRACE:
+            if torch.cuda.is_available():
+                torch.cuda.synchronize()
+            marks.append((what, time.perf_counter()))
+    lap("start")
     shard.upload(chrs, rank, world)
+    lap("upload")
     nparts, hist = shard.scan(k)
+    lap("scan")
     words = shard.words
     send = shard.scatter()
+    lap("scatter")
     dev = send.device
     # --- partition counts of every rank
     h = _comm(torch.from_numpy(hist.astype(np.int64)).to(dev), group)
@@ -73,11 +89,14 @@ def enumerate_sharded(shard, chrs, k, group=None):
     pl = nparts // world
     in_splits = [int(counts[rank, r * pl:(r + 1) * pl].sum()) * words for r in range(world)]
     out_splits = [int(counts[s, rank * pl:(rank + 1) * pl].sum()) * words for s in range(world)]
+    lap("allgather counts")
     # --- THE exchange: every record goes to the rank that owns its hash partition
     s_c = _comm(send, group)
     recv = torch.empty(sum(out_splits), dtype=torch.int64, device=s_c.device)
     dist.all_to_all_single(recv, s_c, out_splits, in_splits, group=group)
+    lap("all_to_all records")
     keys = shard.group(recv.to(dev), counts.astype(np.uint32))
+    lap("group")
     # --- vertex keys of all ranks (variable sizes: pad to the maximum)
     nk = _comm(torch.tensor([keys.numel()], dtype=torch.int64, device=dev), group)
     all_nk = torch.empty(world, dtype=torch.int64, device=nk.device)
@@ -90,7 +109,13 @@ def enumerate_sharded(shard, chrs, k, group=None):
     gathered = torch.empty(world * mx, dtype=torch.int64, device=p_c.device)
     dist.all_gather_into_tensor(gathered, p_c, group=group)
     allkeys = torch.cat([gathered[s * mx:s * mx + all_nk[s]] for s in range(world)]).to(dev)
-    return shard.finish(allkeys)
+    lap("allgather keys")
+    out = shard.finish(allkeys)
+    lap("finish")
+    if _TRACE and rank == 0:
+        print("[sharded] " + "  ".join("%s %.2f ms" % (marks[i][0], (marks[i][1] - marks[i - 1][1]) * 1e3)
+                                       for i in range(1, len(marks))), flush=True)
+    return out
 
 
 def assemble_tables(pos_parts, negtext_parts):

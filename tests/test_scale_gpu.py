@@ -1,0 +1,90 @@
+"""GPU, BASELINE.json full sizes (configs[1] 100 MB random contig, configs[2]/[4] 500 MB 4-strain set incl. the k sweep):
+the oracle cannot run there in test time, so the results are checked through size-independent properties
+  * both tables sorted by (chr, pos), same length, ids < count, every + instance has its - twin at len - pos - k;
+  * the reference's _DEBUG invariant (indexedsequence.cpp:82-102): equal k-mers <=> equal ids, on sampled instances;
+  * ids are lexicographic ranks: sampled instance k-mers sorted by id are sorted as strings;
+  * vertex predicate spot checks: chromosome-end k-mers are vertices (vertexenumeration.cpp:343);
+  * the result does not depend on the hash-partition size (different kernels/launch structure, same tables)."""
+import os
+
+import numpy as np
+import pytest
+
+import sibelia_b200 as sb
+from sibelia_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def kmer_at(chrs, strand, c, p, k):
+    if strand == 0:
+        return chrs[c][p:p + k].tobytes()
+    L = len(chrs[c])
+    return synth.revcomp(chrs[c][L - p - k:L - p]).tobytes()
+
+
+def check_properties(chrs, k, count, pos, neg, rng, nsample=4000):
+    lens = np.array([len(c) for c in chrs], dtype=np.int64)
+    assert len(pos) == len(neg)
+    for t in (pos, neg):
+        key = (t["chr"].astype(np.int64) << 32) | t["pos"].astype(np.int64)
+        assert np.all(np.diff(key) > 0), "table not strictly sorted by (chr, pos)"
+        assert len(t) == 0 or int(t["bifId"].max()) < count
+        assert np.all(t["pos"].astype(np.int64) + k <= lens[t["chr"]])
+    # strand twins
+    tw = np.lexsort((lens[pos["chr"]] - pos["pos"].astype(np.int64) - k, pos["chr"]))
+    assert np.array_equal(pos["chr"][tw], neg["chr"])
+    assert np.array_equal((lens[pos["chr"]] - pos["pos"].astype(np.int64) - k)[tw], neg["pos"].astype(np.int64))
+    # chromosome ends are vertices
+    for c, L in enumerate(lens):
+        if L >= k:
+            first = pos[(pos["chr"] == c)]
+            assert len(first) and first["pos"][0] == 0 and first["pos"][-1] == L - k
+    # equal k-mer <=> equal id, ids in lexicographic order (sampled)
+    if len(pos) == 0:
+        return
+    sel_p = rng.choice(len(pos), size=min(nsample, len(pos)), replace=False)
+    sel_n = rng.choice(len(neg), size=min(nsample, len(neg)), replace=False)
+    items = [(int(pos["bifId"][i]), kmer_at(chrs, 0, int(pos["chr"][i]), int(pos["pos"][i]), k)) for i in sel_p]
+    items += [(int(neg["bifId"][i]), kmer_at(chrs, 1, int(neg["chr"][i]), int(neg["pos"][i]), k)) for i in sel_n]
+    by_id, by_str = {}, {}
+    for i, s in items:
+        assert by_id.setdefault(i, s) == s, "one id, two k-mers"
+        assert by_str.setdefault(s, i) == i, "one k-mer, two ids"
+    order = sorted(by_id)
+    strs = [by_id[i] for i in order]
+    assert strs == sorted(strs), "ids are not lexicographic ranks"
+
+
+@pytest.fixture(scope="module")
+def strains500():
+    return synth.strains(4, 125_000_000)
+
+
+def test_c2_random_100mb(ctx):
+    g = synth.random_genome(100_000_000, 12345)
+    count, pos, neg = ctx.enumerate([g], 25)
+    check_properties([g], 25, count, pos, neg, np.random.default_rng(0))
+    assert count < 1000          # 4^25 >> 10^8: essentially no repeated 25-mers in a random genome
+
+
+@pytest.mark.parametrize("k", [15, 25, 100, 500, 5000])
+def test_c3_c5_strains_500mb_k_sweep(ctx, strains500, k):
+    count, pos, neg = ctx.enumerate(strains500, k)
+    check_properties(strains500, k, count, pos, neg, np.random.default_rng(k))
+    # SNP every ~500 bases per strain: shared 5000-mers are rare, the 16 chromosome-end vertices always exist
+    assert count > 1000 if k <= 500 else count >= 16
+
+
+def test_c3_partition_size_independence(strains500, built):
+    res = []
+    for part in (1 << 20, 1 << 23):
+        os.environ["SIBGPU_PART_RECORDS"] = str(part)
+        try:
+            c = sb.Context(0)
+        finally:
+            del os.environ["SIBGPU_PART_RECORDS"]
+        res.append(c.enumerate(strains500, 25))
+        c.close()
+    assert res[0][0] == res[1][0]
+    assert np.array_equal(res[0][1], res[1][1]) and np.array_equal(res[0][2], res[1][2])
