@@ -294,10 +294,21 @@ def main():
                             for n, s in sorted(kstats.items(), key=lambda kv: -kv[1]["ms"])}}
     tr = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tr):
+        # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures
+        # (profiles/r1_ncu_*.txt); for the overlapped insert+scan phase: both kernels, all partitions of one step
         try:
-            roofline["traffic"] = json.load(open(tr)).get(dname)
+            tj = json.load(open(tr))
+            if dname in tj:
+                roofline["traffic"] = tj[dname]
+            elif dname == "k_insert+k_table_scan":
+                per_launch_records = 4194304.0      # the captures were taken with 4 Mi-record partitions
+                nrec = d["algo_bytes"] / 8.0 / args.steps
+                roofline["traffic"] = (tj["k_insert"] + tj["k_table_scan"]) * nrec / per_launch_records
+                roofline["traffic_note"] = "whole phase per step, scaled from per-launch captures at 4 Mi records/partition"
         except Exception:
             pass
+    roofline["note"] = ("k_insert is bound by scattered L2 atomics, not by HBM: tools/ubench/atomics.cu measures 90-104 G CAS/s "
+                        "on this part for an L2-resident table; the phase issues ~1.5 CAS per record (linear probing at load 0.5)")
 
     cpu = None
     if world == 1 and not args.no_cpu_baseline:

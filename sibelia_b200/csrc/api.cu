@@ -12,6 +12,20 @@ void set_error(const std::string &msg) { g_error = msg; }
 
 using namespace sibgpu;
 
+int sibgpu_ctx::ensure_aux_streams(uint32_t n)
+{
+	if(!ev_fork) SIB_CUDA(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
+	for(uint32_t i = 0; i < n && i < 8; i++)
+	{
+		if(!aux_stream[i])
+		{
+			SIB_CUDA(cudaStreamCreateWithFlags(&aux_stream[i], cudaStreamNonBlocking));
+			SIB_CUDA(cudaEventCreateWithFlags(&ev_join[i], cudaEventDisableTiming));
+		}
+	}
+	return SIBGPU_OK;
+}
+
 cudaEvent_t sibgpu_ctx::get_event()
 {
 	if(events_used == event_pool.size())
@@ -104,6 +118,7 @@ int sibgpu_create(int device, sibgpu_ctx **out)
 		if(v >= 1024) c->part_target = v;
 	}
 	if(const char *e = getenv("SIBGPU_INSERT_VARIANT")) c->insert_variant = atoi(e);
+	if(const char *e = getenv("SIBGPU_STREAMS")) c->n_streams = atoi(e);
 	if(const char *e = getenv("SIBGPU_TABLE_FACTOR"))
 	{
 		int v = atoi(e);
@@ -127,6 +142,12 @@ void sibgpu_destroy(sibgpu_ctx *c)
 	if(c->h_scalars) cudaFreeHost(c->h_scalars);
 	if(c->ev_begin) cudaEventDestroy(c->ev_begin);
 	if(c->ev_end) cudaEventDestroy(c->ev_end);
+	for(int i = 0; i < 8; i++)
+	{
+		if(c->aux_stream[i]) cudaStreamDestroy(c->aux_stream[i]);
+		if(c->ev_join[i]) cudaEventDestroy(c->ev_join[i]);
+	}
+	if(c->ev_fork) cudaEventDestroy(c->ev_fork);
 	if(c->stream) cudaStreamDestroy(c->stream);
 	delete c;
 }

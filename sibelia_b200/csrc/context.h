@@ -51,8 +51,12 @@ struct sibgpu_ctx {
 	sibgpu::TextDesc dist_text = {};
 
 	// tunables (env SIBGPU_PART_RECORDS)
-	uint64_t part_target = 1u << 22;
+	uint64_t part_target = 1u << 20;
 	int insert_variant = 1;                            // 1 = CAS first, one record per thread (env SIBGPU_INSERT_VARIANT, dev)
+	int n_streams = 4;                                 // overlapped partition streams (env SIBGPU_STREAMS)
+	cudaStream_t aux_stream[8] = {};
+	cudaEvent_t ev_fork = nullptr, ev_join[8] = {};
+	int ensure_aux_streams(uint32_t n);
 	int table_factor = 2;                              // slots per record of the largest partition (env SIBGPU_TABLE_FACTOR)
 
 	// profiling

@@ -449,10 +449,11 @@ __global__ void __launch_bounds__(256) k_insert_compact(const uint64_t *__restri
 	}
 }
 
-static void launch_insert_compact(int variant, int sms, cudaStream_t st, const uint64_t *recs, uint64_t n, unsigned long long *tab, uint32_t T)
+static void launch_insert_compact(int variant, int sms, cudaStream_t st, const uint64_t *recs, uint64_t n, unsigned long long *tab, uint32_t T,
+	int blocks_per_sm = 8)
 {
 	auto grid = [&](int ilp) {
-		uint64_t blocks = ((n + ilp - 1) / ilp + 255) / 256, cap = (uint64_t)sms * 8;
+		uint64_t blocks = ((n + ilp - 1) / ilp + 255) / 256, cap = (uint64_t)sms * blocks_per_sm;
 		return (uint32_t)(blocks < 1 ? 1 : (blocks < cap ? blocks : cap));
 	};
 	switch(variant)
@@ -966,26 +967,51 @@ static int enumerate_mode(sibgpu_ctx *ctx, uint32_t k, uint64_t nrec)
 		const uint32_t T = (uint32_t)T64;
 		const bool compact = MODE == 0 && k <= COMPACT_MAX_K;
 		const size_t slot_bytes = compact ? 8 : (MODE == 0 ? sizeof(Slot8) : sizeof(Slot16));
-		SIB_TRY(ctx->d_table.ensure(slot_bytes * T));
-		SIB_CUDA(cudaMemsetAsync(ctx->d_table.p, 0xFF, slot_bytes * T, st));
-		for(uint32_t p = 0; p < P; p++)
+		// S independent tables on S streams: consecutive partitions overlap, so the ramp-up / tail of one partition's
+		// kernels is filled by its neighbours (with S = 1 everything runs on the main stream and is timed per launch)
+		const uint32_t S = ctx->n_streams < 1 ? 1 : (ctx->n_streams > 8 ? 8 : ctx->n_streams);
+		const size_t table_bytes = (slot_bytes * T + 255) / 256 * 256;
+		SIB_TRY(ctx->d_table.ensure(table_bytes * S));
+		SIB_CUDA(cudaMemsetAsync(ctx->d_table.p, 0xFF, table_bytes * S, st));
+		if(S > 1)
 		{
-			const uint64_t n = h_partoff[p + 1] - h_partoff[p];
-			if(n == 0) continue;
-			Rec *part = ctx->d_records.as<Rec>() + h_partoff[p];
+			SIB_TRY(ctx->ensure_aux_streams(S));
+			SIB_CUDA(cudaEventRecord(ctx->ev_fork, st));
+			for(uint32_t i = 0; i < S; i++) SIB_CUDA(cudaStreamWaitEvent(ctx->aux_stream[i], ctx->ev_fork, 0));
+		}
+		const int blocks_per_sm = S > 1 ? 4 : 8;
+		{
+			// with overlapped streams the two kernels are timed together, as one phase on the main stream's timeline
+			const bool phase_span = S > 1 && ctx->profiling;
+			if(phase_span) ctx->prof_begin("k_insert+k_table_scan", nrec * sizeof(Rec));
+			for(uint32_t p = 0; p < P; p++)
 			{
-				ProfScope ps(ctx, "k_insert", n * sizeof(Rec));
-				if(compact) launch_insert_compact(ctx->insert_variant, sms, st, reinterpret_cast<const uint64_t*>(part), n,
-					ctx->d_table.as<unsigned long long>(), T);
-				else k_insert<MODE><<<grid_for(n, 256, sms, 8), 256, 0, st>>>(part, n, ctx->d_table.p, T);
-			}
-			{
-				ProfScope ps(ctx, "k_table_scan", (uint64_t)T * slot_bytes);
-				if(compact) k_table_scan_compact<<<grid_for(T, 256, sms, 8), 256, 0, st>>>(ctx->d_table.as<unsigned long long>(), T,
-					reinterpret_cast<uint64_t*>(part), ctx->d_partcnt.as<uint32_t>() + p);
-				else k_table_scan<MODE><<<grid_for(T, 256, sms, 8), 256, 0, st>>>(ctx->d_table.p, T, part,
+				const uint64_t n = h_partoff[p + 1] - h_partoff[p];
+				if(n == 0) continue;
+				Rec *part = ctx->d_records.as<Rec>() + h_partoff[p];
+				cudaStream_t ps_st = S > 1 ? ctx->aux_stream[p % S] : st;
+				void *table = static_cast<char*>(ctx->d_table.p) + table_bytes * (p % S);
+				ctx->total_launches += 2;
+				if(S == 1 && ctx->profiling) ctx->prof_begin("k_insert", n * sizeof(Rec));
+				if(compact) launch_insert_compact(ctx->insert_variant, sms, ps_st, reinterpret_cast<const uint64_t*>(part), n,
+					static_cast<unsigned long long*>(table), T, blocks_per_sm);
+				else k_insert<MODE><<<grid_for(n, 256, sms, blocks_per_sm), 256, 0, ps_st>>>(part, n, table, T);
+				if(S == 1 && ctx->profiling) { ctx->prof_end(); ctx->prof_begin("k_table_scan", (uint64_t)T * slot_bytes); }
+				if(compact) k_table_scan_compact<<<grid_for(T, 256, sms, blocks_per_sm), 256, 0, ps_st>>>(
+					static_cast<unsigned long long*>(table), T, reinterpret_cast<uint64_t*>(part), ctx->d_partcnt.as<uint32_t>() + p);
+				else k_table_scan<MODE><<<grid_for(T, 256, sms, blocks_per_sm), 256, 0, ps_st>>>(table, T, part,
 					ctx->d_partcnt.as<uint32_t>() + p);
+				if(S == 1 && ctx->profiling) ctx->prof_end();
 			}
+			if(S > 1)
+			{
+				for(uint32_t i = 0; i < S; i++)
+				{
+					SIB_CUDA(cudaEventRecord(ctx->ev_join[i], ctx->aux_stream[i]));
+					SIB_CUDA(cudaStreamWaitEvent(st, ctx->ev_join[i], 0));
+				}
+			}
+			if(phase_span) ctx->prof_end();
 		}
 		{
 			ProfScope ps(ctx, "k_key_offsets", 0);
