@@ -91,6 +91,9 @@ int sibgpu_set_profiling(sibgpu_ctx *ctx, int enabled);
 int sibgpu_kernel_stats(sibgpu_ctx *ctx, sibgpu_kernel_stat *out, int cap);
 /* number of kernels this library launched during the last enumerate / simplify on this context */
 uint64_t sibgpu_last_launches(sibgpu_ctx *ctx);
+/* how often, over the life of the context, a fixed-capacity hash partition overflowed (a k-mer repeated millions of
+ * times) and the enumeration fell back to exactly sized partitions (histogram pass); diagnostic */
+uint64_t sibgpu_partition_fallbacks(sibgpu_ctx *ctx);
 /* device time of the last sibgpu_enumerate_resident / device part of sibgpu_simplify on this context: milliseconds
  * between two CUDA events recorded on the library's stream around the whole operation */
 float sibgpu_last_device_ms(sibgpu_ctx *ctx);

@@ -12,7 +12,7 @@ INST_DTYPE = np.dtype([("bifId", "<u4"), ("chr", "<u4"), ("pos", "<u4")])
 SYMBOLS = [
     "sibgpu_last_error", "sibgpu_version", "sibgpu_device_count", "sibgpu_create", "sibgpu_destroy", "sibgpu_free",
     "sibgpu_enumerate", "sibgpu_upload", "sibgpu_enumerate_resident", "sibgpu_download", "sibgpu_set_profiling",
-    "sibgpu_kernel_stats", "sibgpu_last_launches", "sibgpu_last_device_ms", "sibgpu_simplify", "sibgpu_debug_unordered_order", "sibgpu_dist_upload", "sibgpu_dist_scan", "sibgpu_dist_record_bytes",
+    "sibgpu_kernel_stats", "sibgpu_last_launches", "sibgpu_partition_fallbacks", "sibgpu_last_device_ms", "sibgpu_simplify", "sibgpu_debug_unordered_order", "sibgpu_dist_upload", "sibgpu_dist_scan", "sibgpu_dist_record_bytes",
     "sibgpu_dist_scatter", "sibgpu_dist_group", "sibgpu_dist_keys", "sibgpu_dist_finish",
 ]
 
@@ -52,6 +52,8 @@ def load():
         L.sibgpu_version.restype = C.c_char_p
         L.sibgpu_last_launches.restype = C.c_uint64
         L.sibgpu_last_launches.argtypes = [C.c_void_p]
+        L.sibgpu_partition_fallbacks.restype = C.c_uint64
+        L.sibgpu_partition_fallbacks.argtypes = [C.c_void_p]
         L.sibgpu_last_device_ms.restype = C.c_float
         L.sibgpu_last_device_ms.argtypes = [C.c_void_p]
         L.sibgpu_destroy.argtypes = [C.c_void_p]
@@ -156,6 +158,9 @@ class Context:
 
     def last_launches(self):
         return int(load().sibgpu_last_launches(self._h))
+
+    def partition_fallbacks(self):
+        return int(load().sibgpu_partition_fallbacks(self._h))
 
     # -- sharded enumeration phases (see sibelia_b200/distributed.py for the orchestration)
     def dist_upload(self, chrs, rank, world):

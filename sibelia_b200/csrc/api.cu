@@ -1,4 +1,6 @@
 // extern "C" surface of libsibgpu (include/sibgpu.h): context, upload/download, enumerate.
+#include <chrono>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
@@ -22,6 +24,22 @@ int sibgpu_ctx::ensure_aux_streams(uint32_t n)
 			SIB_CUDA(cudaStreamCreateWithFlags(&aux_stream[i], cudaStreamNonBlocking));
 			SIB_CUDA(cudaEventCreateWithFlags(&ev_join[i], cudaEventDisableTiming));
 		}
+	}
+	return SIBGPU_OK;
+}
+
+int sibgpu_ctx::ensure_copy_stream(uint32_t nchunks)
+{
+	if(!copy_stream)
+	{
+		SIB_CUDA(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
+		SIB_CUDA(cudaEventCreateWithFlags(&ev_fork_copy, cudaEventDisableTiming));
+	}
+	while(ev_chunk.size() < nchunks)
+	{
+		cudaEvent_t e;
+		SIB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+		ev_chunk.push_back(e);
 	}
 	return SIBGPU_OK;
 }
@@ -117,6 +135,8 @@ int sibgpu_create(int device, sibgpu_ctx **out)
 		uint64_t v = strtoull(e, nullptr, 10);
 		if(v >= 1024) c->part_target = v;
 	}
+	if(const char *e = getenv("SIBGPU_PART_SLACK")) c->part_slack = strtoull(e, nullptr, 10);
+	if(const char *e = getenv("SIBGPU_EXACT_HIST")) c->exact_hist = atoi(e) != 0;
 	if(const char *e = getenv("SIBGPU_INSERT_VARIANT")) c->insert_variant = atoi(e);
 	if(const char *e = getenv("SIBGPU_STREAMS")) c->n_streams = atoi(e);
 	if(const char *e = getenv("SIBGPU_TABLE_FACTOR"))
@@ -148,13 +168,18 @@ void sibgpu_destroy(sibgpu_ctx *c)
 		if(c->ev_join[i]) cudaEventDestroy(c->ev_join[i]);
 	}
 	if(c->ev_fork) cudaEventDestroy(c->ev_fork);
+	for(cudaEvent_t e : c->ev_chunk) cudaEventDestroy(e);
+	if(c->ev_fork_copy) cudaEventDestroy(c->ev_fork_copy);
+	if(c->copy_stream) cudaStreamDestroy(c->copy_stream);
 	if(c->stream) cudaStreamDestroy(c->stream);
 	delete c;
 }
 
 void sibgpu_free(void *p) { free(p); }
 
-int sibgpu_upload(sibgpu_ctx *c, const char *const *chr, const uint64_t *len, uint32_t nchr)
+// Plans the text layout '$' chr0 '$' chr1 '$' ... '$' (the DNASequence layout, src/dnasequence.cpp:75-103), allocates,
+// fills the whole buffer with '$' and uploads the chromosome tables; the bases follow with copy_text_range.
+static int upload_layout(sibgpu_ctx *c, const char *const *chr, const uint64_t *len, uint32_t nchr)
 {
 	if(!c || (nchr && (!chr || !len)))
 	{
@@ -188,24 +213,24 @@ int sibgpu_upload(sibgpu_ctx *c, const char *const *chr, const uint64_t *len, ui
 	SIB_TRY(c->d_text.ensure(nwords * 16));
 	SIB_TRY(c->d_chr_start.ensure(sizeof(uint32_t) * (nchr + 1)));
 	SIB_TRY(c->d_chr_len.ensure(sizeof(uint32_t) * (nchr + 1)));
-	// text = '$' chr0 '$' chr1 '$' ... '$' (the DNASequence layout, src/dnasequence.cpp:75-103), '$'-padded
 	SIB_CUDA(cudaMemsetAsync(c->d_text.p, '$', nwords * 16, c->stream));
-	for(uint32_t i = 0; i < nchr; i++)
-	{
-		if(len[i])
-		{
-			SIB_CUDA(cudaMemcpyAsync(c->d_text.as<char>() + c->h_chr_start[i], chr[i], len[i], cudaMemcpyHostToDevice, c->stream));
-		}
-	}
 	if(nchr)
 	{
 		SIB_CUDA(cudaMemcpyAsync(c->d_chr_start.p, c->h_chr_start.data(), sizeof(uint32_t) * nchr, cudaMemcpyHostToDevice, c->stream));
 		SIB_CUDA(cudaMemcpyAsync(c->d_chr_len.p, c->h_chr_len.data(), sizeof(uint32_t) * nchr, cudaMemcpyHostToDevice, c->stream));
 	}
-	SIB_CUDA(cudaStreamSynchronize(c->stream));
 	c->nchr = nchr;
 	c->N = N;
 	c->M = M;
+	return SIBGPU_OK;
+}
+
+int sibgpu_upload(sibgpu_ctx *c, const char *const *chr, const uint64_t *len, uint32_t nchr)
+{
+	SIB_TRY(upload_layout(c, chr, len, nchr));
+	HostSrc src = {chr, len};
+	SIB_TRY(copy_text_range(c, src, 0, c->M, c->stream));
+	SIB_CUDA(cudaStreamSynchronize(c->stream));
 	c->have_text = true;
 	return SIBGPU_OK;
 }
@@ -224,7 +249,7 @@ int sibgpu_enumerate_resident(sibgpu_ctx *c, uint32_t k, uint64_t *ninst, uint32
 	}
 	SIB_CUDA(cudaSetDevice(c->device));
 	SIB_CUDA(cudaEventRecord(c->ev_begin, c->stream));
-	SIB_TRY(enumerate_resident(c, k));
+	SIB_TRY(enumerate_resident(c, k, nullptr));
 	SIB_CUDA(cudaEventRecord(c->ev_end, c->stream));
 	SIB_CUDA(cudaEventSynchronize(c->ev_end));
 	SIB_CUDA(cudaEventElapsedTime(&c->last_ms, c->ev_begin, c->ev_end));
@@ -268,9 +293,33 @@ int sibgpu_download(sibgpu_ctx *c, sibgpu_inst **pos, uint64_t *npos, sibgpu_ins
 int sibgpu_enumerate(sibgpu_ctx *c, const char *const *chr, const uint64_t *len, uint32_t nchr, uint32_t k,
 	sibgpu_inst **pos, uint64_t *npos, sibgpu_inst **neg, uint64_t *nneg, uint32_t *count)
 {
-	SIB_TRY(sibgpu_upload(c, chr, len, nchr));
-	SIB_TRY(sibgpu_enumerate_resident(c, k, nullptr, count));
-	return sibgpu_download(c, pos, npos, neg, nneg);
+	if(k == 0)
+	{
+		set_error("invalid: NULL context or k == 0");
+		return SIBGPU_ERR_INVALID;
+	}
+	// upload, pack and partition are pipelined piece by piece (enumerate.cu); the context ends up in the same state
+	// as after sibgpu_upload + sibgpu_enumerate_resident
+	static const bool trace = getenv("SIBGPU_TRACE") != nullptr;
+	const auto t0 = std::chrono::steady_clock::now();
+	SIB_TRY(upload_layout(c, chr, len, nchr));
+	HostSrc src = {chr, len};
+	SIB_CUDA(cudaEventRecord(c->ev_begin, c->stream));
+	SIB_TRY(enumerate_resident(c, k, &src));
+	c->have_text = true;
+	SIB_CUDA(cudaEventRecord(c->ev_end, c->stream));
+	SIB_CUDA(cudaEventSynchronize(c->ev_end));
+	SIB_CUDA(cudaEventElapsedTime(&c->last_ms, c->ev_begin, c->ev_end));
+	if(count) *count = c->n_vertices;
+	const int rc = sibgpu_download(c, pos, npos, neg, nneg);
+	if(trace)
+	{
+		const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+		fprintf(stderr, "[sibgpu_enumerate] N=%llu nchr=%u k=%u -> V=%u I=%llu  %.3f ms (device %.3f ms, %llu launches)\n",
+			(unsigned long long)c->N, nchr, k, c->n_vertices, (unsigned long long)c->n_inst, ms, c->last_ms,
+			(unsigned long long)c->total_launches);
+	}
+	return rc;
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -434,6 +483,7 @@ int sibgpu_kernel_stats(sibgpu_ctx *c, sibgpu_kernel_stat *out, int cap)
 }
 
 uint64_t sibgpu_last_launches(sibgpu_ctx *c) { return c ? c->total_launches : 0; }
+uint64_t sibgpu_partition_fallbacks(sibgpu_ctx *c) { return c ? c->hist_fallbacks : 0; }
 float sibgpu_last_device_ms(sibgpu_ctx *c) { return c ? c->last_ms : 0.f; }
 
 }

@@ -52,6 +52,14 @@ struct sibgpu_ctx {
 
 	// tunables (env SIBGPU_PART_RECORDS)
 	uint64_t part_target = 1u << 20;
+	uint64_t part_slack = 4096;                        // fixed-capacity partitions: mean + mean/8 + slack (env SIBGPU_PART_SLACK)
+	bool exact_hist = false;                           // always size the partitions with a histogram pass (env SIBGPU_EXACT_HIST)
+	uint64_t hist_fallbacks = 0;                       // times a fixed-capacity partition overflowed and the exact path ran
+	// pipelined upload (sibgpu_enumerate): copies on their own stream, one event per text piece
+	cudaStream_t copy_stream = nullptr;
+	cudaEvent_t ev_fork_copy = nullptr;
+	std::vector<cudaEvent_t> ev_chunk;
+	int ensure_copy_stream(uint32_t nchunks);
 	int insert_variant = 1;                            // 1 = CAS first, one record per thread (env SIBGPU_INSERT_VARIANT, dev)
 	int n_streams = 4;                                 // overlapped partition streams (env SIBGPU_STREAMS)
 	cudaStream_t aux_stream[8] = {};
@@ -92,7 +100,10 @@ struct ProfScope {
 	}
 };
 
-int enumerate_resident(sibgpu_ctx *ctx, uint32_t k);
+// the caller's chromosomes while sibgpu_enumerate streams them in (layout already planned by upload_layout)
+struct HostSrc { const char *const *chr; const uint64_t *len; };
+int copy_text_range(sibgpu_ctx *ctx, const HostSrc &src, uint64_t lo, uint64_t hi, cudaStream_t st);
+int enumerate_resident(sibgpu_ctx *ctx, uint32_t k, const HostSrc *src);
 int dist_scan(sibgpu_ctx *ctx, uint32_t k, uint32_t *hist_out);
 int dist_scatter(sibgpu_ctx *ctx, void *send_dev);
 int dist_group(sibgpu_ctx *ctx, const void *recv_dev, const uint32_t *counts, uint64_t *nkeys_local);

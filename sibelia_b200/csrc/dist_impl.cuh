@@ -52,7 +52,7 @@ static int dist_scatter_mode(sibgpu_ctx *ctx, uint32_t k, void *send_dev)
 		const uint32_t g = ntiles < (uint32_t)ctx->sm_count * 4 ? ntiles : (uint32_t)ctx->sm_count * 4;
 		ProfScope ps(ctx, "k_scatter", (uint64_t)ntiles * TILE_POS / 4 + ctx->dist_nrec_local * sizeof(Rec));
 		k_scatter<MODE><<<g, TILE_THREADS, smem, st>>>(t, nullptr, k, ntiles, ctx->dist_P_total,
-			ctx->d_cursor.as<unsigned long long>(), static_cast<Rec*>(send_dev));
+			ctx->d_cursor.as<unsigned long long>(), static_cast<Rec*>(send_dev), 0ull, nullptr);
 	}
 	SIB_CUDA(cudaStreamSynchronize(st));
 	return SIBGPU_OK;

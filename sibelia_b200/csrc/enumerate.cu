@@ -17,6 +17,7 @@
 // Both strands are handled with ONE record per text position: the record carries the canonical key
 // min(w, revcomp(w)) and the neighbour symbols re-expressed in the canonical orientation, so the class of w and the
 // class of revcomp(w) (which the reference enumerates separately and symmetrically) are decided once.
+#include <algorithm>
 #include <cub/cub.cuh>
 
 #include "enum_common.cuh"
@@ -177,9 +178,14 @@ template<int MODE> struct ScatterSmem {
 template<> struct ScatterSmem<1> : ScatterSmem<0> { uint64_t b[TILE_POS]; };
 template<> struct ScatterSmem<2> : ScatterSmem<1> {};
 
+// cap != 0: partition b owns the fixed region [b * cap, (b + 1) * cap) of `out` and cursor[b] starts at b * cap (no
+// histogram pass needed); a run that does not fit raises *overflow and is dropped -- the host then redoes the
+// partitioning with exact sizes (k_scan_hist + k_part_offsets, cap == 0).
+constexpr uint32_t RUN_DROPPED = 0x80000000u;
 template<int MODE>
 __global__ void __launch_bounds__(TILE_THREADS) k_scatter(TextDesc t, const Rec16 *__restrict__ fp, uint32_t k,
-	uint32_t ntiles, uint32_t P, unsigned long long *__restrict__ cursor, typename RecT<MODE>::type *__restrict__ out)
+	uint32_t ntiles, uint32_t P, unsigned long long *__restrict__ cursor, typename RecT<MODE>::type *__restrict__ out,
+	unsigned long long cap, uint32_t *__restrict__ overflow)
 {
 	extern __shared__ __align__(16) unsigned char smem_raw[];
 	ScatterSmem<MODE> &s = *reinterpret_cast<ScatterSmem<MODE>*>(smem_raw);
@@ -228,6 +234,11 @@ __global__ void __launch_bounds__(TILE_THREADS) k_scatter(TextDesc t, const Rec1
 				unsigned long long g = c[j] ? atomicAdd(&cursor[b], (unsigned long long)c[j]) : 0ull;
 				s.cnt[b] = o[j];
 				s.gbase[b] = g - o[j];
+				if(cap && c[j] && g + c[j] > (b + 1ull) * cap)
+				{
+					*overflow = 1u;
+					s.cnt[b] = o[j] | RUN_DROPPED;
+				}
 			}
 		}
 		if(threadIdx.x == 0) s.total = total;
@@ -240,10 +251,11 @@ __global__ void __launch_bounds__(TILE_THREADS) k_scatter(TextDesc t, const Rec1
 			if(valid & (1u << i))
 			{
 				uint32_t bin = binrank[i] >> 16, rank = binrank[i] & 0xFFFFu;
-				uint32_t l = s.cnt[bin] + rank;
+				const uint32_t first = s.cnt[bin];
+				uint32_t l = (first & ~RUN_DROPPED) + rank;
 				s.a[l] = ra[i];
 				if(MODE != 0) static_cast<ScatterSmem<1>&>(s).b[l] = rb[i];
-				s.bin_of[l] = (uint16_t)bin;
+				s.bin_of[l] = (first & RUN_DROPPED) ? (uint16_t)0xFFFFu : (uint16_t)bin;
 			}
 		}
 		__syncthreads();
@@ -252,7 +264,9 @@ __global__ void __launch_bounds__(TILE_THREADS) k_scatter(TextDesc t, const Rec1
 		const uint32_t n = s.total;
 		for(uint32_t l = threadIdx.x; l < n; l += TILE_THREADS)
 		{
-			unsigned long long g = s.gbase[s.bin_of[l]] + l;
+			const uint32_t bin = s.bin_of[l];
+			if(bin == 0xFFFFu) continue;
+			unsigned long long g = s.gbase[bin] + l;
 			if(MODE == 0) { reinterpret_cast<uint64_t*>(out)[g] = s.a[l]; }
 			else
 			{
@@ -889,8 +903,43 @@ static int ids_and_tables(sibgpu_ctx *ctx, const TextDesc &t, uint32_t k, const 
 	return SIBGPU_OK;
 }
 
+// Copies the bytes [lo, hi) of the concatenated text from the caller's chromosomes (the separators are already there).
+int copy_text_range(sibgpu_ctx *ctx, const HostSrc &src, uint64_t lo, uint64_t hi, cudaStream_t st)
+{
+	const std::vector<uint32_t> &cs = ctx->h_chr_start;
+	size_t c = std::upper_bound(cs.begin(), cs.end(), (uint32_t)lo) - cs.begin();
+	if(c > 0) c--;
+	for(; c < ctx->nchr && cs[c] < hi; c++)
+	{
+		const uint64_t s = cs[c], e = s + ctx->h_chr_len[c];
+		const uint64_t a = s > lo ? s : lo, b = e < hi ? e : hi;
+		if(b > a) SIB_CUDA(cudaMemcpyAsync(ctx->d_text.as<char>() + a, src.chr[c] + (a - s), b - a, cudaMemcpyHostToDevice, st));
+	}
+	return SIBGPU_OK;
+}
+
+static int launch_pack(sibgpu_ctx *ctx, uint64_t w0, uint64_t w1)
+{
+	uint32_t *d_err = reinterpret_cast<uint32_t*>(ctx->d_scalars.as<uint64_t>() + 8);
+	ProfScope ps(ctx, "k_pack", (w1 - w0) * 20);
+	k_pack<<<grid_for(w1 - w0, 256, ctx->sm_count, 8), 256, 0, ctx->stream>>>(ctx->d_text.as<uint4>() + w0,
+		ctx->d_packed.as<uint32_t>() + w0, (uint32_t)(w1 - w0), d_err);
+	return SIBGPU_OK;
+}
+
+static int input_error()
+{
+	set_error("input: a character outside ACGT reached the device; sanitise first (indexedsequence.cpp:31-37)");
+	return SIBGPU_ERR_INPUT;
+}
+
+// src != nullptr: the text is still on the host (sibgpu_enumerate); it is streamed in CHUNK_TILES-tile pieces on the
+// copy stream while the pack and scatter kernels of the previous pieces run (exact modes; the layout, the '$'
+// separators and the chromosome tables are already on the device).  src == nullptr: text resident and packed.
+constexpr uint32_t CHUNK_TILES = 2048;                 // 8 Mi text positions per piece
+
 template<int MODE>
-static int enumerate_mode(sibgpu_ctx *ctx, uint32_t k, uint64_t nrec)
+static int enumerate_mode(sibgpu_ctx *ctx, uint32_t k, uint64_t nrec, const HostSrc *src)
 {
 	typedef typename RecT<MODE>::type Rec;
 	cudaStream_t st = ctx->stream;
@@ -907,6 +956,8 @@ static int enumerate_mode(sibgpu_ctx *ctx, uint32_t k, uint64_t nrec)
 	t.nwords = (uint32_t)((ctx->M + 15) / 16) + 8;
 	t.tile0 = 0;
 	const uint32_t ntiles = (uint32_t)((ctx->M + TILE_POS - 1) / TILE_POS);
+	const size_t scatter_smem = sizeof(ScatterSmem<MODE>);
+	SIB_CUDA(cudaFuncSetAttribute(k_scatter<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scatter_smem));
 
 	for(uint32_t attempt = 0; ; attempt++)
 	{
@@ -921,41 +972,132 @@ static int enumerate_mode(sibgpu_ctx *ctx, uint32_t k, uint64_t nrec)
 		SIB_TRY(ctx->d_cursor.ensure(sizeof(uint64_t) * MAX_PARTS));
 		SIB_TRY(ctx->d_partcnt.ensure(sizeof(uint32_t) * MAX_PARTS));
 		SIB_TRY(ctx->d_keyoff.ensure(sizeof(uint64_t) * (MAX_PARTS + 1)));
-		SIB_TRY(ctx->d_records.ensure(sizeof(Rec) * nrec));
-		SIB_CUDA(cudaMemsetAsync(ctx->d_hist.p, 0, sizeof(uint32_t) * MAX_PARTS, st));
 		SIB_CUDA(cudaMemsetAsync(ctx->d_partcnt.p, 0, sizeof(uint32_t) * MAX_PARTS, st));
+		std::vector<uint64_t> part_base(P + 1), part_cnt(P);
+		uint64_t maxpart = 0;
+		bool have_records = false;
 
-		const uint32_t scan_grid = ntiles < (uint32_t)sms * 8 ? ntiles : (uint32_t)sms * 8;
+		// ---- fast path: no histogram pass.  Hash partitions of distinct k-mers are balanced to a few sigma, so every
+		// partition gets a fixed region of mean + 1/8 (+ 4096) records; a partition that outgrows it (a k-mer repeated
+		// millions of times) raises the overflow flag and the exact two-pass partitioning below takes over.
+		if(!ctx->exact_hist)
 		{
-			ProfScope ps(ctx, "k_scan_hist", MODE == 2 ? ctx->M * 16 : ctx->M / 4);
-			k_scan_hist<MODE><<<scan_grid, TILE_THREADS, 0, st>>>(t, fp, k, ntiles, P, ctx->d_hist.as<uint32_t>());
+			const uint64_t mean = (nrec + P - 1) / P;
+			const uint64_t cap = P == 1 ? nrec : mean + mean / 8 + ctx->part_slack;
+			SIB_TRY(ctx->d_records.ensure(sizeof(Rec) * cap * P));
+			for(uint32_t p = 0; p <= P; p++) part_base[p] = (uint64_t)p * cap;
+			SIB_CUDA(cudaMemcpyAsync(ctx->d_cursor.p, part_base.data(), sizeof(uint64_t) * P, cudaMemcpyHostToDevice, st));
+			SIB_CUDA(cudaMemcpyAsync(ctx->d_partoff.p, part_base.data(), sizeof(uint64_t) * (P + 1), cudaMemcpyHostToDevice, st));
+			uint32_t *d_overflow = reinterpret_cast<uint32_t*>(ds + 10);
+			const uint32_t nchunks = src ? (ntiles + CHUNK_TILES - 1) / CHUNK_TILES : 1;
+			if(src)
+			{
+				SIB_TRY(ctx->ensure_copy_stream(nchunks));
+				SIB_CUDA(cudaEventRecord(ctx->ev_fork_copy, st));              // the '$' fill and the tables precede the copies
+				SIB_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_fork_copy, 0));
+				for(uint32_t c = 0; c < nchunks; c++)
+				{
+					const uint64_t lo = (uint64_t)c * CHUNK_TILES * TILE_POS;
+					const uint64_t hi = c + 1 == nchunks ? ctx->M : lo + (uint64_t)CHUNK_TILES * TILE_POS;
+					SIB_TRY(copy_text_range(ctx, *src, lo, hi, ctx->copy_stream));
+					SIB_CUDA(cudaEventRecord(ctx->ev_chunk[c], ctx->copy_stream));
+				}
+			}
+			uint32_t tiles_done = 0;
+			for(uint32_t c = 0; c < nchunks; c++)
+			{
+				uint32_t tile_hi = ntiles;
+				if(src)
+				{
+					// pack the words of this piece; scatter the tiles whose staged words (one behind, 260 ahead) are packed
+					const uint64_t w0 = (uint64_t)c * CHUNK_TILES * TILE_THREADS;
+					const uint64_t w1 = c + 1 == nchunks ? t.nwords : w0 + (uint64_t)CHUNK_TILES * TILE_THREADS;
+					SIB_CUDA(cudaStreamWaitEvent(st, ctx->ev_chunk[c], 0));
+					SIB_TRY(launch_pack(ctx, w0, w1));
+					if(c + 1 < nchunks) tile_hi = (uint32_t)((w1 - 261) / TILE_THREADS);
+				}
+				if(tile_hi > tiles_done)
+				{
+					const uint32_t nt = tile_hi - tiles_done;
+					const uint32_t g = nt < (uint32_t)sms * 4 ? nt : (uint32_t)sms * 4;
+					TextDesc tc = t;
+					tc.tile0 = tiles_done;
+					ProfScope ps(ctx, "k_scatter", (MODE == 2 ? (uint64_t)nt * TILE_POS * 16 : (uint64_t)nt * TILE_POS / 4)
+						+ nrec * sizeof(Rec) * nt / ntiles);
+					k_scatter<MODE><<<g, TILE_THREADS, scatter_smem, st>>>(tc, fp, k, nt, P, ctx->d_cursor.as<unsigned long long>(),
+						ctx->d_records.as<Rec>(), cap, d_overflow);
+					tiles_done = tile_hi;
+				}
+			}
+			SIB_CUDA(cudaMemcpyAsync(part_cnt.data(), ctx->d_cursor.p, sizeof(uint64_t) * P, cudaMemcpyDeviceToHost, st));
+			SIB_CUDA(cudaMemcpyAsync(hs + 8, ds + 8, sizeof(uint64_t) * 3, cudaMemcpyDeviceToHost, st));
+			SIB_CUDA(cudaStreamSynchronize(st));
+			if(hs[8] & 1u) return input_error();
+			src = nullptr;                                 // the whole text is resident and packed from here on
+			if(hs[10] & 0xFFFFFFFFull)
+			{
+				SIB_CUDA(cudaMemsetAsync(ds + 10, 0, sizeof(uint64_t), st));
+				ctx->hist_fallbacks++;
+			}
+			else
+			{
+				uint64_t total = 0;
+				for(uint32_t p = 0; p < P; p++)
+				{
+					part_cnt[p] -= part_base[p];
+					total += part_cnt[p];
+					if(part_cnt[p] > maxpart) maxpart = part_cnt[p];
+				}
+				if(total != nrec)
+				{
+					set_error("internal: scatter kernel wrote " + std::to_string(total) + " k-mers, expected " + std::to_string(nrec));
+					return SIBGPU_ERR_INTERNAL;
+				}
+				have_records = true;
+			}
 		}
+		else if(src)
 		{
-			ProfScope ps(ctx, "k_part_offsets", 0);
-			k_part_offsets<<<1, MAX_PARTS, 0, st>>>(ctx->d_hist.as<uint32_t>(), P, ctx->d_partoff.as<uint64_t>(),
-				ctx->d_cursor.as<unsigned long long>(), ds);
+			SIB_TRY(copy_text_range(ctx, *src, 0, ctx->M, st));
+			SIB_TRY(launch_pack(ctx, 0, t.nwords));
+			SIB_CUDA(cudaMemcpyAsync(hs + 8, ds + 8, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+			SIB_CUDA(cudaStreamSynchronize(st));
+			if(hs[8] & 1u) return input_error();
+			src = nullptr;
 		}
-		SIB_CUDA(cudaMemcpyAsync(hs, ds, sizeof(uint64_t) * 2, cudaMemcpyDeviceToHost, st));
-		SIB_CUDA(cudaStreamSynchronize(st));
-		if(hs[0] != nrec)
-		{
-			set_error("internal: scan kernel counted " + std::to_string(hs[0]) + " k-mers, expected " + std::to_string(nrec));
-			return SIBGPU_ERR_INTERNAL;
-		}
-		const uint64_t maxpart = hs[1];
-		std::vector<uint64_t> h_partoff(P + 1);
-		SIB_CUDA(cudaMemcpyAsync(h_partoff.data(), ctx->d_partoff.p, sizeof(uint64_t) * (P + 1), cudaMemcpyDeviceToHost, st));
 
-		// ---- scatter
+		// ---- exact path: histogram pass, prefix sums, scatter into exactly sized partitions
+		if(!have_records)
 		{
-			size_t smem = sizeof(ScatterSmem<MODE>);
-			SIB_CUDA(cudaFuncSetAttribute(k_scatter<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-			const uint32_t g = ntiles < (uint32_t)sms * 4 ? ntiles : (uint32_t)sms * 4;
-			ProfScope ps(ctx, "k_scatter", (MODE == 2 ? ctx->M * 16 : ctx->M / 4) + nrec * sizeof(Rec));
-			k_scatter<MODE><<<g, TILE_THREADS, smem, st>>>(t, fp, k, ntiles, P, ctx->d_cursor.as<unsigned long long>(),
-				ctx->d_records.as<Rec>());
+			SIB_TRY(ctx->d_records.ensure(sizeof(Rec) * nrec));
+			SIB_CUDA(cudaMemsetAsync(ctx->d_hist.p, 0, sizeof(uint32_t) * MAX_PARTS, st));
+			const uint32_t scan_grid = ntiles < (uint32_t)sms * 8 ? ntiles : (uint32_t)sms * 8;
+			{
+				ProfScope ps(ctx, "k_scan_hist", MODE == 2 ? ctx->M * 16 : ctx->M / 4);
+				k_scan_hist<MODE><<<scan_grid, TILE_THREADS, 0, st>>>(t, fp, k, ntiles, P, ctx->d_hist.as<uint32_t>());
+			}
+			{
+				ProfScope ps(ctx, "k_part_offsets", 0);
+				k_part_offsets<<<1, MAX_PARTS, 0, st>>>(ctx->d_hist.as<uint32_t>(), P, ctx->d_partoff.as<uint64_t>(),
+					ctx->d_cursor.as<unsigned long long>(), ds);
+			}
+			SIB_CUDA(cudaMemcpyAsync(hs, ds, sizeof(uint64_t) * 2, cudaMemcpyDeviceToHost, st));
+			SIB_CUDA(cudaMemcpyAsync(part_base.data(), ctx->d_partoff.p, sizeof(uint64_t) * (P + 1), cudaMemcpyDeviceToHost, st));
+			SIB_CUDA(cudaStreamSynchronize(st));
+			if(hs[0] != nrec)
+			{
+				set_error("internal: scan kernel counted " + std::to_string(hs[0]) + " k-mers, expected " + std::to_string(nrec));
+				return SIBGPU_ERR_INTERNAL;
+			}
+			maxpart = hs[1];
+			for(uint32_t p = 0; p < P; p++) part_cnt[p] = part_base[p + 1] - part_base[p];
+			{
+				const uint32_t g = ntiles < (uint32_t)sms * 4 ? ntiles : (uint32_t)sms * 4;
+				ProfScope ps(ctx, "k_scatter", (MODE == 2 ? ctx->M * 16 : ctx->M / 4) + nrec * sizeof(Rec));
+				k_scatter<MODE><<<g, TILE_THREADS, scatter_smem, st>>>(t, fp, k, ntiles, P, ctx->d_cursor.as<unsigned long long>(),
+					ctx->d_records.as<Rec>(), 0ull, nullptr);
+			}
 		}
-		SIB_CUDA(cudaStreamSynchronize(st));
 
 		// ---- per-partition L2-resident grouping
 		uint64_t T64 = (uint64_t)ctx->table_factor * maxpart + 1024;
@@ -986,9 +1128,9 @@ static int enumerate_mode(sibgpu_ctx *ctx, uint32_t k, uint64_t nrec)
 			if(phase_span) ctx->prof_begin("k_insert+k_table_scan", nrec * sizeof(Rec));
 			for(uint32_t p = 0; p < P; p++)
 			{
-				const uint64_t n = h_partoff[p + 1] - h_partoff[p];
+				const uint64_t n = part_cnt[p];
 				if(n == 0) continue;
-				Rec *part = ctx->d_records.as<Rec>() + h_partoff[p];
+				Rec *part = ctx->d_records.as<Rec>() + part_base[p];
 				cudaStream_t ps_st = S > 1 ? ctx->aux_stream[p % S] : st;
 				void *table = static_cast<char*>(ctx->d_table.p) + table_bytes * (p % S);
 				ctx->total_launches += 2;
@@ -1054,7 +1196,7 @@ static int enumerate_mode(sibgpu_ctx *ctx, uint32_t k, uint64_t nrec)
 	}
 }
 
-int enumerate_resident(sibgpu_ctx *ctx, uint32_t k)
+int enumerate_resident(sibgpu_ctx *ctx, uint32_t k, const HostSrc *src)
 {
 	cudaStream_t st = ctx->stream;
 	ctx->have_result = false;
@@ -1062,25 +1204,11 @@ int enumerate_resident(sibgpu_ctx *ctx, uint32_t k)
 	ctx->total_launches = 0;
 	SIB_CUDA(cudaSetDevice(ctx->device));
 
-	// K0: pack (+ legality)
 	const uint32_t nwords = (uint32_t)((ctx->M + 15) / 16) + 8;
 	SIB_TRY(ctx->d_packed.ensure(sizeof(uint32_t) * (size_t)nwords));
 	SIB_TRY(ctx->d_scalars.ensure(sizeof(uint64_t) * 64));
 	SIB_CUDA(cudaMemsetAsync(ctx->d_scalars.p, 0, sizeof(uint64_t) * 64, st));
-	uint32_t *d_err = reinterpret_cast<uint32_t*>(ctx->d_scalars.as<uint64_t>() + 8);
-	{
-		ProfScope ps(ctx, "k_pack", ctx->M + ctx->M / 4);
-		k_pack<<<grid_for(nwords, 256, ctx->sm_count, 8), 256, 0, st>>>(ctx->d_text.as<uint4>(), ctx->d_packed.as<uint32_t>(),
-			nwords, d_err);
-	}
 	uint64_t *hs = static_cast<uint64_t*>(ctx->h_scalars);
-	SIB_CUDA(cudaMemcpyAsync(hs + 8, ctx->d_scalars.as<uint64_t>() + 8, 8, cudaMemcpyDeviceToHost, st));
-	SIB_CUDA(cudaStreamSynchronize(st));
-	if(hs[8] & 1u)
-	{
-		set_error("input: a character outside ACGT reached the device; sanitise first (indexedsequence.cpp:31-37)");
-		return SIBGPU_ERR_INPUT;
-	}
 
 	uint64_t nrec = 0;
 	for(uint32_t c = 0; c < ctx->nchr; c++)
@@ -1088,15 +1216,27 @@ int enumerate_resident(sibgpu_ctx *ctx, uint32_t k)
 		if(ctx->h_chr_len[c] >= k) nrec += ctx->h_chr_len[c] - k + 1;
 	}
 	ctx->last_k = k;
+	// K0: pack (+ legality).  With a host source and an exact mode the packing is pipelined with the upload inside
+	// enumerate_mode; otherwise the whole text is brought in (if needed) and packed here.
+	const bool pipelined = src && nrec > 0 && k <= 32;
+	if(!pipelined)
+	{
+		if(src) SIB_TRY(copy_text_range(ctx, *src, 0, ctx->M, st));
+		src = nullptr;
+		SIB_TRY(launch_pack(ctx, 0, nwords));
+		SIB_CUDA(cudaMemcpyAsync(hs + 8, ctx->d_scalars.as<uint64_t>() + 8, 8, cudaMemcpyDeviceToHost, st));
+		SIB_CUDA(cudaStreamSynchronize(st));
+		if(hs[8] & 1u) return input_error();
+	}
 	int rc = SIBGPU_OK;
 	if(nrec == 0)
 	{
 		ctx->n_inst = 0;
 		ctx->n_vertices = 0;
 	}
-	else if(k <= 28) rc = enumerate_mode<0>(ctx, k, nrec);
-	else if(k <= 32) rc = enumerate_mode<1>(ctx, k, nrec);
-	else rc = enumerate_mode<2>(ctx, k, nrec);
+	else if(k <= 28) rc = enumerate_mode<0>(ctx, k, nrec, src);
+	else if(k <= 32) rc = enumerate_mode<1>(ctx, k, nrec, src);
+	else rc = enumerate_mode<2>(ctx, k, nrec, nullptr);
 	if(rc != SIBGPU_OK) return rc;
 	SIB_CUDA(cudaGetLastError());
 	ctx->have_result = true;

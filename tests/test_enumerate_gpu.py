@@ -102,6 +102,69 @@ def test_multi_partition_path(built):
     c.close()
 
 
+def _ctx_with_env(**env):
+    import sibelia_b200 as sb
+    old = {k: os.environ.get(k) for k in env}
+    os.environ.update({k: str(v) for k, v in env.items()})
+    try:
+        return sb.Context(0)
+    finally:
+        for k, v in old.items():
+            if v is None:
+                del os.environ[k]
+            else:
+                os.environ[k] = v
+
+
+def test_partition_overflow_falls_back_to_exact_sizes(built):
+    """Fixed-capacity hash partitions (no histogram pass) overflow when one k-mer is repeated very often; the
+    enumeration must notice, redo the partitioning with exact sizes and still match the oracle."""
+    c = _ctx_with_env(SIBGPU_PART_RECORDS=4096, SIBGPU_PART_SLACK=64)
+    rnd = synth.random_genome(60_000, 4)
+    poly = np.full(50_000, ord("A"), dtype=np.uint8)                  # 50 000 identical k-mers -> one partition
+    chrs = [np.concatenate([rnd[:30_000], poly, rnd[30_000:]]), synth.revcomp(rnd[10_000:40_000])]
+    before = c.partition_fallbacks()
+    for k in (25, 30):
+        helpers.assert_tables_equal(c.enumerate(chrs, k), restate.enumerate_bifurcations(chrs, k), "overflow k=%d" % k)
+    assert c.partition_fallbacks() >= before + 2
+    # balanced input on the same context: no fallback
+    st = helpers.strain_case(4, 50_000, seed=98)
+    before = c.partition_fallbacks()
+    helpers.assert_tables_equal(c.enumerate(st, 25), restate.enumerate_bifurcations(st, 25), "balanced")
+    assert c.partition_fallbacks() == before
+    c.close()
+
+
+def test_exact_histogram_mode_matches(built):
+    c = _ctx_with_env(SIBGPU_PART_RECORDS=8192, SIBGPU_EXACT_HIST=1)
+    st = helpers.strain_case(3, 70_000, seed=97)
+    for k in (25, 32, 40):
+        helpers.assert_tables_equal(c.enumerate(st, k), restate.enumerate_bifurcations(st, k), "exact-hist k=%d" % k)
+    c.close()
+
+
+def test_pipelined_upload_many_pieces(ctx):
+    """sibgpu_enumerate streams the text in 8 Mi-position pieces (copy / pack / scatter overlapped); chromosome and
+    piece boundaries must not matter: same tables as upload + enumerate_resident, which packs in one launch."""
+    g = synth.random_genome(9_000_000, 77)
+
+    def mutated(x, seed):
+        y = x.copy()
+        at = np.random.default_rng(seed).integers(0, len(y), len(y) // 100)
+        y[at] = helpers.ACGT[(np.searchsorted(helpers.ACGT, y[at]) + 1) % 4]
+        return y
+    chrs = [g[:8_388_000], synth.revcomp(mutated(g[1_000_000:1_400_000], 1)), g[8_388_000:],
+            mutated(g[8_200_000:8_500_000], 2)]                        # a chromosome boundary near the first piece edge
+    for k in (25, 31):
+        got = ctx.enumerate(chrs, k)
+        ctx.upload(chrs)
+        count, ninst = ctx.enumerate_resident(k)
+        pos, neg = ctx.download()
+        helpers.assert_tables_equal(got, (count, pos, neg), "pipelined vs resident k=%d" % k)
+        assert count > 1000
+    helpers.assert_tables_equal(got, restate.enumerate_bifurcations(chrs, 31), "pipelined vs oracle")
+
+
 def test_rejects_unsanitised_input(ctx):
     import sibelia_b200 as sb
     with pytest.raises(sb.SibgpuError) as e:
