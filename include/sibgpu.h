@@ -142,6 +142,26 @@ int sibgpu_dist_group(sibgpu_ctx *ctx, const void *recv_dev, const uint32_t *cou
 int sibgpu_dist_keys(sibgpu_ctx *ctx, void *keys_dev);
 int sibgpu_dist_finish(sibgpu_ctx *ctx, const void *allkeys_dev, uint64_t nkeys_total, uint64_t *ninst_local, uint32_t *count);
 
+/* Peer variant of the same sharded enumeration: no histogram pass and no separate exchange step.
+ *
+ *   sibgpu_dist_scatter_local  pack + scatter the own text range into the context's own send buffer: one segment of
+ *                              *seg_cap records per GLOBAL partition p (at record index p * seg_cap); counts[p] =
+ *                              records written to segment p (counts must hold 1024 entries).  *overflow != 0: a
+ *                              segment did not fit (a k-mer repeated very often) -- use the histogram path above.
+ *   sibgpu_dist_export_send    CUDA IPC handle (64 bytes) of the send buffer
+ *   [all_gather: counts, seg_cap, overflow, handle -- this is also the barrier after which every send buffer is final]
+ *   sibgpu_dist_import_peers   handles[world][64]: maps the other ranks' send buffers (cached while unchanged)
+ *   sibgpu_dist_group_peer     counts[world][nparts_total], seg_caps[world]: for every owned partition the insert kernel
+ *                              reads its `world` segments directly from the peers' send buffers over NVLink (the
+ *                              exchange is fused into the grouping kernel; nothing is received into a buffer)
+ *   [all_gather keys (sibgpu_dist_keys) -- also the barrier before any send buffer may be rewritten]
+ *   sibgpu_dist_finish         as above
+ */
+int sibgpu_dist_scatter_local(sibgpu_ctx *ctx, uint32_t k, uint32_t *nparts_total, uint64_t *counts, uint64_t *seg_cap, int *overflow);
+int sibgpu_dist_export_send(sibgpu_ctx *ctx, void *handle64);
+int sibgpu_dist_import_peers(sibgpu_ctx *ctx, const void *handles);
+int sibgpu_dist_group_peer(sibgpu_ctx *ctx, const uint64_t *counts, const uint64_t *seg_caps, uint64_t *nkeys_local);
+
 /* Test hook (host only, no GPU needed): iteration order of the reference's boost::unordered_map<size_t, BranchData>
  * (Boost 1.54, src/bulgeremoval.cpp:168,203-215) after inserting n distinct keys in the given order, as restated in
  * sibelia_b200/csrc/boost_order.h.  out receives the n keys in begin()..end() order. */

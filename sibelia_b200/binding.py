@@ -14,6 +14,7 @@ SYMBOLS = [
     "sibgpu_enumerate", "sibgpu_upload", "sibgpu_enumerate_resident", "sibgpu_download", "sibgpu_set_profiling",
     "sibgpu_kernel_stats", "sibgpu_last_launches", "sibgpu_partition_fallbacks", "sibgpu_last_device_ms", "sibgpu_simplify", "sibgpu_debug_unordered_order", "sibgpu_dist_upload", "sibgpu_dist_scan", "sibgpu_dist_record_bytes",
     "sibgpu_dist_scatter", "sibgpu_dist_group", "sibgpu_dist_keys", "sibgpu_dist_finish",
+    "sibgpu_dist_scatter_local", "sibgpu_dist_export_send", "sibgpu_dist_import_peers", "sibgpu_dist_group_peer",
 ]
 
 
@@ -185,6 +186,31 @@ class Context:
         counts = np.ascontiguousarray(counts, dtype=np.uint32)
         nkeys = C.c_uint64()
         _check(load().sibgpu_dist_group(self._h, C.c_void_p(recv_ptr), C.c_void_p(counts.ctypes.data), C.byref(nkeys)))
+        return nkeys.value
+
+    # -- peer variant: fixed-capacity segments in the own send buffer, peers read them over NVLink (CUDA IPC)
+    def dist_scatter_local(self, k):
+        counts = np.zeros(1024, dtype=np.uint64)
+        nparts, cap, ovf = C.c_uint32(), C.c_uint64(), C.c_int()
+        _check(load().sibgpu_dist_scatter_local(self._h, C.c_uint32(k), C.byref(nparts), C.c_void_p(counts.ctypes.data),
+                                                C.byref(cap), C.byref(ovf)))
+        return nparts.value, counts[:nparts.value].copy(), cap.value, bool(ovf.value)
+
+    def dist_export_send(self):
+        h = np.zeros(64, dtype=np.uint8)
+        _check(load().sibgpu_dist_export_send(self._h, C.c_void_p(h.ctypes.data)))
+        return h
+
+    def dist_import_peers(self, handles):
+        handles = np.ascontiguousarray(handles, dtype=np.uint8)
+        _check(load().sibgpu_dist_import_peers(self._h, C.c_void_p(handles.ctypes.data)))
+
+    def dist_group_peer(self, counts, seg_caps):
+        counts = np.ascontiguousarray(counts, dtype=np.uint64)
+        seg_caps = np.ascontiguousarray(seg_caps, dtype=np.uint64)
+        nkeys = C.c_uint64()
+        _check(load().sibgpu_dist_group_peer(self._h, C.c_void_p(counts.ctypes.data), C.c_void_p(seg_caps.ctypes.data),
+                                             C.byref(nkeys)))
         return nkeys.value
 
     def dist_keys(self, keys_ptr):

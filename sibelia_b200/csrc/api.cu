@@ -157,6 +157,11 @@ void sibgpu_destroy(sibgpu_ctx *c)
 		&c->d_map, &c->d_filter, &c->d_hitmask, &c->d_tilecnt, &c->d_tileoff, &c->d_pos, &c->d_negtmp, &c->d_neg,
 		&c->d_chrinst, &c->d_scalars, &c->d_fp, &c->d_rep, &c->d_order, &c->d_s_ch, &c->d_s_m0, &c->d_s_m1, &c->d_s_off,
 		&c->d_s_inst, &c->d_s_flag};
+	for(void *pp : c->peer_ptr)
+	{
+		if(pp) cudaIpcCloseMemHandle(pp);
+	}
+	c->d_keystage.release();
 	for(DevBuf *b : bufs) b->release();
 	for(cudaEvent_t e : c->event_pool) cudaEventDestroy(e);
 	if(c->h_scalars) cudaFreeHost(c->h_scalars);
@@ -459,6 +464,79 @@ int sibgpu_dist_finish(sibgpu_ctx *c, const void *allkeys_dev, uint64_t nkeys_to
 	if(ninst_local) *ninst_local = c->n_inst;
 	if(count) *count = c->n_vertices;
 	return SIBGPU_OK;
+}
+
+int sibgpu_dist_scatter_local(sibgpu_ctx *c, uint32_t k, uint32_t *nparts_total, uint64_t *counts, uint64_t *seg_cap, int *overflow)
+{
+	if(!c || !counts || !nparts_total || !seg_cap || !overflow || k == 0 || k > 32)
+	{
+		set_error("invalid: the sharded path supports 1 <= k <= 32");
+		return SIBGPU_ERR_INVALID;
+	}
+	if(!c->have_text)
+	{
+		set_error("state: sibgpu_dist_upload must come first");
+		return SIBGPU_ERR_STATE;
+	}
+	SIB_CUDA(cudaSetDevice(c->device));
+	SIB_CUDA(cudaEventRecord(c->ev_begin, c->stream));
+	SIB_TRY(dist_scatter_local(c, k, counts, seg_cap, overflow));
+	*nparts_total = c->dist_P_total;
+	return SIBGPU_OK;
+}
+
+int sibgpu_dist_export_send(sibgpu_ctx *c, void *handle64)
+{
+	if(!c || !handle64 || !c->d_records.p)
+	{
+		set_error("invalid: NULL argument or no send buffer yet (sibgpu_dist_scatter_local comes first)");
+		return SIBGPU_ERR_INVALID;
+	}
+	static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+	SIB_CUDA(cudaSetDevice(c->device));
+	cudaIpcMemHandle_t h;
+	SIB_CUDA(cudaIpcGetMemHandle(&h, c->d_records.p));
+	memcpy(handle64, &h, 64);
+	return SIBGPU_OK;
+}
+
+int sibgpu_dist_import_peers(sibgpu_ctx *c, const void *handles)
+{
+	if(!c || !handles)
+	{
+		set_error("invalid: NULL argument");
+		return SIBGPU_ERR_INVALID;
+	}
+	SIB_CUDA(cudaSetDevice(c->device));
+	const uint32_t W = c->dist_world;
+	c->peer_ptr.resize(W, nullptr);
+	c->peer_handle.resize(W);
+	for(uint32_t s = 0; s < W; s++)
+	{
+		if(s == c->dist_rank) continue;
+		const unsigned char *h = static_cast<const unsigned char*>(handles) + 64 * (size_t)s;
+		if(c->peer_ptr[s] && c->peer_handle[s].size() == 64 && memcmp(c->peer_handle[s].data(), h, 64) == 0) continue;
+		if(c->peer_ptr[s])
+		{
+			cudaIpcCloseMemHandle(c->peer_ptr[s]);
+			c->peer_ptr[s] = nullptr;
+		}
+		cudaIpcMemHandle_t ih;
+		memcpy(&ih, h, 64);
+		SIB_CUDA(cudaIpcOpenMemHandle(&c->peer_ptr[s], ih, cudaIpcMemLazyEnablePeerAccess));
+		c->peer_handle[s].assign(h, h + 64);
+	}
+	return SIBGPU_OK;
+}
+
+int sibgpu_dist_group_peer(sibgpu_ctx *c, const uint64_t *counts, const uint64_t *seg_caps, uint64_t *nkeys_local)
+{
+	if(!c || !counts || !seg_caps || !nkeys_local)
+	{
+		set_error("invalid: NULL argument");
+		return SIBGPU_ERR_INVALID;
+	}
+	return dist_group_peer(c, counts, seg_caps, nkeys_local);
 }
 
 int sibgpu_set_profiling(sibgpu_ctx *c, int enabled)

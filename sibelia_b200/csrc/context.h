@@ -48,6 +48,11 @@ struct sibgpu_ctx {
 	uint32_t dist_rank = 0, dist_world = 1, dist_tile_lo = 0, dist_tile_hi = 0, dist_P_local = 0, dist_P_total = 0;
 	uint64_t dist_byte_lo = 0, dist_byte_hi = 0, dist_nrec_local = 0, dist_nkeys_local = 0;
 	bool dist_result = false;
+	// peer path: fixed-capacity segments in the own send buffer (d_records), peers' send buffers mapped through CUDA IPC
+	uint64_t dist_seg_cap = 0;
+	std::vector<void*> peer_ptr;                       // [world], nullptr for the own rank / not mapped
+	std::vector<std::vector<unsigned char>> peer_handle;
+	sibgpu::DevBuf d_keystage;
 	sibgpu::TextDesc dist_text = {};
 
 	// tunables (env SIBGPU_PART_RECORDS)
@@ -108,4 +113,6 @@ int dist_scan(sibgpu_ctx *ctx, uint32_t k, uint32_t *hist_out);
 int dist_scatter(sibgpu_ctx *ctx, void *send_dev);
 int dist_group(sibgpu_ctx *ctx, const void *recv_dev, const uint32_t *counts, uint64_t *nkeys_local);
 int dist_finish(sibgpu_ctx *ctx, const void *allkeys_dev, uint64_t nkeys_total);
+int dist_scatter_local(sibgpu_ctx *ctx, uint32_t k, uint64_t *counts_out, uint64_t *seg_cap_out, int *overflow_out);
+int dist_group_peer(sibgpu_ctx *ctx, const uint64_t *counts, const uint64_t *seg_caps, uint64_t *nkeys_local);
 } // namespace sibgpu

@@ -168,7 +168,8 @@ static int dist_finish_mode(sibgpu_ctx *ctx, uint32_t k, const void *allkeys_dev
 		ntiles ? ntiles : 0, nullptr, false, &collision);
 }
 
-int dist_scan(sibgpu_ctx *ctx, uint32_t k, uint32_t *hist_out)
+// pack the words of the own range (+ halo), partition plan, text descriptor
+static int dist_prepare(sibgpu_ctx *ctx, uint32_t k)
 {
 	cudaStream_t st = ctx->stream;
 	SIB_CUDA(cudaSetDevice(ctx->device));
@@ -187,14 +188,6 @@ int dist_scan(sibgpu_ctx *ctx, uint32_t k, uint32_t *hist_out)
 		ProfScope ps(ctx, "k_pack", (w_hi - w_lo) * 20);
 		k_pack<<<grid_for(w_hi - w_lo, 256, ctx->sm_count, 8), 256, 0, st>>>(ctx->d_text.as<uint4>() + w_lo,
 			ctx->d_packed.as<uint32_t>() + w_lo, (uint32_t)(w_hi - w_lo), d_err);
-	}
-	uint64_t *hs = static_cast<uint64_t*>(ctx->h_scalars);
-	SIB_CUDA(cudaMemcpyAsync(hs + 8, ctx->d_scalars.as<uint64_t>() + 8, 8, cudaMemcpyDeviceToHost, st));
-	SIB_CUDA(cudaStreamSynchronize(st));
-	if(hs[8] & 1u)
-	{
-		set_error("input: a character outside ACGT reached the device; sanitise first (indexedsequence.cpp:31-37)");
-		return SIBGPU_ERR_INPUT;
 	}
 	uint64_t nrec = 0;
 	for(uint32_t c = 0; c < ctx->nchr; c++)
@@ -217,12 +210,207 @@ int dist_scan(sibgpu_ctx *ctx, uint32_t k, uint32_t *hist_out)
 	t.M = (uint32_t)ctx->M;
 	t.nwords = nwords_all;
 	t.tile0 = ctx->dist_tile_lo;
+	return SIBGPU_OK;
+}
+
+int dist_scan(sibgpu_ctx *ctx, uint32_t k, uint32_t *hist_out)
+{
+	cudaStream_t st = ctx->stream;
+	SIB_TRY(dist_prepare(ctx, k));
+	uint64_t *hs = static_cast<uint64_t*>(ctx->h_scalars);
+	SIB_CUDA(cudaMemcpyAsync(hs + 8, ctx->d_scalars.as<uint64_t>() + 8, 8, cudaMemcpyDeviceToHost, st));
+	SIB_CUDA(cudaStreamSynchronize(st));
+	if(hs[8] & 1u) return input_error();
 	int rc = k <= 28 ? dist_scan_mode<0>(ctx, k, hist_out) : dist_scan_mode<1>(ctx, k, hist_out);
 	if(rc != SIBGPU_OK) return rc;
 	uint64_t local = 0;
 	for(uint32_t p = 0; p < ctx->dist_P_total; p++) local += hist_out[p];
 	ctx->dist_nrec_local = local;
 	return SIBGPU_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Peer path: no histogram pass and no separate exchange.  Every rank scatters the records of its text range into its
+// OWN send buffer, one fixed-capacity segment per global partition (segment p at p * seg_cap records); the ranks then
+// swap the per-segment counts (one small all-gather, which is also the barrier), and the owner of partition p reads
+// the W segments of p straight out of the W send buffers (CUDA IPC mappings, NVLink) inside its insert kernel.
+// ---------------------------------------------------------------------------------------------------------------
+template<int MODE>
+static int dist_scatter_local_mode(sibgpu_ctx *ctx, uint32_t k, uint64_t *counts_out, uint64_t *seg_cap_out, int *overflow_out)
+{
+	typedef typename RecT<MODE>::type Rec;
+	cudaStream_t st = ctx->stream;
+	uint64_t *hs = static_cast<uint64_t*>(ctx->h_scalars);
+	uint64_t *ds = ctx->d_scalars.as<uint64_t>();
+	TextDesc t = ctx->dist_text;
+	const uint32_t ntiles = ctx->dist_tile_hi - ctx->dist_tile_lo, PT = ctx->dist_P_total;
+	// at most one record per text position of the own range
+	const uint64_t mean = ((uint64_t)ntiles * TILE_POS + PT - 1) / PT;
+	const uint64_t cap = mean + mean / 8 + ctx->part_slack;
+	ctx->dist_seg_cap = cap;
+	SIB_TRY(ctx->d_records.ensure(sizeof(Rec) * cap * PT + 256));
+	SIB_TRY(ctx->d_cursor.ensure(sizeof(uint64_t) * MAX_PARTS));
+	std::vector<uint64_t> base(PT);
+	for(uint32_t p = 0; p < PT; p++) base[p] = (uint64_t)p * cap;
+	SIB_CUDA(cudaMemcpyAsync(ctx->d_cursor.p, base.data(), sizeof(uint64_t) * PT, cudaMemcpyHostToDevice, st));
+	if(ntiles)
+	{
+		size_t smem = sizeof(ScatterSmem<MODE>);
+		SIB_CUDA(cudaFuncSetAttribute(k_scatter<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+		const uint32_t g = ntiles < (uint32_t)ctx->sm_count * 4 ? ntiles : (uint32_t)ctx->sm_count * 4;
+		ProfScope ps(ctx, "k_scatter", (uint64_t)ntiles * TILE_POS / 4 + (uint64_t)ntiles * TILE_POS * sizeof(Rec));
+		k_scatter<MODE><<<g, TILE_THREADS, smem, st>>>(t, nullptr, k, ntiles, PT, ctx->d_cursor.as<unsigned long long>(),
+			ctx->d_records.as<Rec>(), cap, reinterpret_cast<uint32_t*>(ds + 10));
+	}
+	SIB_CUDA(cudaMemcpyAsync(counts_out, ctx->d_cursor.p, sizeof(uint64_t) * PT, cudaMemcpyDeviceToHost, st));
+	SIB_CUDA(cudaMemcpyAsync(hs + 8, ds + 8, sizeof(uint64_t) * 3, cudaMemcpyDeviceToHost, st));
+	SIB_CUDA(cudaStreamSynchronize(st));
+	if(hs[8] & 1u) return input_error();
+	*overflow_out = (hs[10] & 0xFFFFFFFFull) ? 1 : 0;
+	if(*overflow_out) ctx->hist_fallbacks++;
+	uint64_t local = 0;
+	for(uint32_t p = 0; p < PT; p++)
+	{
+		counts_out[p] -= base[p];
+		local += counts_out[p];
+	}
+	ctx->dist_nrec_local = local;
+	*seg_cap_out = cap;
+	return SIBGPU_OK;
+}
+
+int dist_scatter_local(sibgpu_ctx *ctx, uint32_t k, uint64_t *counts_out, uint64_t *seg_cap_out, int *overflow_out)
+{
+	SIB_TRY(dist_prepare(ctx, k));
+	return k <= 28 ? dist_scatter_local_mode<0>(ctx, k, counts_out, seg_cap_out, overflow_out)
+		: dist_scatter_local_mode<1>(ctx, k, counts_out, seg_cap_out, overflow_out);
+}
+
+template<int MODE>
+static int dist_group_peer_mode(sibgpu_ctx *ctx, uint32_t k, const uint64_t *counts, const uint64_t *seg_caps, uint64_t *nkeys_local)
+{
+	typedef typename RecT<MODE>::type Rec;
+	cudaStream_t st = ctx->stream;
+	const int sms = ctx->sm_count;
+	const uint32_t W = ctx->dist_world, PL = ctx->dist_P_local, PT = ctx->dist_P_total, b0 = ctx->dist_rank * PL;
+	uint64_t *hs = static_cast<uint64_t*>(ctx->h_scalars);
+	uint64_t *ds = ctx->d_scalars.as<uint64_t>();
+	std::vector<uint64_t> stage_off(PL + 1, 0);
+	uint64_t maxpart = 0;
+	for(uint32_t p = 0; p < PL; p++)
+	{
+		uint64_t sum = 0;
+		for(uint32_t s = 0; s < W; s++) sum += counts[(size_t)s * PT + b0 + p];
+		stage_off[p + 1] = stage_off[p] + sum;
+		if(sum > maxpart) maxpart = sum;
+	}
+	const uint64_t recv_total = stage_off[PL];
+	*nkeys_local = 0;
+	ctx->dist_nkeys_local = 0;
+	if(recv_total == 0) return SIBGPU_OK;
+	const uint64_t T64 = (uint64_t)ctx->table_factor * maxpart + 1024;
+	if(T64 > 0xFFFFFF00ull)
+	{
+		set_error("internal: hash partition does not fit a 32-bit table");
+		return SIBGPU_ERR_INTERNAL;
+	}
+	const uint32_t T = (uint32_t)T64;
+	const bool compact = MODE == 0 && k <= COMPACT_MAX_K;
+	const size_t slot_bytes = compact ? 8 : (MODE == 0 ? sizeof(Slot8) : sizeof(Slot16));
+	const uint32_t S = ctx->n_streams < 1 ? 1 : (ctx->n_streams > 8 ? 8 : ctx->n_streams);
+	const size_t table_bytes = (slot_bytes * T + 255) / 256 * 256;
+	SIB_TRY(ctx->d_table.ensure(table_bytes * S));
+	SIB_CUDA(cudaMemsetAsync(ctx->d_table.p, 0xFF, table_bytes * S, st));
+	// the vertex keys of partition p are staged at stage_off[p] (a partition has at most as many classes as records);
+	// the send buffer cannot serve as staging here: the peers are still reading it
+	SIB_TRY(ctx->d_keystage.ensure(sizeof(Rec) * recv_total));
+	SIB_TRY(ctx->d_partcnt.ensure(sizeof(uint32_t) * MAX_PARTS));
+	SIB_TRY(ctx->d_keyoff.ensure(sizeof(uint64_t) * (MAX_PARTS + 1)));
+	SIB_TRY(ctx->d_partoff.ensure(sizeof(uint64_t) * (MAX_PARTS + 1)));
+	SIB_CUDA(cudaMemsetAsync(ctx->d_partcnt.p, 0, sizeof(uint32_t) * MAX_PARTS, st));
+	SIB_CUDA(cudaMemcpyAsync(ctx->d_partoff.p, stage_off.data(), sizeof(uint64_t) * (PL + 1), cudaMemcpyHostToDevice, st));
+	if(S > 1)
+	{
+		SIB_TRY(ctx->ensure_aux_streams(S));
+		SIB_CUDA(cudaEventRecord(ctx->ev_fork, st));
+		for(uint32_t i = 0; i < S; i++) SIB_CUDA(cudaStreamWaitEvent(ctx->aux_stream[i], ctx->ev_fork, 0));
+	}
+	const int blocks_per_sm = S > 1 ? 4 : 8;
+	const bool phase_span = ctx->profiling;
+	if(phase_span) ctx->prof_begin("k_insert_seg+k_table_scan", recv_total * sizeof(Rec));
+	for(uint32_t p = 0; p < PL; p++)
+	{
+		const uint64_t n = stage_off[p + 1] - stage_off[p];
+		if(n == 0) continue;
+		SegList segs;
+		uint32_t nseg = 0;
+		for(uint32_t s = 0; s < W; s++)
+		{
+			const uint64_t c = counts[(size_t)s * PT + b0 + p];
+			if(c == 0) continue;
+			const Rec *base = static_cast<const Rec*>(s == ctx->dist_rank ? ctx->d_records.p : ctx->peer_ptr[s]);
+			segs.ptr[nseg] = base + (uint64_t)(b0 + p) * seg_caps[s];
+			segs.cnt[nseg] = (uint32_t)c;
+			nseg++;
+		}
+		for(uint32_t i = nseg; i < MAX_PEERS; i++) { segs.ptr[i] = nullptr; segs.cnt[i] = 0; }
+		cudaStream_t ps_st = S > 1 ? ctx->aux_stream[p % S] : st;
+		void *table = static_cast<char*>(ctx->d_table.p) + table_bytes * (p % S);
+		Rec *out = ctx->d_keystage.as<Rec>() + stage_off[p];
+		ctx->total_launches += 2;
+		const uint32_t g = grid_for(n, 256, sms, blocks_per_sm);
+		if(compact) k_insert_seg<MODE, true><<<g, 256, 0, ps_st>>>(segs, nseg, n, table, T);
+		else k_insert_seg<MODE, false><<<g, 256, 0, ps_st>>>(segs, nseg, n, table, T);
+		if(compact) k_table_scan_compact<<<grid_for(T, 256, sms, blocks_per_sm), 256, 0, ps_st>>>(
+			static_cast<unsigned long long*>(table), T, reinterpret_cast<uint64_t*>(out), ctx->d_partcnt.as<uint32_t>() + p);
+		else k_table_scan<MODE><<<grid_for(T, 256, sms, blocks_per_sm), 256, 0, ps_st>>>(table, T, out, ctx->d_partcnt.as<uint32_t>() + p);
+	}
+	if(S > 1)
+	{
+		for(uint32_t i = 0; i < S; i++)
+		{
+			SIB_CUDA(cudaEventRecord(ctx->ev_join[i], ctx->aux_stream[i]));
+			SIB_CUDA(cudaStreamWaitEvent(st, ctx->ev_join[i], 0));
+		}
+	}
+	if(phase_span) ctx->prof_end();
+	k_key_offsets<<<1, MAX_PARTS, 0, st>>>(ctx->d_partcnt.as<uint32_t>(), PL, ctx->d_keyoff.as<uint64_t>(), ds);
+	ctx->total_launches++;
+	SIB_CUDA(cudaMemcpyAsync(hs + 2, ds + 2, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+	SIB_CUDA(cudaStreamSynchronize(st));
+	const uint64_t Vc = hs[2];
+	if(Vc)
+	{
+		SIB_TRY(ctx->d_ckeys.ensure(sizeof(Rec) * Vc));
+		ProfScope ps(ctx, "k_gather_keys", 2 * Vc * sizeof(Rec));
+		dim3 g(8, PL);
+		k_gather_keys<MODE><<<g, 256, 0, st>>>(ctx->d_keystage.as<Rec>(), ctx->d_partoff.as<uint64_t>(),
+			ctx->d_partcnt.as<uint32_t>(), ctx->d_keyoff.as<uint64_t>(), ctx->d_ckeys.as<Rec>());
+		SIB_CUDA(cudaStreamSynchronize(st));
+	}
+	ctx->dist_nkeys_local = Vc;
+	*nkeys_local = Vc;
+	return SIBGPU_OK;
+}
+
+int dist_group_peer(sibgpu_ctx *ctx, const uint64_t *counts, const uint64_t *seg_caps, uint64_t *nkeys_local)
+{
+	SIB_CUDA(cudaSetDevice(ctx->device));
+	if(ctx->dist_world > (uint32_t)MAX_PEERS)
+	{
+		set_error("invalid: the peer path supports at most 16 ranks");
+		return SIBGPU_ERR_INVALID;
+	}
+	for(uint32_t s = 0; s < ctx->dist_world; s++)
+	{
+		if(s != ctx->dist_rank && (ctx->peer_ptr.size() <= s || !ctx->peer_ptr[s]))
+		{
+			set_error("state: sibgpu_dist_import_peers must precede sibgpu_dist_group_peer");
+			return SIBGPU_ERR_STATE;
+		}
+	}
+	return ctx->last_k <= 28 ? dist_group_peer_mode<0>(ctx, ctx->last_k, counts, seg_caps, nkeys_local)
+		: dist_group_peer_mode<1>(ctx, ctx->last_k, counts, seg_caps, nkeys_local);
 }
 
 int dist_scatter(sibgpu_ctx *ctx, void *send_dev)

@@ -284,58 +284,66 @@ __global__ void __launch_bounds__(TILE_THREADS) k_scatter(TextDesc t, const Rec1
 struct Slot8 { unsigned long long key; uint32_t pay; uint32_t pad; };             // 16 B
 struct Slot16 { unsigned long long a, b; uint32_t pay; uint32_t pad[3]; };        // 32 B
 
+// one occurrence into the 16-byte (MODE 0) / 32-byte (MODE 1, 2) slot tables
+template<int MODE>
+__device__ __forceinline__ void insert_wide_rec(const typename RecT<MODE>::type *__restrict__ recs, uint64_t i,
+	void *__restrict__ table, uint32_t T)
+{
+	if(MODE == 0)
+	{
+		Slot8 *tab = static_cast<Slot8*>(table);
+		const uint64_t rec = __ldcs(reinterpret_cast<const uint64_t*>(recs) + i);
+		const unsigned long long key = rec >> 7;
+		const uint32_t ctx = (uint32_t)rec & 127u;
+		uint32_t slot = __umulhi((uint32_t)rec_hash(key, 0), T);
+		uint32_t bits = payload_bits(ctx);
+		for(;;)
+		{
+			// CAS first (no peek): measured 1.7x faster than load-then-CAS on B200 (tools/ubench/atomics.cu)
+			unsigned long long old = atomicCAS(&tab[slot].key, EMPTY64, key);
+			if(old == EMPTY64 || old == key)
+			{
+				if(old == key) bits |= PAY_MULTI;
+				atomicAnd(&tab[slot].pay, ~bits);
+				break;
+			}
+			slot = slot + 1 == T ? 0 : slot + 1;
+		}
+	}
+	else
+	{
+		Slot16 *tab = static_cast<Slot16*>(table);
+		const ulonglong2 rec = __ldcs(reinterpret_cast<const ulonglong2*>(recs) + i);
+		const unsigned long long a = rec.x, b = rec.y >> 8;    // b < 2^56, never the "unclaimed" sentinel
+		const uint32_t ctx = (uint32_t)rec.y & 127u;
+		uint32_t slot = __umulhi((uint32_t)rec_hash(a, b), T);
+		uint32_t bits = payload_bits(ctx);
+		for(;;)
+		{
+			unsigned long long oa = atomicCAS(&tab[slot].a, EMPTY64, a);
+			if(oa == EMPTY64 || oa == a)
+			{
+				// second word: claimed by whoever CASes it first; a different b means another class
+				unsigned long long ob = atomicCAS(&tab[slot].b, EMPTY64, b);
+				if(ob == EMPTY64 || ob == b)
+				{
+					if(ob == b) bits |= PAY_MULTI;
+					atomicAnd(&tab[slot].pay, ~bits);
+					break;
+				}
+			}
+			slot = slot + 1 == T ? 0 : slot + 1;
+		}
+	}
+}
+
 template<int MODE>
 __global__ void __launch_bounds__(256) k_insert(const typename RecT<MODE>::type *__restrict__ recs, uint64_t n,
 	void *__restrict__ table, uint32_t T)
 {
 	for(uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
 	{
-		if(MODE == 0)
-		{
-			Slot8 *tab = static_cast<Slot8*>(table);
-			const uint64_t rec = reinterpret_cast<const uint64_t*>(recs)[i];
-			const unsigned long long key = rec >> 7;
-			const uint32_t ctx = (uint32_t)rec & 127u;
-			uint32_t slot = __umulhi((uint32_t)rec_hash(key, 0), T);
-			uint32_t bits = payload_bits(ctx);
-			for(;;)
-			{
-				// CAS first (no peek): measured 1.7x faster than load-then-CAS on B200 (tools/ubench/atomics.cu)
-				unsigned long long old = atomicCAS(&tab[slot].key, EMPTY64, key);
-				if(old == EMPTY64 || old == key)
-				{
-					if(old == key) bits |= PAY_MULTI;
-					atomicAnd(&tab[slot].pay, ~bits);
-					break;
-				}
-				slot = slot + 1 == T ? 0 : slot + 1;
-			}
-		}
-		else
-		{
-			Slot16 *tab = static_cast<Slot16*>(table);
-			const ulonglong2 rec = reinterpret_cast<const ulonglong2*>(recs)[i];
-			const unsigned long long a = rec.x, b = rec.y >> 8;    // b < 2^56, never the "unclaimed" sentinel
-			const uint32_t ctx = (uint32_t)rec.y & 127u;
-			uint32_t slot = __umulhi((uint32_t)rec_hash(a, b), T);
-			uint32_t bits = payload_bits(ctx);
-			for(;;)
-			{
-				unsigned long long oa = atomicCAS(&tab[slot].a, EMPTY64, a);
-				if(oa == EMPTY64 || oa == a)
-				{
-					// second word: claimed by whoever CASes it first; a different b means another class
-					unsigned long long ob = atomicCAS(&tab[slot].b, EMPTY64, b);
-					if(ob == EMPTY64 || ob == b)
-					{
-						if(ob == b) bits |= PAY_MULTI;
-						atomicAnd(&tab[slot].pay, ~bits);
-						break;
-					}
-				}
-				slot = slot + 1 == T ? 0 : slot + 1;
-			}
-		}
+		insert_wide_rec<MODE>(recs, i, table, T);
 	}
 }
 
@@ -476,6 +484,45 @@ static void launch_insert_compact(int variant, int sms, cudaStream_t st, const u
 	case 1: k_insert_compact<1, 1><<<grid(1), 256, 0, st>>>(recs, n, tab, T); break;
 	case 2: k_insert_compact<1, INSERT_ILP><<<grid(INSERT_ILP), 256, 0, st>>>(recs, n, tab, T); break;
 	default: k_insert_compact<0, INSERT_ILP><<<grid(INSERT_ILP), 256, 0, st>>>(recs, n, tab, T); break;
+	}
+}
+
+// Sharded path: the records of one partition arrive as one segment per source rank, and a segment may live in the
+// source rank's memory (CUDA IPC mapping, read over NVLink): the exchange is fused into the grouping kernel -- every
+// lane streams its record straight from the peer's send buffer (coalesced 256-byte reads per warp) and inserts it
+// into the local L2-resident table, so the transfer overlaps the atomics and no receive buffer is ever written.
+constexpr int MAX_PEERS = 16;
+struct SegList { const void *ptr[MAX_PEERS]; uint32_t cnt[MAX_PEERS]; };
+
+template<int MODE, bool COMPACT>
+__global__ void __launch_bounds__(256) k_insert_seg(const SegList segs, uint32_t nseg, uint64_t total,
+	void *__restrict__ table, uint32_t T)
+{
+	for(uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < total; i += (uint64_t)gridDim.x * blockDim.x)
+	{
+		uint64_t j = i;
+		uint32_t sg = 0;
+		while(sg + 1 < nseg && j >= segs.cnt[sg]) { j -= segs.cnt[sg]; sg++; }
+		if(COMPACT)
+		{
+			unsigned long long *tab = static_cast<unsigned long long*>(table);
+			const uint64_t rec = __ldcs(static_cast<const uint64_t*>(segs.ptr[sg]) + j);
+			const unsigned long long key = rec >> 7;
+			const unsigned long long word = (key << 11) | payload_bits((uint32_t)rec & 127u);
+			uint32_t slot = __umulhi((uint32_t)rec_hash(key, 0), T);
+			for(;;)
+			{
+				const unsigned long long old = atomicCAS(&tab[slot], EMPTY64, word);
+				if(old == EMPTY64) break;
+				if((old >> 11) == key)
+				{
+					atomicOr(&tab[slot], (word & 2047ull) | PAY_MULTI);
+					break;
+				}
+				slot = slot + 1 == T ? 0 : slot + 1;
+			}
+		}
+		else insert_wide_rec<MODE>(static_cast<const typename RecT<MODE>::type*>(segs.ptr[sg]), j, table, T);
 	}
 }
 

@@ -3,10 +3,16 @@
     count, pos_part, negtext_part = enumerate_sharded(GpuShard(ctx), chrs, k)      # on every rank
     count, pos, neg = gather_tables(count, pos_part, negtext_part)                  # full tables on rank 0
 
-The compute phases live in libsibgpu (sibgpu_dist_*, include/sibgpu.h); this module moves the two variable-size
-payloads between ranks: ONE all-to-all of the k-mer records (bucketed by hash prefix = owner rank) and one all-gather
-of the vertex keys.  With the NCCL backend the collectives run on the device buffers the kernels wrote (NVLink /
-NVSwitch); with gloo (CPU tests, or two ranks sharing one GPU) the same tensors are staged through host memory.
+The compute phases live in libsibgpu (sibgpu_dist_*, include/sibgpu.h).  Two exchange strategies:
+
+* peer (default on GPUs): every rank scatters its records into fixed-capacity segments of its own send buffer (no
+  histogram pass); the ranks all-gather the segment counts + the CUDA IPC handle of the buffer (one small collective,
+  which is also the barrier), and the owner of a hash partition reads that partition's segments straight out of the
+  peers' send buffers over NVLink inside its insert kernel -- the all-to-all is fused into the grouping kernel.
+* staged (fallback when a segment overflows, and the path of the CPU test double): histogram, scatter into an exactly
+  sized send buffer, ONE all-to-all of the k-mer records (NCCL on the device buffers, or gloo through host memory).
+
+Either way one all-gather of the (few) vertex keys follows, so every rank can compute the global ids.
 """
 import os
 import time
@@ -28,6 +34,25 @@ class GpuShard:
     def upload(self, chrs, rank, world):
         self.ctx.dist_upload(chrs, rank, world)
 
+    # -- peer strategy
+    peer = os.environ.get("SIBGPU_DIST_PEER", "1") != "0"
+
+    def scatter_local(self, k):
+        out = self.ctx.dist_scatter_local(k)
+        self.words = self.ctx.dist_record_bytes() // 8
+        return out
+
+    def export_send(self):
+        return self.ctx.dist_export_send()
+
+    def group_peer(self, handles, counts, seg_caps):
+        self.ctx.dist_import_peers(handles)
+        n = self.ctx.dist_group_peer(counts, seg_caps)
+        keys = torch.empty(max(n * self.words, 1), dtype=torch.int64, device=self.device)
+        self.ctx.dist_keys(keys.data_ptr())
+        return keys[:n * self.words]
+
+    # -- staged strategy
     def scan(self, k):
         nparts, hist, self.nrec = self.ctx.dist_scan(k)
         self.words = self.ctx.dist_record_bytes() // 8
@@ -75,6 +100,49 @@ def enumerate_sharded(shard, chrs, k, group=None):
     lap("start")
     shard.upload(chrs, rank, world)
     lap("upload")
+    keys = None
+    if getattr(shard, "peer", False) and world <= 16:
+        # --- peer strategy: scatter into the own send buffer, swap counts + IPC handles, read the peers' segments
+        nparts, cnt, cap, ovf = shard.scatter_local(k)
+        lap("pack+scatter")
+        handle = shard.export_send()
+        mine = np.concatenate([cnt.astype(np.int64), np.array([cap, int(ovf)], dtype=np.int64), handle.view(np.int64)])
+        dev = shard.device
+        m = _comm(torch.from_numpy(mine).to(dev), group)
+        allm = torch.empty(world * len(mine), dtype=torch.int64, device=m.device)
+        dist.all_gather_into_tensor(allm, m, group=group)
+        allm = allm.cpu().numpy().reshape(world, len(mine))
+        lap("allgather counts+handles")
+        if not allm[:, nparts + 1].any():
+            keys = shard.group_peer(np.ascontiguousarray(allm[:, nparts + 2:]).view(np.uint8).reshape(world, 64),
+                                    allm[:, :nparts].astype(np.uint64), allm[:, nparts].astype(np.uint64))
+            lap("group (peer reads)")
+            words = shard.words
+    if keys is None:
+        keys, words, dev = _staged_exchange(shard, k, rank, world, group, lap)
+    # --- vertex keys of all ranks (variable sizes: pad to the maximum)
+    nk = _comm(torch.tensor([keys.numel()], dtype=torch.int64, device=dev), group)
+    all_nk = torch.empty(world, dtype=torch.int64, device=nk.device)
+    dist.all_gather_into_tensor(all_nk, nk, group=group)
+    all_nk = [int(x) for x in all_nk.cpu()]
+    mx = max(max(all_nk), 1)
+    padded = torch.zeros(mx, dtype=torch.int64, device=dev)
+    padded[:keys.numel()] = keys
+    p_c = _comm(padded, group)
+    gathered = torch.empty(world * mx, dtype=torch.int64, device=p_c.device)
+    dist.all_gather_into_tensor(gathered, p_c, group=group)
+    allkeys = torch.cat([gathered[s * mx:s * mx + all_nk[s]] for s in range(world)]).to(dev)
+    lap("allgather keys")
+    out = shard.finish(allkeys)
+    lap("finish")
+    if _TRACE and rank == 0:
+        print("[sharded] " + "  ".join("%s %.2f ms" % (marks[i][0], (marks[i][1] - marks[i - 1][1]) * 1e3)
+                                       for i in range(1, len(marks))), flush=True)
+    return out
+
+
+def _staged_exchange(shard, k, rank, world, group, lap):
+    """histogram -> exactly sized send buffer -> ONE all-to-all of the records -> grouping of the received records"""
     nparts, hist = shard.scan(k)
     lap("scan")
     words = shard.words
@@ -97,25 +165,7 @@ def enumerate_sharded(shard, chrs, k, group=None):
     lap("all_to_all records")
     keys = shard.group(recv.to(dev), counts.astype(np.uint32))
     lap("group")
-    # --- vertex keys of all ranks (variable sizes: pad to the maximum)
-    nk = _comm(torch.tensor([keys.numel()], dtype=torch.int64, device=dev), group)
-    all_nk = torch.empty(world, dtype=torch.int64, device=nk.device)
-    dist.all_gather_into_tensor(all_nk, nk, group=group)
-    all_nk = [int(x) for x in all_nk.cpu()]
-    mx = max(max(all_nk), 1)
-    padded = torch.zeros(mx, dtype=torch.int64, device=dev)
-    padded[:keys.numel()] = keys
-    p_c = _comm(padded, group)
-    gathered = torch.empty(world * mx, dtype=torch.int64, device=p_c.device)
-    dist.all_gather_into_tensor(gathered, p_c, group=group)
-    allkeys = torch.cat([gathered[s * mx:s * mx + all_nk[s]] for s in range(world)]).to(dev)
-    lap("allgather keys")
-    out = shard.finish(allkeys)
-    lap("finish")
-    if _TRACE and rank == 0:
-        print("[sharded] " + "  ".join("%s %.2f ms" % (marks[i][0], (marks[i][1] - marks[i - 1][1]) * 1e3)
-                                       for i in range(1, len(marks))), flush=True)
-    return out
+    return keys, words, dev
 
 
 def assemble_tables(pos_parts, negtext_parts):
