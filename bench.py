@@ -8,9 +8,11 @@ A "step" is one construction of the de Bruijn-graph index of one synthetic genom
 replacement of IndexedSequence's EnumerateBifurcationsSArrayInRAM (/root/reference/src/vertexenumeration.cpp:263-364).
 Workload at N=1 is BASELINE.json configs[1]: 100 MB random-ACGT single contig, numpy default_rng(12345), k=25.
 With N>1 ranks (torchrun, one process per GPU) the workload is ONE genome of N such contigs (seed 12345+c), sharded by
-contiguous text range over the ranks (weak scaling: 100 Mbases per GPU): scan/scatter locally, one NCCL all-to-all of
-the k-mer records bucketed by hash prefix, per-rank grouping, all-gather of the vertex keys, local instance tables
-(sibelia_b200/distributed.py); `value` = total bases / max-over-ranks step time.
+contiguous text range over the ranks (weak scaling: 100 Mbases per GPU): every rank scatters its k-mer records, bucketed
+by hash prefix, into its own send buffer; one small NCCL all-gather swaps the bucket counts; the owner of a bucket
+reads the bucket's segments straight out of the peers' send buffers over NVLink inside its grouping kernel (TMA bulk
+copies into a shared-memory ring -- the all-to-all is fused into the kernel); all-gather of the vertex keys; local
+instance tables (sibelia_b200/distributed.py); `value` = total bases / max-over-ranks step time.
 
 One JSON line is printed by rank 0 (see the task contract): value = device-resident throughput, e2e = the same
 metric through sibgpu_enumerate with pinned HOST buffers (H2D + D2H inside the timed region), roofline = dominant
@@ -336,7 +338,8 @@ def main():
         "config": {"workload": ("synthetic %g MB random-ACGT single contig, numpy default_rng(12345), k=%d (BASELINE configs[1])"
                                 % (args.mbases, args.k)) if world == 1 else
                                ("one synthetic genome of %d random-ACGT contigs x %g MB (default_rng(12345+c)), k=%d, sharded by "
-                                "text range over %d GPUs with one NCCL all-to-all of k-mer records" % (world, args.mbases, args.k, world)),
+                                "text range over %d GPUs; k-mer records exchanged by peer reads over NVLink fused into the "
+                                "grouping kernel (NCCL only for the bucket counts and the vertex keys)" % (world, args.mbases, args.k, world)),
                    "k": args.k, "bases_per_gpu": N, "vertices": int(count), "instances_per_strand": int(ninst),
                    "l2": "256 MB L2 flush between timed iterations (outside the event-timed region)",
                    "timing": ("CUDA events on the library stream around each whole step" if world == 1 else

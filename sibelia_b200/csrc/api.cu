@@ -549,6 +549,7 @@ int sibgpu_set_profiling(sibgpu_ctx *c, int enabled)
 int sibgpu_kernel_stats(sibgpu_ctx *c, sibgpu_kernel_stat *out, int cap)
 {
 	if(!c) return 0;
+	if(c->profiling && !c->spans.empty() && c->stats.empty()) c->prof_collect();   // phases run outside a whole enumerate
 	int n = (int)c->stats.size();
 	for(int i = 0; i < n && i < cap; i++)
 	{

@@ -52,7 +52,7 @@ struct sibgpu_ctx {
 	uint64_t dist_seg_cap = 0;
 	std::vector<void*> peer_ptr;                       // [world], nullptr for the own rank / not mapped
 	std::vector<std::vector<unsigned char>> peer_handle;
-	sibgpu::DevBuf d_keystage;
+	sibgpu::DevBuf d_keystage;                         // vertex keys of the owned partitions
 	sibgpu::TextDesc dist_text = {};
 
 	// tunables (env SIBGPU_PART_RECORDS)

@@ -246,7 +246,7 @@ static int dist_scatter_local_mode(sibgpu_ctx *ctx, uint32_t k, uint64_t *counts
 	const uint32_t ntiles = ctx->dist_tile_hi - ctx->dist_tile_lo, PT = ctx->dist_P_total;
 	// at most one record per text position of the own range
 	const uint64_t mean = ((uint64_t)ntiles * TILE_POS + PT - 1) / PT;
-	const uint64_t cap = mean + mean / 8 + ctx->part_slack;
+	const uint64_t cap = (mean + mean / 8 + ctx->part_slack + 31) / 32 * 32;   // segments start 16-byte aligned (TMA)
 	ctx->dist_seg_cap = cap;
 	SIB_TRY(ctx->d_records.ensure(sizeof(Rec) * cap * PT + 256));
 	SIB_TRY(ctx->d_cursor.ensure(sizeof(uint64_t) * MAX_PARTS));
@@ -336,21 +336,29 @@ static int dist_group_peer_mode(sibgpu_ctx *ctx, uint32_t k, const uint64_t *cou
 		for(uint32_t i = 0; i < S; i++) SIB_CUDA(cudaStreamWaitEvent(ctx->aux_stream[i], ctx->ev_fork, 0));
 	}
 	const int blocks_per_sm = S > 1 ? 4 : 8;
-	const bool phase_span = ctx->profiling;
+	const bool phase_span = ctx->profiling && S > 1;
+	static const bool debug_local = getenv("SIBGPU_DEBUG_LOCAL_SEGS") != nullptr;   // timing experiment only: wrong results
+	// Measured on 2 B200s (100 M records per rank, half of them remote; profiles/r1_sharded_peer_read.txt): plain loads
+	// from the peer 3.41 ms, remote segments first pulled into a local buffer by the copy engines 2.20 ms, TMA ring
+	// reading the peer directly 2.21 ms at 8 CTAs per SM -- the ring hides the NVLink latency without a staging copy.
+	static const int seg_ctas_per_sm = getenv("SIBGPU_SEG_CTAS") ? atoi(getenv("SIBGPU_SEG_CTAS")) : 8;
+	static const int seg_kernel = getenv("SIBGPU_SEG_KERNEL") ? atoi(getenv("SIBGPU_SEG_KERNEL")) : 1;   // 0 = loads, 1 = TMA ring
+	const uint64_t tile_rec = SEG_TILE_BYTES / sizeof(Rec);
 	if(phase_span) ctx->prof_begin("k_insert_seg+k_table_scan", recv_total * sizeof(Rec));
 	for(uint32_t p = 0; p < PL; p++)
 	{
 		const uint64_t n = stage_off[p + 1] - stage_off[p];
 		if(n == 0) continue;
 		SegList segs;
-		uint32_t nseg = 0;
+		uint32_t nseg = 0, seg_tiles = 0;
 		for(uint32_t s = 0; s < W; s++)
 		{
 			const uint64_t c = counts[(size_t)s * PT + b0 + p];
 			if(c == 0) continue;
-			const Rec *base = static_cast<const Rec*>(s == ctx->dist_rank ? ctx->d_records.p : ctx->peer_ptr[s]);
-			segs.ptr[nseg] = base + (uint64_t)(b0 + p) * seg_caps[s];
+			if(s == ctx->dist_rank || debug_local) segs.ptr[nseg] = ctx->d_records.as<Rec>() + (uint64_t)(b0 + p) * seg_caps[s];
+			else segs.ptr[nseg] = static_cast<const Rec*>(ctx->peer_ptr[s]) + (uint64_t)(b0 + p) * seg_caps[s];
 			segs.cnt[nseg] = (uint32_t)c;
+			seg_tiles += (uint32_t)((c + tile_rec - 1) / tile_rec);
 			nseg++;
 		}
 		for(uint32_t i = nseg; i < MAX_PEERS; i++) { segs.ptr[i] = nullptr; segs.cnt[i] = 0; }
@@ -358,12 +366,22 @@ static int dist_group_peer_mode(sibgpu_ctx *ctx, uint32_t k, const uint64_t *cou
 		void *table = static_cast<char*>(ctx->d_table.p) + table_bytes * (p % S);
 		Rec *out = ctx->d_keystage.as<Rec>() + stage_off[p];
 		ctx->total_launches += 2;
-		const uint32_t g = grid_for(n, 256, sms, blocks_per_sm);
-		if(compact) k_insert_seg<MODE, true><<<g, 256, 0, ps_st>>>(segs, nseg, n, table, T);
-		else k_insert_seg<MODE, false><<<g, 256, 0, ps_st>>>(segs, nseg, n, table, T);
+		const uint32_t seg_ctas = (uint32_t)sms * seg_ctas_per_sm;
+		const uint32_t g = seg_tiles < seg_ctas ? seg_tiles : seg_ctas;
+		if(S == 1 && ctx->profiling) ctx->prof_begin("k_insert_seg", n * sizeof(Rec));
+		if(seg_kernel == 0)
+		{
+			const uint32_t gl = grid_for(n, 256, sms, blocks_per_sm);
+			if(compact) k_insert_seg_ld<MODE, true, 1><<<gl, 256, 0, ps_st>>>(segs, nseg, n, table, T);
+			else k_insert_seg_ld<MODE, false, 1><<<gl, 256, 0, ps_st>>>(segs, nseg, n, table, T);
+		}
+		else if(compact) k_insert_seg<MODE, true><<<g, 256, 0, ps_st>>>(segs, nseg, seg_tiles, table, T);
+		else k_insert_seg<MODE, false><<<g, 256, 0, ps_st>>>(segs, nseg, seg_tiles, table, T);
+		if(S == 1 && ctx->profiling) { ctx->prof_end(); ctx->prof_begin("k_table_scan", (uint64_t)T * slot_bytes); }
 		if(compact) k_table_scan_compact<<<grid_for(T, 256, sms, blocks_per_sm), 256, 0, ps_st>>>(
 			static_cast<unsigned long long*>(table), T, reinterpret_cast<uint64_t*>(out), ctx->d_partcnt.as<uint32_t>() + p);
 		else k_table_scan<MODE><<<grid_for(T, 256, sms, blocks_per_sm), 256, 0, ps_st>>>(table, T, out, ctx->d_partcnt.as<uint32_t>() + p);
+		if(S == 1 && ctx->profiling) ctx->prof_end();
 	}
 	if(S > 1)
 	{

@@ -285,14 +285,18 @@ struct Slot8 { unsigned long long key; uint32_t pay; uint32_t pad; };           
 struct Slot16 { unsigned long long a, b; uint32_t pay; uint32_t pad[3]; };        // 32 B
 
 // one occurrence into the 16-byte (MODE 0) / 32-byte (MODE 1, 2) slot tables
+template<int MODE> struct RecVal { typedef ulonglong2 type; };
+template<> struct RecVal<0> { typedef unsigned long long type; };
 template<int MODE>
-__device__ __forceinline__ void insert_wide_rec(const typename RecT<MODE>::type *__restrict__ recs, uint64_t i,
-	void *__restrict__ table, uint32_t T)
+__device__ __forceinline__ typename RecVal<MODE>::type load_rec(const void *__restrict__ recs, uint64_t i)
 {
-	if(MODE == 0)
+	return __ldcs(static_cast<const typename RecVal<MODE>::type*>(recs) + i);
+}
+
+__device__ __forceinline__ void insert_wide_rec(unsigned long long rec, void *__restrict__ table, uint32_t T)
+{
 	{
 		Slot8 *tab = static_cast<Slot8*>(table);
-		const uint64_t rec = __ldcs(reinterpret_cast<const uint64_t*>(recs) + i);
 		const unsigned long long key = rec >> 7;
 		const uint32_t ctx = (uint32_t)rec & 127u;
 		uint32_t slot = __umulhi((uint32_t)rec_hash(key, 0), T);
@@ -310,10 +314,12 @@ __device__ __forceinline__ void insert_wide_rec(const typename RecT<MODE>::type 
 			slot = slot + 1 == T ? 0 : slot + 1;
 		}
 	}
-	else
+}
+
+__device__ __forceinline__ void insert_wide_rec(ulonglong2 rec, void *__restrict__ table, uint32_t T)
+{
 	{
 		Slot16 *tab = static_cast<Slot16*>(table);
-		const ulonglong2 rec = __ldcs(reinterpret_cast<const ulonglong2*>(recs) + i);
 		const unsigned long long a = rec.x, b = rec.y >> 8;    // b < 2^56, never the "unclaimed" sentinel
 		const uint32_t ctx = (uint32_t)rec.y & 127u;
 		uint32_t slot = __umulhi((uint32_t)rec_hash(a, b), T);
@@ -343,7 +349,7 @@ __global__ void __launch_bounds__(256) k_insert(const typename RecT<MODE>::type 
 {
 	for(uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
 	{
-		insert_wide_rec<MODE>(recs, i, table, T);
+		insert_wide_rec(load_rec<MODE>(recs, i), table, T);
 	}
 }
 
@@ -494,35 +500,133 @@ static void launch_insert_compact(int variant, int sms, cudaStream_t st, const u
 constexpr int MAX_PEERS = 16;
 struct SegList { const void *ptr[MAX_PEERS]; uint32_t cnt[MAX_PEERS]; };
 
-template<int MODE, bool COMPACT>
-__global__ void __launch_bounds__(256) k_insert_seg(const SegList segs, uint32_t nseg, uint64_t total,
+__device__ __forceinline__ void insert_compact_rec(unsigned long long rec, unsigned long long *__restrict__ tab, uint32_t T)
+{
+	const unsigned long long key = rec >> 7;
+	const unsigned long long word = (key << 11) | payload_bits((uint32_t)rec & 127u);
+	uint32_t slot = __umulhi((uint32_t)rec_hash(key, 0), T);
+	for(;;)
+	{
+		const unsigned long long old = atomicCAS(&tab[slot], EMPTY64, word);
+		if(old == EMPTY64) break;
+		if((old >> 11) == key)
+		{
+			atomicOr(&tab[slot], (word & 2047ull) | PAY_MULTI);
+			break;
+		}
+		slot = slot + 1 == T ? 0 : slot + 1;
+	}
+}
+
+// Variant with plain coalesced loads (SEG_ILP records in flight per thread).
+template<int MODE, bool COMPACT, int SEG_ILP>
+__global__ void __launch_bounds__(256) k_insert_seg_ld(const SegList segs, uint32_t nseg, uint64_t total,
 	void *__restrict__ table, uint32_t T)
 {
-	for(uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < total; i += (uint64_t)gridDim.x * blockDim.x)
+	const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+	for(uint64_t i0 = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i0 < total; i0 += stride * SEG_ILP)
 	{
-		uint64_t j = i;
-		uint32_t sg = 0;
-		while(sg + 1 < nseg && j >= segs.cnt[sg]) { j -= segs.cnt[sg]; sg++; }
-		if(COMPACT)
+		typename RecVal<MODE>::type rec[SEG_ILP];
+#pragma unroll
+		for(int u = 0; u < SEG_ILP; u++)
 		{
-			unsigned long long *tab = static_cast<unsigned long long*>(table);
-			const uint64_t rec = __ldcs(static_cast<const uint64_t*>(segs.ptr[sg]) + j);
-			const unsigned long long key = rec >> 7;
-			const unsigned long long word = (key << 11) | payload_bits((uint32_t)rec & 127u);
-			uint32_t slot = __umulhi((uint32_t)rec_hash(key, 0), T);
-			for(;;)
+			uint64_t j = i0 + u * stride;
+			if(j < total)
 			{
-				const unsigned long long old = atomicCAS(&tab[slot], EMPTY64, word);
-				if(old == EMPTY64) break;
-				if((old >> 11) == key)
-				{
-					atomicOr(&tab[slot], (word & 2047ull) | PAY_MULTI);
-					break;
-				}
-				slot = slot + 1 == T ? 0 : slot + 1;
+				uint32_t sg = 0;
+				while(sg + 1 < nseg && j >= segs.cnt[sg]) { j -= segs.cnt[sg]; sg++; }
+				rec[u] = load_rec<MODE>(segs.ptr[sg], j);
 			}
 		}
-		else insert_wide_rec<MODE>(static_cast<const typename RecT<MODE>::type*>(segs.ptr[sg]), j, table, T);
+#pragma unroll
+		for(int u = 0; u < SEG_ILP; u++)
+		{
+			if(i0 + u * stride < total)
+			{
+				if(COMPACT) insert_compact_rec(*reinterpret_cast<unsigned long long*>(&rec[u]), static_cast<unsigned long long*>(table), T);
+				else insert_wide_rec(rec[u], table, T);
+			}
+		}
+	}
+}
+
+// The segments are streamed through a ring of SEG_STAGES shared-memory tiles of SEG_TILE_BYTES filled by TMA bulk
+// copies (cp.async.bulk + mbarrier complete_tx): one elected thread keeps up to SEG_STAGES tiles per CTA in flight,
+// so the NVLink round trip of a peer read is paid by the copy engine of the SM, not by thread slots that should be
+// issuing atomics.  Tile t of the launch = records [t', t' + n) of one segment; a segment starts 16-byte aligned.
+constexpr int SEG_TILE_BYTES = 8192, SEG_STAGES = 2;
+
+__device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+template<int MODE, bool COMPACT>
+__global__ void __launch_bounds__(256) k_insert_seg(const SegList segs, uint32_t nseg, uint32_t ntiles,
+	void *__restrict__ table, uint32_t T)
+{
+	typedef typename RecVal<MODE>::type RV;
+	constexpr uint32_t TILE_REC = SEG_TILE_BYTES / sizeof(RV);
+	__shared__ __align__(128) unsigned char buf[SEG_STAGES][SEG_TILE_BYTES];
+	__shared__ __align__(8) unsigned long long bar[SEG_STAGES];
+	__shared__ uint32_t tile_n[SEG_STAGES];
+	if(threadIdx.x == 0)
+	{
+		for(int st = 0; st < SEG_STAGES; st++) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_addr(&bar[st])));
+		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+	}
+	__syncthreads();
+	// elected thread: start the bulk copy of tile t into stage st
+	auto issue = [&](uint32_t t, int st) {
+		uint32_t sg = 0, left = t;
+		for(;;)
+		{
+			const uint32_t tiles_here = (segs.cnt[sg] + TILE_REC - 1) / TILE_REC;
+			if(left < tiles_here || sg + 1 == nseg) break;
+			left -= tiles_here;
+			sg++;
+		}
+		const uint32_t first = left * TILE_REC;
+		const uint32_t n = segs.cnt[sg] - first < TILE_REC ? segs.cnt[sg] - first : TILE_REC;
+		const uint32_t bytes = (uint32_t)((n * sizeof(RV) + 15u) & ~15u);
+		const unsigned char *src = static_cast<const unsigned char*>(segs.ptr[sg]) + (size_t)first * sizeof(RV);
+		tile_n[st] = n;
+		asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_addr(&bar[st])), "r"(bytes) : "memory");
+		asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+			:: "r"(smem_addr(buf[st])), "l"(src), "r"(bytes), "r"(smem_addr(&bar[st])) : "memory");
+	};
+	if(threadIdx.x == 0)
+	{
+		uint32_t t = blockIdx.x;
+		for(int st = 0; st < SEG_STAGES && t < ntiles; st++, t += gridDim.x) issue(t, st);
+	}
+	int stage = 0;
+	uint32_t phase = 0;
+	for(uint32_t t = blockIdx.x; t < ntiles; t += gridDim.x)
+	{
+		uint32_t ok = 0;
+		while(!ok)
+		{
+			asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+				: "=r"(ok) : "r"(smem_addr(&bar[stage])), "r"(phase) : "memory");
+		}
+		const uint32_t n = tile_n[stage];
+		const RV *w = reinterpret_cast<const RV*>(buf[stage]);
+#pragma unroll
+		for(uint32_t u = 0; u < TILE_REC / 256; u++)
+		{
+			const uint32_t j = u * 256 + threadIdx.x;
+			if(j < n)
+			{
+				RV rec = w[j];
+				if(COMPACT) insert_compact_rec(*reinterpret_cast<unsigned long long*>(&rec), static_cast<unsigned long long*>(table), T);
+				else insert_wide_rec(rec, table, T);
+			}
+		}
+		__syncthreads();                                   // every lane has read its records: the stage can be refilled
+		if(threadIdx.x == 0)
+		{
+			const uint64_t tn = (uint64_t)t + (uint64_t)SEG_STAGES * gridDim.x;
+			if(tn < ntiles) issue((uint32_t)tn, stage);
+		}
+		if(++stage == SEG_STAGES) { stage = 0; phase ^= 1u; }
 	}
 }
 
