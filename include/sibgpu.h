@@ -118,6 +118,29 @@ int sibgpu_simplify(sibgpu_ctx *ctx, char **seq, uint32_t **origpos, uint64_t *l
 	sibgpu_progress_fn progress, void *user, uint64_t *bulges);
 
 /* ---------------------------------------------------------------------------------------------------------------
+ * sibgpu_list_edges: replaces the pair
+ *     IndexedSequence iseq(rawSeq_, originalPos_, k, tempDir_);
+ *     ListEdges(iseq.Sequence(), iseq.BifStorage(), k, edge);
+ * of BlockFinder::GenerateSyntenyBlocks (src/synteny.cpp:238-241) and SerializeCondensedGraph
+ * (src/serialization.cpp:90-93): the edges of the condensed de Bruijn graph, i.e. one BlockFinder::Edge
+ * (src/blockfinder.h:59-85, built by BlockFinder::ListEdges, src/serialization.cpp:56-86) per pair of consecutive
+ * vertex marks on each strand of each chromosome, in the reference's order (positive strand: chromosomes in order,
+ * positions ascending; then the negative strand likewise in its own coordinates).  No host-side index is built.
+ *   seq / origpos / len   rawSeq_, originalPos_ (NULL = identity) and their lengths; seq must be sanitised ACGT
+ *   *edges, *nedges       library-allocated array (release with sibgpu_free)
+ */
+typedef struct sibgpu_edge {
+	uint32_t chr;
+	uint32_t direction;           /* 0 = DNASequence::positive, 1 = DNASequence::negative (src/dnasequence.h:24-28) */
+	uint32_t start_vertex, end_vertex;
+	uint32_t actual_position, actual_length;
+	uint32_t original_position, original_length;
+	uint32_t first_char;          /* ASCII, read along the strand */
+} sibgpu_edge;
+int sibgpu_list_edges(sibgpu_ctx *ctx, const char *const *seq, const uint32_t *const *origpos, const uint64_t *len,
+	uint32_t nchr, uint32_t k, sibgpu_edge **edges, uint64_t *nedges);
+
+/* ---------------------------------------------------------------------------------------------------------------
  * Sharded enumeration over `world` GPUs of one box, ONE PROCESS PER GPU (k <= 32).  The concatenated genome is split
  * into `world` contiguous text ranges; records are bucketed by hash prefix so that partition p belongs to rank
  * p / (nparts_total / world); the caller moves them with one all-to-all (NCCL) between two device buffers it owns,

@@ -110,6 +110,31 @@ def simplify(chrs, origpos, k, D, iters=4):
     return new_chrs, new_op, bulges.value, sec.value
 
 
+EDGE_DTYPE = np.dtype([("chr", "<u4"), ("direction", "<u4"), ("start_vertex", "<u4"), ("end_vertex", "<u4"),
+                       ("actual_position", "<u4"), ("actual_length", "<u4"), ("original_position", "<u4"),
+                       ("original_length", "<u4"), ("first_char", "<u4")])
+
+
+def list_edges(chrs, origpos, k):
+    """IndexedSequence(rawSeq_, originalPos_, k, "") + BlockFinder::ListEdges of the reference (synteny.cpp:238-241).
+    Returns (edges structured array in the reference's order, seconds)."""
+    L = lib()
+    chrs = _as_bytes_list(chrs)
+    n = len(chrs)
+    arr = (C.c_char_p * n)(*chrs)
+    ops = [np.ascontiguousarray(o, dtype=np.uint32) for o in origpos]
+    op = (C.c_void_p * n)(*[o.ctypes.data for o in ops])
+    lens = (C.c_uint64 * n)(*[len(c) for c in chrs])
+    edges = C.c_void_p()
+    ne = C.c_uint64()
+    sec = C.c_double()
+    L.ref_list_edges.restype = C.c_int
+    rc = L.ref_list_edges(C.c_uint32(n), arr, op, lens, C.c_uint32(k), C.byref(edges), C.byref(ne), C.byref(sec))
+    if rc != 0:
+        raise RuntimeError(L.ref_last_error().decode())
+    return _take(edges, ne.value, EDGE_DTYPE), sec.value
+
+
 def boost_order(keys):
     """Iteration order of the vendored boost::unordered_map<size_t,int> after inserting distinct keys in order."""
     keys = np.ascontiguousarray(keys, dtype=np.uint64)

@@ -11,6 +11,7 @@
 //   IndexedSequence ctor            /root/reference/src/indexedsequence.h:29-30
 //   BifurcationStorage::ListPositions / GetBifurcation   src/bifurcationstorage.h:39,59-72
 //   BlockFinder::PerformGraphSimplifications             src/blockfinder.h:45
+//   BlockFinder::ListEdges (private)                     src/blockfinder.h:112, src/serialization.cpp:56-86
 #include <chrono>
 #include <cstdint>
 #include <cstdlib>
@@ -199,6 +200,56 @@ int ref_simplify(uint32_t nchr, char** seq, uint32_t** origpos, uint64_t* len,
 			memcpy(seq[i], s.data(), s.size());
 			origpos[i] = static_cast<uint32_t*>(malloc(sizeof(uint32_t) * (s.size() + 1)));
 			memcpy(origpos[i], finder.originalPos_[i].data(), sizeof(uint32_t) * s.size());
+		}
+
+		return 0;
+	}
+	catch(std::exception & e)
+	{
+		g_err = e.what();
+		return 1;
+	}
+}
+
+
+// The edge list GenerateSyntenyBlocks starts from (src/synteny.cpp:238-241): IndexedSequence(rawSeq_, originalPos_, k, "")
+// followed by BlockFinder::ListEdges, for an arbitrary inter-stage state.  9 x uint32 per edge.
+struct ref_edge { uint32_t chr, direction, startVertex, endVertex, actualPosition, actualLength, originalPosition, originalLength, firstChar; };
+int ref_list_edges(uint32_t nchr, const char* const* seq, const uint32_t* const* origpos, const uint64_t* len, uint32_t k,
+	ref_edge** edges, uint64_t* nedges, double* seconds)
+{
+	try
+	{
+		std::vector<FASTARecord> chrList;
+		for(uint32_t i = 0; i < nchr; i++)
+		{
+			chrList.push_back(FASTARecord(std::string(seq[i], seq[i] + len[i]), "chr", i));
+		}
+
+		BlockFinder finder(chrList);
+		for(uint32_t i = 0; i < nchr; i++)
+		{
+			finder.originalPos_[i].assign(origpos[i], origpos[i] + len[i]);
+		}
+
+		std::vector<BlockFinder::Edge> edge;
+		double t0 = now_s();
+		{
+			IndexedSequence iseq(finder.rawSeq_, finder.originalPos_, k, "");
+			finder.ListEdges(iseq.Sequence(), iseq.BifStorage(), k, edge);
+		}
+		double t1 = now_s();
+		if(seconds) *seconds = t1 - t0;
+		*nedges = edge.size();
+		*edges = static_cast<ref_edge*>(malloc(sizeof(ref_edge) * (edge.size() + 1)));
+		for(size_t i = 0; i < edge.size(); i++)
+		{
+			ref_edge e = {static_cast<uint32_t>(edge[i].GetChr()), edge[i].GetDirection() == DNASequence::positive ? 0u : 1u,
+				static_cast<uint32_t>(edge[i].GetStartVertex()), static_cast<uint32_t>(edge[i].GetEndVertex()),
+				static_cast<uint32_t>(edge[i].GetActualPosition()), static_cast<uint32_t>(edge[i].GetActualLength()),
+				static_cast<uint32_t>(edge[i].GetOriginalPosition()), static_cast<uint32_t>(edge[i].GetOriginalLength()),
+				static_cast<uint32_t>(static_cast<unsigned char>(edge[i].GetFirstChar()))};
+			(*edges)[i] = e;
 		}
 
 		return 0;

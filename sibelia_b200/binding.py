@@ -7,11 +7,14 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 INST_DTYPE = np.dtype([("bifId", "<u4"), ("chr", "<u4"), ("pos", "<u4")])
+EDGE_DTYPE = np.dtype([("chr", "<u4"), ("direction", "<u4"), ("start_vertex", "<u4"), ("end_vertex", "<u4"),
+                       ("actual_position", "<u4"), ("actual_length", "<u4"), ("original_position", "<u4"),
+                       ("original_length", "<u4"), ("first_char", "<u4")])
 
 # every symbol include/sibgpu.h declares (tests/test_abi.py cross-checks this list against the header)
 SYMBOLS = [
     "sibgpu_last_error", "sibgpu_version", "sibgpu_device_count", "sibgpu_create", "sibgpu_destroy", "sibgpu_free",
-    "sibgpu_enumerate", "sibgpu_upload", "sibgpu_enumerate_resident", "sibgpu_download", "sibgpu_set_profiling",
+    "sibgpu_enumerate", "sibgpu_list_edges", "sibgpu_upload", "sibgpu_enumerate_resident", "sibgpu_download", "sibgpu_set_profiling",
     "sibgpu_kernel_stats", "sibgpu_last_launches", "sibgpu_partition_fallbacks", "sibgpu_last_device_ms", "sibgpu_simplify", "sibgpu_debug_unordered_order", "sibgpu_dist_upload", "sibgpu_dist_scan", "sibgpu_dist_record_bytes",
     "sibgpu_dist_scatter", "sibgpu_dist_group", "sibgpu_dist_keys", "sibgpu_dist_finish",
     "sibgpu_dist_scatter_local", "sibgpu_dist_export_send", "sibgpu_dist_import_peers", "sibgpu_dist_group_peer",
@@ -128,6 +131,26 @@ class Context:
         _check(L.sibgpu_enumerate(self._h, ptrs, lens, C.c_uint32(n), C.c_uint32(k), C.byref(pos), C.byref(npos),
                                   C.byref(neg), C.byref(nneg), C.byref(cnt)))
         return cnt.value, _take(pos, npos.value), _take(neg, nneg.value)
+
+    # -- sibgpu_list_edges: index + ListEdges without a host-side index
+    def list_edges(self, chrs, origpos, k):
+        L = load()
+        bufs, ptrs, lens, n = _chr_args(chrs)
+        if origpos is None:
+            op = None
+        else:
+            ops = [np.ascontiguousarray(o, dtype=np.uint32) for o in origpos]
+            op = (C.c_void_p * max(n, 1))(*[o.ctypes.data if len(o) else None for o in ops])
+        edges, ne = C.c_void_p(), C.c_uint64()
+        _check(L.sibgpu_list_edges(self._h, ptrs, op, lens, C.c_uint32(n), C.c_uint32(k), C.byref(edges), C.byref(ne)))
+        if ne.value:
+            buf = (C.c_char * (ne.value * EDGE_DTYPE.itemsize)).from_address(edges.value)
+            out = np.frombuffer(buf, dtype=EDGE_DTYPE, count=ne.value).copy()
+        else:
+            out = np.zeros(0, dtype=EDGE_DTYPE)
+        if edges.value:
+            L.sibgpu_free(edges)
+        return out
 
     # -- staged form
     def upload(self, chrs):

@@ -8,6 +8,8 @@
 #include "context.h"
 
 namespace sibgpu {
+static const std::chrono::steady_clock::time_point g_loaded = std::chrono::steady_clock::now();
+double since_load_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - g_loaded).count(); }
 static thread_local std::string g_error;
 void set_error(const std::string &msg) { g_error = msg; }
 } // namespace sibgpu
@@ -156,7 +158,7 @@ void sibgpu_destroy(sibgpu_ctx *c)
 		&c->d_records, &c->d_table, &c->d_partcnt, &c->d_keyoff, &c->d_ckeys, &c->d_vkeys, &c->d_vkeys_alt, &c->d_cubtmp,
 		&c->d_map, &c->d_filter, &c->d_hitmask, &c->d_tilecnt, &c->d_tileoff, &c->d_pos, &c->d_negtmp, &c->d_neg,
 		&c->d_chrinst, &c->d_scalars, &c->d_fp, &c->d_rep, &c->d_order, &c->d_s_ch, &c->d_s_m0, &c->d_s_m1, &c->d_s_off,
-		&c->d_s_inst, &c->d_s_flag};
+		&c->d_s_inst, &c->d_s_flag, &c->d_edges, &c->d_edge_skip};
 	for(void *pp : c->peer_ptr)
 	{
 		if(pp) cudaIpcCloseMemHandle(pp);
@@ -320,11 +322,55 @@ int sibgpu_enumerate(sibgpu_ctx *c, const char *const *chr, const uint64_t *len,
 	if(trace)
 	{
 		const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
-		fprintf(stderr, "[sibgpu_enumerate] N=%llu nchr=%u k=%u -> V=%u I=%llu  %.3f ms (device %.3f ms, %llu launches)\n",
-			(unsigned long long)c->N, nchr, k, c->n_vertices, (unsigned long long)c->n_inst, ms, c->last_ms,
+		fprintf(stderr, "[sibgpu_enumerate] t=%.0f ms  N=%llu nchr=%u k=%u -> V=%u I=%llu  %.3f ms (device %.3f ms, %llu launches)\n",
+			since_load_ms(), (unsigned long long)c->N, nchr, k, c->n_vertices, (unsigned long long)c->n_inst, ms, c->last_ms,
 			(unsigned long long)c->total_launches);
 	}
 	return rc;
+}
+
+int sibgpu_list_edges(sibgpu_ctx *c, const char *const *seq, const uint32_t *const *origpos, const uint64_t *len, uint32_t nchr,
+	uint32_t k, sibgpu_edge **edges, uint64_t *nedges)
+{
+	if(!c || !edges || !nedges || k == 0)
+	{
+		set_error("invalid: NULL argument or k == 0");
+		return SIBGPU_ERR_INVALID;
+	}
+	static const bool trace = getenv("SIBGPU_TRACE") != nullptr;
+	const auto t0 = std::chrono::steady_clock::now();
+	SIB_TRY(upload_layout(c, seq, len, nchr));
+	HostSrc src = {seq, len};
+	SIB_CUDA(cudaEventRecord(c->ev_begin, c->stream));
+	SIB_TRY(enumerate_resident(c, k, &src));
+	c->have_text = true;
+	SIB_TRY(list_edges_device(c, k, edges, nedges));
+	SIB_CUDA(cudaEventRecord(c->ev_end, c->stream));
+	SIB_CUDA(cudaEventSynchronize(c->ev_end));
+	SIB_CUDA(cudaEventElapsedTime(&c->last_ms, c->ev_begin, c->ev_end));
+	// original coordinates (SpellOriginal, src/dnasequence.cpp:254-260): the kernel left the element indices of the
+	// first and the last element of every edge; originalPos_ lives on the host
+	sibgpu_edge *e = *edges;
+	for(uint64_t i = 0; i < *nedges; i++)
+	{
+		uint32_t o1 = e[i].original_position, o2 = e[i].original_length;
+		if(origpos)
+		{
+			o1 = origpos[e[i].chr][o1];
+			o2 = origpos[e[i].chr][o2];
+		}
+		const uint32_t lo = o1 < o2 ? o1 : o2, hi = o1 < o2 ? o2 : o1;
+		e[i].original_position = lo;
+		e[i].original_length = hi + 1 - lo;
+	}
+	if(trace)
+	{
+		const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+		fprintf(stderr, "[sibgpu_list_edges] t=%.0f ms  N=%llu nchr=%u k=%u -> V=%u I=%llu E=%llu  %.3f ms (device %.3f ms)\n",
+			since_load_ms(), (unsigned long long)c->N, nchr, k, c->n_vertices, (unsigned long long)c->n_inst,
+			(unsigned long long)*nedges, ms, c->last_ms);
+	}
+	return SIBGPU_OK;
 }
 
 // ---------------------------------------------------------------------------------------------------------------

@@ -35,7 +35,7 @@ struct sibgpu_ctx {
 	// enumeration workspace
 	sibgpu::DevBuf d_hist, d_partoff, d_cursor, d_records, d_table, d_partcnt, d_keyoff, d_ckeys, d_vkeys, d_vkeys_alt,
 		d_cubtmp, d_map, d_filter, d_hitmask, d_tilecnt, d_tileoff, d_pos, d_negtmp, d_neg, d_chrinst, d_scalars,
-		d_fp, d_rep, d_order, d_s_ch, d_s_m0, d_s_m1, d_s_off, d_s_inst, d_s_flag;
+		d_fp, d_rep, d_order, d_s_ch, d_s_m0, d_s_m1, d_s_off, d_s_inst, d_s_flag, d_edges, d_edge_skip;
 	void *h_scalars = nullptr;                         // pinned, 64 x u64
 
 	// last result
@@ -109,6 +109,7 @@ struct ProfScope {
 struct HostSrc { const char *const *chr; const uint64_t *len; };
 int copy_text_range(sibgpu_ctx *ctx, const HostSrc &src, uint64_t lo, uint64_t hi, cudaStream_t st);
 int enumerate_resident(sibgpu_ctx *ctx, uint32_t k, const HostSrc *src);
+int list_edges_device(sibgpu_ctx *ctx, uint32_t k, sibgpu_edge **edges_out, uint64_t *nedges_out);   // edges.cu
 int dist_scan(sibgpu_ctx *ctx, uint32_t k, uint32_t *hist_out);
 int dist_scatter(sibgpu_ctx *ctx, void *send_dev);
 int dist_group(sibgpu_ctx *ctx, const void *recv_dev, const uint32_t *counts, uint64_t *nkeys_local);

@@ -30,12 +30,27 @@ namespace sibgpu {
 __global__ void __launch_bounds__(256) k_pack(const uint4 *__restrict__ text, uint32_t *__restrict__ packed,
 	uint32_t nwords, uint32_t *__restrict__ err)
 {
+	// PACK_ILP independent 128-bit loads in flight per thread (a 100 MB text is only ~40 us of HBM time: latency, not
+	// issue, is what has to be hidden); streaming loads, the ASCII text is read exactly once
+	constexpr int PACK_ILP = 4;
 	uint32_t bad = 0;
-	for(uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < nwords; i += gridDim.x * blockDim.x)
+	const uint32_t stride = gridDim.x * blockDim.x;
+	for(uint32_t i0 = blockIdx.x * blockDim.x + threadIdx.x; i0 < nwords; i0 += stride * PACK_ILP)
 	{
-		uint4 v = __ldg(text + i);
-		bad |= ~(legal_bytes(v.x) & legal_bytes(v.y) & legal_bytes(v.z) & legal_bytes(v.w)) & 0x80808080u;
-		packed[i] = (encode4(v.x) << 24) | (encode4(v.y) << 16) | (encode4(v.z) << 8) | encode4(v.w);
+		uint4 v[PACK_ILP];
+#pragma unroll
+		for(int u = 0; u < PACK_ILP; u++)
+		{
+			const uint32_t i = i0 + u * stride;
+			v[u] = i < nwords ? __ldcs(text + i) : make_uint4(0x41414141u, 0x41414141u, 0x41414141u, 0x41414141u);
+		}
+#pragma unroll
+		for(int u = 0; u < PACK_ILP; u++)
+		{
+			const uint32_t i = i0 + u * stride;
+			bad |= ~(legal_bytes(v[u].x) & legal_bytes(v[u].y) & legal_bytes(v[u].z) & legal_bytes(v[u].w)) & 0x80808080u;
+			if(i < nwords) packed[i] = (encode4(v[u].x) << 24) | (encode4(v[u].y) << 16) | (encode4(v[u].z) << 8) | encode4(v[u].w);
+		}
 	}
 	if(__any_sync(0xffffffffu, bad != 0) && (threadIdx.x & 31) == 0) atomicOr(err, 1u);
 }

@@ -27,6 +27,7 @@
 
 namespace sibgpu {
 
+double since_load_ms();                                // api.cu
 using namespace simp;
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -126,7 +127,7 @@ extern "C" int sibgpu_simplify(sibgpu_ctx *ctx, char **seq, uint32_t **origpos, 
 		if(trace)
 		{
 			const double t = now();
-			fprintf(stderr, "[sibgpu_simplify] %-28s %8.2f ms\n", what, (t - t_mark) * 1e3);
+			fprintf(stderr, "[sibgpu_simplify] t=%.0f ms  %-28s %8.2f ms\n", since_load_ms(), what, (t - t_mark) * 1e3);
 			t_mark = t;
 		}
 	};
