@@ -141,6 +141,22 @@ int sibgpu_list_edges(sibgpu_ctx *ctx, const char *const *seq, const uint32_t *c
 	uint32_t nchr, uint32_t k, sibgpu_edge **edges, uint64_t *nedges);
 
 /* ---------------------------------------------------------------------------------------------------------------
+ * sibgpu_trim_blocks: replaces the index-and-search part of
+ *     bool BlockFinder::TrimBlocks(std::vector<Edge> & block, size_t trimK, size_t minSize)   src/synteny.cpp:31-122
+ * (IndexedSequence iseq(blockSeq, trimK, "") + ConstructChrIndex + the walk over every vertex mark and all of its
+ * instances; GenerateSyntenyBlocks calls it in a loop for every block, src/synteny.cpp:263).
+ *   seq[i], len[i]     blockSeq[i] (sanitised ACGT), the original sequence spelled by block[i]
+ *   direction[i]       block[i].GetDirection(): 0 = positive, 1 = negative
+ *   out[i]             found = 0: no vertex of sequence i (read along its direction) occurs on another sequence
+ *                      (the reference sets drop = true); otherwise start / end = element index (0-based position in
+ *                      seq[i], positive-strand coordinates) of the reference's trimStart / trimEnd iterators.
+ * The caller finishes like synteny.cpp:105-116 (size test against minSize, std::advance(trimEnd, trimK - 1), Edge).
+ */
+typedef struct sibgpu_trim { uint32_t found, start, end; } sibgpu_trim;
+int sibgpu_trim_blocks(sibgpu_ctx *ctx, const char *const *seq, const uint64_t *len, const uint8_t *direction,
+	uint32_t nchr, uint32_t trim_k, sibgpu_trim *out);
+
+/* ---------------------------------------------------------------------------------------------------------------
  * Sharded enumeration over `world` GPUs of one box, ONE PROCESS PER GPU (k <= 32).  The concatenated genome is split
  * into `world` contiguous text ranges; records are bucketed by hash prefix so that partition p belongs to rank
  * p / (nparts_total / world); the caller moves them with one all-to-all (NCCL) between two device buffers it owns,

@@ -135,6 +135,25 @@ def list_edges(chrs, origpos, k):
     return _take(edges, ne.value, EDGE_DTYPE), sec.value
 
 
+def trim_blocks(chrs, directions, trim_k, min_size):
+    """BlockFinder::TrimBlocks of the reference on a block made of whole sequences (block[i] = sequence i read along
+    directions[i]).  Returns (list of (chr, originalPosition, originalLength), drop)."""
+    L = lib()
+    chrs = _as_bytes_list(chrs)
+    n = len(chrs)
+    arr = (C.c_char_p * max(n, 1))(*chrs)
+    lens = (C.c_uint64 * max(n, 1))(*[len(c) for c in chrs])
+    d = np.ascontiguousarray(directions, dtype=np.uint8)
+    out = np.zeros(3 * max(n, 1), dtype=np.uint32)
+    nout, drop = C.c_uint32(), C.c_int()
+    L.ref_trim_blocks.restype = C.c_int
+    rc = L.ref_trim_blocks(C.c_uint32(n), arr, lens, C.c_void_p(d.ctypes.data), C.c_uint32(trim_k), C.c_uint32(min_size),
+                           C.c_void_p(out.ctypes.data), C.byref(nout), C.byref(drop))
+    if rc != 0:
+        raise RuntimeError(L.ref_last_error().decode())
+    return [tuple(int(x) for x in out[3 * i:3 * i + 3]) for i in range(nout.value)], bool(drop.value)
+
+
 def boost_order(keys):
     """Iteration order of the vendored boost::unordered_map<size_t,int> after inserting distinct keys in order."""
     keys = np.ascontiguousarray(keys, dtype=np.uint64)

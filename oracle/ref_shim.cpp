@@ -261,4 +261,44 @@ int ref_list_edges(uint32_t nchr, const char* const* seq, const uint32_t* const*
 	}
 }
 
+
+// BlockFinder::TrimBlocks (src/synteny.cpp:31-122) on a block whose sequences are whole "chromosomes": block[i] =
+// Edge(chr i, direction dir[i], original position 0, original length len[i]).  Returns the surviving edges as
+// (chr, originalPosition, originalLength) triples and the function's return value (drop).
+int ref_trim_blocks(uint32_t nchr, const char* const* seq, const uint64_t* len, const uint8_t* dir, uint32_t trimK, uint32_t minSize,
+	uint32_t* out_triples, uint32_t* nout, int* drop)
+{
+	try
+	{
+		std::vector<FASTARecord> chrList;
+		for(uint32_t i = 0; i < nchr; i++)
+		{
+			chrList.push_back(FASTARecord(std::string(seq[i], seq[i] + len[i]), "chr", i));
+		}
+
+		BlockFinder finder(chrList);
+		std::vector<BlockFinder::Edge> block;
+		for(uint32_t i = 0; i < nchr; i++)
+		{
+			block.push_back(BlockFinder::Edge(i, dir[i] ? DNASequence::negative : DNASequence::positive, 0, 0, 0, 0, 0, len[i], 'A'));
+		}
+
+		*drop = finder.TrimBlocks(block, trimK, minSize) ? 1 : 0;
+		*nout = static_cast<uint32_t>(block.size());
+		for(size_t i = 0; i < block.size(); i++)
+		{
+			out_triples[3 * i] = static_cast<uint32_t>(block[i].GetChr());
+			out_triples[3 * i + 1] = static_cast<uint32_t>(block[i].GetOriginalPosition());
+			out_triples[3 * i + 2] = static_cast<uint32_t>(block[i].GetOriginalLength());
+		}
+
+		return 0;
+	}
+	catch(std::exception & e)
+	{
+		g_err = e.what();
+		return 1;
+	}
+}
+
 }

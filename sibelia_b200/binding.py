@@ -14,7 +14,7 @@ EDGE_DTYPE = np.dtype([("chr", "<u4"), ("direction", "<u4"), ("start_vertex", "<
 # every symbol include/sibgpu.h declares (tests/test_abi.py cross-checks this list against the header)
 SYMBOLS = [
     "sibgpu_last_error", "sibgpu_version", "sibgpu_device_count", "sibgpu_create", "sibgpu_destroy", "sibgpu_free",
-    "sibgpu_enumerate", "sibgpu_list_edges", "sibgpu_upload", "sibgpu_enumerate_resident", "sibgpu_download", "sibgpu_set_profiling",
+    "sibgpu_enumerate", "sibgpu_list_edges", "sibgpu_trim_blocks", "sibgpu_upload", "sibgpu_enumerate_resident", "sibgpu_download", "sibgpu_set_profiling",
     "sibgpu_kernel_stats", "sibgpu_last_launches", "sibgpu_partition_fallbacks", "sibgpu_last_device_ms", "sibgpu_simplify", "sibgpu_debug_unordered_order", "sibgpu_dist_upload", "sibgpu_dist_scan", "sibgpu_dist_record_bytes",
     "sibgpu_dist_scatter", "sibgpu_dist_group", "sibgpu_dist_keys", "sibgpu_dist_finish",
     "sibgpu_dist_scatter_local", "sibgpu_dist_export_send", "sibgpu_dist_import_peers", "sibgpu_dist_group_peer",
@@ -151,6 +151,15 @@ class Context:
         if edges.value:
             L.sibgpu_free(edges)
         return out
+
+    # -- sibgpu_trim_blocks: the index-and-search part of BlockFinder::TrimBlocks
+    def trim_blocks(self, chrs, directions, trim_k):
+        bufs, ptrs, lens, n = _chr_args(chrs)
+        d = np.ascontiguousarray(directions, dtype=np.uint8)
+        out = np.zeros((max(n, 1), 3), dtype=np.uint32)
+        _check(load().sibgpu_trim_blocks(self._h, ptrs, lens, C.c_void_p(d.ctypes.data), C.c_uint32(n), C.c_uint32(trim_k),
+                                         C.c_void_p(out.ctypes.data)))
+        return out[:n]
 
     # -- staged form
     def upload(self, chrs):

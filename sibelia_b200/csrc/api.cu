@@ -373,6 +373,70 @@ int sibgpu_list_edges(sibgpu_ctx *c, const char *const *seq, const uint32_t *con
 	return SIBGPU_OK;
 }
 
+// BlockFinder::TrimBlocks (src/synteny.cpp:31-122) without the host-side index.  The reference walks every sequence of
+// the block along the block's direction and, at every vertex mark `it`, looks at all instances `kmer` of that vertex
+// that lie on ANOTHER sequence (either strand); with distances measured in elements from the two ends of a sequence
+// as seen along its block direction (IndexedSequence::StrandIteratorDistance, src/indexedsequence.cpp:162-167) it keeps
+//     trimStart = first `it` minimising (dStart(it) + dStart(kmer), vertex id),   trimEnd likewise with dEnd.
+// Only the minimum over the kmers matters, so per vertex we keep the smallest dStart/dEnd together with the sequence it
+// comes from and the smallest one from any other sequence; the scan over the marks is then O(instances).
+int sibgpu_trim_blocks(sibgpu_ctx *c, const char *const *seq, const uint64_t *len, const uint8_t *direction, uint32_t nchr,
+	uint32_t trim_k, sibgpu_trim *out)
+{
+	if(!c || (nchr && (!seq || !len || !direction || !out)) || trim_k == 0)
+	{
+		set_error("invalid: NULL argument or trim_k == 0");
+		return SIBGPU_ERR_INVALID;
+	}
+	sibgpu_inst *tab[2] = {nullptr, nullptr};
+	uint64_t ntab[2] = {0, 0};
+	uint32_t count = 0;
+	SIB_TRY(sibgpu_enumerate(c, seq, len, nchr, trim_k, &tab[0], &ntab[0], &tab[1], &ntab[1], &count));
+	const uint32_t INF = 0xFFFFFFFFu;
+	struct Best { uint32_t b1, c1, b2; };
+	std::vector<Best> bs(count, Best{INF, INF, INF}), be(count, Best{INF, INF, INF});
+	auto add = [&](std::vector<Best> &v, uint32_t id, uint32_t d, uint32_t chr) {
+		Best &b = v[id];
+		if(chr == b.c1) { if(d < b.b1) b.b1 = d; }
+		else if(d < b.b1) { b.b2 = b.b1; b.b1 = d; b.c1 = chr; }
+		else if(d < b.b2) b.b2 = d;
+	};
+	for(int strand = 0; strand < 2; strand++)
+	{
+		for(uint64_t i = 0; i < ntab[strand]; i++)
+		{
+			const sibgpu_inst &x = tab[strand][i];
+			const uint32_t L = (uint32_t)len[x.chr];
+			const uint32_t elem = strand == 0 ? x.pos : L - 1 - x.pos;
+			const uint32_t dstart = direction[x.chr] == 0 ? elem : L - 1 - elem;       // along the block direction of ITS sequence
+			add(bs, x.bifId, dstart, x.chr);
+			add(be, x.bifId, L - 1 - dstart, x.chr);
+		}
+	}
+	for(uint32_t chr = 0; chr < nchr; chr++) out[chr] = sibgpu_trim{0u, 0u, 0u};
+	std::vector<uint64_t> best_s(nchr, ~0ull), best_e(nchr, ~0ull);              // (sum << 32 | vertex id), first minimum wins
+	for(int strand = 0; strand < 2; strand++)
+	{
+		for(uint64_t i = 0; i < ntab[strand]; i++)
+		{
+			const sibgpu_inst &x = tab[strand][i];
+			if((direction[x.chr] != 0) != (strand != 0)) continue;              // `it` walks the block direction only
+			const uint32_t L = (uint32_t)len[x.chr];
+			const Best &s0 = bs[x.bifId], &e0 = be[x.bifId];
+			const uint32_t os = s0.c1 != x.chr ? s0.b1 : s0.b2, oe = e0.c1 != x.chr ? e0.b1 : e0.b2;
+			if(os == INF) continue;                                             // the vertex occurs on this sequence only
+			const uint32_t elem = strand == 0 ? x.pos : L - 1 - x.pos;
+			const uint64_t ks = ((uint64_t)(x.pos + os) << 32) | x.bifId, ke = ((uint64_t)(L - 1 - x.pos + oe) << 32) | x.bifId;
+			if(ks < best_s[x.chr]) { best_s[x.chr] = ks; out[x.chr].start = elem; }
+			if(ke < best_e[x.chr]) { best_e[x.chr] = ke; out[x.chr].end = elem; }
+			out[x.chr].found = 1;
+		}
+	}
+	sibgpu_free(tab[0]);
+	sibgpu_free(tab[1]);
+	return SIBGPU_OK;
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // sharded enumeration (one process per GPU)
 // ---------------------------------------------------------------------------------------------------------------
