@@ -162,14 +162,13 @@ extern "C" int sibgpu_simplify(sibgpu_ctx *ctx, char **seq, uint32_t **origpos, 
 	do
 	{
 		iterations++;
-		// ---- snapshot of the sweep's initial state -> GPU detection of every vertex
-		if(iterations > 1)
+		// ---- first sweep: snapshot of the initial state -> GPU detection of every vertex.  Later sweeps need no
+		// snapshot: `dirty` is cleared when a vertex is visited and set by every later change its walks can see, so a
+		// vertex that is clean at its next visit would repeat its last (empty) outcome -- RemoveBulges only changes
+		// state through collapses, and a call that collapsed something always dirties its own vertex.
+		int rc = SIBGPU_OK;
+		if(iterations == 1)
 		{
-			S.compact();
-			S.compact_nodes();
-		}
-		lap("renumber");
-		std::fill(S.dirty.begin(), S.dirty.end(), 0);
 		const size_t total = S.ch.size();
 		inst_elem.clear();
 		for(size_t id = 0; id <= max_id; id++)
@@ -181,7 +180,6 @@ extern "C" int sibgpu_simplify(sibgpu_ctx *ctx, char **seq, uint32_t **origpos, 
 			}
 		}
 		inst_off[max_id + 1] = inst_elem.size();
-		int rc = SIBGPU_OK;
 		auto dev = [&]() -> int {
 			SIB_CUDA(cudaSetDevice(ctx->device));
 			SIB_TRY(d_ch.ensure(total));
@@ -216,6 +214,8 @@ extern "C" int sibgpu_simplify(sibgpu_ctx *ctx, char **seq, uint32_t **origpos, 
 		};
 		lap("instance CSR");
 		rc = dev();
+		}
+		else std::fill(flag.begin(), flag.end(), 0);
 		if(rc != SIBGPU_OK)
 		{
 			release();
@@ -231,6 +231,7 @@ extern "C" int sibgpu_simplify(sibgpu_ctx *ctx, char **seq, uint32_t **origpos, 
 			if(flag[id] || S.dirty[id])
 			{
 				n_calls++;
+				S.dirty[id] = 0;                            // clean as of this visit; the call itself may dirty it again
 				total_bulges += S.remove_bulges(id);
 			}
 			if(++cnt >= threshold && progress)

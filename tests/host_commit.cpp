@@ -1,6 +1,7 @@
 // Test harness (CPU): drives the host-side committer of sibgpu_simplify (sibelia_b200/csrc/simplifier.h) without a GPU.
 // The vertex tables come from the caller (the tests pass the oracle's), and EVERY vertex is treated as flagged, i.e. the
 // exact RemoveBulges restatement runs for all ids in order -- which must reproduce the reference stage bit for bit.
+// With dirty_mode the later sweeps visit only the vertices dirtied since their last visit (the product's policy).
 // Built by tests/test_host_commit.py into tests/_build/libhostcommit.so.
 #include <cstdlib>
 
@@ -10,7 +11,7 @@ using namespace sibgpu::simp;
 
 extern "C" int host_simplify(uint32_t nchr, char **seq, uint32_t **origpos, uint64_t *len, uint32_t k, uint32_t D,
 	uint32_t max_iterations, const sibgpu_inst *pos, uint64_t npos, const sibgpu_inst *neg, uint64_t nneg, uint32_t count,
-	uint64_t *bulges, uint64_t *exact_calls)
+	uint64_t *bulges, uint64_t *exact_calls, int dirty_mode)
 {
 	Simplifier S;
 	S.build(nchr, seq, origpos, len, k, D, count, pos, npos, neg, nneg);
@@ -19,13 +20,17 @@ extern "C" int host_simplify(uint32_t nchr, char **seq, uint32_t **origpos, uint
 	do
 	{
 		iterations++;
-		if(iterations > 1)
+		if(iterations > 1 && !dirty_mode)
 		{
 			S.compact();
 			S.compact_nodes();
 		}
 		for(size_t id = 0; id <= count; id++)
 		{
+			// dirty_mode = the sweep policy of sibgpu_simplify: every vertex in the first sweep (there the GPU flags a
+			// superset of the vertices with bulges), afterwards only the vertices dirtied since their last visit
+			if(dirty_mode && iterations > 1 && !S.dirty[id]) continue;
+			S.dirty[id] = 0;
 			total_bulges += S.remove_bulges(id);
 			calls++;
 		}

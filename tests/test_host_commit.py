@@ -28,7 +28,7 @@ def hc():
     return C.CDLL(LIB)
 
 
-def host_simplify(lib, chrs, origpos, k, D, iters=4):
+def host_simplify(lib, chrs, origpos, k, D, iters=4, dirty_mode=0):
     count, pos, neg = restate.enumerate_bifurcations(chrs, k)
     n = len(chrs)
     bufs = [np.frombuffer(bytes(c), dtype=np.uint8).copy() for c in chrs]
@@ -41,7 +41,7 @@ def host_simplify(lib, chrs, origpos, k, D, iters=4):
     neg = np.ascontiguousarray(neg)
     rc = lib.host_simplify(C.c_uint32(n), seq, op, lens, C.c_uint32(k), C.c_uint32(D), C.c_uint32(iters),
                            C.c_void_p(pos.ctypes.data), C.c_uint64(len(pos)), C.c_void_p(neg.ctypes.data),
-                           C.c_uint64(len(neg)), C.c_uint32(count), C.byref(bulges), C.byref(calls))
+                           C.c_uint64(len(neg)), C.c_uint32(count), C.byref(bulges), C.byref(calls), C.c_int(dirty_mode))
     assert rc == 0
     out_c, out_o = [], []
     lib.host_free.argtypes = [C.c_void_p]
@@ -65,14 +65,15 @@ def assert_state_equal(got, want, what):
 FILES = sorted(glob.glob(os.path.join(GOLD, "simplify_*.npz")))
 
 
+@pytest.mark.parametrize("dirty_mode", [0, 1])
 @pytest.mark.parametrize("path", FILES, ids=[os.path.basename(p)[:-4] for p in FILES])
-def test_golden_stages(hc, path):
+def test_golden_stages(hc, path, dirty_mode):
     z = np.load(path)
     n = int(z["n"])
     chrs = [z["in_seq_%d" % i].tobytes() for i in range(n)]
     op = [np.arange(len(c), dtype=np.uint32) for c in chrs]
     for s, (k, D) in enumerate(z["stages"]):
-        chrs, op, bulges = host_simplify(hc, chrs, op, int(k), int(D), 4)
+        chrs, op, bulges = host_simplify(hc, chrs, op, int(k), int(D), 4, dirty_mode)
         want = ([z["seq_%d_%d" % (s, i)].tobytes() for i in range(n)], [z["op_%d_%d" % (s, i)] for i in range(n)],
                 int(z["bulges_%d" % s]))
         assert_state_equal((chrs, op, bulges), want, "%s stage %d" % (os.path.basename(path), s))
@@ -89,15 +90,20 @@ def test_random_small_against_reference(hc):
         iters = int(rng.integers(1, 5))
         D = int(rng.integers(k + 1, 50))
         want = ref.simplify(chrs, op, k, D, iters)[:3]
-        assert_state_equal(host_simplify(hc, chrs, op, k, D, iters), want, "case %d k=%d D=%d iters=%d" % (it, k, D, iters))
+        for dm in (0, 1):
+            assert_state_equal(host_simplify(hc, chrs, op, k, D, iters, dm), want,
+                               "case %d k=%d D=%d iters=%d dirty_mode=%d" % (it, k, D, iters, dm))
 
 
 @pytest.mark.skipif(not ref.available(), reason="oracle/_ref not built (needs /root/reference)")
-def test_strains_against_reference(hc):
-    chrs = [c.tobytes() for c in helpers.strain_case(4, 40_000, p_sub=0.02, inv_len=3000, seed=91)]
+@pytest.mark.parametrize("dirty_mode,seed,ps", [(0, 91, 0.02), (1, 91, 0.02), (1, 92, 0.05), (1, 93, 0.005)])
+def test_strains_against_reference(hc, dirty_mode, seed, ps):
+    """dirty_mode = 1 is the sweep policy of sibgpu_simplify: later sweeps visit only vertices dirtied since their
+    last visit (no snapshot, no renumbering); it must give the reference's result exactly like visiting everything."""
+    chrs = [c.tobytes() for c in helpers.strain_case(4, 40_000, p_sub=ps, inv_len=3000, seed=seed)]
     op = [np.arange(len(c), dtype=np.uint32) for c in chrs]
     rc, ro = chrs, op
     for (k, D) in [(25, 150), (100, 1000)]:
         rc, ro, rb, _ = ref.simplify(rc, ro, k, D, 4)
-        chrs, op, b = host_simplify(hc, chrs, op, k, D, 4)
+        chrs, op, b = host_simplify(hc, chrs, op, k, D, 4, dirty_mode)
         assert_state_equal((chrs, op, b), (rc, ro, rb), "stage (%d,%d)" % (k, D))
