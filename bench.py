@@ -303,10 +303,11 @@ def main():
             if dname in tj:
                 roofline["traffic"] = tj[dname]
             elif dname == "k_insert+k_table_scan":
-                per_launch_records = 4194304.0      # the captures were taken with 4 Mi-record partitions
+                per_launch_records = 1048576.0      # the captures were taken with the default 1 Mi-record partitions
                 nrec = d["algo_bytes"] / 8.0 / args.steps
                 roofline["traffic"] = (tj["k_insert"] + tj["k_table_scan"]) * nrec / per_launch_records
-                roofline["traffic_note"] = "whole phase per step, scaled from per-launch captures at 4 Mi records/partition"
+                roofline["traffic_note"] = ("whole phase per step = per-launch dram bytes of the two kernels (ncu --set full, warm L2: the "
+                                            "table and most of the freshly scattered records are L2-resident) x partitions per step")
         except Exception:
             pass
     roofline["note"] = ("k_insert is bound by scattered L2 atomics, not by HBM: tools/ubench/atomics.cu measures 90-104 G CAS/s "

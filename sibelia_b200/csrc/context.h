@@ -72,6 +72,12 @@ struct sibgpu_ctx {
 	int ensure_aux_streams(uint32_t n);
 	int table_factor = 2;                              // slots per record of the largest partition (env SIBGPU_TABLE_FACTOR)
 
+	// sibgpu_simplify: the per-element host arrays of a stage are recycled between stages (a fresh 30 B/element
+	// allocation per stage costs more in page faults than the stage's device work)
+	std::vector<char> pool_ch;
+	std::vector<uint32_t> pool_u32[3];
+	std::vector<int32_t> pool_i32[4];
+
 	// profiling
 	bool profiling = false;
 	struct Span { const char *name; cudaEvent_t a, b; uint64_t bytes; };

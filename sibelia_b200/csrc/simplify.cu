@@ -140,6 +140,17 @@ extern "C" int sibgpu_simplify(sibgpu_ctx *ctx, char **seq, uint32_t **origpos, 
 	float device_ms = ctx->last_ms;
 	lap("enumerate (host buffers)");
 	Simplifier S;
+	auto recycle = [&]() {                              // swaps the big per-element arrays with the context's pool
+		S.ch.swap(ctx->pool_ch);
+		S.opos.swap(ctx->pool_u32[0]);
+		S.mark[0].swap(ctx->pool_u32[1]);
+		S.mark[1].swap(ctx->pool_u32[2]);
+		S.nxt.swap(ctx->pool_i32[0]);
+		S.prv.swap(ctx->pool_i32[1]);
+		S.node_of[0].swap(ctx->pool_i32[2]);
+		S.node_of[1].swap(ctx->pool_i32[3]);
+	};
+	recycle();
 	S.build(nchr, seq, origpos, len, k, min_branch_size, count, pos, npos, neg, nneg);
 	free(pos);
 	free(neg);
@@ -297,6 +308,7 @@ extern "C" int sibgpu_simplify(sibgpu_ctx *ctx, char **seq, uint32_t **origpos, 
 		len[c] = n;
 	}
 	lap("copy-back");
+	recycle();
 	*bulges = total_bulges;
 	return SIBGPU_OK;
 }

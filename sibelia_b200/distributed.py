@@ -45,8 +45,18 @@ class GpuShard:
     def export_send(self):
         return self.ctx.dist_export_send()
 
-    def group_peer(self, handles, counts, seg_caps):
-        self.ctx.dist_import_peers(handles)
+    def import_peers(self, handles):
+        """Maps the other ranks' send buffers (CUDA IPC); False if this rank cannot (no peer access, IPC unavailable)."""
+        try:
+            self.ctx.dist_import_peers(handles)
+            return True
+        except Exception as e:                       # noqa: BLE001 -- reported once, the staged exchange takes over
+            if not getattr(self, "_warned", False):
+                print("sibelia_b200.distributed: peer mapping unavailable (%s); using the staged all-to-all" % e, flush=True)
+                self._warned = True
+            return False
+
+    def group_peer(self, counts, seg_caps):
         n = self.ctx.dist_group_peer(counts, seg_caps)
         keys = torch.empty(max(n * self.words, 1), dtype=torch.int64, device=self.device)
         self.ctx.dist_keys(keys.data_ptr())
@@ -114,10 +124,21 @@ def enumerate_sharded(shard, chrs, k, group=None):
         allm = allm.cpu().numpy().reshape(world, len(mine))
         lap("allgather counts+handles")
         if not allm[:, nparts + 1].any():
-            keys = shard.group_peer(np.ascontiguousarray(allm[:, nparts + 2:]).view(np.uint8).reshape(world, 64),
-                                    allm[:, :nparts].astype(np.uint64), allm[:, nparts].astype(np.uint64))
-            lap("group (peer reads)")
-            words = shard.words
+            handles = np.ascontiguousarray(allm[:, nparts + 2:]).view(np.uint8).reshape(world, 64)
+            ok = shard.import_peers(handles)
+            if getattr(shard, "_peer_handles", None) is None or not np.array_equal(shard._peer_handles, handles):
+                # new mappings: every rank must have succeeded, or all take the staged path together (one tiny
+                # collective, only when a send buffer was (re)allocated -- normally the first call)
+                flag = _comm(torch.tensor([1 if ok else 0], dtype=torch.int64, device=dev), group)
+                dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+                ok = bool(int(flag.cpu()[0]))
+                shard._peer_handles = handles.copy() if ok else None
+                if not ok:
+                    shard.peer = False
+            if ok:
+                keys = shard.group_peer(allm[:, :nparts].astype(np.uint64), allm[:, nparts].astype(np.uint64))
+                lap("group (peer reads)")
+                words = shard.words
     if keys is None:
         keys, words, dev = _staged_exchange(shard, k, rank, world, group, lap)
     # --- vertex keys of all ranks (variable sizes: pad to the maximum)

@@ -23,36 +23,38 @@ PATS = [r"^gpu__time_duration\.sum$", r"^dram__bytes_(read|write)\.sum$", r"^lts
         r"^launch__occupancy_limit_(registers|shared_mem|warps)$", r"^launch__shared_mem_per_block_(dynamic|static)$"]
 traffic = {}
 for f in sorted(os.listdir(GO)):
-    m = re.match(r"r1_(k_\w+)\.ncu-rep$", f)
-    if not m:
+    if not re.match(r"r1_\w+\.ncu-rep$", f):
         continue
-    name = m.group(1)
     raw = subprocess.run(["ncu", "-i", os.path.join(GO, f), "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(raw)))
     if len(rows) < 3:
         continue
-    hdr, units, data = rows[0], rows[1], rows[2:]
-    lines = ["# ncu --set full --clock-control none --cache-control none, %d launch(es) of %s" % (len(data), name),
-             "# command: python bench.py --steps 1 --warmup 3 (100 MB random contig, k=25) unless noted", ""]
+    hdr, units, alldata = rows[0], rows[1], rows[2:]
     kn = hdr.index("Kernel Name")
-    lines.append("kernel: " + " | ".join(sorted(set(r[kn] for r in data))))
-    vals = {}
-    for i, h in enumerate(hdr):
-        if any(re.search(p, h) for p in PATS):
-            vals[h] = [r[i] for r in data]
-            lines.append("%-80s %-10s %s" % (h, units[i], "  ".join(r[i] for r in data)))
-    try:
-        rd = [float(x.replace(",", "")) for x in vals["dram__bytes_read.sum"]]
-        wr = [float(x.replace(",", "")) for x in vals["dram__bytes_write.sum"]]
-        ui = units[hdr.index("dram__bytes_read.sum")]
-        scale = {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1.0}.get(ui, 1.0)
-        traffic[name] = (sum(rd) + sum(wr)) / len(rd) * scale
-        lines.append("")
-        lines.append("dram traffic per launch (read+write): %.1f MB" % (traffic[name] / 1e6))
-    except Exception as e:
-        lines.append("traffic: n/a (%s)" % e)
-    open(os.path.join(OUT, "r1_ncu_%s.txt" % name), "w").write("\n".join(lines) + "\n")
-    print(name, "->", "r1_ncu_%s.txt" % name, "%.1f MB/launch" % (traffic.get(name, 0) / 1e6))
+    groups = collections.OrderedDict()
+    for r in alldata:
+        base = re.sub(r"^void\s+", "", r[kn]).split("<")[0].split("(")[0].split("::")[-1]
+        groups.setdefault(base, []).append(r)
+    for name, data in groups.items():
+        lines = ["# ncu --set full --clock-control none --cache-control none, %d launch(es) of %s (report %s)" % (len(data), name, f),
+                 "# command: see tools/profile_all.sh (python bench.py --steps 1 --warmup 3: 100 MB random contig, k=25, unless noted)", ""]
+        lines.append("kernel: " + " | ".join(sorted(set(r[kn] for r in data))))
+        vals = {}
+        for i, h in enumerate(hdr):
+            if any(re.search(p, h) for p in PATS):
+                vals[h] = [r[i] for r in data]
+                lines.append("%-80s %-10s %s" % (h, units[i], "  ".join(r[i] for r in data)))
+        try:
+            SC = {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1.0}
+            rd = [float(x.replace(",", "")) * SC.get(units[hdr.index("dram__bytes_read.sum")], 1.0) for x in vals["dram__bytes_read.sum"]]
+            wr = [float(x.replace(",", "")) * SC.get(units[hdr.index("dram__bytes_write.sum")], 1.0) for x in vals["dram__bytes_write.sum"]]
+            traffic[name] = (sum(rd) + sum(wr)) / len(rd)
+            lines.append("")
+            lines.append("dram traffic per launch (read+write): %.1f MB" % (traffic[name] / 1e6))
+        except Exception as e:
+            lines.append("traffic: n/a (%s)" % e)
+        open(os.path.join(OUT, "r1_ncu_%s.txt" % name), "w").write("\n".join(lines) + "\n")
+        print(name, "->", "r1_ncu_%s.txt" % name, "%.1f MB/launch" % (traffic.get(name, 0) / 1e6))
 # bench.py looks kernels up by their profiler-span names
 alias = {"k_insert_compact": "k_insert", "k_table_scan_compact": "k_table_scan"}
 tj = {alias.get(k, k): v for k, v in traffic.items()}
@@ -75,7 +77,7 @@ if os.path.exists(src):
         a[1] += float(r[mv].replace(",", ""))
     tot = sum(v[1] for v in agg.values())
     with open(os.path.join(OUT, "r1_launches_summary.txt"), "w") as f:
-        f.write("# ncu --metrics gpu__time_duration.sum --clock-control none -c 260 python bench.py --steps 1 --warmup 3\n")
+        f.write("# ncu --metrics gpu__time_duration.sum --clock-control none -c 900 python bench.py --steps 1 --warmup 3\n")
         f.write("# (4 enumerations of the 100 MB random contig, k=25, + torch fill kernels; cold-cache serialised times: compare SHARES)\n")
         for n, (c, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
             f.write("%-70s launches %4d  total %10.1f us  share %5.1f%%\n" % (n[:70], c, t / 1000, 100 * t / tot))
