@@ -172,6 +172,23 @@ def test_rejects_unsanitised_input(ctx):
     assert e.value.status == 3
 
 
+def test_rejects_every_illegal_byte_in_every_lane(ctx):
+    """the pack kernel's SWAR legality test: any byte other than A, C, G, T must raise SIBGPU_ERR_INPUT, whatever its
+    position inside the 16-byte load ('$' is the text separator and therefore not distinguishable on the device)"""
+    import sibelia_b200 as sb
+    base = np.frombuffer(b"ACGTTGCAGGATCCAT" * 8, dtype=np.uint8)
+    ok = set(b"ACGT$")
+    for b in range(256):
+        if b in ok:
+            continue
+        a = base.copy()
+        a[(b * 7) % len(a)] = b
+        with pytest.raises(sb.SibgpuError) as e:
+            ctx.enumerate([a], 5)
+        assert e.value.status == 3, "byte 0x%02x" % b
+    helpers.assert_tables_equal(ctx.enumerate([base], 5), restate.enumerate_bifurcations([base], 5), "legal text")
+
+
 def test_staged_api_reuses_upload(ctx):
     st = helpers.strain_case(3, 40_000, seed=5)
     ctx.upload(st)
