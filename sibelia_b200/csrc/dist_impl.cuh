@@ -41,7 +41,7 @@ static int dist_scatter_mode(sibgpu_ctx *ctx, uint32_t k, void *send_dev)
 	TextDesc t = ctx->dist_text;
 	const uint32_t ntiles = ctx->dist_tile_hi - ctx->dist_tile_lo;
 	SIB_TRY(ctx->d_partoff.ensure(sizeof(uint64_t) * (MAX_PARTS + 1)));
-	SIB_TRY(ctx->d_cursor.ensure(sizeof(uint64_t) * MAX_PARTS));
+	SIB_TRY(ctx->d_cursor.ensure(sizeof(uint64_t) * MAX_PARTS * CURSOR_STRIDE));
 	k_part_offsets<<<1, MAX_PARTS, 0, st>>>(ctx->d_hist.as<uint32_t>(), ctx->dist_P_total, ctx->d_partoff.as<uint64_t>(),
 		ctx->d_cursor.as<unsigned long long>(), ctx->d_scalars.as<uint64_t>());
 	ctx->total_launches++;
@@ -249,10 +249,10 @@ static int dist_scatter_local_mode(sibgpu_ctx *ctx, uint32_t k, uint64_t *counts
 	const uint64_t cap = (mean + mean / 8 + ctx->part_slack + 31) / 32 * 32;   // segments start 16-byte aligned (TMA)
 	ctx->dist_seg_cap = cap;
 	SIB_TRY(ctx->d_records.ensure(sizeof(Rec) * cap * PT + 256));
-	SIB_TRY(ctx->d_cursor.ensure(sizeof(uint64_t) * MAX_PARTS));
-	std::vector<uint64_t> base(PT);
-	for(uint32_t p = 0; p < PT; p++) base[p] = (uint64_t)p * cap;
-	SIB_CUDA(cudaMemcpyAsync(ctx->d_cursor.p, base.data(), sizeof(uint64_t) * PT, cudaMemcpyHostToDevice, st));
+	SIB_TRY(ctx->d_cursor.ensure(sizeof(uint64_t) * MAX_PARTS * CURSOR_STRIDE));
+	std::vector<uint64_t> base(PT), cur((size_t)PT * CURSOR_STRIDE, 0);
+	for(uint32_t p = 0; p < PT; p++) cur[(size_t)p * CURSOR_STRIDE] = base[p] = (uint64_t)p * cap;
+	SIB_CUDA(cudaMemcpyAsync(ctx->d_cursor.p, cur.data(), sizeof(uint64_t) * cur.size(), cudaMemcpyHostToDevice, st));
 	if(ntiles)
 	{
 		size_t smem = sizeof(ScatterSmem<MODE>);
@@ -262,7 +262,7 @@ static int dist_scatter_local_mode(sibgpu_ctx *ctx, uint32_t k, uint64_t *counts
 		k_scatter<MODE><<<g, TILE_THREADS, smem, st>>>(t, nullptr, k, ntiles, PT, ctx->d_cursor.as<unsigned long long>(),
 			ctx->d_records.as<Rec>(), cap, reinterpret_cast<uint32_t*>(ds + 10));
 	}
-	SIB_CUDA(cudaMemcpyAsync(counts_out, ctx->d_cursor.p, sizeof(uint64_t) * PT, cudaMemcpyDeviceToHost, st));
+	SIB_CUDA(cudaMemcpyAsync(cur.data(), ctx->d_cursor.p, sizeof(uint64_t) * cur.size(), cudaMemcpyDeviceToHost, st));
 	SIB_CUDA(cudaMemcpyAsync(hs + 8, ds + 8, sizeof(uint64_t) * 3, cudaMemcpyDeviceToHost, st));
 	SIB_CUDA(cudaStreamSynchronize(st));
 	if(hs[8] & 1u) return input_error();
@@ -271,7 +271,7 @@ static int dist_scatter_local_mode(sibgpu_ctx *ctx, uint32_t k, uint64_t *counts
 	uint64_t local = 0;
 	for(uint32_t p = 0; p < PT; p++)
 	{
-		counts_out[p] -= base[p];
+		counts_out[p] = cur[(size_t)p * CURSOR_STRIDE] - base[p];
 		local += counts_out[p];
 	}
 	ctx->dist_nrec_local = local;

@@ -12,6 +12,10 @@ constexpr int POS_PER_THREAD = 16;                     // one packed 32-bit word
 constexpr int TILE_POS = TILE_THREADS * POS_PER_THREAD; // 4096 text positions per tile
 constexpr int MAX_PARTS = 1024;
 constexpr uint64_t EMPTY64 = ~0ull;
+// The partition cursors are bumped by one returning atomicAdd per (tile, partition): packed 8 bytes apart, 16 of them
+// share an L2 line and the line's atomic unit serialises all CTAs (ncu: barrier + long-scoreboard stalls triple as soon
+// as a second warp of every CTA has cursors to bump).  One cursor per 128-byte line spreads them over the L2 slices.
+constexpr uint32_t CURSOR_STRIDE = 16;
 
 // occurrence context, 8 bits:  [7] forward k-mer is the canonical one  [6] palindrome  [5:3] prev  [2:0] next
 // (prev/next are symbols 0..3 = ACGT, 4 = chromosome end '#', already in canonical orientation)

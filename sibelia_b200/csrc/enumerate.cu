@@ -175,7 +175,7 @@ __global__ void __launch_bounds__(MAX_PARTS) k_part_offsets(const uint32_t *__re
 	Scan(tmp.s).ExclusiveSum((uint64_t)c, off, total);
 	__syncthreads();
 	uint32_t mx = Red(tmp.r).Reduce(c, cub::Max());
-	if(threadIdx.x < P) { partoff[threadIdx.x] = off; cursor[threadIdx.x] = off; }
+	if(threadIdx.x < P) { partoff[threadIdx.x] = off; cursor[threadIdx.x * CURSOR_STRIDE] = off; }
 	if(threadIdx.x == 0) { partoff[P] = total; scalars[0] = total; scalars[1] = mx; }
 }
 
@@ -246,7 +246,7 @@ __global__ void __launch_bounds__(TILE_THREADS) k_scatter(TextDesc t, const Rec1
 			excl += c[j];
 			if(b < P)
 			{
-				unsigned long long g = c[j] ? atomicAdd(&cursor[b], (unsigned long long)c[j]) : 0ull;
+				unsigned long long g = c[j] ? atomicAdd(&cursor[b * CURSOR_STRIDE], (unsigned long long)c[j]) : 0ull;
 				s.cnt[b] = o[j];
 				s.gbase[b] = g - o[j];
 				if(cap && c[j] && g + c[j] > (b + 1ull) * cap)
@@ -1135,7 +1135,7 @@ static int enumerate_mode(sibgpu_ctx *ctx, uint32_t k, uint64_t nrec, const Host
 		const uint32_t P = (uint32_t)(P64 < 1 ? 1 : (P64 > MAX_PARTS ? MAX_PARTS : P64));
 		SIB_TRY(ctx->d_hist.ensure(sizeof(uint32_t) * MAX_PARTS));
 		SIB_TRY(ctx->d_partoff.ensure(sizeof(uint64_t) * (MAX_PARTS + 1)));
-		SIB_TRY(ctx->d_cursor.ensure(sizeof(uint64_t) * MAX_PARTS));
+		SIB_TRY(ctx->d_cursor.ensure(sizeof(uint64_t) * MAX_PARTS * CURSOR_STRIDE));
 		SIB_TRY(ctx->d_partcnt.ensure(sizeof(uint32_t) * MAX_PARTS));
 		SIB_TRY(ctx->d_keyoff.ensure(sizeof(uint64_t) * (MAX_PARTS + 1)));
 		SIB_CUDA(cudaMemsetAsync(ctx->d_partcnt.p, 0, sizeof(uint32_t) * MAX_PARTS, st));
@@ -1152,7 +1152,9 @@ static int enumerate_mode(sibgpu_ctx *ctx, uint32_t k, uint64_t nrec, const Host
 			const uint64_t cap = P == 1 ? nrec : mean + mean / 8 + ctx->part_slack;
 			SIB_TRY(ctx->d_records.ensure(sizeof(Rec) * cap * P));
 			for(uint32_t p = 0; p <= P; p++) part_base[p] = (uint64_t)p * cap;
-			SIB_CUDA(cudaMemcpyAsync(ctx->d_cursor.p, part_base.data(), sizeof(uint64_t) * P, cudaMemcpyHostToDevice, st));
+			std::vector<uint64_t> cur((size_t)P * CURSOR_STRIDE, 0);
+			for(uint32_t p = 0; p < P; p++) cur[(size_t)p * CURSOR_STRIDE] = part_base[p];
+			SIB_CUDA(cudaMemcpyAsync(ctx->d_cursor.p, cur.data(), sizeof(uint64_t) * cur.size(), cudaMemcpyHostToDevice, st));
 			SIB_CUDA(cudaMemcpyAsync(ctx->d_partoff.p, part_base.data(), sizeof(uint64_t) * (P + 1), cudaMemcpyHostToDevice, st));
 			uint32_t *d_overflow = reinterpret_cast<uint32_t*>(ds + 10);
 			const uint32_t nchunks = src ? (ntiles + CHUNK_TILES - 1) / CHUNK_TILES : 1;
@@ -1195,7 +1197,7 @@ static int enumerate_mode(sibgpu_ctx *ctx, uint32_t k, uint64_t nrec, const Host
 					tiles_done = tile_hi;
 				}
 			}
-			SIB_CUDA(cudaMemcpyAsync(part_cnt.data(), ctx->d_cursor.p, sizeof(uint64_t) * P, cudaMemcpyDeviceToHost, st));
+			SIB_CUDA(cudaMemcpyAsync(cur.data(), ctx->d_cursor.p, sizeof(uint64_t) * cur.size(), cudaMemcpyDeviceToHost, st));
 			SIB_CUDA(cudaMemcpyAsync(hs + 8, ds + 8, sizeof(uint64_t) * 3, cudaMemcpyDeviceToHost, st));
 			SIB_CUDA(cudaStreamSynchronize(st));
 			if(hs[8] & 1u) return input_error();
@@ -1210,7 +1212,7 @@ static int enumerate_mode(sibgpu_ctx *ctx, uint32_t k, uint64_t nrec, const Host
 				uint64_t total = 0;
 				for(uint32_t p = 0; p < P; p++)
 				{
-					part_cnt[p] -= part_base[p];
+					part_cnt[p] = cur[(size_t)p * CURSOR_STRIDE] - part_base[p];
 					total += part_cnt[p];
 					if(part_cnt[p] > maxpart) maxpart = part_cnt[p];
 				}
