@@ -135,7 +135,7 @@ int sibgpu_create(int device, sibgpu_ctx **out)
 	if(const char *e = getenv("SIBGPU_PART_RECORDS"))
 	{
 		uint64_t v = strtoull(e, nullptr, 10);
-		if(v >= 1024) c->part_target = v;
+		if(v >= 1024) { c->part_target = v; c->part_explicit = true; }
 	}
 	if(const char *e = getenv("SIBGPU_PART_SLACK")) c->part_slack = strtoull(e, nullptr, 10);
 	if(const char *e = getenv("SIBGPU_EXACT_HIST")) c->exact_hist = atoi(e) != 0;

@@ -56,7 +56,17 @@ struct sibgpu_ctx {
 	sibgpu::TextDesc dist_text = {};
 
 	// tunables (env SIBGPU_PART_RECORDS)
-	uint64_t part_target = 1u << 20;
+	uint64_t part_target = 1u << 20;                   // records per partition for 8-byte table slots ...
+	bool part_explicit = false;                        // ... scaled down for wider slots unless the env var pins it
+	// records per hash partition such that one partition's table (table_factor slots per record) stays near 16 MB and
+	// the tables of the overlapped streams stay L2-resident: 8-byte slots (k <= 26) 1 Mi, 16-byte (k <= 32) 512 Ki, 32-byte 256 Ki
+	uint64_t part_records(uint32_t k) const
+	{
+		if(part_explicit) return part_target;
+		const uint64_t slot = k <= 26 ? 8 : (k <= 32 ? 16 : 32);
+		const uint64_t r = part_target * 8 / slot;
+		return r < 65536 ? 65536 : r;
+	}
 	uint64_t part_slack = 4096;                        // fixed-capacity partitions: mean + mean/8 + slack (env SIBGPU_PART_SLACK)
 	bool exact_hist = false;                           // always size the partitions with a histogram pass (env SIBGPU_EXACT_HIST)
 	uint64_t hist_fallbacks = 0;                       // times a fixed-capacity partition overflowed and the exact path ran

@@ -95,7 +95,7 @@ static int dist_group_mode(sibgpu_ctx *ctx, uint32_t k, const void *recv_dev, co
 	}
 	const uint32_t T = (uint32_t)T64;
 	const bool compact = MODE == 0 && k <= COMPACT_MAX_K;
-	const size_t slot_bytes = compact ? 8 : (MODE == 0 ? sizeof(Slot8) : sizeof(Slot16));
+	const size_t slot_bytes = compact ? 8 : (MODE <= 1 ? sizeof(Slot8) : sizeof(Slot16));
 	SIB_TRY(ctx->d_table.ensure(slot_bytes * T));
 	SIB_CUDA(cudaMemsetAsync(ctx->d_table.p, 0xFF, slot_bytes * T, st));
 	SIB_TRY(ctx->d_records.ensure(sizeof(Rec) * recv_total));          // staging area of the vertex keys, per partition
@@ -196,7 +196,8 @@ static int dist_prepare(sibgpu_ctx *ctx, uint32_t k)
 	}
 	const uint32_t W = ctx->dist_world;
 	uint64_t per_rank = (nrec + W - 1) / W;
-	uint64_t PL = (per_rank + ctx->part_target - 1) / ctx->part_target;
+	const uint64_t part_rec = ctx->part_records(k);
+	uint64_t PL = (per_rank + part_rec - 1) / part_rec;
 	if(PL < 1) PL = 1;
 	if(PL > MAX_PARTS / W) PL = MAX_PARTS / W;
 	ctx->dist_P_local = (uint32_t)PL;
@@ -316,7 +317,7 @@ static int dist_group_peer_mode(sibgpu_ctx *ctx, uint32_t k, const uint64_t *cou
 	}
 	const uint32_t T = (uint32_t)T64;
 	const bool compact = MODE == 0 && k <= COMPACT_MAX_K;
-	const size_t slot_bytes = compact ? 8 : (MODE == 0 ? sizeof(Slot8) : sizeof(Slot16));
+	const size_t slot_bytes = compact ? 8 : (MODE <= 1 ? sizeof(Slot8) : sizeof(Slot16));
 	const uint32_t S = ctx->n_streams < 1 ? 1 : (ctx->n_streams > 8 ? 8 : ctx->n_streams);
 	const size_t table_bytes = (slot_bytes * T + 255) / 256 * 256;
 	SIB_TRY(ctx->d_table.ensure(table_bytes * S));

@@ -198,7 +198,7 @@ template<> struct ScatterSmem<2> : ScatterSmem<1> {};
 // partitioning with exact sizes (k_scan_hist + k_part_offsets, cap == 0).
 constexpr uint32_t RUN_DROPPED = 0x80000000u;
 template<int MODE>
-__global__ void __launch_bounds__(TILE_THREADS) k_scatter(TextDesc t, const Rec16 *__restrict__ fp, uint32_t k,
+__global__ void __launch_bounds__(TILE_THREADS, MODE == 0 ? 4 : 2) k_scatter(TextDesc t, const Rec16 *__restrict__ fp, uint32_t k,
 	uint32_t ntiles, uint32_t P, unsigned long long *__restrict__ cursor, typename RecT<MODE>::type *__restrict__ out,
 	unsigned long long cap, uint32_t *__restrict__ overflow)
 {
@@ -308,12 +308,12 @@ __device__ __forceinline__ typename RecVal<MODE>::type load_rec(const void *__re
 	return __ldcs(static_cast<const typename RecVal<MODE>::type*>(recs) + i);
 }
 
-__device__ __forceinline__ void insert_wide_rec(unsigned long long rec, void *__restrict__ table, uint32_t T)
+// 16-byte slots {key, payload}: exact keys up to 64 bits (k <= 32).  A canonical key is never all ones (the reverse
+// complement of T...T is A...A = 0), so EMPTY64 can mark a free slot even at k = 32.
+__device__ __forceinline__ void insert_slot8(unsigned long long key, uint32_t ctx, void *__restrict__ table, uint32_t T)
 {
 	{
 		Slot8 *tab = static_cast<Slot8*>(table);
-		const unsigned long long key = rec >> 7;
-		const uint32_t ctx = (uint32_t)rec & 127u;
 		uint32_t slot = __umulhi((uint32_t)rec_hash(key, 0), T);
 		uint32_t bits = payload_bits(ctx);
 		for(;;)
@@ -331,7 +331,8 @@ __device__ __forceinline__ void insert_wide_rec(unsigned long long rec, void *__
 	}
 }
 
-__device__ __forceinline__ void insert_wide_rec(ulonglong2 rec, void *__restrict__ table, uint32_t T)
+// 32-byte slots {a, b, payload}: 117-bit fingerprints (k > 32)
+__device__ __forceinline__ void insert_slot16(ulonglong2 rec, void *__restrict__ table, uint32_t T)
 {
 	{
 		Slot16 *tab = static_cast<Slot16*>(table);
@@ -359,12 +360,20 @@ __device__ __forceinline__ void insert_wide_rec(ulonglong2 rec, void *__restrict
 }
 
 template<int MODE>
+__device__ __forceinline__ void insert_wide_rec(typename RecVal<MODE>::type rec, void *__restrict__ table, uint32_t T)
+{
+	if constexpr(MODE == 0) insert_slot8(rec >> 7, (uint32_t)rec & 127u, table, T);
+	else if constexpr(MODE == 1) insert_slot8(rec.x, (uint32_t)rec.y & 127u, table, T);
+	else insert_slot16(rec, table, T);
+}
+
+template<int MODE>
 __global__ void __launch_bounds__(256) k_insert(const typename RecT<MODE>::type *__restrict__ recs, uint64_t n,
 	void *__restrict__ table, uint32_t T)
 {
 	for(uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
 	{
-		insert_wide_rec(load_rec<MODE>(recs, i), table, T);
+		insert_wide_rec<MODE>(load_rec<MODE>(recs, i), table, T);
 	}
 }
 
@@ -382,7 +391,7 @@ __global__ void __launch_bounds__(256) k_table_scan(void *__restrict__ table, ui
 		unsigned long long a = 0, b = 0;
 		if(sidx < T)
 		{
-			if(MODE == 0)
+			if(MODE <= 1)
 			{
 				Slot8 *tab = static_cast<Slot8*>(table);
 				a = tab[sidx].key;
@@ -559,7 +568,7 @@ __global__ void __launch_bounds__(256) k_insert_seg_ld(const SegList segs, uint3
 			if(i0 + u * stride < total)
 			{
 				if(COMPACT) insert_compact_rec(*reinterpret_cast<unsigned long long*>(&rec[u]), static_cast<unsigned long long*>(table), T);
-				else insert_wide_rec(rec[u], table, T);
+				else insert_wide_rec<MODE>(rec[u], table, T);
 			}
 		}
 	}
@@ -632,7 +641,7 @@ __global__ void __launch_bounds__(256) k_insert_seg(const SegList segs, uint32_t
 			{
 				RV rec = w[j];
 				if(COMPACT) insert_compact_rec(*reinterpret_cast<unsigned long long*>(&rec), static_cast<unsigned long long*>(table), T);
-				else insert_wide_rec(rec, table, T);
+				else insert_wide_rec<MODE>(rec, table, T);
 			}
 		}
 		__syncthreads();                                   // every lane has read its records: the stage can be refilled
@@ -1131,7 +1140,8 @@ static int enumerate_mode(sibgpu_ctx *ctx, uint32_t k, uint64_t nrec, const Host
 		const Rec16 *fp = ctx->d_fp.as<Rec16>();
 
 		// ---- partition plan
-		uint64_t P64 = (nrec + ctx->part_target - 1) / ctx->part_target;
+		const uint64_t part_rec = ctx->part_records(k);
+		uint64_t P64 = (nrec + part_rec - 1) / part_rec;
 		const uint32_t P = (uint32_t)(P64 < 1 ? 1 : (P64 > MAX_PARTS ? MAX_PARTS : P64));
 		SIB_TRY(ctx->d_hist.ensure(sizeof(uint32_t) * MAX_PARTS));
 		SIB_TRY(ctx->d_partoff.ensure(sizeof(uint64_t) * (MAX_PARTS + 1)));
@@ -1276,7 +1286,7 @@ static int enumerate_mode(sibgpu_ctx *ctx, uint32_t k, uint64_t nrec, const Host
 		}
 		const uint32_t T = (uint32_t)T64;
 		const bool compact = MODE == 0 && k <= COMPACT_MAX_K;
-		const size_t slot_bytes = compact ? 8 : (MODE == 0 ? sizeof(Slot8) : sizeof(Slot16));
+		const size_t slot_bytes = compact ? 8 : (MODE <= 1 ? sizeof(Slot8) : sizeof(Slot16));
 		// S independent tables on S streams: consecutive partitions overlap, so the ramp-up / tail of one partition's
 		// kernels is filled by its neighbours (with S = 1 everything runs on the main stream and is timed per launch)
 		const uint32_t S = ctx->n_streams < 1 ? 1 : (ctx->n_streams > 8 ? 8 : ctx->n_streams);
