@@ -197,6 +197,10 @@ int sibgpu_dist_finish(sibgpu_ctx *ctx, const void *allkeys_dev, uint64_t nkeys_
  *   sibgpu_dist_finish         as above
  */
 int sibgpu_dist_scatter_local(sibgpu_ctx *ctx, uint32_t k, uint32_t *nparts_total, uint64_t *counts, uint64_t *seg_cap, int *overflow);
+/* sibgpu_dist_upload + sibgpu_dist_scatter_local in one call with the host-to-device copy of the own text range
+ * pipelined against the pack and scatter kernels (pieces of 8 Mi positions, as in sibgpu_enumerate) */
+int sibgpu_dist_upload_scatter(sibgpu_ctx *ctx, const char *const *chr, const uint64_t *len, uint32_t nchr, uint32_t rank,
+	uint32_t world, uint32_t k, uint32_t *nparts_total, uint64_t *counts, uint64_t *seg_cap, int *overflow);
 int sibgpu_dist_export_send(sibgpu_ctx *ctx, void *handle64);
 int sibgpu_dist_import_peers(sibgpu_ctx *ctx, const void *handles);
 int sibgpu_dist_group_peer(sibgpu_ctx *ctx, const uint64_t *counts, const uint64_t *seg_caps, uint64_t *nkeys_local);

@@ -17,7 +17,7 @@ SYMBOLS = [
     "sibgpu_enumerate", "sibgpu_list_edges", "sibgpu_trim_blocks", "sibgpu_upload", "sibgpu_enumerate_resident", "sibgpu_download", "sibgpu_set_profiling",
     "sibgpu_kernel_stats", "sibgpu_last_launches", "sibgpu_partition_fallbacks", "sibgpu_last_device_ms", "sibgpu_simplify", "sibgpu_debug_unordered_order", "sibgpu_dist_upload", "sibgpu_dist_scan", "sibgpu_dist_record_bytes",
     "sibgpu_dist_scatter", "sibgpu_dist_group", "sibgpu_dist_keys", "sibgpu_dist_finish",
-    "sibgpu_dist_scatter_local", "sibgpu_dist_export_send", "sibgpu_dist_import_peers", "sibgpu_dist_group_peer",
+    "sibgpu_dist_scatter_local", "sibgpu_dist_upload_scatter", "sibgpu_dist_export_send", "sibgpu_dist_import_peers", "sibgpu_dist_group_peer",
 ]
 
 
@@ -226,6 +226,15 @@ class Context:
         nparts, cap, ovf = C.c_uint32(), C.c_uint64(), C.c_int()
         _check(load().sibgpu_dist_scatter_local(self._h, C.c_uint32(k), C.byref(nparts), C.c_void_p(counts.ctypes.data),
                                                 C.byref(cap), C.byref(ovf)))
+        return nparts.value, counts[:nparts.value].copy(), cap.value, bool(ovf.value)
+
+    def dist_upload_scatter(self, chrs, rank, world, k):
+        bufs, ptrs, lens, n = _chr_args(chrs)
+        counts = np.zeros(1024, dtype=np.uint64)
+        nparts, cap, ovf = C.c_uint32(), C.c_uint64(), C.c_int()
+        _check(load().sibgpu_dist_upload_scatter(self._h, ptrs, lens, C.c_uint32(n), C.c_uint32(rank), C.c_uint32(world),
+                                                 C.c_uint32(k), C.byref(nparts), C.c_void_p(counts.ctypes.data),
+                                                 C.byref(cap), C.byref(ovf)))
         return nparts.value, counts[:nparts.value].copy(), cap.value, bool(ovf.value)
 
     def dist_export_send(self):

@@ -440,7 +440,8 @@ int sibgpu_trim_blocks(sibgpu_ctx *c, const char *const *seq, const uint64_t *le
 // ---------------------------------------------------------------------------------------------------------------
 // sharded enumeration (one process per GPU)
 // ---------------------------------------------------------------------------------------------------------------
-int sibgpu_dist_upload(sibgpu_ctx *c, const char *const *chr, const uint64_t *len, uint32_t nchr, uint32_t rank, uint32_t world)
+// Layout of a sharded run: this rank's tile range, the bytes it reads (tiles + halos), buffers, '$' fill, tables.
+static int dist_layout(sibgpu_ctx *c, const char *const *chr, const uint64_t *len, uint32_t nchr, uint32_t rank, uint32_t world)
 {
 	if(!c || (nchr && (!chr || !len)) || world == 0 || rank >= world || world > 64)
 	{
@@ -485,26 +486,42 @@ int sibgpu_dist_upload(sibgpu_ctx *c, const char *const *chr, const uint64_t *le
 	SIB_TRY(c->d_chr_start.ensure(sizeof(uint32_t) * (nchr + 1)));
 	SIB_TRY(c->d_chr_len.ensure(sizeof(uint32_t) * (nchr + 1)));
 	if(b_hi > b_lo) SIB_CUDA(cudaMemsetAsync(c->d_text.as<char>() + b_lo, '$', b_hi - b_lo, c->stream));
-	for(uint32_t i = 0; i < nchr; i++)
-	{
-		const uint64_t s = c->h_chr_start[i], e = s + len[i];
-		const uint64_t lo = s > b_lo ? s : b_lo, hi = e < b_hi ? e : b_hi;
-		if(hi > lo)
-		{
-			SIB_CUDA(cudaMemcpyAsync(c->d_text.as<char>() + lo, chr[i] + (lo - s), hi - lo, cudaMemcpyHostToDevice, c->stream));
-		}
-	}
 	if(nchr)
 	{
 		SIB_CUDA(cudaMemcpyAsync(c->d_chr_start.p, c->h_chr_start.data(), sizeof(uint32_t) * nchr, cudaMemcpyHostToDevice, c->stream));
 		SIB_CUDA(cudaMemcpyAsync(c->d_chr_len.p, c->h_chr_len.data(), sizeof(uint32_t) * nchr, cudaMemcpyHostToDevice, c->stream));
 	}
-	SIB_CUDA(cudaStreamSynchronize(c->stream));
 	c->nchr = nchr;
 	c->N = N;
 	c->M = M;
-	c->have_text = true;
 	c->dist_result = false;
+	return SIBGPU_OK;
+}
+
+int sibgpu_dist_upload(sibgpu_ctx *c, const char *const *chr, const uint64_t *len, uint32_t nchr, uint32_t rank, uint32_t world)
+{
+	SIB_TRY(dist_layout(c, chr, len, nchr, rank, world));
+	HostSrc src = {chr, len};
+	if(c->dist_byte_hi > c->dist_byte_lo) SIB_TRY(copy_text_range(c, src, c->dist_byte_lo, c->dist_byte_hi, c->stream));
+	SIB_CUDA(cudaStreamSynchronize(c->stream));
+	c->have_text = true;
+	return SIBGPU_OK;
+}
+
+int sibgpu_dist_upload_scatter(sibgpu_ctx *c, const char *const *chr, const uint64_t *len, uint32_t nchr, uint32_t rank, uint32_t world,
+	uint32_t k, uint32_t *nparts_total, uint64_t *counts, uint64_t *seg_cap, int *overflow)
+{
+	if(!counts || !nparts_total || !seg_cap || !overflow || k == 0 || k > 32)
+	{
+		set_error("invalid: the sharded path supports 1 <= k <= 32");
+		return SIBGPU_ERR_INVALID;
+	}
+	SIB_TRY(dist_layout(c, chr, len, nchr, rank, world));
+	HostSrc src = {chr, len};
+	SIB_CUDA(cudaEventRecord(c->ev_begin, c->stream));
+	SIB_TRY(dist_scatter_local(c, k, counts, seg_cap, overflow, &src));
+	c->have_text = true;
+	*nparts_total = c->dist_P_total;
 	return SIBGPU_OK;
 }
 
@@ -590,7 +607,7 @@ int sibgpu_dist_scatter_local(sibgpu_ctx *c, uint32_t k, uint32_t *nparts_total,
 	}
 	SIB_CUDA(cudaSetDevice(c->device));
 	SIB_CUDA(cudaEventRecord(c->ev_begin, c->stream));
-	SIB_TRY(dist_scatter_local(c, k, counts, seg_cap, overflow));
+	SIB_TRY(dist_scatter_local(c, k, counts, seg_cap, overflow, nullptr));
 	*nparts_total = c->dist_P_total;
 	return SIBGPU_OK;
 }

@@ -130,6 +130,6 @@ int dist_scan(sibgpu_ctx *ctx, uint32_t k, uint32_t *hist_out);
 int dist_scatter(sibgpu_ctx *ctx, void *send_dev);
 int dist_group(sibgpu_ctx *ctx, const void *recv_dev, const uint32_t *counts, uint64_t *nkeys_local);
 int dist_finish(sibgpu_ctx *ctx, const void *allkeys_dev, uint64_t nkeys_total);
-int dist_scatter_local(sibgpu_ctx *ctx, uint32_t k, uint64_t *counts_out, uint64_t *seg_cap_out, int *overflow_out);
+int dist_scatter_local(sibgpu_ctx *ctx, uint32_t k, uint64_t *counts_out, uint64_t *seg_cap_out, int *overflow_out, const HostSrc *src);
 int dist_group_peer(sibgpu_ctx *ctx, const uint64_t *counts, const uint64_t *seg_caps, uint64_t *nkeys_local);
 } // namespace sibgpu

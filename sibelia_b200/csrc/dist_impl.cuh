@@ -168,8 +168,8 @@ static int dist_finish_mode(sibgpu_ctx *ctx, uint32_t k, const void *allkeys_dev
 		ntiles ? ntiles : 0, nullptr, false, &collision);
 }
 
-// pack the words of the own range (+ halo), partition plan, text descriptor
-static int dist_prepare(sibgpu_ctx *ctx, uint32_t k)
+// pack the words of the own range (+ halo) unless the caller pipelines that with the upload, partition plan, text descriptor
+static int dist_prepare(sibgpu_ctx *ctx, uint32_t k, bool pack = true)
 {
 	cudaStream_t st = ctx->stream;
 	SIB_CUDA(cudaSetDevice(ctx->device));
@@ -183,7 +183,7 @@ static int dist_prepare(sibgpu_ctx *ctx, uint32_t k)
 	SIB_TRY(ctx->d_scalars.ensure(sizeof(uint64_t) * 64));
 	SIB_CUDA(cudaMemsetAsync(ctx->d_scalars.p, 0, sizeof(uint64_t) * 64, st));
 	uint32_t *d_err = reinterpret_cast<uint32_t*>(ctx->d_scalars.as<uint64_t>() + 8);
-	if(w_hi > w_lo)
+	if(pack && w_hi > w_lo)
 	{
 		ProfScope ps(ctx, "k_pack", (w_hi - w_lo) * 20);
 		k_pack<<<grid_for(w_hi - w_lo, 256, ctx->sm_count, 8), 256, 0, st>>>(ctx->d_text.as<uint4>() + w_lo,
@@ -237,7 +237,8 @@ int dist_scan(sibgpu_ctx *ctx, uint32_t k, uint32_t *hist_out)
 // the W segments of p straight out of the W send buffers (CUDA IPC mappings, NVLink) inside its insert kernel.
 // ---------------------------------------------------------------------------------------------------------------
 template<int MODE>
-static int dist_scatter_local_mode(sibgpu_ctx *ctx, uint32_t k, uint64_t *counts_out, uint64_t *seg_cap_out, int *overflow_out)
+static int dist_scatter_local_mode(sibgpu_ctx *ctx, uint32_t k, uint64_t *counts_out, uint64_t *seg_cap_out, int *overflow_out,
+	const HostSrc *src)
 {
 	typedef typename RecT<MODE>::type Rec;
 	cudaStream_t st = ctx->stream;
@@ -258,10 +259,48 @@ static int dist_scatter_local_mode(sibgpu_ctx *ctx, uint32_t k, uint64_t *counts
 	{
 		size_t smem = sizeof(ScatterSmem<MODE>);
 		SIB_CUDA(cudaFuncSetAttribute(k_scatter<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-		const uint32_t g = ntiles < (uint32_t)ctx->sm_count * 4 ? ntiles : (uint32_t)ctx->sm_count * 4;
-		ProfScope ps(ctx, "k_scatter", (uint64_t)ntiles * TILE_POS / 4 + (uint64_t)ntiles * TILE_POS * sizeof(Rec));
-		k_scatter<MODE><<<g, TILE_THREADS, smem, st>>>(t, nullptr, k, ntiles, PT, ctx->d_cursor.as<unsigned long long>(),
-			ctx->d_records.as<Rec>(), cap, reinterpret_cast<uint32_t*>(ds + 10));
+		// src: the own byte range is still on the host -- stream it in pieces of CHUNK_TILES tiles on the copy stream and
+		// pack + scatter every piece as it lands (same pipeline as sibgpu_enumerate, enumerate.cu)
+		const uint32_t nchunks = src ? (ntiles + CHUNK_TILES - 1) / CHUNK_TILES : 1;
+		auto piece_byte = [&](uint32_t c) -> uint64_t {               // first byte of piece c (multiples of 16)
+			if(c == 0) return ctx->dist_byte_lo;
+			if(c >= nchunks) return ctx->dist_byte_hi;
+			return (uint64_t)(ctx->dist_tile_lo + c * CHUNK_TILES) * TILE_POS;
+		};
+		if(src)
+		{
+			SIB_TRY(ctx->ensure_copy_stream(nchunks));
+			SIB_CUDA(cudaEventRecord(ctx->ev_fork_copy, st));
+			SIB_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_fork_copy, 0));
+			for(uint32_t c = 0; c < nchunks; c++)
+			{
+				SIB_TRY(copy_text_range(ctx, *src, piece_byte(c), piece_byte(c + 1), ctx->copy_stream));
+				SIB_CUDA(cudaEventRecord(ctx->ev_chunk[c], ctx->copy_stream));
+			}
+		}
+		uint32_t tiles_done = ctx->dist_tile_lo;                      // absolute tile index
+		for(uint32_t c = 0; c < nchunks; c++)
+		{
+			uint32_t tile_end = ctx->dist_tile_hi;
+			if(src)
+			{
+				const uint64_t w0 = piece_byte(c) / 16, w1 = (piece_byte(c + 1) + 15) / 16;
+				SIB_CUDA(cudaStreamWaitEvent(st, ctx->ev_chunk[c], 0));
+				if(w1 > w0) SIB_TRY(launch_pack(ctx, w0, w1));
+				if(c + 1 < nchunks) tile_end = (uint32_t)((w1 - 261) / TILE_THREADS);   // staged words of these tiles are packed
+			}
+			if(tile_end > tiles_done)
+			{
+				const uint32_t nt = tile_end - tiles_done;
+				const uint32_t g = nt < (uint32_t)ctx->sm_count * 4 ? nt : (uint32_t)ctx->sm_count * 4;
+				TextDesc tc = t;
+				tc.tile0 = tiles_done;
+				ProfScope ps(ctx, "k_scatter", (uint64_t)nt * TILE_POS / 4 + (uint64_t)nt * TILE_POS * sizeof(Rec));
+				k_scatter<MODE><<<g, TILE_THREADS, smem, st>>>(tc, nullptr, k, nt, PT, ctx->d_cursor.as<unsigned long long>(),
+					ctx->d_records.as<Rec>(), cap, reinterpret_cast<uint32_t*>(ds + 10));
+				tiles_done = tile_end;
+			}
+		}
 	}
 	SIB_CUDA(cudaMemcpyAsync(cur.data(), ctx->d_cursor.p, sizeof(uint64_t) * cur.size(), cudaMemcpyDeviceToHost, st));
 	SIB_CUDA(cudaMemcpyAsync(hs + 8, ds + 8, sizeof(uint64_t) * 3, cudaMemcpyDeviceToHost, st));
@@ -280,11 +319,11 @@ static int dist_scatter_local_mode(sibgpu_ctx *ctx, uint32_t k, uint64_t *counts
 	return SIBGPU_OK;
 }
 
-int dist_scatter_local(sibgpu_ctx *ctx, uint32_t k, uint64_t *counts_out, uint64_t *seg_cap_out, int *overflow_out)
+int dist_scatter_local(sibgpu_ctx *ctx, uint32_t k, uint64_t *counts_out, uint64_t *seg_cap_out, int *overflow_out, const HostSrc *src)
 {
-	SIB_TRY(dist_prepare(ctx, k));
-	return k <= 28 ? dist_scatter_local_mode<0>(ctx, k, counts_out, seg_cap_out, overflow_out)
-		: dist_scatter_local_mode<1>(ctx, k, counts_out, seg_cap_out, overflow_out);
+	SIB_TRY(dist_prepare(ctx, k, src == nullptr));
+	return k <= 28 ? dist_scatter_local_mode<0>(ctx, k, counts_out, seg_cap_out, overflow_out, src)
+		: dist_scatter_local_mode<1>(ctx, k, counts_out, seg_cap_out, overflow_out, src);
 }
 
 template<int MODE>

@@ -8,7 +8,7 @@ change a maintainer of the reference would make by hand:
     vertex marks become one sibgpu_trim_blocks call, the final size test / Edge construction (:105-116) is kept.
 
 The reference source is read where it lies and edited by anchors; nothing of it is stored in this repository and the
-output (oracle/_ref/obj/synteny_patched.cpp) is a build artefact.
+output (a file in the build directory of whoever links the bound CLI) is a build artefact.
 
     python patch_synteny.py /root/reference/src/synteny.cpp out.cpp
 """

@@ -32,13 +32,24 @@ class GpuShard:
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
 
     def upload(self, chrs, rank, world):
-        self.ctx.dist_upload(chrs, rank, world)
+        # deferred: the peer strategy pipelines the copy of the own text range with its pack and scatter kernels
+        self._pending = (chrs, rank, world)
+
+    def _upload_now(self):
+        if getattr(self, "_pending", None) is not None:
+            self.ctx.dist_upload(*self._pending)
+            self._pending = None
 
     # -- peer strategy
     peer = os.environ.get("SIBGPU_DIST_PEER", "1") != "0"
 
     def scatter_local(self, k):
-        out = self.ctx.dist_scatter_local(k)
+        if getattr(self, "_pending", None) is not None:
+            chrs, rank, world = self._pending
+            self._pending = None
+            out = self.ctx.dist_upload_scatter(chrs, rank, world, k)
+        else:
+            out = self.ctx.dist_scatter_local(k)
         self.words = self.ctx.dist_record_bytes() // 8
         return out
 
@@ -64,6 +75,7 @@ class GpuShard:
 
     # -- staged strategy
     def scan(self, k):
+        self._upload_now()
         nparts, hist, self.nrec = self.ctx.dist_scan(k)
         self.words = self.ctx.dist_record_bytes() // 8
         return nparts, hist
