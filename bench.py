@@ -288,7 +288,7 @@ def main():
     dname, d = dom
     achieved = d["algo_bytes"] / 1e9 / (d["ms"] / 1e3) if d["ms"] > 0 else 0.0
     roofline = {"bound": "hbm", "kernel": dname, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "frac": achieved / peak, "frac_of_nominal_8TBps": achieved / 8000.0, "traffic": None, "peak_source": peak_src,
                 "launches_per_step": d["launches"] / args.steps, "ms_per_step": d["ms"] / args.steps,
                 "share_of_step": d["ms"] / dev_ms if dev_ms else None,
                 "kernels": {n: {"ms_per_step": s["ms"] / args.steps, "launches_per_step": s["launches"] / args.steps,

@@ -377,7 +377,6 @@ static int dist_group_peer_mode(sibgpu_ctx *ctx, uint32_t k, const uint64_t *cou
 	}
 	const int blocks_per_sm = S > 1 ? 4 : 8;
 	const bool phase_span = ctx->profiling && S > 1;
-	static const bool debug_local = getenv("SIBGPU_DEBUG_LOCAL_SEGS") != nullptr;   // timing experiment only: wrong results
 	// Measured on 2 B200s (100 M records per rank, half of them remote; profiles/r1_sharded_peer_read.txt): plain loads
 	// from the peer 3.41 ms, remote segments first pulled into a local buffer by the copy engines 2.20 ms, TMA ring
 	// reading the peer directly 2.21 ms at 8 CTAs per SM -- the ring hides the NVLink latency without a staging copy.
@@ -395,7 +394,7 @@ static int dist_group_peer_mode(sibgpu_ctx *ctx, uint32_t k, const uint64_t *cou
 		{
 			const uint64_t c = counts[(size_t)s * PT + b0 + p];
 			if(c == 0) continue;
-			if(s == ctx->dist_rank || debug_local) segs.ptr[nseg] = ctx->d_records.as<Rec>() + (uint64_t)(b0 + p) * seg_caps[s];
+			if(s == ctx->dist_rank) segs.ptr[nseg] = ctx->d_records.as<Rec>() + (uint64_t)(b0 + p) * seg_caps[s];
 			else segs.ptr[nseg] = static_cast<const Rec*>(ctx->peer_ptr[s]) + (uint64_t)(b0 + p) * seg_caps[s];
 			segs.cnt[nseg] = (uint32_t)c;
 			seg_tiles += (uint32_t)((c + tile_rec - 1) / tile_rec);
