@@ -5,6 +5,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "hostvec.h"
 
 namespace sibgpu {
 // device-side description of the concatenated text '$' chr0 '$' chr1 ... '$'
@@ -84,9 +85,9 @@ struct sibgpu_ctx {
 
 	// sibgpu_simplify: the per-element host arrays of a stage are recycled between stages (a fresh 30 B/element
 	// allocation per stage costs more in page faults than the stage's device work)
-	std::vector<char> pool_ch;
-	std::vector<uint32_t> pool_u32[3];
-	std::vector<int32_t> pool_i32[4];
+	sibgpu::HostChars pool_ch;
+	sibgpu::HostU32 pool_u32[3];
+	sibgpu::HostI32 pool_i32[4];
 
 	// profiling
 	bool profiling = false;

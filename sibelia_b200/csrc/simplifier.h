@@ -7,11 +7,13 @@
 #include <cstring>
 #include <iterator>
 #include <string>
+#include <thread>
 #include <utility>
 #include <vector>
 
 #include "../../include/sibgpu.h"
 #include "boost_order.h"
+#include "hostvec.h"
 
 namespace sibgpu {
 namespace simp {
@@ -37,6 +39,25 @@ inline char complement(char c)                          // DNASequence::compleme
 	return c;
 }
 
+// Runs fn(begin, end) over [0, n) split across host threads (the per-element arrays of a stage are 30 B/element: at
+// 500 Mbases filling them single-threaded costs more than all the device work of the stage).  fn must be data-parallel.
+template<class F>
+inline void parallel_ranges(size_t n, F fn)
+{
+	const size_t min_chunk = 1u << 20;
+	size_t nt = std::thread::hardware_concurrency();
+	nt = nt < 1 ? 1 : (nt > 16 ? 16 : nt);
+	if(nt > (n + min_chunk - 1) / min_chunk) nt = (n + min_chunk - 1) / min_chunk;
+	if(nt <= 1)
+	{
+		fn((size_t)0, n);
+		return;
+	}
+	std::vector<std::thread> th;
+	for(size_t t = 0; t < nt; t++) th.emplace_back(fn, n * t / nt, n * (t + 1) / nt);
+	for(std::thread &x : th) x.join();
+}
+
 // DNASequence::StrandIterator over the element arrays: e = element, d = 0 positive / 1 negative strand
 struct It {
 	int32_t e;
@@ -59,11 +80,11 @@ struct BifurcationMark {                                // bulgeremoval.cpp:20-3
 class Simplifier {
 public:
 	// ---- sequence (DNASequence, dnasequence.cpp:75-103): element 0 is the leading '$'
-	std::vector<char> ch;
-	std::vector<uint32_t> opos;
-	std::vector<int32_t> nxt, prv;
-	std::vector<uint32_t> mark[2];                      // vertex id whose k-mer starts here on that strand, or NO_BIF
-	std::vector<int32_t> node_of[2];                    // instance-list node of that mark
+	HostChars ch;                                       // (hostvec.h: resize() does not value-initialise)
+	HostU32 opos;
+	HostI32 nxt, prv;
+	HostU32 mark[2];                                    // vertex id whose k-mer starts here on that strand, or NO_BIF
+	HostI32 node_of[2];                                 // instance-list node of that mark
 	std::vector<int32_t> chr_first_sep;                 // the '$' in front of chromosome c (chr c = elements after it
 	int32_t last_sep = 0;                               //   up to the next '$')
 	size_t live = 0;
@@ -181,40 +202,53 @@ public:
 		max_id = count;
 		size_t total = 1;
 		for(uint32_t c = 0; c < nchr; c++) total += len[c] + 1;
+		// sizes first (no value-initialising pass over recycled storage), then one parallel fill of all per-element arrays
 		ch.resize(total);
 		opos.resize(total);
 		nxt.resize(total);
 		prv.resize(total);
 		for(int s = 0; s < 2; s++)
 		{
-			mark[s].assign(total, NO_BIF);
-			node_of[s].assign(total, -1);
+			mark[s].resize(total);
+			node_of[s].resize(total);
 			head[s].assign((size_t)count + 1, -1);
 			lsize[s].assign((size_t)count + 1, 0);
 		}
 		dirty.assign((size_t)count + 1, 0);
 		chr_first_sep.resize(nchr);
-		size_t at = 0;
-		ch[at] = SEP;
-		opos[at] = 0;
-		at++;
 		std::vector<size_t> start(nchr);
+		size_t at = 1;
 		for(uint32_t c = 0; c < nchr; c++)
 		{
 			chr_first_sep[c] = (int32_t)(at - 1);
 			start[c] = at;
-			memcpy(&ch[at], seq[c], len[c]);
-			for(uint64_t i = 0; i < len[c]; i++) opos[at + i] = origpos[c][i] & POS_MASK;
-			at += len[c];
-			ch[at] = SEP;
-			opos[at] = (uint32_t)len[c] & POS_MASK;        // dnasequence.cpp:96-97
-			at++;
+			at += len[c] + 1;
 		}
-		for(size_t i = 0; i < total; i++)
+		ch[0] = SEP;
+		opos[0] = 0;
+		for(uint32_t c = 0; c < nchr; c++)
 		{
-			nxt[i] = (int32_t)i + 1;
-			prv[i] = (int32_t)i - 1;
+			const size_t s0 = start[c];
+			const char *sq = seq[c];
+			const uint32_t *op = origpos[c];
+			parallel_ranges(len[c], [&, s0, sq, op](size_t b, size_t e) {
+				memcpy(&ch[s0 + b], sq + b, e - b);
+				for(size_t i = b; i < e; i++) opos[s0 + i] = op[i] & POS_MASK;
+			});
+			ch[s0 + len[c]] = SEP;
+			opos[s0 + len[c]] = (uint32_t)len[c] & POS_MASK;   // dnasequence.cpp:96-97
 		}
+		parallel_ranges(total, [&](size_t b, size_t e) {
+			for(size_t i = b; i < e; i++)
+			{
+				nxt[i] = (int32_t)i + 1;
+				prv[i] = (int32_t)i - 1;
+				mark[0][i] = NO_BIF;
+				mark[1][i] = NO_BIF;
+				node_of[0][i] = -1;
+				node_of[1][i] = -1;
+			}
+		});
 		nxt[total - 1] = -1;
 		last_sep = (int32_t)total - 1;
 		live = total;
@@ -242,9 +276,9 @@ public:
 	{
 		const size_t total = live;
 		std::vector<int32_t> newidx(ch.size(), -1);
-		std::vector<char> ch2(total);
-		std::vector<uint32_t> op2(total), m0(total), m1(total);
-		std::vector<int32_t> no0(total), no1(total);
+		HostChars ch2(total);
+		HostU32 op2(total), m0(total), m1(total);
+		HostI32 no0(total), no1(total);
 		size_t j = 0;
 		for(int32_t e = 0; e >= 0; e = nxt[e], j++)
 		{

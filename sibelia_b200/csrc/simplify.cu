@@ -21,6 +21,7 @@
 #include <cstring>
 #include <iterator>
 #include <string>
+#include <thread>
 
 #include "context.h"
 #include "simplifier.h"
@@ -285,27 +286,46 @@ extern "C" int sibgpu_simplify(sibgpu_ctx *ctx, char **seq, uint32_t **origpos, 
 	ctx->total_launches = launches;
 	ctx->last_ms = device_ms;
 
-	// ---- copy-back, blockfinder.cpp:85-95
-	for(uint32_t c = 0; c < nchr; c++)
+	// ---- copy-back, blockfinder.cpp:85-95 (one host thread per chromosome: the walks are independent)
 	{
-		size_t n = 0;
-		for(int32_t e = S.nxt[S.chr_first_sep[c]]; S.ch[e] != SEP; e = S.nxt[e]) n++;
-		char *out_seq = static_cast<char*>(malloc(n + 1));
-		uint32_t *out_pos = static_cast<uint32_t*>(malloc(sizeof(uint32_t) * (n + 1)));
-		if(!out_seq || !out_pos)
+		std::vector<int> ok(nchr, 1);
+		auto copy_chr = [&](uint32_t c) {
+			size_t n = 0;
+			for(int32_t e = S.nxt[S.chr_first_sep[c]]; S.ch[e] != SEP; e = S.nxt[e]) n++;
+			char *out_seq = static_cast<char*>(malloc(n + 1));
+			uint32_t *out_pos = static_cast<uint32_t*>(malloc(sizeof(uint32_t) * (n + 1)));
+			if(!out_seq || !out_pos)
+			{
+				free(out_seq);
+				free(out_pos);
+				ok[c] = 0;
+				return;
+			}
+			size_t j = 0;
+			for(int32_t e = S.nxt[S.chr_first_sep[c]]; S.ch[e] != SEP; e = S.nxt[e], j++)
+			{
+				out_seq[j] = S.ch[e];
+				out_pos[j] = S.opos[e];
+			}
+			seq[c] = out_seq;
+			origpos[c] = out_pos;
+			len[c] = n;
+		};
+		std::vector<std::thread> th;
+		for(uint32_t c = 0; c < nchr; c += 16)
 		{
-			set_error("invalid: host allocation failed");
-			return SIBGPU_ERR_INVALID;
+			th.clear();
+			for(uint32_t d = c; d < nchr && d < c + 16; d++) th.emplace_back(copy_chr, d);
+			for(std::thread &x : th) x.join();
 		}
-		size_t j = 0;
-		for(int32_t e = S.nxt[S.chr_first_sep[c]]; S.ch[e] != SEP; e = S.nxt[e], j++)
+		for(uint32_t c = 0; c < nchr; c++)
 		{
-			out_seq[j] = S.ch[e];
-			out_pos[j] = S.opos[e];
+			if(!ok[c])
+			{
+				set_error("invalid: host allocation failed");
+				return SIBGPU_ERR_INVALID;
+			}
 		}
-		seq[c] = out_seq;
-		origpos[c] = out_pos;
-		len[c] = n;
 	}
 	lap("copy-back");
 	recycle();

@@ -24,7 +24,7 @@ def hc():
     src = os.path.join(HERE, "host_commit.cpp")
     hdr = os.path.join(HERE, "..", "sibelia_b200", "csrc", "simplifier.h")
     if not os.path.exists(LIB) or max(os.path.getmtime(src), os.path.getmtime(hdr)) > os.path.getmtime(LIB):
-        subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-o", LIB, src])
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-pthread", "-fPIC", "-shared", "-o", LIB, src])
     return C.CDLL(LIB)
 
 
