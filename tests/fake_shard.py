@@ -1,7 +1,13 @@
 """Test double for sibelia_b200.distributed: the per-rank phases of the sharded enumeration restated in numpy, so the
 orchestration (splits, all-to-all layout, key all-gather, assembly) can run under gloo on CPU with world_size > 1.
 It follows the same contract as GpuShard: same tile split, records ordered by partition, partition p owned by rank
-p // (nparts / world).  k <= 28."""
+p // (nparts / world).  k <= 28.
+
+NumpyPeerShard additionally stands in for the peer strategy: fixed-capacity segments in a per-rank "send buffer" (a
+file under a shared temp directory plays the CUDA IPC mapping: its 64-byte "handle" is the file name), counts + handle
+swapped in one all-gather, the owner of a partition reads the peers' segments itself; a segment that outgrows its
+capacity reports overflow, upon which enumerate_sharded must take the staged path on every rank."""
+import os
 import numpy as np
 import torch
 
@@ -135,3 +141,51 @@ class NumpyShard:
         Nt = np.zeros(len(pos), inst)
         Nt["bifId"], Nt["chr"], Nt["pos"] = np.searchsorted(v, r), chr_, self.lens[chr_] - pos - self.k
         return len(v), P, Nt
+
+
+class NumpyPeerShard(NumpyShard):
+    peer = True
+    device = "cpu"
+
+    def __init__(self, tmpdir, nparts_local=3, seg_cap=None):
+        super().__init__(nparts_local)
+        self.tmpdir = tmpdir
+        self.seg_cap = seg_cap
+        self.fallbacks = 0
+
+    def scatter_local(self, k):
+        nparts, hist = self.scan(k)                       # self.send = records ordered by partition
+        cap = int(self.seg_cap) if self.seg_cap is not None else int(hist.max()) + 8
+        ovf = bool((hist > cap).any())
+        buf = np.zeros(nparts * cap, dtype=np.uint64)     # segment p at p * cap, like the device send buffer
+        if not ovf:
+            off = np.concatenate([[0], np.cumsum(hist)]).astype(np.int64)
+            for p in range(nparts):
+                buf[p * cap:p * cap + hist[p]] = self.send[off[p]:off[p + 1]]
+        else:
+            self.fallbacks += 1
+        self.path = os.path.join(self.tmpdir, "send_rank%d.npy" % self.rank)
+        np.save(self.path, buf)
+        self.nparts = nparts
+        return nparts, hist.astype(np.uint64), cap, ovf
+
+    def export_send(self):
+        h = np.zeros(64, dtype=np.uint8)
+        name = os.path.basename(self.path).encode()
+        h[:len(name)] = np.frombuffer(name, dtype=np.uint8)
+        return h
+
+    def import_peers(self, handles):
+        self.peer_files = [os.path.join(self.tmpdir, bytes(h[h != 0]).decode()) for h in np.asarray(handles, dtype=np.uint8)]
+        return all(os.path.exists(f) for f in self.peer_files)
+
+    def group_peer(self, counts, seg_caps):
+        pl = self.nparts // self.world
+        segs = []
+        for p in range(self.rank * pl, (self.rank + 1) * pl):
+            for s in range(self.world):
+                buf = np.load(self.peer_files[s], mmap_mode="r")
+                cap, n = int(seg_caps[s]), int(counts[s, p])
+                segs.append(np.asarray(buf[p * cap:p * cap + n]))
+        rec = np.concatenate(segs) if segs else np.zeros(0, dtype=np.uint64)
+        return self.group(torch.from_numpy(rec.view(np.int64).copy()), None)

@@ -24,29 +24,29 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, k, seed, q):
+def _worker(rank, world, port, k, seed, q, peer_dir=None, seg_cap=None):
     sys.path.insert(0, HERE)
     sys.path.insert(0, os.path.dirname(HERE))
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     from sibelia_b200 import distributed as D
-    from fake_shard import NumpyShard
+    from fake_shard import NumpyShard, NumpyPeerShard
     chrs = helpers.strain_case(3, 9_000, p_sub=0.02, inv_len=700, seed=seed)
-    count, pos_part, neg_part = D.enumerate_sharded(NumpyShard(), chrs, k)
+    shard = NumpyPeerShard(peer_dir, seg_cap=seg_cap) if peer_dir else NumpyShard()
+    count, pos_part, neg_part = D.enumerate_sharded(shard, chrs, k)
     count, pos, neg = D.gather_tables(count, pos_part, neg_part)
     if rank == 0:
-        q.put((count, pos, neg))
+        q.put((count, pos, neg, getattr(shard, "fallbacks", 0), getattr(shard, "peer", False)))
     dist.barrier()
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,k,seed", [(2, 12, 1), (2, 25, 2), (3, 17, 3)])
-def test_sharded_orchestration_matches_oracle(world, k, seed):
+def _run(world, k, seed, peer_dir=None, seg_cap=None):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, k, seed, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, k, seed, q, peer_dir, seg_cap)) for r in range(world)]
     for p in procs:
         p.start()
     got = q.get(timeout=240)
@@ -54,4 +54,23 @@ def test_sharded_orchestration_matches_oracle(world, k, seed):
         p.join(timeout=60)
         assert p.exitcode == 0
     chrs = helpers.strain_case(3, 9_000, p_sub=0.02, inv_len=700, seed=seed)
-    helpers.assert_tables_equal(got, restate.enumerate_bifurcations(chrs, k), "world=%d k=%d" % (world, k))
+    helpers.assert_tables_equal(got[:3], restate.enumerate_bifurcations(chrs, k), "world=%d k=%d" % (world, k))
+    return got[3], got[4]
+
+
+@pytest.mark.parametrize("world,k,seed", [(2, 12, 1), (2, 25, 2), (3, 17, 3)])
+def test_sharded_orchestration_matches_oracle(world, k, seed):
+    """staged strategy: histogram, all-to-all of the records, key all-gather"""
+    _run(world, k, seed)
+
+
+@pytest.mark.parametrize("world,k,seed", [(2, 25, 2), (3, 14, 4)])
+def test_peer_orchestration_matches_oracle(tmp_path, world, k, seed):
+    """peer strategy: counts + capacity + overflow flag + 64-byte handle in one all-gather, owners read the peers' segments"""
+    fallbacks, still_peer = _run(world, k, seed, str(tmp_path))
+    assert fallbacks == 0 and still_peer
+
+
+def test_peer_overflow_takes_the_staged_path_on_every_rank(tmp_path):
+    fallbacks, _ = _run(2, 25, 5, str(tmp_path), seg_cap=16)       # far too small: every rank reports overflow
+    assert fallbacks == 1
