@@ -210,6 +210,11 @@ int sibgpu_dist_group_peer(sibgpu_ctx *ctx, const uint64_t *counts, const uint64
  * sibelia_b200/csrc/boost_order.h.  out receives the n keys in begin()..end() order. */
 void sibgpu_debug_unordered_order(const uint64_t *keys, uint64_t n, uint64_t *out);
 
+/* Test hook (host only, no GPU needed): the O(instances) part of sibgpu_trim_blocks, fed with the two instance tables of
+ * an enumeration of the block's sequences at trim_k (any source: the CPU tests pass the oracle's). */
+void sibgpu_debug_trim_from_tables(const sibgpu_inst *pos, uint64_t npos, const sibgpu_inst *neg, uint64_t nneg,
+	uint32_t count, const uint64_t *len, const uint8_t *direction, uint32_t nchr, sibgpu_trim *out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -87,3 +87,56 @@ def list_positions(count, pos, neg, lens):
     off = np.zeros(count + 2, dtype=np.uint64)
     np.cumsum(np.bincount(ids, minlength=count + 1), out=off[1:])
     return off, gidx[order].astype(np.uint32), strand[order]
+
+
+EDGE_DTYPE = np.dtype([("chr", "<u4"), ("direction", "<u4"), ("start_vertex", "<u4"), ("end_vertex", "<u4"),
+                       ("actual_position", "<u4"), ("actual_length", "<u4"), ("original_position", "<u4"),
+                       ("original_length", "<u4"), ("first_char", "<u4")])
+_COMP = np.arange(256, dtype=np.uint8)
+for _a, _b in zip(b"ACGT", b"TGCA"):
+    _COMP[_a] = _b
+
+
+def list_edges(chrs, origpos, k):
+    """numpy restatement of `IndexedSequence iseq(rawSeq_, originalPos_, k, ""); ListEdges(...)`
+    (/root/reference/src/synteny.cpp:238-241, src/serialization.cpp:56-86), pinned against oracle/_ref in
+    tests/test_oracle.py: per strand and chromosome the walk emits one Edge per pair of consecutive vertex marks --
+    start/end vertex = the two ids, step = distance between the marks, actualPosition = pos (positive strand) or
+    length - (pos + step + k) (negative), actualLength = step + k, firstChar = the base k steps after the first mark read
+    along the strand (:75), original coordinates = min/max of the stored positions of the first and the last element
+    spelled by the edge (DNASequence::SpellOriginal, src/dnasequence.cpp:254-260)."""
+    chrs = [np.frombuffer(c, dtype=np.uint8) if isinstance(c, (bytes, bytearray)) else np.asarray(c, dtype=np.uint8)
+            for c in chrs]
+    count, pos, neg = enumerate_bifurcations(chrs, k)
+    lens = np.array([len(c) for c in chrs], dtype=np.int64)
+    out = []
+    for strand, tab in ((0, pos), (1, neg)):
+        if len(tab) < 2:
+            continue
+        same = tab["chr"][:-1] == tab["chr"][1:]
+        a, b = tab[:-1][same], tab[1:][same]
+        c = a["chr"].astype(np.int64)
+        p = a["pos"].astype(np.int64)
+        step = b["pos"].astype(np.int64) - p
+        L = lens[c]
+        e = np.zeros(len(a), dtype=EDGE_DTYPE)
+        e["chr"], e["direction"], e["start_vertex"], e["end_vertex"] = c, strand, a["bifId"], b["bifId"]
+        e["actual_position"] = p if strand == 0 else L - (p + step + k)
+        e["actual_length"] = step + k
+        first_el = p if strand == 0 else L - 1 - p                 # element indices in positive coordinates
+        last_el = p + step + k - 1 if strand == 0 else L - 1 - (p + step + k - 1)
+        char_el = p + k if strand == 0 else L - 1 - (p + k)
+        fc = np.zeros(len(a), dtype=np.uint8)
+        o1 = np.zeros(len(a), dtype=np.int64)
+        o2 = np.zeros(len(a), dtype=np.int64)
+        for ci in np.unique(c):
+            m = c == ci
+            seq = chrs[ci]
+            fc[m] = seq[char_el[m]] if strand == 0 else _COMP[seq[char_el[m]]]
+            op = np.arange(len(seq), dtype=np.int64) if origpos is None else np.asarray(origpos[ci], dtype=np.int64)
+            o1[m], o2[m] = op[first_el[m]], op[last_el[m]]
+        e["first_char"] = fc
+        e["original_position"] = np.minimum(o1, o2)
+        e["original_length"] = np.maximum(o1, o2) + 1 - np.minimum(o1, o2)
+        out.append(e)
+    return np.concatenate(out) if out else np.zeros(0, dtype=EDGE_DTYPE)

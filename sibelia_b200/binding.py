@@ -15,7 +15,7 @@ EDGE_DTYPE = np.dtype([("chr", "<u4"), ("direction", "<u4"), ("start_vertex", "<
 SYMBOLS = [
     "sibgpu_last_error", "sibgpu_version", "sibgpu_device_count", "sibgpu_create", "sibgpu_destroy", "sibgpu_free",
     "sibgpu_enumerate", "sibgpu_list_edges", "sibgpu_trim_blocks", "sibgpu_upload", "sibgpu_enumerate_resident", "sibgpu_download", "sibgpu_set_profiling",
-    "sibgpu_kernel_stats", "sibgpu_last_launches", "sibgpu_partition_fallbacks", "sibgpu_last_device_ms", "sibgpu_simplify", "sibgpu_debug_unordered_order", "sibgpu_dist_upload", "sibgpu_dist_scan", "sibgpu_dist_record_bytes",
+    "sibgpu_kernel_stats", "sibgpu_last_launches", "sibgpu_partition_fallbacks", "sibgpu_last_device_ms", "sibgpu_simplify", "sibgpu_debug_unordered_order", "sibgpu_debug_trim_from_tables", "sibgpu_dist_upload", "sibgpu_dist_scan", "sibgpu_dist_record_bytes",
     "sibgpu_dist_scatter", "sibgpu_dist_group", "sibgpu_dist_keys", "sibgpu_dist_finish",
     "sibgpu_dist_scatter_local", "sibgpu_dist_upload_scatter", "sibgpu_dist_export_send", "sibgpu_dist_import_peers", "sibgpu_dist_group_peer",
 ]
@@ -282,6 +282,20 @@ class Context:
             L.sibgpu_free(C.c_void_p(seq[i]))
             L.sibgpu_free(C.c_void_p(op[i]))
         return new_chrs, new_op, bulges.value
+
+
+def debug_trim_from_tables(count, pos, neg, lens, directions):
+    """Host-only test hook: trim points from given instance tables (see sibgpu_trim_blocks)."""
+    pos = np.ascontiguousarray(pos, dtype=INST_DTYPE)
+    neg = np.ascontiguousarray(neg, dtype=INST_DTYPE)
+    lens = np.ascontiguousarray(lens, dtype=np.uint64)
+    d = np.ascontiguousarray(directions, dtype=np.uint8)
+    out = np.zeros((max(len(lens), 1), 3), dtype=np.uint32)
+    f = load().sibgpu_debug_trim_from_tables
+    f.restype = None
+    f(C.c_void_p(pos.ctypes.data), C.c_uint64(len(pos)), C.c_void_p(neg.ctypes.data), C.c_uint64(len(neg)), C.c_uint32(count),
+      C.c_void_p(lens.ctypes.data), C.c_void_p(d.ctypes.data), C.c_uint32(len(lens)), C.c_void_p(out.ctypes.data))
+    return out[:len(lens)]
 
 
 def debug_unordered_order(keys):

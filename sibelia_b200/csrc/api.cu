@@ -380,18 +380,10 @@ int sibgpu_list_edges(sibgpu_ctx *c, const char *const *seq, const uint32_t *con
 //     trimStart = first `it` minimising (dStart(it) + dStart(kmer), vertex id),   trimEnd likewise with dEnd.
 // Only the minimum over the kmers matters, so per vertex we keep the smallest dStart/dEnd together with the sequence it
 // comes from and the smallest one from any other sequence; the scan over the marks is then O(instances).
-int sibgpu_trim_blocks(sibgpu_ctx *c, const char *const *seq, const uint64_t *len, const uint8_t *direction, uint32_t nchr,
-	uint32_t trim_k, sibgpu_trim *out)
+// the O(instances) part of sibgpu_trim_blocks: the two instance tables of the enumeration -> trim points
+static void trim_from_tables(const sibgpu_inst *const tab[2], const uint64_t ntab[2], uint32_t count, const uint64_t *len,
+	const uint8_t *direction, uint32_t nchr, sibgpu_trim *out)
 {
-	if(!c || (nchr && (!seq || !len || !direction || !out)) || trim_k == 0)
-	{
-		set_error("invalid: NULL argument or trim_k == 0");
-		return SIBGPU_ERR_INVALID;
-	}
-	sibgpu_inst *tab[2] = {nullptr, nullptr};
-	uint64_t ntab[2] = {0, 0};
-	uint32_t count = 0;
-	SIB_TRY(sibgpu_enumerate(c, seq, len, nchr, trim_k, &tab[0], &ntab[0], &tab[1], &ntab[1], &count));
 	const uint32_t INF = 0xFFFFFFFFu;
 	struct Best { uint32_t b1, c1, b2; };
 	std::vector<Best> bs(count, Best{INF, INF, INF}), be(count, Best{INF, INF, INF});
@@ -432,9 +424,32 @@ int sibgpu_trim_blocks(sibgpu_ctx *c, const char *const *seq, const uint64_t *le
 			out[x.chr].found = 1;
 		}
 	}
+}
+
+int sibgpu_trim_blocks(sibgpu_ctx *c, const char *const *seq, const uint64_t *len, const uint8_t *direction, uint32_t nchr,
+	uint32_t trim_k, sibgpu_trim *out)
+{
+	if(!c || (nchr && (!seq || !len || !direction || !out)) || trim_k == 0)
+	{
+		set_error("invalid: NULL argument or trim_k == 0");
+		return SIBGPU_ERR_INVALID;
+	}
+	sibgpu_inst *tab[2] = {nullptr, nullptr};
+	uint64_t ntab[2] = {0, 0};
+	uint32_t count = 0;
+	SIB_TRY(sibgpu_enumerate(c, seq, len, nchr, trim_k, &tab[0], &ntab[0], &tab[1], &ntab[1], &count));
+	trim_from_tables(tab, ntab, count, len, direction, nchr, out);
 	sibgpu_free(tab[0]);
 	sibgpu_free(tab[1]);
 	return SIBGPU_OK;
+}
+
+void sibgpu_debug_trim_from_tables(const sibgpu_inst *pos, uint64_t npos, const sibgpu_inst *neg, uint64_t nneg, uint32_t count,
+	const uint64_t *len, const uint8_t *direction, uint32_t nchr, sibgpu_trim *out)
+{
+	const sibgpu_inst *tab[2] = {pos, neg};
+	const uint64_t ntab[2] = {npos, nneg};
+	trim_from_tables(tab, ntab, count, len, direction, nchr, out);
 }
 
 // ---------------------------------------------------------------------------------------------------------------

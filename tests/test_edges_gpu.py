@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 
 import helpers
-from oracle import ref
+from oracle import ref, restate
 
 pytestmark = pytest.mark.gpu
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
@@ -56,6 +56,16 @@ def test_tiny_and_degenerate(ctx):
         assert_edges_equal(ctx.list_edges(chrs, op, k), want, "tiny %d k=%d" % (it, k))
     assert len(ctx.list_edges([], [], 5)) == 0
     assert len(ctx.list_edges([b"ACG"], None, 5)) == 0
+
+
+def test_against_restatement(ctx):
+    """the numpy restatement of ListEdges (oracle/restate.py, pinned against the reference in tests/test_oracle.py) needs
+    no oracle/_ref on the box"""
+    rng = np.random.default_rng(10)
+    st = helpers.strain_case(4, 50_000, p_sub=0.01, inv_len=3_000, seed=48)
+    op = [rng.permutation(len(c)).astype(np.uint32) for c in st]
+    for k in (12, 25, 32, 40):
+        assert_edges_equal(ctx.list_edges(st, op, k), restate.list_edges(st, op, k), "restatement k=%d" % k)
 
 
 def test_identity_origpos_when_null(ctx):

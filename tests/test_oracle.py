@@ -93,3 +93,36 @@ def test_restatement_on_reference_example_genome():
     count, pos, neg = restate.enumerate_bifurcations(hp, 25)
     assert (count, len(pos) + len(neg)) == (74442, 152956)
     assert hashlib.sha256(pos.tobytes() + neg.tobytes()).hexdigest() == want[25][2]
+
+
+# ---- edge list (IndexedSequence + BlockFinder::ListEdges): numpy restatement vs golden fixtures and the reference
+EDGE_FILES = sorted(glob.glob(os.path.join(GOLD, "edges_*.npz")))
+
+
+def _edges_equal(got, want, what):
+    assert len(got) == len(want), "%s: %d edges != %d" % (what, len(got), len(want))
+    for f in want.dtype.names:
+        assert np.array_equal(got[f], want[f]), "%s: field %s differs" % (what, f)
+
+
+@pytest.mark.parametrize("path", EDGE_FILES, ids=[os.path.basename(p)[:-4] for p in EDGE_FILES])
+def test_edge_restatement_matches_golden(path):
+    z = np.load(path)
+    n = int(z["n"])
+    _edges_equal(restate.list_edges([z["seq_%d" % i] for i in range(n)], [z["op_%d" % i] for i in range(n)], int(z["k"])),
+                 z["edges"], os.path.basename(path))
+
+
+@pytest.mark.skipif(not ref.available(), reason="oracle/_ref not built (needs /root/reference)")
+def test_edge_restatement_matches_reference():
+    rng = np.random.default_rng(12)
+    for it in range(60):
+        chrs, k = helpers.random_case(rng, max_rec=5, max_len=80, kmax=10)
+        chrs = [c.tobytes() for c in chrs]
+        op = [rng.permutation(len(c)).astype(np.uint32) for c in chrs]
+        _edges_equal(restate.list_edges(chrs, op, k), ref.list_edges(chrs, op, k)[0], "tiny %d k=%d" % (it, k))
+    st = [c.tobytes() for c in helpers.strain_case(3, 20_000, seed=77)]
+    op = [np.arange(len(c), dtype=np.uint32) for c in st]
+    st2, op2, _, _ = ref.simplify(st, op, 30, 150, 4)
+    for k in (30, 100):
+        _edges_equal(restate.list_edges(st2, op2, k), ref.list_edges(st2, op2, k)[0], "simplified k=%d" % k)
