@@ -77,3 +77,11 @@ def test_helicobacter_pylori_loose(tmp_path):
     got = compare(["-s", "loose", os.path.join(DATA, "Helicobacter_pylori.fasta")], tmp_path)
     assert hashlib.md5(got["blocks_coords.txt"]).hexdigest() == "9cf97c63809c08c961a5f30036e3dc28"
     assert hashlib.md5(got["genomes_permutations.txt"]).hexdigest() == "a1d4765580a36622839e9065873304d4"
+
+
+@pytest.mark.skipif(not (have and os.path.exists(os.path.join(DATA, "Staphylococcus.fasta"))),
+                    reason="reference example genome did not travel")
+def test_staphylococcus_aureus_loose(tmp_path):
+    """The reference's second example dataset (4 records, 11.6 Mb; SURVEY.md section 4 known answers: 37 380 / 821 / 255 /
+    46 bulges over the four `-s loose` stages): all three output files byte-identical to the unmodified CLI."""
+    compare(["-s", "loose", os.path.join(DATA, "Staphylococcus.fasta")], tmp_path)
