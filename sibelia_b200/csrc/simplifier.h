@@ -719,11 +719,29 @@ public:
 	std::vector<BifurcationMark> visit;
 	std::vector<int> ord;
 
+	static const int PREFETCH_LINES = 10;                // 10 x 16 elements ~ the 150-element reach of the first stage
 	size_t remove_bulges(size_t bif_id)                  // RemoveBulges, :330-430
 	{
 		size_t ret = 0;
 		list_positions(bif_id, start_kmer);
 		if(start_kmer.size() < 2) return ret;
+		// The instances of a vertex lie far apart (different strains): start all their cache misses at once.  The walks
+		// below read ch / nxt|prv / mark[d] of up to D elements after each instance; elements are mostly contiguous in
+		// index, so the lines ahead of the start element are the ones that will be needed (prefetches have no effect on
+		// the result).
+		for(size_t i = 0; i < start_kmer.size(); i++)
+		{
+			const It it = node_it(start_kmer[i]);
+			const int32_t step = it.d == 0 ? 16 : -16;
+			const int32_t *link = it.d == 0 ? nxt.data() : prv.data();
+			const int32_t limit = (int32_t)ch.size();
+			for(int32_t j = 0, e = it.e; j < PREFETCH_LINES && e >= 0 && e < limit; j++, e += step)
+			{
+				__builtin_prefetch(link + e);
+				__builtin_prefetch(mark[it.d].data() + e);
+				if((j & 3) == 0) __builtin_prefetch(ch.data() + e);
+			}
+		}
 		end_char.assign(start_kmer.size(), EMPTY);
 		for(size_t i = 0; i < start_kmer.size(); i++)
 		{
