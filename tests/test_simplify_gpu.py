@@ -69,3 +69,25 @@ def test_max_iterations_and_tiny_inputs(ctx):
         want = ref.simplify(chrs, op, k, D, iters)[:3]
         got = ctx.simplify(chrs, op, k, D, iters)
         assert_state_equal(got, want, "tiny %d (k=%d D=%d iters=%d)" % (it, k, D, iters))
+
+
+def test_large_strain_set_against_reference_digests(ctx):
+    """SURVEY 8(d) strain recipe at 4 x 12.5 Mb through the four loose stages: 143 410 collapses in stage 1 (Boost
+    rehashes past 16 buckets, multi-group vertices, the overlap guard and the double accumulation en masse).  The
+    reference's states are pinned by sha256 digests (tests/golden/make_golden_simplify_large.py, ~4 min of CPU)."""
+    import hashlib
+    import json
+    from sibelia_b200 import synth
+    z = json.load(open(os.path.join(GOLD, "simplify_large_digests.json")))
+    chrs = [c.tobytes() for c in synth.strains(z["n_strains"], z["base_len"], base_seed=z["base_seed"],
+                                               strain_seed=z["strain_seed"], p_sub=z["p_sub"])]
+    assert [hashlib.sha256(c).hexdigest() for c in chrs] == z["input"]["seq_sha256"], "generator drifted"
+    op = [np.arange(len(c), dtype=np.uint32) for c in chrs]
+    for st in z["after"]:
+        chrs, op, bulges = ctx.simplify(chrs, op, st["k"], st["D"], z["iters"])
+        what = "stage (%d,%d)" % (st["k"], st["D"])
+        assert bulges == st["bulges"], "%s bulges %d != %d" % (what, bulges, st["bulges"])
+        assert [len(c) for c in chrs] == st["len"], what + " lengths differ"
+        assert [hashlib.sha256(bytes(c)).hexdigest() for c in chrs] == st["seq_sha256"], what + " sequences differ"
+        assert [hashlib.sha256(np.ascontiguousarray(o, dtype=np.uint32).tobytes()).hexdigest() for o in op] == st["origpos_sha256"], \
+            what + " original positions differ"
