@@ -94,6 +94,9 @@ uint64_t sibgpu_last_launches(sibgpu_ctx *ctx);
 /* how often, over the life of the context, a fixed-capacity hash partition overflowed (a k-mer repeated millions of
  * times) and the enumeration fell back to exactly sized partitions (histogram pass); diagnostic */
 uint64_t sibgpu_partition_fallbacks(sibgpu_ctx *ctx);
+/* how often a shared-memory bucket (~1 Ki records, fixed capacity) overflowed -- one k-mer repeated hundreds of times --
+ * and the enumeration regrouped the partitions through the L2-resident tables instead; diagnostic */
+uint64_t sibgpu_bucket_fallbacks(sibgpu_ctx *ctx);
 /* device time of the last sibgpu_enumerate_resident / device part of sibgpu_simplify on this context: milliseconds
  * between two CUDA events recorded on the library's stream around the whole operation */
 float sibgpu_last_device_ms(sibgpu_ctx *ctx);

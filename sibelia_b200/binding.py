@@ -15,7 +15,7 @@ EDGE_DTYPE = np.dtype([("chr", "<u4"), ("direction", "<u4"), ("start_vertex", "<
 SYMBOLS = [
     "sibgpu_last_error", "sibgpu_version", "sibgpu_device_count", "sibgpu_create", "sibgpu_destroy", "sibgpu_free",
     "sibgpu_enumerate", "sibgpu_list_edges", "sibgpu_trim_blocks", "sibgpu_upload", "sibgpu_enumerate_resident", "sibgpu_download", "sibgpu_set_profiling",
-    "sibgpu_kernel_stats", "sibgpu_last_launches", "sibgpu_partition_fallbacks", "sibgpu_last_device_ms", "sibgpu_simplify", "sibgpu_debug_unordered_order", "sibgpu_debug_trim_from_tables", "sibgpu_dist_upload", "sibgpu_dist_scan", "sibgpu_dist_record_bytes",
+    "sibgpu_kernel_stats", "sibgpu_last_launches", "sibgpu_partition_fallbacks", "sibgpu_bucket_fallbacks", "sibgpu_last_device_ms", "sibgpu_simplify", "sibgpu_debug_unordered_order", "sibgpu_debug_trim_from_tables", "sibgpu_dist_upload", "sibgpu_dist_scan", "sibgpu_dist_record_bytes",
     "sibgpu_dist_scatter", "sibgpu_dist_group", "sibgpu_dist_keys", "sibgpu_dist_finish",
     "sibgpu_dist_scatter_local", "sibgpu_dist_upload_scatter", "sibgpu_dist_export_send", "sibgpu_dist_import_peers", "sibgpu_dist_group_peer",
 ]
@@ -58,6 +58,8 @@ def load():
         L.sibgpu_last_launches.argtypes = [C.c_void_p]
         L.sibgpu_partition_fallbacks.restype = C.c_uint64
         L.sibgpu_partition_fallbacks.argtypes = [C.c_void_p]
+        L.sibgpu_bucket_fallbacks.restype = C.c_uint64
+        L.sibgpu_bucket_fallbacks.argtypes = [C.c_void_p]
         L.sibgpu_last_device_ms.restype = C.c_float
         L.sibgpu_last_device_ms.argtypes = [C.c_void_p]
         L.sibgpu_destroy.argtypes = [C.c_void_p]
@@ -194,6 +196,9 @@ class Context:
 
     def partition_fallbacks(self):
         return int(load().sibgpu_partition_fallbacks(self._h))
+
+    def bucket_fallbacks(self):
+        return int(load().sibgpu_bucket_fallbacks(self._h))
 
     # -- sharded enumeration phases (see sibelia_b200/distributed.py for the orchestration)
     def dist_upload(self, chrs, rank, world):

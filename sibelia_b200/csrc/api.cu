@@ -141,6 +141,8 @@ int sibgpu_create(int device, sibgpu_ctx **out)
 	if(const char *e = getenv("SIBGPU_EXACT_HIST")) c->exact_hist = atoi(e) != 0;
 	if(const char *e = getenv("SIBGPU_INSERT_VARIANT")) c->insert_variant = atoi(e);
 	if(const char *e = getenv("SIBGPU_STREAMS")) c->n_streams = atoi(e);
+	if(const char *e = getenv("SIBGPU_GROUP_SMEM")) c->group_smem = atoi(e);
+	if(const char *e = getenv("SIBGPU_CKEYS_INIT")) c->ckeys_init = strtoull(e, nullptr, 10);
 	if(const char *e = getenv("SIBGPU_TABLE_FACTOR"))
 	{
 		int v = atoi(e);
@@ -158,7 +160,7 @@ void sibgpu_destroy(sibgpu_ctx *c)
 		&c->d_records, &c->d_table, &c->d_partcnt, &c->d_keyoff, &c->d_ckeys, &c->d_vkeys, &c->d_vkeys_alt, &c->d_cubtmp,
 		&c->d_map, &c->d_filter, &c->d_hitmask, &c->d_tilecnt, &c->d_tileoff, &c->d_pos, &c->d_negtmp, &c->d_neg,
 		&c->d_chrinst, &c->d_scalars, &c->d_fp, &c->d_rep, &c->d_order, &c->d_s_ch, &c->d_s_m0, &c->d_s_m1, &c->d_s_off,
-		&c->d_s_inst, &c->d_s_flag, &c->d_edges, &c->d_edge_skip};
+		&c->d_s_inst, &c->d_s_flag, &c->d_edges, &c->d_edge_skip, &c->d_records2, &c->d_cnt2};
 	for(void *pp : c->peer_ptr)
 	{
 		if(pp) cudaIpcCloseMemHandle(pp);
@@ -705,6 +707,7 @@ int sibgpu_kernel_stats(sibgpu_ctx *c, sibgpu_kernel_stat *out, int cap)
 
 uint64_t sibgpu_last_launches(sibgpu_ctx *c) { return c ? c->total_launches : 0; }
 uint64_t sibgpu_partition_fallbacks(sibgpu_ctx *c) { return c ? c->hist_fallbacks : 0; }
+uint64_t sibgpu_bucket_fallbacks(sibgpu_ctx *c) { return c ? c->smem_fallbacks : 0; }
 float sibgpu_last_device_ms(sibgpu_ctx *c) { return c ? c->last_ms : 0.f; }
 
 }

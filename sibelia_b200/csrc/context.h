@@ -36,7 +36,7 @@ struct sibgpu_ctx {
 	// enumeration workspace
 	sibgpu::DevBuf d_hist, d_partoff, d_cursor, d_records, d_table, d_partcnt, d_keyoff, d_ckeys, d_vkeys, d_vkeys_alt,
 		d_cubtmp, d_map, d_filter, d_hitmask, d_tilecnt, d_tileoff, d_pos, d_negtmp, d_neg, d_chrinst, d_scalars,
-		d_fp, d_rep, d_order, d_s_ch, d_s_m0, d_s_m1, d_s_off, d_s_inst, d_s_flag, d_edges, d_edge_skip;
+		d_fp, d_rep, d_order, d_records2, d_cnt2, d_s_ch, d_s_m0, d_s_m1, d_s_off, d_s_inst, d_s_flag, d_edges, d_edge_skip;
 	void *h_scalars = nullptr;                         // pinned, 64 x u64
 
 	// last result
@@ -81,6 +81,11 @@ struct sibgpu_ctx {
 	cudaStream_t aux_stream[8] = {};
 	cudaEvent_t ev_fork = nullptr, ev_join[8] = {};
 	int ensure_aux_streams(uint32_t n);
+	// grouping of 8-byte records (k <= 28): 1 = buckets of ~1 Ki records grouped in shared memory (k_split + k_group),
+	// 0 = one L2-resident table per hash partition (k_insert + k_table_scan; also the fallback when a bucket overflows)
+	int group_smem = 1;                                // env SIBGPU_GROUP_SMEM
+	uint64_t ckeys_init = 1u << 20;                    // initial capacity of the vertex-key list (env SIBGPU_CKEYS_INIT, tests)
+	uint64_t smem_fallbacks = 0;                       // times a bucket overflowed and the L2-table path took over
 	int table_factor = 2;                              // slots per record of the largest partition (env SIBGPU_TABLE_FACTOR)
 
 	// sibgpu_simplify: the per-element host arrays of a stage are recycled between stages (a fresh 30 B/element

@@ -21,6 +21,7 @@
 #include <cub/cub.cuh>
 
 #include "enum_common.cuh"
+#include "group_smem.cuh"
 
 namespace sibgpu {
 
@@ -1140,9 +1141,14 @@ static int enumerate_mode(sibgpu_ctx *ctx, uint32_t k, uint64_t nrec, const Host
 		const Rec16 *fp = ctx->d_fp.as<Rec16>();
 
 		// ---- partition plan
-		const uint64_t part_rec = ctx->part_records(k);
+		// 8-byte records: level-1 partitions of 512 Ki records, split into ~1 Ki-record buckets and grouped in shared
+		// memory (group_smem.cuh); otherwise one L2-resident table per partition
+		const bool smem_group = MODE == 0 && ctx->group_smem && !ctx->exact_hist;
+		const uint64_t part_rec = smem_group && !ctx->part_explicit ? (uint64_t)512 << 10 : ctx->part_records(k);
 		uint64_t P64 = (nrec + part_rec - 1) / part_rec;
 		const uint32_t P = (uint32_t)(P64 < 1 ? 1 : (P64 > MAX_PARTS ? MAX_PARTS : P64));
+		bool grouped = false;                              // vertex keys already in d_ckeys (shared-memory path)
+		uint64_t Vc = 0;
 		SIB_TRY(ctx->d_hist.ensure(sizeof(uint32_t) * MAX_PARTS));
 		SIB_TRY(ctx->d_partoff.ensure(sizeof(uint64_t) * (MAX_PARTS + 1)));
 		SIB_TRY(ctx->d_cursor.ensure(sizeof(uint64_t) * MAX_PARTS * CURSOR_STRIDE));
@@ -1207,14 +1213,53 @@ static int enumerate_mode(sibgpu_ctx *ctx, uint32_t k, uint64_t nrec, const Host
 					tiles_done = tile_hi;
 				}
 			}
+			// ---- shared-memory grouping, launched behind the scatter without a host round trip: the level-1 fill counts
+			// are read on the device; the flags (input error, level-1 / level-2 overflow) are checked once, below
+			bool smem_launched = false;
+			uint32_t nbuckets = 0;
+			uint32_t ckeys_cap = 0;
+			if constexpr(MODE == 0)
+			{
+				uint32_t sub_bits = 0;
+				while(((mean + ((uint64_t)1 << sub_bits) - 1) >> sub_bits) > GROUP_MEAN) sub_bits++;
+				if(smem_group && sub_bits <= SUB_BITS_MAX)
+				{
+					nbuckets = P << sub_bits;
+					SIB_TRY(ctx->d_records2.ensure(sizeof(uint64_t) * (size_t)nbuckets * GROUP_CAP + 64));
+					SIB_TRY(ctx->d_cnt2.ensure(sizeof(uint32_t) * (size_t)nbuckets));
+					SIB_TRY(ctx->d_ckeys.ensure(sizeof(uint64_t) * (ctx->ckeys_init ? ctx->ckeys_init : 1)));
+					ckeys_cap = (uint32_t)std::min<size_t>(ctx->d_ckeys.cap / sizeof(uint64_t), 0xFFFFFFF0u);
+					SIB_CUDA(cudaMemsetAsync(ctx->d_cnt2.p, 0, sizeof(uint32_t) * (size_t)nbuckets, st));
+					SIB_CUDA(cudaFuncSetAttribute(k_split, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SplitSmem)));
+					SIB_CUDA(cudaFuncSetAttribute(k_group, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(GroupSmem)));
+					const uint32_t tiles_per_part = (uint32_t)((cap + SPLIT_TILE - 1) / SPLIT_TILE);
+					const uint64_t split_tiles = (uint64_t)P * tiles_per_part;
+					{
+						ProfScope ps(ctx, "k_split", nrec * 16);
+						k_split<<<(uint32_t)std::min<uint64_t>(split_tiles, (uint64_t)sms * 2), SPLIT_THREADS, sizeof(SplitSmem), st>>>(
+							ctx->d_records.as<uint64_t>(), ctx->d_partoff.as<uint64_t>(), ctx->d_cursor.as<unsigned long long>(), P,
+							tiles_per_part, sub_bits, ctx->d_records2.as<uint64_t>(), ctx->d_cnt2.as<uint32_t>(), GROUP_CAP,
+							reinterpret_cast<uint32_t*>(ds + 11));
+					}
+					{
+						ProfScope ps(ctx, "k_group", nrec * 8);
+						k_group<<<std::min<uint32_t>(nbuckets, (uint32_t)sms * 3), GROUP_THREADS, sizeof(GroupSmem), st>>>(
+							ctx->d_records2.as<uint64_t>(), ctx->d_cnt2.as<uint32_t>(), nbuckets, GROUP_CAP,
+							reinterpret_cast<uint32_t*>(ds + 11), ctx->d_ckeys.as<uint64_t>(), ckeys_cap, reinterpret_cast<uint32_t*>(ds + 2));
+					}
+					smem_launched = true;
+				}
+			}
 			SIB_CUDA(cudaMemcpyAsync(cur.data(), ctx->d_cursor.p, sizeof(uint64_t) * cur.size(), cudaMemcpyDeviceToHost, st));
-			SIB_CUDA(cudaMemcpyAsync(hs + 8, ds + 8, sizeof(uint64_t) * 3, cudaMemcpyDeviceToHost, st));
+			SIB_CUDA(cudaMemcpyAsync(hs + 8, ds + 8, sizeof(uint64_t) * 4, cudaMemcpyDeviceToHost, st));
+			SIB_CUDA(cudaMemcpyAsync(hs + 2, ds + 2, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
 			SIB_CUDA(cudaStreamSynchronize(st));
 			if(hs[8] & 1u) return input_error();
 			src = nullptr;                                 // the whole text is resident and packed from here on
 			if(hs[10] & 0xFFFFFFFFull)
 			{
-				SIB_CUDA(cudaMemsetAsync(ds + 10, 0, sizeof(uint64_t), st));
+				SIB_CUDA(cudaMemsetAsync(ds + 10, 0, sizeof(uint64_t) * 2, st));
+				SIB_CUDA(cudaMemsetAsync(ds + 2, 0, sizeof(uint64_t), st));
 				ctx->hist_fallbacks++;
 			}
 			else
@@ -1232,6 +1277,36 @@ static int enumerate_mode(sibgpu_ctx *ctx, uint32_t k, uint64_t nrec, const Host
 					return SIBGPU_ERR_INTERNAL;
 				}
 				have_records = true;
+				if(smem_launched)
+				{
+					if(hs[11] & 0xFFFFFFFFull)
+					{
+						// a bucket outgrew its fixed region (one k-mer repeated hundreds of times): the L2-table path below
+						// regroups the intact level-1 partitions
+						SIB_CUDA(cudaMemsetAsync(ds + 11, 0, sizeof(uint64_t), st));
+						SIB_CUDA(cudaMemsetAsync(ds + 2, 0, sizeof(uint64_t), st));
+						ctx->smem_fallbacks++;
+					}
+					else
+					{
+						Vc = hs[2] & 0xFFFFFFFFull;
+						if constexpr(MODE == 0)
+						{
+							if(Vc > ckeys_cap)
+							{
+								// the key list was too small (k_group kept counting): regrow, group again -- the buckets are intact
+								SIB_TRY(ctx->d_ckeys.ensure(sizeof(uint64_t) * Vc));
+								SIB_CUDA(cudaMemsetAsync(ds + 2, 0, sizeof(uint64_t), st));
+								ProfScope ps(ctx, "k_group", nrec * 8);
+								k_group<<<std::min<uint32_t>(nbuckets, (uint32_t)sms * 3), GROUP_THREADS, sizeof(GroupSmem), st>>>(
+									ctx->d_records2.as<uint64_t>(), ctx->d_cnt2.as<uint32_t>(), nbuckets, GROUP_CAP,
+									reinterpret_cast<uint32_t*>(ds + 11), ctx->d_ckeys.as<uint64_t>(), (uint32_t)Vc, reinterpret_cast<uint32_t*>(ds + 2));
+								SIB_CUDA(cudaStreamSynchronize(st));
+							}
+						}
+						grouped = true;
+					}
+				}
 			}
 		}
 		else if(src)
@@ -1278,6 +1353,8 @@ static int enumerate_mode(sibgpu_ctx *ctx, uint32_t k, uint64_t nrec, const Host
 		}
 
 		// ---- per-partition L2-resident grouping
+		if(!grouped)
+		{
 		uint64_t T64 = (uint64_t)ctx->table_factor * maxpart + 1024;
 		if(T64 > 0xFFFFFF00ull)
 		{
@@ -1339,7 +1416,8 @@ static int enumerate_mode(sibgpu_ctx *ctx, uint32_t k, uint64_t nrec, const Host
 		}
 		SIB_CUDA(cudaMemcpyAsync(hs + 2, ds + 2, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
 		SIB_CUDA(cudaStreamSynchronize(st));
-		const uint64_t Vc = hs[2];                         // canonical vertex classes
+		Vc = hs[2];                                        // canonical vertex classes
+		}
 		if(Vc == 0)
 		{
 			ctx->n_inst = 0;
@@ -1351,8 +1429,9 @@ static int enumerate_mode(sibgpu_ctx *ctx, uint32_t k, uint64_t nrec, const Host
 			set_error("invalid: more than 2^32 vertices");
 			return SIBGPU_ERR_INVALID;
 		}
-		SIB_TRY(ctx->d_ckeys.ensure(sizeof(Rec) * Vc));
+		if(!grouped)
 		{
+			SIB_TRY(ctx->d_ckeys.ensure(sizeof(Rec) * Vc));
 			ProfScope ps(ctx, "k_gather_keys", 2 * Vc * sizeof(Rec));
 			dim3 g(8, P);
 			k_gather_keys<MODE><<<g, 256, 0, st>>>(ctx->d_records.as<Rec>(), ctx->d_partoff.as<uint64_t>(),

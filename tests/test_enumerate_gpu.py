@@ -135,6 +135,43 @@ def test_partition_overflow_falls_back_to_exact_sizes(built):
     c.close()
 
 
+def test_bucket_overflow_falls_back_to_l2_tables(built):
+    """Shared-memory grouping: a bucket (~1 Ki records, fixed capacity 1664) overflows when one k-mer occurs thousands of
+    times; the enumeration must notice and regroup the intact level-1 partitions through the L2-resident tables."""
+    import sibelia_b200 as sb
+    c = sb.Context(0)
+    rnd = synth.random_genome(300_000, 14)
+    poly = np.full(6_000, ord("A"), dtype=np.uint8)
+    chrs = [np.concatenate([rnd[:100_000], poly, rnd[100_000:]]), synth.revcomp(rnd[50_000:90_000])]
+    for k in (25, 28):
+        before = c.bucket_fallbacks()
+        helpers.assert_tables_equal(c.enumerate(chrs, k), restate.enumerate_bifurcations(chrs, k), "bucket overflow k=%d" % k)
+        assert c.bucket_fallbacks() == before + 1
+    st = helpers.strain_case(4, 50_000, seed=96)
+    before = c.bucket_fallbacks()
+    helpers.assert_tables_equal(c.enumerate(st, 25), restate.enumerate_bifurcations(st, 25), "balanced")
+    assert c.bucket_fallbacks() == before and c.partition_fallbacks() == 0
+    c.close()
+
+
+def test_vertex_key_list_regrows(built):
+    """k_group counts every bifurcation class even when the key list is full; the host regrows it and groups again."""
+    c = _ctx_with_env(SIBGPU_CKEYS_INIT=8)
+    st = helpers.strain_case(4, 60_000, seed=95)
+    for k in (25, 16):
+        helpers.assert_tables_equal(c.enumerate(st, k), restate.enumerate_bifurcations(st, k), "regrow k=%d" % k)
+    c.close()
+
+
+@pytest.mark.parametrize("k", [11, 25, 28])
+def test_l2_table_grouping_still_matches(built, k):
+    """SIBGPU_GROUP_SMEM=0: the per-partition L2-table grouping (the fallback of the shared-memory path)."""
+    c = _ctx_with_env(SIBGPU_GROUP_SMEM=0, SIBGPU_PART_RECORDS=16384)
+    st = helpers.strain_case(4, 60_000, seed=94)
+    helpers.assert_tables_equal(c.enumerate(st, k), restate.enumerate_bifurcations(st, k), "l2 tables k=%d" % k)
+    c.close()
+
+
 def test_exact_histogram_mode_matches(built):
     c = _ctx_with_env(SIBGPU_PART_RECORDS=8192, SIBGPU_EXACT_HIST=1)
     st = helpers.strain_case(3, 70_000, seed=97)
