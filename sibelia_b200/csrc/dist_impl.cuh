@@ -48,10 +48,10 @@ static int dist_scatter_mode(sibgpu_ctx *ctx, uint32_t k, void *send_dev)
 	if(ntiles)
 	{
 		size_t smem = sizeof(ScatterSmem<MODE>);
-		SIB_CUDA(cudaFuncSetAttribute(k_scatter<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+		SIB_CUDA(cudaFuncSetAttribute(k_scatter<MODE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 		const uint32_t g = ntiles < (uint32_t)ctx->sm_count * 4 ? ntiles : (uint32_t)ctx->sm_count * 4;
 		ProfScope ps(ctx, "k_scatter", (uint64_t)ntiles * TILE_POS / 4 + ctx->dist_nrec_local * sizeof(Rec));
-		k_scatter<MODE><<<g, TILE_THREADS, smem, st>>>(t, nullptr, k, ntiles, ctx->dist_P_total,
+		k_scatter<MODE, false><<<g, TILE_THREADS, smem, st>>>(t, nullptr, k, ntiles, ctx->dist_P_total,
 			ctx->d_cursor.as<unsigned long long>(), static_cast<Rec*>(send_dev), 0ull, nullptr);
 	}
 	SIB_CUDA(cudaStreamSynchronize(st));
@@ -258,7 +258,7 @@ static int dist_scatter_local_mode(sibgpu_ctx *ctx, uint32_t k, uint64_t *counts
 	if(ntiles)
 	{
 		size_t smem = sizeof(ScatterSmem<MODE>);
-		SIB_CUDA(cudaFuncSetAttribute(k_scatter<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+		SIB_CUDA(cudaFuncSetAttribute(k_scatter<MODE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 		// src: the own byte range is still on the host -- stream it in pieces of CHUNK_TILES tiles on the copy stream and
 		// pack + scatter every piece as it lands (same pipeline as sibgpu_enumerate, enumerate.cu)
 		const uint32_t nchunks = src ? (ntiles + CHUNK_TILES - 1) / CHUNK_TILES : 1;
@@ -296,7 +296,7 @@ static int dist_scatter_local_mode(sibgpu_ctx *ctx, uint32_t k, uint64_t *counts
 				TextDesc tc = t;
 				tc.tile0 = tiles_done;
 				ProfScope ps(ctx, "k_scatter", (uint64_t)nt * TILE_POS / 4 + (uint64_t)nt * TILE_POS * sizeof(Rec));
-				k_scatter<MODE><<<g, TILE_THREADS, smem, st>>>(tc, nullptr, k, nt, PT, ctx->d_cursor.as<unsigned long long>(),
+				k_scatter<MODE, false><<<g, TILE_THREADS, smem, st>>>(tc, nullptr, k, nt, PT, ctx->d_cursor.as<unsigned long long>(),
 					ctx->d_records.as<Rec>(), cap, reinterpret_cast<uint32_t*>(ds + 10));
 				tiles_done = tile_end;
 			}

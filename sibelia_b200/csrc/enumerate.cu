@@ -198,7 +198,9 @@ template<> struct ScatterSmem<2> : ScatterSmem<1> {};
 // histogram pass needed); a run that does not fit raises *overflow and is dropped -- the host then redoes the
 // partitioning with exact sizes (k_scan_hist + k_part_offsets, cap == 0).
 constexpr uint32_t RUN_DROPPED = 0x80000000u;
-template<int MODE>
+// MIXED (8-byte records only): the record carries mix56(key) instead of the key and the partition is a bit field of it
+// (group_smem.cuh)
+template<int MODE, bool MIXED>
 __global__ void __launch_bounds__(TILE_THREADS, MODE == 0 ? 4 : 2) k_scatter(TextDesc t, const Rec16 *__restrict__ fp, uint32_t k,
 	uint32_t ntiles, uint32_t P, unsigned long long *__restrict__ cursor, typename RecT<MODE>::type *__restrict__ out,
 	unsigned long long cap, uint32_t *__restrict__ overflow)
@@ -219,7 +221,8 @@ __global__ void __launch_bounds__(TILE_THREADS, MODE == 0 ? 4 : 2) k_scatter(Tex
 		uint32_t binrank[POS_PER_THREAD];
 		uint32_t valid = 0;
 		scan16<MODE>(t, fp, s.sw, t.tile0 + tile, k, [&](int i, uint64_t a, uint64_t b, uint32_t ctx) {
-			uint32_t bin = __umulhi((uint32_t)(rec_hash(a, b) >> 32), P);
+			if(MIXED) a = mix56(a);
+			uint32_t bin = MIXED ? mixed_part(a, P) : __umulhi((uint32_t)(rec_hash(a, b) >> 32), P);
 			uint32_t rank = atomicAdd(&s.cnt[bin], 1u);
 			binrank[i] = (bin << 16) | rank;             // rank < 4096, bin < 1024
 			valid |= 1u << i;
@@ -1133,7 +1136,8 @@ static int enumerate_mode(sibgpu_ctx *ctx, uint32_t k, uint64_t nrec, const Host
 	t.tile0 = 0;
 	const uint32_t ntiles = (uint32_t)((ctx->M + TILE_POS - 1) / TILE_POS);
 	const size_t scatter_smem = sizeof(ScatterSmem<MODE>);
-	SIB_CUDA(cudaFuncSetAttribute(k_scatter<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scatter_smem));
+	SIB_CUDA(cudaFuncSetAttribute(k_scatter<MODE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scatter_smem));
+	if(MODE == 0) SIB_CUDA(cudaFuncSetAttribute(k_scatter<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScatterSmem<0>)));
 
 	for(uint32_t attempt = 0; ; attempt++)
 	{
@@ -1147,6 +1151,7 @@ static int enumerate_mode(sibgpu_ctx *ctx, uint32_t k, uint64_t nrec, const Host
 		const uint64_t part_rec = smem_group && !ctx->part_explicit ? (uint64_t)512 << 10 : ctx->part_records(k);
 		uint64_t P64 = (nrec + part_rec - 1) / part_rec;
 		const uint32_t P = (uint32_t)(P64 < 1 ? 1 : (P64 > MAX_PARTS ? MAX_PARTS : P64));
+		bool mixed = false;                                // the records carry mix56(key) (shared-memory path)
 		bool grouped = false;                              // vertex keys already in d_ckeys (shared-memory path)
 		uint64_t Vc = 0;
 		SIB_TRY(ctx->d_hist.ensure(sizeof(uint32_t) * MAX_PARTS));
@@ -1165,8 +1170,11 @@ static int enumerate_mode(sibgpu_ctx *ctx, uint32_t k, uint64_t nrec, const Host
 		if(!ctx->exact_hist)
 		{
 			const uint64_t mean = (nrec + P - 1) / P;
-			const uint64_t cap = P == 1 ? nrec : mean + mean / 8 + ctx->part_slack;
-			SIB_TRY(ctx->d_records.ensure(sizeof(Rec) * cap * P));
+			const uint64_t cap = ((P == 1 ? nrec : mean + mean / 8 + ctx->part_slack) + 1) & ~1ull;   // even: 16-byte aligned partitions
+			uint32_t sub_bits = 0;                         // level-2 fan-out of the shared-memory grouping
+			while(((mean + ((uint64_t)1 << sub_bits) - 1) >> sub_bits) > GROUP_MEAN) sub_bits++;
+			mixed = smem_group && sub_bits <= SUB_BITS_MAX;
+			SIB_TRY(ctx->d_records.ensure(sizeof(Rec) * cap * P + 64));
 			for(uint32_t p = 0; p <= P; p++) part_base[p] = (uint64_t)p * cap;
 			std::vector<uint64_t> cur((size_t)P * CURSOR_STRIDE, 0);
 			for(uint32_t p = 0; p < P; p++) cur[(size_t)p * CURSOR_STRIDE] = part_base[p];
@@ -1208,7 +1216,9 @@ static int enumerate_mode(sibgpu_ctx *ctx, uint32_t k, uint64_t nrec, const Host
 					tc.tile0 = tiles_done;
 					ProfScope ps(ctx, "k_scatter", (MODE == 2 ? (uint64_t)nt * TILE_POS * 16 : (uint64_t)nt * TILE_POS / 4)
 						+ nrec * sizeof(Rec) * nt / ntiles);
-					k_scatter<MODE><<<g, TILE_THREADS, scatter_smem, st>>>(tc, fp, k, nt, P, ctx->d_cursor.as<unsigned long long>(),
+					if(mixed) k_scatter<0, true><<<g, TILE_THREADS, sizeof(ScatterSmem<0>), st>>>(tc, fp, k, nt, P,
+						ctx->d_cursor.as<unsigned long long>(), ctx->d_records.as<uint64_t>(), cap, d_overflow);
+					else k_scatter<MODE, false><<<g, TILE_THREADS, scatter_smem, st>>>(tc, fp, k, nt, P, ctx->d_cursor.as<unsigned long long>(),
 						ctx->d_records.as<Rec>(), cap, d_overflow);
 					tiles_done = tile_hi;
 				}
@@ -1220,9 +1230,7 @@ static int enumerate_mode(sibgpu_ctx *ctx, uint32_t k, uint64_t nrec, const Host
 			uint32_t ckeys_cap = 0;
 			if constexpr(MODE == 0)
 			{
-				uint32_t sub_bits = 0;
-				while(((mean + ((uint64_t)1 << sub_bits) - 1) >> sub_bits) > GROUP_MEAN) sub_bits++;
-				if(smem_group && sub_bits <= SUB_BITS_MAX)
+				if(mixed)
 				{
 					nbuckets = P << sub_bits;
 					SIB_TRY(ctx->d_records2.ensure(sizeof(uint64_t) * (size_t)nbuckets * GROUP_CAP + 64));
@@ -1261,6 +1269,7 @@ static int enumerate_mode(sibgpu_ctx *ctx, uint32_t k, uint64_t nrec, const Host
 				SIB_CUDA(cudaMemsetAsync(ds + 10, 0, sizeof(uint64_t) * 2, st));
 				SIB_CUDA(cudaMemsetAsync(ds + 2, 0, sizeof(uint64_t), st));
 				ctx->hist_fallbacks++;
+				mixed = false;                             // the exact path below scatters plain records again
 			}
 			else
 			{
@@ -1347,7 +1356,7 @@ static int enumerate_mode(sibgpu_ctx *ctx, uint32_t k, uint64_t nrec, const Host
 			{
 				const uint32_t g = ntiles < (uint32_t)sms * 4 ? ntiles : (uint32_t)sms * 4;
 				ProfScope ps(ctx, "k_scatter", (MODE == 2 ? ctx->M * 16 : ctx->M / 4) + nrec * sizeof(Rec));
-				k_scatter<MODE><<<g, TILE_THREADS, scatter_smem, st>>>(t, fp, k, ntiles, P, ctx->d_cursor.as<unsigned long long>(),
+				k_scatter<MODE, false><<<g, TILE_THREADS, scatter_smem, st>>>(t, fp, k, ntiles, P, ctx->d_cursor.as<unsigned long long>(),
 					ctx->d_records.as<Rec>(), 0ull, nullptr);
 			}
 		}
@@ -1362,7 +1371,7 @@ static int enumerate_mode(sibgpu_ctx *ctx, uint32_t k, uint64_t nrec, const Host
 			return SIBGPU_ERR_INTERNAL;
 		}
 		const uint32_t T = (uint32_t)T64;
-		const bool compact = MODE == 0 && k <= COMPACT_MAX_K;
+		const bool compact = MODE == 0 && k <= COMPACT_MAX_K && !mixed;   // a mixed key needs all 56 bits
 		const size_t slot_bytes = compact ? 8 : (MODE <= 1 ? sizeof(Slot8) : sizeof(Slot16));
 		// S independent tables on S streams: consecutive partitions overlap, so the ramp-up / tail of one partition's
 		// kernels is filled by its neighbours (with S = 1 everything runs on the main stream and is timed per launch)
@@ -1436,6 +1445,7 @@ static int enumerate_mode(sibgpu_ctx *ctx, uint32_t k, uint64_t nrec, const Host
 			dim3 g(8, P);
 			k_gather_keys<MODE><<<g, 256, 0, st>>>(ctx->d_records.as<Rec>(), ctx->d_partoff.as<uint64_t>(),
 				ctx->d_partcnt.as<uint32_t>(), ctx->d_keyoff.as<uint64_t>(), ctx->d_ckeys.as<Rec>());
+			if(mixed) k_unmix<<<(uint32_t)((Vc + 255) / 256), 256, 0, st>>>(ctx->d_ckeys.as<uint64_t>(), Vc);
 		}
 
 		bool collision = false;

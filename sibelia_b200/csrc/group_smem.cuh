@@ -1,41 +1,103 @@
 // Shared-memory grouping of the k-mer records (included by enumerate.cu; 8-byte records, k <= 28).
 //
-// The hash partitions written by k_scatter (level 1, ~512 Ki records each) are split once more by other bits of the same
-// hash into buckets of ~1 Ki records (k_split: one coalesced read + one coalesced write of every record), and each
-// bucket is then grouped entirely inside one SM (k_group): a TMA bulk copy (cp.async.bulk + mbarrier) brings the
-// bucket's records into shared memory, every record claims the slot of its key in a shared-memory open-addressing
-// table with a 64-bit shared CAS and ORs its predecessor/successor symbols into the slot's 32-bit payload, and the
-// record that created a class evaluates the reference's predicate (vertexenumeration.cpp:67-70,330,348) on the final
-// payload; bifurcation k-mers are appended to the global key list by a warp-ballot aggregated atomic.
-// Shared atomics run at 2.6 (CAS.64) / 8.7 (OR.32) lane-operations per clock per SM on B200
+// The hash partitions written by k_scatter (level 1, ~512 Ki records each) are split once more into buckets of ~1 Ki
+// records (k_split: one coalesced read + one coalesced write of every record), and each bucket is then grouped
+// entirely inside one SM (k_group): a TMA bulk copy (cp.async.bulk + mbarrier) brings the bucket's records into shared
+// memory, every record claims the slot of its key in a shared-memory open-addressing table of 32-bit entries
+// {20-bit tag, index of the record that created the class} with a shared CAS and ORs its predecessor/successor
+// symbols into the 32-bit payload of the class's first record; that record then evaluates the reference's predicate
+// (vertexenumeration.cpp:67-70,330,348) on the final payload, and the bifurcation k-mers are appended to the global
+// key list by a warp-ballot aggregated atomic.
+//
+// Records of this path carry the key MIXED by a bijection of the 56-bit key space (mix56): partition, bucket, table
+// slot and tag are then plain bit fields of the record -- the hash is computed once, in k_scatter, and never again --
+// and equal keys stay equal; the (few) vertex keys are un-mixed when they are appended (unmix56).
+//
+// Shared atomics run at 4.4 (CAS.32) / 2.6 (CAS.64) / 8.7 (OR.32, ADD.32) lane-operations per clock per SM on B200
 // (tools/ubench/smem.cu, profiles/r2_smem_atomics.txt) against ~0.35 per clock per SM for CAS on an L2-resident table.
 #pragma once
 
 namespace sibgpu {
 
+constexpr uint64_t MIX_MASK = (1ull << 56) - 1;
+constexpr uint64_t MIX_C1 = 0x51afd7ed558ccdull, MIX_C2 = 0xceb9fe1a85ec53ull;       // odd
+constexpr uint64_t MIX_I1 = 0x74430c22a54005ull, MIX_I2 = 0xb4b2f8129337dbull;       // inverses mod 2^56
+
+// bijection of [0, 2^56): two rounds of xor-shift (by half the width: an involution) and odd multiplication
+__host__ __device__ __forceinline__ uint64_t mix56(uint64_t x)
+{
+	x ^= x >> 28;
+	x = (x * MIX_C1) & MIX_MASK;
+	x ^= x >> 28;
+	x = (x * MIX_C2) & MIX_MASK;
+	x ^= x >> 28;
+	return x;
+}
+__host__ __device__ __forceinline__ uint64_t unmix56(uint64_t x)
+{
+	x ^= x >> 28;
+	x = (x * MIX_I2) & MIX_MASK;
+	x ^= x >> 28;
+	x = (x * MIX_I1) & MIX_MASK;
+	x ^= x >> 28;
+	return x;
+}
+// bit fields of a mixed key m:  level-1 partition = top bits, bucket = bits 0-9, table slot = bits 10-21, tag = bits 22-41
+__device__ __forceinline__ uint32_t mixed_part(uint64_t m, uint32_t P) { return __umulhi((uint32_t)(m >> 24), P); }
+
 constexpr int SPLIT_THREADS = 512;
-constexpr int SPLIT_TILE = 8192;                       // records per tile (64 KB of shared memory)
+constexpr int SPLIT_TILE = 4096;                       // records per tile
 constexpr int SPLIT_PER_THREAD = SPLIT_TILE / SPLIT_THREADS;
 constexpr int SPLIT_MAX_BINS = 1024;
-constexpr uint32_t SPLIT_DROPPED = 0x80000000u;
 constexpr uint32_t GROUP_THREADS = 256;
 constexpr uint32_t GROUP_SLOTS = 4096;                 // shared-memory table slots (load <= 0.41)
 constexpr uint32_t GROUP_MEAN = 1024;                  // target records per bucket
 constexpr uint32_t GROUP_CAP = 1664;                   // fixed capacity of a bucket's region: mean + 1/2 + 128 (even: 16-byte aligned)
 constexpr uint32_t GROUP_STAGES = 2;
-constexpr uint32_t SUB_BITS_MAX = 10;                  // level-2 bucket = low bits of the hash, table slot = the next 12
+constexpr uint32_t SUB_BITS_MAX = 10;
+constexpr uint32_t EMPTY32 = 0xFFFFFFFFu;
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(void *bar, uint32_t count)
+{
+	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_wait(void *bar, uint32_t parity)
+{
+	uint32_t ok = 0;
+	while(!ok)
+	{
+		asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+			: "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+	}
+}
+// elected thread: bulk copy of `bytes` (multiple of 16, source 16-byte aligned) into shared memory, completing `bar`
+__device__ __forceinline__ void bulk_load(void *dst, const void *src, uint32_t bytes, void *bar)
+{
+	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+	if(bytes)
+	{
+		asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+			:: "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+	}
+}
 
 struct SplitSmem {
-	uint64_t rec[SPLIT_TILE];
-	uint32_t cnt[SPLIT_MAX_BINS];                      // per-bin count of this tile, then exclusive local offset (| SPLIT_DROPPED)
+	uint64_t in[SPLIT_TILE];                           // the tile as it lies in the partition (TMA destination)
+	uint64_t sorted[SPLIT_TILE];                       // the tile ordered by bucket
+	uint32_t cnt[SPLIT_MAX_BINS];                      // per-bin count of this tile, then exclusive local offset
 	uint32_t gbase[SPLIT_MAX_BINS];                    // index of the bin's run in the partition's level-2 region minus the local offset
+	uint32_t dropmask[SPLIT_MAX_BINS / 32];            // bins whose run did not fit (overflow: the caller discards the run)
+	uint32_t anydrop;
+	unsigned long long bar;
 };
 
 // Level 2: partition p's records [partbase[p], cursor[p]) -> B2 buckets of fixed capacity cap2 at out[(p * B2 + b) * cap2].
-// A tile is 8192 consecutive records of one partition, counting-sorted by bucket in shared memory (rank = returning
-// shared atomic) and copied out in coalesced runs; cnt2[p * B2 + b] is the bucket's fill count.  Consecutive tile
-// indices belong to different partitions, so concurrently running CTAs bump different bucket counters.
-__global__ void __launch_bounds__(SPLIT_THREADS, 2) k_split(const uint64_t *__restrict__ recs, const uint64_t *__restrict__ partbase,
+// A tile is 4096 consecutive records of one partition: TMA bulk copy into shared memory (the next tile's copy runs
+// while this one is written out), counting sort by bucket (rank = returning shared atomic), coalesced copy-out of the
+// runs; cnt2[p * B2 + b] is the bucket's fill count.  Consecutive tile indices belong to different partitions, so
+// concurrently running CTAs bump different bucket counters.  Partition bases must be 16-byte aligned.
+__global__ void __launch_bounds__(SPLIT_THREADS, 3) k_split(const uint64_t *__restrict__ recs, const uint64_t *__restrict__ partbase,
 	const unsigned long long *__restrict__ cursor, uint32_t P1, uint32_t tiles_per_part, uint32_t sub_bits,
 	uint64_t *__restrict__ out, uint32_t *__restrict__ cnt2, uint32_t cap2, uint32_t *__restrict__ overflow)
 {
@@ -43,44 +105,60 @@ __global__ void __launch_bounds__(SPLIT_THREADS, 2) k_split(const uint64_t *__re
 	SplitSmem &s = *reinterpret_cast<SplitSmem*>(smem_raw);
 	typedef cub::BlockScan<uint32_t, SPLIT_THREADS> Scan;
 	__shared__ typename Scan::TempStorage scan_tmp;
+	__shared__ uint32_t tile_n, tile_p;
 	const uint32_t B2 = 1u << sub_bits, sub_mask = B2 - 1u;
 	const uint32_t ntiles = P1 * tiles_per_part;
-	for(uint32_t t = blockIdx.x; t < ntiles; t += gridDim.x)
+	if(threadIdx.x == 0)
 	{
-		const uint32_t p = t % P1, chunk = t / P1;
-		const uint64_t base = partbase[p];
-		uint64_t np = cursor[(size_t)p * CURSOR_STRIDE] - base;
-		const uint64_t room = partbase[p + 1] - base;
-		if(np > room) np = room;                       // an overflowed level-1 partition: the caller discards this run anyway
-		const uint64_t first = (uint64_t)chunk * SPLIT_TILE;
-		if(first >= np) continue;                      // CTA-uniform
-		const uint32_t n = np - first < SPLIT_TILE ? (uint32_t)(np - first) : SPLIT_TILE;
+		mbar_init(&s.bar, 1);
+		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+	}
+	__syncthreads();
+	// elected thread: first non-empty tile at or after t (stride gridDim.x); starts its bulk copy and publishes (n, p)
+	auto fetch = [&](uint32_t t) -> uint32_t {
+		for(; t < ntiles; t += gridDim.x)
+		{
+			const uint32_t p = t % P1, chunk = t / P1;
+			const uint64_t base = partbase[p];
+			uint64_t np = cursor[(size_t)p * CURSOR_STRIDE] - base;
+			const uint64_t room = partbase[p + 1] - base;
+			if(np > room) np = room;                   // an overflowed level-1 partition: the caller discards this run anyway
+			const uint64_t first = (uint64_t)chunk * SPLIT_TILE;
+			if(first >= np) continue;
+			const uint32_t n = np - first < SPLIT_TILE ? (uint32_t)(np - first) : SPLIT_TILE;
+			tile_n = n;
+			tile_p = p;
+			bulk_load(s.in, recs + base + first, (n * 8u + 15u) & ~15u, &s.bar);
+			return t;
+		}
+		tile_n = 0;
+		return ntiles;
+	};
+	uint32_t t_cur = ntiles;
+	if(threadIdx.x == 0) t_cur = fetch(blockIdx.x);
+	uint32_t phase = 0;
+	for(;;)
+	{
 		for(uint32_t b = threadIdx.x; b < B2; b += SPLIT_THREADS) s.cnt[b] = 0;
-		__syncthreads();
+		if(threadIdx.x < SPLIT_MAX_BINS / 32) s.dropmask[threadIdx.x] = 0;
+		if(threadIdx.x == 0) s.anydrop = 0;
+		__syncthreads();                               // also publishes tile_n / tile_p of the fetch
+		const uint32_t n = tile_n, p = tile_p;
+		if(n == 0) break;
+		mbar_wait(&s.bar, phase);
+		phase ^= 1u;
 
-		const uint64_t *src = recs + base + first;
-		uint64_t r[SPLIT_PER_THREAD];
-		uint32_t binrank[SPLIT_PER_THREAD];
+		uint32_t rank[SPLIT_PER_THREAD];
 #pragma unroll
 		for(int j = 0; j < SPLIT_PER_THREAD; j++)
 		{
 			const uint32_t i = j * SPLIT_THREADS + threadIdx.x;
-			r[j] = i < n ? __ldcs(src + i) : 0ull;
-		}
-#pragma unroll
-		for(int j = 0; j < SPLIT_PER_THREAD; j++)
-		{
-			const uint32_t i = j * SPLIT_THREADS + threadIdx.x;
-			if(i < n)
-			{
-				const uint32_t bin = (uint32_t)rec_hash(r[j] >> 7, 0) & sub_mask;
-				binrank[j] = (bin << 16) | atomicAdd(&s.cnt[bin], 1u);    // rank < 8192
-			}
+			if(i < n) rank[j] = atomicAdd(&s.cnt[(uint32_t)(s.in[i] >> 7) & sub_mask], 1u);
 		}
 		__syncthreads();
 
-		// exclusive scan over the bins (2 per thread) + reservation of the runs in the buckets
-		uint32_t c[2], sum = 0;
+		// exclusive scan over the bins (2 per thread); the runs are reserved in the buckets while the tile is sorted
+		uint32_t c[2], g[2], sum = 0;
 #pragma unroll
 		for(int j = 0; j < 2; j++)
 		{
@@ -94,84 +172,78 @@ __global__ void __launch_bounds__(SPLIT_THREADS, 2) k_split(const uint64_t *__re
 		for(int j = 0; j < 2; j++)
 		{
 			const uint32_t b = threadIdx.x * 2 + j;
-			if(b < B2)
-			{
-				uint32_t o = excl, g = 0;
-				if(c[j])
-				{
-					g = atomicAdd(&cnt2[(size_t)p * B2 + b], c[j]);
-					if(g + c[j] > cap2)
-					{
-						*overflow = 1u;
-						o |= SPLIT_DROPPED;
-					}
-				}
-				s.cnt[b] = o;
-				s.gbase[b] = b * cap2 + g - excl;          // 32-bit wrap-around arithmetic: + local index >= excl
-			}
-			excl += c[j];
+			g[j] = c[j] ? atomicAdd(&cnt2[(size_t)p * B2 + b], c[j]) : 0u;
+			if(b < B2) s.cnt[b] = excl + (j ? c[0] : 0u);
 		}
 		__syncthreads();
-
 #pragma unroll
 		for(int j = 0; j < SPLIT_PER_THREAD; j++)
 		{
 			const uint32_t i = j * SPLIT_THREADS + threadIdx.x;
-			if(i < n) s.rec[(s.cnt[binrank[j] >> 16] & ~SPLIT_DROPPED) + (binrank[j] & 0xFFFFu)] = r[j];
+			if(i < n)
+			{
+				const uint64_t rec = s.in[i];
+				s.sorted[s.cnt[(uint32_t)(rec >> 7) & sub_mask] + rank[j]] = rec;
+			}
 		}
-		__syncthreads();
+#pragma unroll
+		for(int j = 0; j < 2; j++)
+		{
+			const uint32_t b = threadIdx.x * 2 + j;
+			if(b < B2)
+			{
+				s.gbase[b] = b * cap2 + g[j] - (excl + (j ? c[0] : 0u));   // 32-bit wrap-around arithmetic: + local index >= offset
+				if(g[j] + c[j] > cap2)
+				{
+					*overflow = 1u;
+					atomicOr(&s.dropmask[b >> 5], 1u << (b & 31u));
+					s.anydrop = 1u;
+				}
+			}
+		}
+		__syncthreads();                               // s.in is consumed: the next tile may land
+		if(threadIdx.x == 0) t_cur = fetch(t_cur + gridDim.x);
 
 		uint64_t *dst = out + (uint64_t)p * B2 * cap2;
+		const bool drops = s.anydrop != 0;
 		for(uint32_t l = threadIdx.x; l < n; l += SPLIT_THREADS)
 		{
-			const uint64_t rec = s.rec[l];
-			const uint32_t bin = (uint32_t)rec_hash(rec >> 7, 0) & sub_mask;
-			if(!(s.cnt[bin] & SPLIT_DROPPED)) dst[s.gbase[bin] + l] = rec;
+			const uint64_t rec = s.sorted[l];
+			const uint32_t bin = (uint32_t)(rec >> 7) & sub_mask;
+			if(!drops || !((s.dropmask[bin >> 5] >> (bin & 31u)) & 1u)) dst[s.gbase[bin] + l] = rec;
 		}
 		__syncthreads();
 	}
 }
 
 struct GroupSmem {
-	unsigned long long keys[GROUP_SLOTS];
 	unsigned long long stage[GROUP_STAGES][GROUP_CAP];
-	uint32_t pay[GROUP_SLOTS];
+	uint32_t tab[GROUP_SLOTS];                         // {tag : 20, index of the class's first record : 12} or EMPTY32
+	uint32_t pay[GROUP_CAP];                           // payload of the class whose first record has this index (else 0)
 	unsigned long long bar[GROUP_STAGES];
 	uint32_t n_stage[GROUP_STAGES];
 };
 
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
 // Level 3: one bucket at a time per CTA (persistent grid, GROUP_STAGES buckets in flight per CTA through the TMA ring).
 // nkeys counts every bifurcation class even when the key list is full (the caller then regrows it and runs again).
-__global__ void __launch_bounds__(GROUP_THREADS, 3) k_group(const uint64_t *__restrict__ recs2, const uint32_t *__restrict__ cnt2,
+__global__ void __launch_bounds__(GROUP_THREADS, 4) k_group(const uint64_t *__restrict__ recs2, const uint32_t *__restrict__ cnt2,
 	uint32_t nbuckets, uint32_t cap2, const uint32_t *__restrict__ overflow, uint64_t *__restrict__ ckeys, uint32_t ckeys_cap,
 	uint32_t *__restrict__ nkeys)
 {
 	extern __shared__ __align__(16) unsigned char smem_raw[];
 	GroupSmem &s = *reinterpret_cast<GroupSmem*>(smem_raw);
 	if(*overflow) return;                                  // a bucket outgrew its region: the caller takes the L2-table path
-	for(uint32_t i = threadIdx.x; i < GROUP_SLOTS; i += GROUP_THREADS)
-	{
-		s.keys[i] = EMPTY64;
-		s.pay[i] = 0u;
-	}
+	for(uint32_t i = threadIdx.x; i < GROUP_SLOTS; i += GROUP_THREADS) s.tab[i] = EMPTY32;
+	for(uint32_t i = threadIdx.x; i < GROUP_CAP; i += GROUP_THREADS) s.pay[i] = 0u;
 	if(threadIdx.x == 0)
 	{
-		for(uint32_t st = 0; st < GROUP_STAGES; st++) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(&s.bar[st])));
+		for(uint32_t st = 0; st < GROUP_STAGES; st++) mbar_init(&s.bar[st], 1);
 		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 	}
 	__syncthreads();
-	// elected thread: bulk copy of bucket q (n records) into stage st; completes the stage's mbarrier
 	auto issue = [&](uint32_t q, uint32_t n, uint32_t st) {
-		const uint32_t bytes = (n * 8u + 15u) & ~15u;
 		s.n_stage[st] = n;
-		asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(&s.bar[st])), "r"(bytes) : "memory");
-		if(bytes)
-		{
-			asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-				:: "r"(smem_u32(s.stage[st])), "l"(recs2 + (uint64_t)q * cap2), "r"(bytes), "r"(smem_u32(&s.bar[st])) : "memory");
-		}
+		bulk_load(s.stage[st], recs2 + (uint64_t)q * cap2, (n * 8u + 15u) & ~15u, &s.bar[st]);
 	};
 	uint32_t n_ahead = 0;                                  // thread 0: fill count of the bucket it will issue next
 	if(threadIdx.x == 0)
@@ -184,70 +256,79 @@ __global__ void __launch_bounds__(GROUP_THREADS, 3) k_group(const uint64_t *__re
 	const uint32_t lane = threadIdx.x & 31u;
 	for(uint32_t q = blockIdx.x; q < nbuckets; q += gridDim.x)
 	{
-		uint32_t ok = 0;
-		while(!ok)
-		{
-			asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
-				: "=r"(ok) : "r"(smem_u32(&s.bar[stage])), "r"(phase) : "memory");
-		}
+		mbar_wait(&s.bar[stage], phase);
 		const uint32_t n = s.n_stage[stage];
-		unsigned long long *w = s.stage[stage];
-		uint32_t *w32 = reinterpret_cast<uint32_t*>(w);
+		const unsigned long long *w = s.stage[stage];
 		// the bucket after the next: its count is fetched now and used when this stage is refilled below
 		const uint64_t qn = (uint64_t)q + (uint64_t)GROUP_STAGES * gridDim.x;
-		uint32_t n_next = n_ahead;
+		const uint32_t n_next = n_ahead;
 		if(threadIdx.x == 0 && qn + gridDim.x < nbuckets) n_ahead = __ldg(cnt2 + qn + gridDim.x);
 
 		for(uint32_t i = threadIdx.x; i < n; i += GROUP_THREADS)
 		{
 			const unsigned long long rec = w[i];
-			const unsigned long long key = rec >> 7;
-			uint32_t slot = ((uint32_t)rec_hash(key, 0) >> SUB_BITS_MAX) & (GROUP_SLOTS - 1u);
-			uint32_t bits = payload_bits((uint32_t)rec & 127u), leader = 0;
+			const unsigned long long m = rec >> 7;
+			uint32_t slot = ((uint32_t)m >> SUB_BITS_MAX) & (GROUP_SLOTS - 1u);
+			const uint32_t entry = ((uint32_t)(m >> 22) << 12) | i;
+			uint32_t bits = payload_bits((uint32_t)rec & 127u), target = i;
 			for(;;)
 			{
-				const unsigned long long old = atomicCAS(&s.keys[slot], EMPTY64, key);
-				if(old == EMPTY64) { leader = 0x80000000u; break; }
-				if(old == key) { bits |= PAY_MULTI; break; }
+				const uint32_t old = atomicCAS(&s.tab[slot], EMPTY32, entry);
+				if(old == EMPTY32) break;                      // first record of its class
+				if((old ^ entry) < 4096u)                      // same tag: compare the keys
+				{
+					const uint32_t j = old & 4095u;
+					if((w[j] >> 7) == m)
+					{
+						target = j;
+						bits |= PAY_MULTI;
+						break;
+					}
+				}
 				slot = (slot + 1u) & (GROUP_SLOTS - 1u);
 			}
-			atomicOr(&s.pay[slot], bits);
-			w32[2 * i] = slot | leader;                        // the record is consumed: its low word remembers the slot
+			atomicOr(&s.pay[target], bits);
 		}
 		__syncthreads();
+		// table reset for the next bucket (16 KB: cheaper than each class finding its slot again)
+		{
+			uint4 *t4 = reinterpret_cast<uint4*>(s.tab);
+			for(uint32_t i = threadIdx.x; i < GROUP_SLOTS / 4; i += GROUP_THREADS) t4[i] = make_uint4(EMPTY32, EMPTY32, EMPTY32, EMPTY32);
+		}
 		const uint32_t n_round = (n + 31u) & ~31u;
 		for(uint32_t i = threadIdx.x; i < n_round; i += GROUP_THREADS)
 		{
 			bool bif = false;
-			unsigned long long key = 0;
 			if(i < n)
 			{
-				const uint32_t v = w32[2 * i];
-				if(v & 0x80000000u)
+				const uint32_t pay = s.pay[i];                     // non-zero exactly for the first record of a class
+				if(pay)
 				{
-					const uint32_t slot = v & 0x7FFFFFFFu;
-					key = s.keys[slot];
-					bif = is_bifurcation(s.pay[slot]);
-					s.keys[slot] = EMPTY64;                        // leave the table clean for the next bucket
-					s.pay[slot] = 0u;
+					bif = is_bifurcation(pay);
+					s.pay[i] = 0u;
 				}
 			}
-			const uint32_t m = __ballot_sync(0xffffffffu, bif);
-			if(m)
+			const uint32_t mk = __ballot_sync(0xffffffffu, bif);
+			if(mk)
 			{
 				uint32_t base = 0;
-				if(lane == (uint32_t)(__ffs(m) - 1)) base = atomicAdd(nkeys, (uint32_t)__popc(m));
-				base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
-				const uint32_t idx = base + __popc(m & ((1u << lane) - 1u));
-				if(bif && idx < ckeys_cap) ckeys[idx] = key;
+				if(lane == (uint32_t)(__ffs(mk) - 1)) base = atomicAdd(nkeys, (uint32_t)__popc(mk));
+				base = __shfl_sync(0xffffffffu, base, __ffs(mk) - 1);
+				const uint32_t idx = base + __popc(mk & ((1u << lane) - 1u));
+				if(bif && idx < ckeys_cap) ckeys[idx] = unmix56(w[i] >> 7);
 			}
 		}
-		// the slot notes above are generic-proxy writes into a buffer the bulk copy (async proxy) overwrites next
-		asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-		__syncthreads();                                       // stage consumed, table clean
+		__syncthreads();                                       // stage consumed, table and payloads clean
 		if(threadIdx.x == 0 && qn < nbuckets) issue((uint32_t)qn, n_next, stage);
 		if(++stage == GROUP_STAGES) { stage = 0; phase ^= 1u; }
 	}
+}
+
+// vertex keys of the L2-table fallback on mixed records -> plain canonical keys
+__global__ void __launch_bounds__(256) k_unmix(uint64_t *__restrict__ keys, uint64_t n)
+{
+	const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+	if(i < n) keys[i] = unmix56(keys[i]);
 }
 
 } // namespace sibgpu
