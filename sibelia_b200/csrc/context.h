@@ -84,6 +84,7 @@ struct sibgpu_ctx {
 	// grouping of 8-byte records (k <= 28): 1 = buckets of ~1 Ki records grouped in shared memory (k_split + k_group),
 	// 0 = one L2-resident table per hash partition (k_insert + k_table_scan; also the fallback when a bucket overflows)
 	int group_smem = 1;                                // env SIBGPU_GROUP_SMEM
+	int split_stages = 2;                              // input tiles in flight per CTA of k_split (env SIBGPU_SPLIT_STAGES, dev)
 	uint64_t ckeys_init = 1u << 20;                    // initial capacity of the vertex-key list (env SIBGPU_CKEYS_INIT, tests)
 	uint64_t smem_fallbacks = 0;                       // times a bucket overflowed and the L2-table path took over
 	int table_factor = 2;                              // slots per record of the largest partition (env SIBGPU_TABLE_FACTOR)

@@ -1238,20 +1238,31 @@ static int enumerate_mode(sibgpu_ctx *ctx, uint32_t k, uint64_t nrec, const Host
 					SIB_TRY(ctx->d_ckeys.ensure(sizeof(uint64_t) * (ctx->ckeys_init ? ctx->ckeys_init : 1)));
 					ckeys_cap = (uint32_t)std::min<size_t>(ctx->d_ckeys.cap / sizeof(uint64_t), 0xFFFFFFF0u);
 					SIB_CUDA(cudaMemsetAsync(ctx->d_cnt2.p, 0, sizeof(uint32_t) * (size_t)nbuckets, st));
-					SIB_CUDA(cudaFuncSetAttribute(k_split, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SplitSmem)));
+					SIB_CUDA(cudaFuncSetAttribute(k_split<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SplitSmem<1>)));
+					SIB_CUDA(cudaFuncSetAttribute(k_split<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SplitSmem<2>)));
 					SIB_CUDA(cudaFuncSetAttribute(k_group, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(GroupSmem)));
 					const uint32_t tiles_per_part = (uint32_t)((cap + SPLIT_TILE - 1) / SPLIT_TILE);
 					const uint64_t split_tiles = (uint64_t)P * tiles_per_part;
 					{
 						ProfScope ps(ctx, "k_split", nrec * 16);
-						k_split<<<(uint32_t)std::min<uint64_t>(split_tiles, (uint64_t)sms * 2), SPLIT_THREADS, sizeof(SplitSmem), st>>>(
-							ctx->d_records.as<uint64_t>(), ctx->d_partoff.as<uint64_t>(), ctx->d_cursor.as<unsigned long long>(), P,
-							tiles_per_part, sub_bits, ctx->d_records2.as<uint64_t>(), ctx->d_cnt2.as<uint32_t>(), GROUP_CAP,
-							reinterpret_cast<uint32_t*>(ds + 11));
+						if(ctx->split_stages == 1)
+						{
+							k_split<1><<<(uint32_t)std::min<uint64_t>(split_tiles, (uint64_t)sms * 3), SPLIT_THREADS, sizeof(SplitSmem<1>), st>>>(
+								ctx->d_records.as<uint64_t>(), ctx->d_partoff.as<uint64_t>(), ctx->d_cursor.as<unsigned long long>(), P,
+								tiles_per_part, sub_bits, ctx->d_records2.as<uint64_t>(), ctx->d_cnt2.as<uint32_t>(), GROUP_CAP,
+								reinterpret_cast<uint32_t*>(ds + 11));
+						}
+						else
+						{
+							k_split<2><<<(uint32_t)std::min<uint64_t>(split_tiles, (uint64_t)sms * 2), SPLIT_THREADS, sizeof(SplitSmem<2>), st>>>(
+								ctx->d_records.as<uint64_t>(), ctx->d_partoff.as<uint64_t>(), ctx->d_cursor.as<unsigned long long>(), P,
+								tiles_per_part, sub_bits, ctx->d_records2.as<uint64_t>(), ctx->d_cnt2.as<uint32_t>(), GROUP_CAP,
+								reinterpret_cast<uint32_t*>(ds + 11));
+						}
 					}
 					{
 						ProfScope ps(ctx, "k_group", nrec * 8);
-						k_group<<<std::min<uint32_t>(nbuckets, (uint32_t)sms * 3), GROUP_THREADS, sizeof(GroupSmem), st>>>(
+						k_group<<<std::min<uint32_t>(nbuckets, (uint32_t)sms * 4), GROUP_THREADS, sizeof(GroupSmem), st>>>(
 							ctx->d_records2.as<uint64_t>(), ctx->d_cnt2.as<uint32_t>(), nbuckets, GROUP_CAP,
 							reinterpret_cast<uint32_t*>(ds + 11), ctx->d_ckeys.as<uint64_t>(), ckeys_cap, reinterpret_cast<uint32_t*>(ds + 2));
 					}
@@ -1307,7 +1318,7 @@ static int enumerate_mode(sibgpu_ctx *ctx, uint32_t k, uint64_t nrec, const Host
 								SIB_TRY(ctx->d_ckeys.ensure(sizeof(uint64_t) * Vc));
 								SIB_CUDA(cudaMemsetAsync(ds + 2, 0, sizeof(uint64_t), st));
 								ProfScope ps(ctx, "k_group", nrec * 8);
-								k_group<<<std::min<uint32_t>(nbuckets, (uint32_t)sms * 3), GROUP_THREADS, sizeof(GroupSmem), st>>>(
+								k_group<<<std::min<uint32_t>(nbuckets, (uint32_t)sms * 4), GROUP_THREADS, sizeof(GroupSmem), st>>>(
 									ctx->d_records2.as<uint64_t>(), ctx->d_cnt2.as<uint32_t>(), nbuckets, GROUP_CAP,
 									reinterpret_cast<uint32_t*>(ds + 11), ctx->d_ckeys.as<uint64_t>(), (uint32_t)Vc, reinterpret_cast<uint32_t*>(ds + 2));
 								SIB_CUDA(cudaStreamSynchronize(st));

@@ -82,40 +82,43 @@ __device__ __forceinline__ void bulk_load(void *dst, const void *src, uint32_t b
 	}
 }
 
-struct SplitSmem {
-	uint64_t in[SPLIT_TILE];                           // the tile as it lies in the partition (TMA destination)
-	uint64_t sorted[SPLIT_TILE];                       // the tile ordered by bucket
+template<int STAGES> struct SplitSmem {
+	uint64_t in[STAGES][SPLIT_TILE];                   // tiles as they lie in the partition (TMA destinations)
+	uint64_t sorted[SPLIT_TILE];                       // the current tile ordered by bucket
 	uint32_t cnt[SPLIT_MAX_BINS];                      // per-bin count of this tile, then exclusive local offset
 	uint32_t gbase[SPLIT_MAX_BINS];                    // index of the bin's run in the partition's level-2 region minus the local offset
 	uint32_t dropmask[SPLIT_MAX_BINS / 32];            // bins whose run did not fit (overflow: the caller discards the run)
 	uint32_t anydrop;
-	unsigned long long bar;
+	uint32_t tile_n[STAGES], tile_p[STAGES];
+	unsigned long long bar[STAGES];
 };
 
 // Level 2: partition p's records [partbase[p], cursor[p]) -> B2 buckets of fixed capacity cap2 at out[(p * B2 + b) * cap2].
-// A tile is 4096 consecutive records of one partition: TMA bulk copy into shared memory (the next tile's copy runs
-// while this one is written out), counting sort by bucket (rank = returning shared atomic), coalesced copy-out of the
-// runs; cnt2[p * B2 + b] is the bucket's fill count.  Consecutive tile indices belong to different partitions, so
-// concurrently running CTAs bump different bucket counters.  Partition bases must be 16-byte aligned.
-__global__ void __launch_bounds__(SPLIT_THREADS, 3) k_split(const uint64_t *__restrict__ recs, const uint64_t *__restrict__ partbase,
-	const unsigned long long *__restrict__ cursor, uint32_t P1, uint32_t tiles_per_part, uint32_t sub_bits,
-	uint64_t *__restrict__ out, uint32_t *__restrict__ cnt2, uint32_t cap2, uint32_t *__restrict__ overflow)
+// A tile is 4096 consecutive records of one partition: TMA bulk copy into shared memory (STAGES tiles in flight: the
+// copies of the following tiles run while this one is sorted and written out), counting sort by bucket (rank =
+// returning shared atomic), coalesced copy-out of the runs; cnt2[p * B2 + b] is the bucket's fill count.  Consecutive
+// tile indices belong to different partitions, so concurrently running CTAs bump different bucket counters.
+// Partition bases must be 16-byte aligned.
+template<int STAGES>
+__global__ void __launch_bounds__(SPLIT_THREADS, STAGES == 1 ? 3 : 2) k_split(const uint64_t *__restrict__ recs,
+	const uint64_t *__restrict__ partbase, const unsigned long long *__restrict__ cursor, uint32_t P1, uint32_t tiles_per_part,
+	uint32_t sub_bits, uint64_t *__restrict__ out, uint32_t *__restrict__ cnt2, uint32_t cap2, uint32_t *__restrict__ overflow)
 {
 	extern __shared__ __align__(16) unsigned char smem_raw[];
-	SplitSmem &s = *reinterpret_cast<SplitSmem*>(smem_raw);
+	SplitSmem<STAGES> &s = *reinterpret_cast<SplitSmem<STAGES>*>(smem_raw);
 	typedef cub::BlockScan<uint32_t, SPLIT_THREADS> Scan;
 	__shared__ typename Scan::TempStorage scan_tmp;
-	__shared__ uint32_t tile_n, tile_p;
 	const uint32_t B2 = 1u << sub_bits, sub_mask = B2 - 1u;
 	const uint32_t ntiles = P1 * tiles_per_part;
 	if(threadIdx.x == 0)
 	{
-		mbar_init(&s.bar, 1);
+		for(int st = 0; st < STAGES; st++) mbar_init(&s.bar[st], 1);
 		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 	}
 	__syncthreads();
-	// elected thread: first non-empty tile at or after t (stride gridDim.x); starts its bulk copy and publishes (n, p)
-	auto fetch = [&](uint32_t t) -> uint32_t {
+	// elected thread: first non-empty tile at or after t (stride gridDim.x); starts its bulk copy into stage st and
+	// publishes (n, p) there; n = 0: no tile left
+	auto fetch = [&](uint32_t t, int st) -> uint32_t {
 		for(; t < ntiles; t += gridDim.x)
 		{
 			const uint32_t p = t % P1, chunk = t / P1;
@@ -126,34 +129,38 @@ __global__ void __launch_bounds__(SPLIT_THREADS, 3) k_split(const uint64_t *__re
 			const uint64_t first = (uint64_t)chunk * SPLIT_TILE;
 			if(first >= np) continue;
 			const uint32_t n = np - first < SPLIT_TILE ? (uint32_t)(np - first) : SPLIT_TILE;
-			tile_n = n;
-			tile_p = p;
-			bulk_load(s.in, recs + base + first, (n * 8u + 15u) & ~15u, &s.bar);
+			s.tile_n[st] = n;
+			s.tile_p[st] = p;
+			bulk_load(s.in[st], recs + base + first, (n * 8u + 15u) & ~15u, &s.bar[st]);
 			return t;
 		}
-		tile_n = 0;
+		s.tile_n[st] = 0;
 		return ntiles;
 	};
 	uint32_t t_cur = ntiles;
-	if(threadIdx.x == 0) t_cur = fetch(blockIdx.x);
-	uint32_t phase = 0;
+	if(threadIdx.x == 0)
+	{
+		t_cur = fetch(blockIdx.x, 0);
+		for(int st = 1; st < STAGES; st++) t_cur = fetch(t_cur + gridDim.x, st);
+	}
+	uint32_t stage = 0, phase = 0;
 	for(;;)
 	{
 		for(uint32_t b = threadIdx.x; b < B2; b += SPLIT_THREADS) s.cnt[b] = 0;
 		if(threadIdx.x < SPLIT_MAX_BINS / 32) s.dropmask[threadIdx.x] = 0;
 		if(threadIdx.x == 0) s.anydrop = 0;
 		__syncthreads();                               // also publishes tile_n / tile_p of the fetch
-		const uint32_t n = tile_n, p = tile_p;
+		const uint32_t n = s.tile_n[stage], p = s.tile_p[stage];
 		if(n == 0) break;
-		mbar_wait(&s.bar, phase);
-		phase ^= 1u;
+		mbar_wait(&s.bar[stage], phase);
+		const uint64_t *in = s.in[stage];
 
 		uint32_t rank[SPLIT_PER_THREAD];
 #pragma unroll
 		for(int j = 0; j < SPLIT_PER_THREAD; j++)
 		{
 			const uint32_t i = j * SPLIT_THREADS + threadIdx.x;
-			if(i < n) rank[j] = atomicAdd(&s.cnt[(uint32_t)(s.in[i] >> 7) & sub_mask], 1u);
+			if(i < n) rank[j] = atomicAdd(&s.cnt[(uint32_t)(in[i] >> 7) & sub_mask], 1u);
 		}
 		__syncthreads();
 
@@ -182,7 +189,7 @@ __global__ void __launch_bounds__(SPLIT_THREADS, 3) k_split(const uint64_t *__re
 			const uint32_t i = j * SPLIT_THREADS + threadIdx.x;
 			if(i < n)
 			{
-				const uint64_t rec = s.in[i];
+				const uint64_t rec = in[i];
 				s.sorted[s.cnt[(uint32_t)(rec >> 7) & sub_mask] + rank[j]] = rec;
 			}
 		}
@@ -201,8 +208,8 @@ __global__ void __launch_bounds__(SPLIT_THREADS, 3) k_split(const uint64_t *__re
 				}
 			}
 		}
-		__syncthreads();                               // s.in is consumed: the next tile may land
-		if(threadIdx.x == 0) t_cur = fetch(t_cur + gridDim.x);
+		__syncthreads();                               // this stage's input is consumed: the tile after the ones in flight may land
+		if(threadIdx.x == 0) t_cur = fetch(t_cur + gridDim.x, stage);
 
 		uint64_t *dst = out + (uint64_t)p * B2 * cap2;
 		const bool drops = s.anydrop != 0;
@@ -212,14 +219,20 @@ __global__ void __launch_bounds__(SPLIT_THREADS, 3) k_split(const uint64_t *__re
 			const uint32_t bin = (uint32_t)(rec >> 7) & sub_mask;
 			if(!drops || !((s.dropmask[bin >> 5] >> (bin & 31u)) & 1u)) dst[s.gbase[bin] + l] = rec;
 		}
+		if(++stage == STAGES) { stage = 0; phase ^= 1u; }
 		__syncthreads();
 	}
 }
+
+constexpr uint32_t GROUP_WARPS = GROUP_THREADS / 32;
+constexpr uint32_t GROUP_DEFER_CAP = (GROUP_CAP + GROUP_THREADS - 1) / GROUP_THREADS * 32;   // records one warp handles per bucket
 
 struct GroupSmem {
 	unsigned long long stage[GROUP_STAGES][GROUP_CAP];
 	uint32_t tab[GROUP_SLOTS];                         // {tag : 20, index of the class's first record : 12} or EMPTY32
 	uint32_t pay[GROUP_CAP];                           // payload of the class whose first record has this index (else 0)
+	uint16_t defer[GROUP_WARPS][GROUP_DEFER_CAP];      // per warp: records whose home slot holds another key
+	uint16_t lut[128];                                 // payload_bits of every 7-bit context
 	unsigned long long bar[GROUP_STAGES];
 	uint32_t n_stage[GROUP_STAGES];
 };
@@ -235,6 +248,7 @@ __global__ void __launch_bounds__(GROUP_THREADS, 4) k_group(const uint64_t *__re
 	if(*overflow) return;                                  // a bucket outgrew its region: the caller takes the L2-table path
 	for(uint32_t i = threadIdx.x; i < GROUP_SLOTS; i += GROUP_THREADS) s.tab[i] = EMPTY32;
 	for(uint32_t i = threadIdx.x; i < GROUP_CAP; i += GROUP_THREADS) s.pay[i] = 0u;
+	if(threadIdx.x < 128) s.lut[threadIdx.x] = (uint16_t)payload_bits(threadIdx.x);
 	if(threadIdx.x == 0)
 	{
 		for(uint32_t st = 0; st < GROUP_STAGES; st++) mbar_init(&s.bar[st], 1);
@@ -264,15 +278,51 @@ __global__ void __launch_bounds__(GROUP_THREADS, 4) k_group(const uint64_t *__re
 		const uint32_t n_next = n_ahead;
 		if(threadIdx.x == 0 && qn + gridDim.x < nbuckets) n_ahead = __ldg(cnt2 + qn + gridDim.x);
 
-		for(uint32_t i = threadIdx.x; i < n; i += GROUP_THREADS)
+		// Fast pass: one CAS on the home slot decides most records (first of its class, or the class is there already).
+		// A record whose home slot holds another key is set aside in the warp's list; the list is then probed with all
+		// lanes busy -- a probing loop inside the fast pass would run at the pace of the warp's unluckiest lane.
+		const uint32_t n_round = (n + 31u) & ~31u;
+		const uint32_t warp = threadIdx.x >> 5, lt_mask = (1u << lane) - 1u;
+		uint32_t ndef = 0;
+		for(uint32_t i = threadIdx.x; i < n_round; i += GROUP_THREADS)
 		{
+			bool later = false;
+			if(i < n)
+			{
+				const unsigned long long rec = w[i];
+				const unsigned long long m = rec >> 7;
+				const uint32_t slot = ((uint32_t)m >> SUB_BITS_MAX) & (GROUP_SLOTS - 1u);
+				const uint32_t entry = ((uint32_t)(m >> 22) << 12) | i;
+				uint32_t bits = s.lut[(uint32_t)rec & 127u], target = i;
+				const uint32_t old = atomicCAS(&s.tab[slot], EMPTY32, entry);
+				if(old != EMPTY32)
+				{
+					const uint32_t j = old & 4095u;
+					if((old ^ entry) < 4096u && (w[j] >> 7) == m)      // same tag, same key
+					{
+						target = j;
+						bits |= PAY_MULTI;
+					}
+					else later = true;
+				}
+				if(!later) atomicOr(&s.pay[target], bits);
+			}
+			const uint32_t dm = __ballot_sync(0xffffffffu, later);
+			if(later) s.defer[warp][ndef + __popc(dm & lt_mask)] = (uint16_t)i;
+			ndef += __popc(dm);
+		}
+		__syncwarp();
+		for(uint32_t d = lane; d < ndef; d += 32)
+		{
+			const uint32_t i = s.defer[warp][d];
 			const unsigned long long rec = w[i];
 			const unsigned long long m = rec >> 7;
 			uint32_t slot = ((uint32_t)m >> SUB_BITS_MAX) & (GROUP_SLOTS - 1u);
 			const uint32_t entry = ((uint32_t)(m >> 22) << 12) | i;
-			uint32_t bits = payload_bits((uint32_t)rec & 127u), target = i;
+			uint32_t bits = s.lut[(uint32_t)rec & 127u], target = i;
 			for(;;)
 			{
+				slot = (slot + 1u) & (GROUP_SLOTS - 1u);
 				const uint32_t old = atomicCAS(&s.tab[slot], EMPTY32, entry);
 				if(old == EMPTY32) break;                      // first record of its class
 				if((old ^ entry) < 4096u)                      // same tag: compare the keys
@@ -285,7 +335,6 @@ __global__ void __launch_bounds__(GROUP_THREADS, 4) k_group(const uint64_t *__re
 						break;
 					}
 				}
-				slot = (slot + 1u) & (GROUP_SLOTS - 1u);
 			}
 			atomicOr(&s.pay[target], bits);
 		}
@@ -295,7 +344,6 @@ __global__ void __launch_bounds__(GROUP_THREADS, 4) k_group(const uint64_t *__re
 			uint4 *t4 = reinterpret_cast<uint4*>(s.tab);
 			for(uint32_t i = threadIdx.x; i < GROUP_SLOTS / 4; i += GROUP_THREADS) t4[i] = make_uint4(EMPTY32, EMPTY32, EMPTY32, EMPTY32);
 		}
-		const uint32_t n_round = (n + 31u) & ~31u;
 		for(uint32_t i = threadIdx.x; i < n_round; i += GROUP_THREADS)
 		{
 			bool bif = false;
