@@ -88,6 +88,28 @@ __device__ __forceinline__ void scan16_exact(const TextDesc &t, const uint32_t *
 	uint32_t prevc = wm1 & 3u;
 	ChrCursor cur;
 	cur.init(t, p0);
+	// Interior fast path: all 16 k-mers, their predecessors and their successors lie inside one chromosome (true for
+	// all but a handful of threads of the whole text): no cursor, no validity tests, no '#' contexts.
+	if(p0 > cur.cs && (uint64_t)p0 + (POS_PER_THREAD - 1) + k < cur.ce)
+	{
+		const uint32_t top = kk - 2;
+#pragma unroll
+		for(int i = 0; i < POS_PER_THREAD; i++)
+		{
+			const uint32_t nextc = (uint32_t)(stream >> 62);
+			const bool fw = f <= r;
+			const uint64_t canon = fw ? f : r;
+			// forward: prev << 3 | next;  reverse: comp(next) << 3 | comp(prev) = 27 - 8 next - prev
+			uint32_t ctx = fw ? ((prevc << 3) | nextc) : (27u - (nextc << 3) - prevc);
+			ctx |= (f == r ? 64u : 0u) | (fw ? 128u : 0u);
+			f_emit(i, canon, (uint64_t)0, ctx);
+			prevc = (uint32_t)(f >> top) & 3u;
+			f = ((f << 2) | nextc) & mask;
+			r = (r >> 2) | ((uint64_t)(3u - nextc) << top);
+			stream <<= 2;
+		}
+		return;
+	}
 #pragma unroll
 	for(int i = 0; i < POS_PER_THREAD; i++)
 	{
@@ -187,9 +209,10 @@ template<int MODE> struct ScatterSmem {
 	uint32_t sw[TILE_THREADS + 5];
 	uint32_t cnt[MAX_PARTS];           // per-bin count of this tile, then exclusive local offset
 	unsigned long long gbase[MAX_PARTS]; // global index of the bin's run minus its local offset
-	uint32_t total;
+	uint32_t dropmask[MAX_PARTS / 32]; // bins whose run did not fit its fixed-capacity region
+	uint32_t total, anydrop;
 	uint64_t a[TILE_POS];
-	uint16_t bin_of[TILE_POS];         // bin of the record at each sorted local index
+	uint16_t bin_of[TILE_POS];         // bin of the record at each sorted local index (plain records only)
 };
 template<> struct ScatterSmem<1> : ScatterSmem<0> { uint64_t b[TILE_POS]; };
 template<> struct ScatterSmem<2> : ScatterSmem<1> {};
@@ -197,7 +220,6 @@ template<> struct ScatterSmem<2> : ScatterSmem<1> {};
 // cap != 0: partition b owns the fixed region [b * cap, (b + 1) * cap) of `out` and cursor[b] starts at b * cap (no
 // histogram pass needed); a run that does not fit raises *overflow and is dropped -- the host then redoes the
 // partitioning with exact sizes (k_scan_hist + k_part_offsets, cap == 0).
-constexpr uint32_t RUN_DROPPED = 0x80000000u;
 // MIXED (8-byte records only): the record carries mix56(key) instead of the key and the partition is a bit field of it
 // (group_smem.cuh)
 template<int MODE, bool MIXED>
@@ -214,6 +236,8 @@ __global__ void __launch_bounds__(TILE_THREADS, MODE == 0 ? 4 : 2) k_scatter(Tex
 	for(uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x)
 	{
 		for(uint32_t b = threadIdx.x; b < P; b += TILE_THREADS) s.cnt[b] = 0;
+		if(threadIdx.x < MAX_PARTS / 32) s.dropmask[threadIdx.x] = 0;
+		if(threadIdx.x == 0) s.anydrop = 0;
 		if(MODE != 2) stage_tile(t, t.tile0 + tile, s.sw);
 		__syncthreads();
 
@@ -231,8 +255,10 @@ __global__ void __launch_bounds__(TILE_THREADS, MODE == 0 ? 4 : 2) k_scatter(Tex
 		});
 		__syncthreads();
 
-		// exclusive scan over the bins (4 per thread) + reservation of the global runs
+		// exclusive scan over the bins (4 per thread); the global runs are reserved (one returning atomic per bin) while
+		// the records are put in bin order in shared memory -- the placement only needs the local offsets
 		uint32_t c[BINS_PER_THREAD], o[BINS_PER_THREAD], sum = 0;
+		unsigned long long g[BINS_PER_THREAD];
 #pragma unroll
 		for(int j = 0; j < BINS_PER_THREAD; j++)
 		{
@@ -248,50 +274,51 @@ __global__ void __launch_bounds__(TILE_THREADS, MODE == 0 ? 4 : 2) k_scatter(Tex
 			uint32_t b = threadIdx.x * BINS_PER_THREAD + j;
 			o[j] = excl;
 			excl += c[j];
-			if(b < P)
-			{
-				unsigned long long g = c[j] ? atomicAdd(&cursor[b * CURSOR_STRIDE], (unsigned long long)c[j]) : 0ull;
-				s.cnt[b] = o[j];
-				s.gbase[b] = g - o[j];
-				if(cap && c[j] && g + c[j] > (b + 1ull) * cap)
-				{
-					*overflow = 1u;
-					s.cnt[b] = o[j] | RUN_DROPPED;
-				}
-			}
+			g[j] = c[j] ? atomicAdd(&cursor[b * CURSOR_STRIDE], (unsigned long long)c[j]) : 0ull;
+			if(b < P) s.cnt[b] = o[j];
 		}
 		if(threadIdx.x == 0) s.total = total;
 		__syncthreads();
 
-		// place the records in bin order in shared memory
 #pragma unroll
 		for(int i = 0; i < POS_PER_THREAD; i++)
 		{
 			if(valid & (1u << i))
 			{
-				uint32_t bin = binrank[i] >> 16, rank = binrank[i] & 0xFFFFu;
-				const uint32_t first = s.cnt[bin];
-				uint32_t l = (first & ~RUN_DROPPED) + rank;
+				const uint32_t bin = binrank[i] >> 16, l = s.cnt[bin] + (binrank[i] & 0xFFFFu);
 				s.a[l] = ra[i];
 				if(MODE != 0) static_cast<ScatterSmem<1>&>(s).b[l] = rb[i];
-				s.bin_of[l] = (first & RUN_DROPPED) ? (uint16_t)0xFFFFu : (uint16_t)bin;
+				if(!MIXED) s.bin_of[l] = (uint16_t)bin;
+			}
+		}
+#pragma unroll
+		for(int j = 0; j < BINS_PER_THREAD; j++)
+		{
+			uint32_t b = threadIdx.x * BINS_PER_THREAD + j;
+			if(b < P)
+			{
+				s.gbase[b] = g[j] - o[j];
+				if(cap && c[j] && g[j] + c[j] > (b + 1ull) * cap)
+				{
+					*overflow = 1u;
+					atomicOr(&s.dropmask[b >> 5], 1u << (b & 31u));
+					s.anydrop = 1u;
+				}
 			}
 		}
 		__syncthreads();
 
 		// coalesced copy-out: consecutive l of the same bin go to consecutive global slots
 		const uint32_t n = s.total;
+		const bool drops = s.anydrop != 0;
 		for(uint32_t l = threadIdx.x; l < n; l += TILE_THREADS)
 		{
-			const uint32_t bin = s.bin_of[l];
-			if(bin == 0xFFFFu) continue;
-			unsigned long long g = s.gbase[bin] + l;
-			if(MODE == 0) { reinterpret_cast<uint64_t*>(out)[g] = s.a[l]; }
-			else
-			{
-				Rec16 v; v.a = s.a[l]; v.b = static_cast<ScatterSmem<1>&>(s).b[l];
-				reinterpret_cast<ulonglong2*>(out)[g] = make_ulonglong2(v.a, v.b);
-			}
+			const uint64_t a = s.a[l];
+			const uint32_t bin = MIXED ? mixed_part(a >> 7, P) : s.bin_of[l];
+			if(drops && ((s.dropmask[bin >> 5] >> (bin & 31u)) & 1u)) continue;
+			unsigned long long gi = s.gbase[bin] + l;
+			if(MODE == 0) { reinterpret_cast<uint64_t*>(out)[gi] = a; }
+			else reinterpret_cast<ulonglong2*>(out)[gi] = make_ulonglong2(a, static_cast<ScatterSmem<1>&>(s).b[l]);
 		}
 		__syncthreads();
 	}
