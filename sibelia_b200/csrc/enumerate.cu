@@ -790,11 +790,12 @@ __device__ __forceinline__ void map_insert(MapSlot *map, uint32_t Tm, uint32_t *
 
 template<int MODE>
 __global__ void __launch_bounds__(256) k_build_map(const typename RecT<MODE>::type *__restrict__ ckeys, uint64_t n, uint32_t k,
-	const uint64_t *__restrict__ vsorted, uint32_t V, MapSlot *__restrict__ map, uint32_t Tm,
+	const uint64_t *__restrict__ vsorted, const uint32_t *__restrict__ npal, MapSlot *__restrict__ map, uint32_t Tm,
 	uint32_t *__restrict__ filter, uint32_t fshift)
 {
 	uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
 	if(i >= n) return;
+	const uint32_t V = MODE == 2 ? 0u : (uint32_t)(2 * n) - *npal;   // vertices = {c, revcomp(c)} minus the palindromes counted twice
 	if(MODE == 2)
 	{
 		// fingerprint classes: ids are assigned after the lexicographic ranking (fingerprint.cu)
@@ -871,7 +872,7 @@ template<int MODE>
 __global__ void __launch_bounds__(TILE_THREADS) k_emit(TextDesc t, const Rec16 *__restrict__ fp, uint32_t k, uint32_t ntiles,
 	const MapSlot *__restrict__ map, uint32_t Tm, const uint32_t *__restrict__ filter, uint32_t fshift,
 	const uint16_t *__restrict__ hitmask, const uint64_t *__restrict__ tileoff,
-	sibgpu_inst *__restrict__ pos_out, sibgpu_inst *__restrict__ neg_tmp,
+	sibgpu_inst *__restrict__ pos_out, sibgpu_inst *__restrict__ neg_tmp, uint64_t inst_cap,
 	const unsigned long long *__restrict__ rep, uint32_t *__restrict__ collision)
 {
 	typedef cub::BlockScan<uint32_t, TILE_THREADS> Scan;
@@ -922,20 +923,31 @@ __global__ void __launch_bounds__(TILE_THREADS) k_emit(TextDesc t, const Rec16 *
 			const uint32_t c = cur.nc - 1, ppos = p - cur.cs, len = cur.ce - cur.cs;
 			sibgpu_inst ip = {fw ? idc : idr, c, ppos};
 			sibgpu_inst in = {fw ? idr : idc, c, len - ppos - k};
-			pos_out[o] = ip;
-			neg_tmp[o] = in;
+			if(o < inst_cap)                               // a full table is regrown by the host and the emission repeated
+			{
+				pos_out[o] = ip;
+				neg_tmp[o] = in;
+			}
 			o++;
 		}
 	}
 }
 
+// number of instances = offset + count of the last tile, clipped to the capacity of the tables
+__device__ __forceinline__ uint64_t inst_total(const uint64_t *__restrict__ tileoff, const uint64_t *__restrict__ tilecnt,
+	uint32_t ntiles, uint64_t inst_cap)
+{
+	const uint64_t n = tileoff[ntiles - 1] + tilecnt[ntiles - 1];
+	return n < inst_cap ? n : inst_cap;
+}
+
 // chrinst[c] = first index in the (text-ordered) negative table whose chr >= c, for c in 0..nchr
-__global__ void __launch_bounds__(256) k_chr_bounds(const sibgpu_inst *__restrict__ neg_tmp, uint64_t n, uint32_t nchr,
-	uint64_t *__restrict__ chrinst)
+__global__ void __launch_bounds__(256) k_chr_bounds(const sibgpu_inst *__restrict__ neg_tmp, const uint64_t *__restrict__ tileoff,
+	const uint64_t *__restrict__ tilecnt, uint32_t ntiles, uint64_t inst_cap, uint32_t nchr, uint64_t *__restrict__ chrinst)
 {
 	uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
 	if(c > nchr) return;
-	uint64_t lo = 0, hi = n;
+	uint64_t lo = 0, hi = inst_total(tileoff, tilecnt, ntiles, inst_cap);
 	while(lo < hi)
 	{
 		uint64_t mid = (lo + hi) >> 1;
@@ -946,13 +958,16 @@ __global__ void __launch_bounds__(256) k_chr_bounds(const sibgpu_inst *__restric
 
 // The negative-strand table is sorted by (chr, position in the reverse complement): within a chromosome that is
 // descending text order, so every chromosome's run is reversed.
-__global__ void __launch_bounds__(256) k_reverse_neg(const sibgpu_inst *__restrict__ neg_tmp, uint64_t n,
-	const uint64_t *__restrict__ chrinst, sibgpu_inst *__restrict__ neg_out)
+__global__ void __launch_bounds__(256) k_reverse_neg(const sibgpu_inst *__restrict__ neg_tmp, const uint64_t *__restrict__ tileoff,
+	const uint64_t *__restrict__ tilecnt, uint32_t ntiles, uint64_t inst_cap, const uint64_t *__restrict__ chrinst,
+	sibgpu_inst *__restrict__ neg_out)
 {
-	uint64_t j = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
-	if(j >= n) return;
-	sibgpu_inst v = neg_tmp[j];
-	neg_out[chrinst[v.chr] + chrinst[v.chr + 1] - 1 - j] = v;
+	const uint64_t n = inst_total(tileoff, tilecnt, ntiles, inst_cap);
+	for(uint64_t j = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; j < n; j += (uint64_t)gridDim.x * blockDim.x)
+	{
+		sibgpu_inst v = neg_tmp[j];
+		neg_out[chrinst[v.chr] + chrinst[v.chr + 1] - 1 - j] = v;
+	}
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -1012,13 +1027,10 @@ static int ids_and_tables(sibgpu_ctx *ctx, const TextDesc &t, uint32_t k, const 
 			ProfScope ps(ctx, "cub_sort_vertex_keys", 2 * Vc * 8 * 2, 8);
 			SIB_CUDA(cub::DeviceRadixSort::SortKeys(ctx->d_cubtmp.p, tmp_bytes, dbuf, (int)(2 * Vc), 0, 64, st));
 		}
-		SIB_CUDA(cudaMemcpyAsync(hs + 3, ds + 3, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
-		SIB_CUDA(cudaStreamSynchronize(st));
-		const uint32_t npal = (uint32_t)(hs[3] & 0xFFFFFFFFu);
-		V = (uint32_t)(2 * Vc - npal);
 		{
+			// V = 2 Vc - #palindromes is read by the kernel from the device counter; the host learns it with the final sync
 			ProfScope ps(ctx, "k_build_map", Vc * (sizeof(Rec) + sizeof(MapSlot)));
-			k_build_map<MODE><<<(uint32_t)((Vc + 255) / 256), 256, 0, st>>>(ckeys, Vc, k, dbuf.Current(), V,
+			k_build_map<MODE><<<(uint32_t)((Vc + 255) / 256), 256, 0, st>>>(ckeys, Vc, k, dbuf.Current(), reinterpret_cast<uint32_t*>(ds + 3),
 				ctx->d_map.as<MapSlot>(), Tm, ctx->d_filter.as<uint32_t>(), fshift);
 		}
 	}
@@ -1028,16 +1040,17 @@ static int ids_and_tables(sibgpu_ctx *ctx, const TextDesc &t, uint32_t k, const 
 		SIB_TRY(ctx->d_rep.ensure(sizeof(uint64_t) * Vc));
 		SIB_CUDA(cudaMemsetAsync(ctx->d_rep.p, 0xFF, sizeof(uint64_t) * Vc, st));
 		ProfScope ps(ctx, "k_build_map", Vc * (sizeof(Rec) + sizeof(MapSlot)));
-		k_build_map<MODE><<<(uint32_t)((Vc + 255) / 256), 256, 0, st>>>(ckeys, Vc, k, nullptr, 0,
+		k_build_map<MODE><<<(uint32_t)((Vc + 255) / 256), 256, 0, st>>>(ckeys, Vc, k, nullptr, nullptr,
 			ctx->d_map.as<MapSlot>(), Tm, ctx->d_filter.as<uint32_t>(), fshift);
 	}
 
 	if(ntiles == 0)
 	{
 		// a rank without text (tiny input, many ranks) still reports the global vertex count
+		SIB_CUDA(cudaMemcpyAsync(hs + 3, ds + 3, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
 		SIB_CUDA(cudaStreamSynchronize(st));
 		ctx->n_inst = 0;
-		ctx->n_vertices = V;
+		ctx->n_vertices = MODE == 2 ? V : (uint32_t)(2 * Vc - (hs[3] & 0xFFFFFFFFu));
 		return SIBGPU_OK;
 	}
 	// ---- instance tables
@@ -1059,51 +1072,54 @@ static int ids_and_tables(sibgpu_ctx *ctx, const TextDesc &t, uint32_t k, const 
 		ProfScope ps(ctx, "cub_scan_tile_counts", ntiles * 12ull, 2);
 		SIB_CUDA(cub::DeviceScan::ExclusiveSum(ctx->d_cubtmp.p, tmp_bytes, in, ctx->d_tileoff.as<uint64_t>(), (int)ntiles, st));
 	}
-	uint64_t last_off = 0;
-	uint64_t last_cnt = 0;
-	SIB_CUDA(cudaMemcpyAsync(&last_off, ctx->d_tileoff.as<uint64_t>() + (ntiles - 1), 8, cudaMemcpyDeviceToHost, st));
-	SIB_CUDA(cudaMemcpyAsync(&last_cnt, ctx->d_tilecnt.as<uint64_t>() + (ntiles - 1), 8, cudaMemcpyDeviceToHost, st));
-	SIB_CUDA(cudaStreamSynchronize(st));
-	const uint64_t I = last_off + last_cnt;
-	SIB_TRY(ctx->d_pos.ensure(sizeof(sibgpu_inst) * (I + 1)));
-	SIB_TRY(ctx->d_negtmp.ensure(sizeof(sibgpu_inst) * (I + 1)));
-	SIB_TRY(ctx->d_neg.ensure(sizeof(sibgpu_inst) * (I + 1)));
+	// The tables are emitted into the capacity at hand (grow-only buffers: the previous call's size, at least 64 Ki
+	// instances) without asking the device for the instance count first; if they turn out too small the count is known
+	// by then, the buffers are regrown and only the emission is repeated.
 	SIB_TRY(ctx->d_chrinst.ensure(sizeof(uint64_t) * (ctx->nchr + 2)));
-	if(I)
+	SIB_TRY(ctx->d_pos.ensure(sizeof(sibgpu_inst) * 65536));
+	SIB_TRY(ctx->d_negtmp.ensure(sizeof(sibgpu_inst) * 65536));
+	SIB_TRY(ctx->d_neg.ensure(sizeof(sibgpu_inst) * 65536));
+	uint64_t I = 0;
+	for(int pass = 0; pass < 2; pass++)
 	{
+		const uint64_t inst_cap = std::min(std::min(ctx->d_pos.cap, ctx->d_negtmp.cap), ctx->d_neg.cap) / sizeof(sibgpu_inst);
 		{
 			ProfScope ps(ctx, "k_emit", ctx->M / 8 + I * 24);
 			k_emit<MODE><<<scan_grid, TILE_THREADS, 0, st>>>(t, fp, k, ntiles, ctx->d_map.as<MapSlot>(), Tm,
 				ctx->d_filter.as<uint32_t>(), fshift, ctx->d_hitmask.as<uint16_t>(), ctx->d_tileoff.as<uint64_t>(),
-				ctx->d_pos.as<sibgpu_inst>(), ctx->d_negtmp.as<sibgpu_inst>(), ctx->d_rep.as<unsigned long long>(),
+				ctx->d_pos.as<sibgpu_inst>(), ctx->d_negtmp.as<sibgpu_inst>(), inst_cap, ctx->d_rep.as<unsigned long long>(),
 				reinterpret_cast<uint32_t*>(ds + 9));
 		}
 		if(reverse_neg)
 		{
-			ProfScope ps(ctx, "k_chr_bounds", 0);
-			k_chr_bounds<<<(ctx->nchr + 1 + 255) / 256, 256, 0, st>>>(ctx->d_negtmp.as<sibgpu_inst>(), I, ctx->nchr,
-				ctx->d_chrinst.as<uint64_t>());
-		}
-		if(reverse_neg)
-		{
+			{
+				ProfScope ps(ctx, "k_chr_bounds", 0);
+				k_chr_bounds<<<(ctx->nchr + 1 + 255) / 256, 256, 0, st>>>(ctx->d_negtmp.as<sibgpu_inst>(), ctx->d_tileoff.as<uint64_t>(),
+					ctx->d_tilecnt.as<uint64_t>(), ntiles, inst_cap, ctx->nchr, ctx->d_chrinst.as<uint64_t>());
+			}
 			ProfScope ps(ctx, "k_reverse_neg", I * 24);
-			k_reverse_neg<<<(uint32_t)((I + 255) / 256), 256, 0, st>>>(ctx->d_negtmp.as<sibgpu_inst>(), I,
-				ctx->d_chrinst.as<uint64_t>(), ctx->d_neg.as<sibgpu_inst>());
+			k_reverse_neg<<<(uint32_t)sms * 8, 256, 0, st>>>(ctx->d_negtmp.as<sibgpu_inst>(), ctx->d_tileoff.as<uint64_t>(),
+				ctx->d_tilecnt.as<uint64_t>(), ntiles, inst_cap, ctx->d_chrinst.as<uint64_t>(), ctx->d_neg.as<sibgpu_inst>());
 		}
-	}
-	if(MODE == 2)
-	{
+		SIB_CUDA(cudaMemcpyAsync(hs + 4, ctx->d_tileoff.as<uint64_t>() + (ntiles - 1), 8, cudaMemcpyDeviceToHost, st));
+		SIB_CUDA(cudaMemcpyAsync(hs + 5, ctx->d_tilecnt.as<uint64_t>() + (ntiles - 1), 8, cudaMemcpyDeviceToHost, st));
+		SIB_CUDA(cudaMemcpyAsync(hs + 3, ds + 3, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
 		SIB_CUDA(cudaMemcpyAsync(hs + 9, ds + 9, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
 		SIB_CUDA(cudaStreamSynchronize(st));
-		if(hs[9] & 1u)
-		{
-			// two different k-mers shared a fingerprint inside a vertex class: the caller starts over with other bases
-			SIB_CUDA(cudaMemsetAsync(ds + 9, 0, sizeof(uint64_t), st));
-			*collision = true;
-			return SIBGPU_OK;
-		}
+		I = hs[4] + hs[5];
+		if(I <= inst_cap) break;
+		SIB_TRY(ctx->d_pos.ensure(sizeof(sibgpu_inst) * (I + 1)));
+		SIB_TRY(ctx->d_negtmp.ensure(sizeof(sibgpu_inst) * (I + 1)));
+		SIB_TRY(ctx->d_neg.ensure(sizeof(sibgpu_inst) * (I + 1)));
 	}
-	SIB_CUDA(cudaStreamSynchronize(st));
+	if(MODE != 2) V = (uint32_t)(2 * Vc - (hs[3] & 0xFFFFFFFFu));
+	if(MODE == 2 && (hs[9] & 1u))
+	{
+		// two different k-mers shared a fingerprint inside a vertex class: the caller starts over with other bases
+		SIB_CUDA(cudaMemsetAsync(ds + 9, 0, sizeof(uint64_t), st));
+		*collision = true;
+		return SIBGPU_OK;
+	}
 	ctx->n_inst = I;
 	ctx->n_vertices = V;
 	return SIBGPU_OK;
