@@ -7,12 +7,15 @@ A "step" is one construction of the de Bruijn-graph index of one synthetic genom
 (pack -> scan/histogram -> scatter -> L2-resident hash grouping -> vertex ranking -> instance tables), the GPU
 replacement of IndexedSequence's EnumerateBifurcationsSArrayInRAM (/root/reference/src/vertexenumeration.cpp:263-364).
 Workload at N=1 is BASELINE.json configs[1]: 100 MB random-ACGT single contig, numpy default_rng(12345), k=25.
-With N>1 ranks (torchrun, one process per GPU) the workload is ONE genome of N such contigs (seed 12345+c), sharded by
-contiguous text range over the ranks (weak scaling: 100 Mbases per GPU): every rank scatters its k-mer records, bucketed
-by hash prefix, into its own send buffer; one small NCCL all-gather swaps the bucket counts; the owner of a bucket
-reads the bucket's segments straight out of the peers' send buffers over NVLink inside its grouping kernel (TMA bulk
-copies into a shared-memory ring -- the all-to-all is fused into the kernel); all-gather of the vertex keys; local
-instance tables (sibelia_b200/distributed.py); `value` = total bases / max-over-ranks step time.
+With N>1 ranks (torchrun, one process per GPU) the workload is the SURVEY 8(d) strain recipe with N strains of 125 MB
+(N = 8: BASELINE configs[3], 10^9 bases), ONE genome sharded by contiguous text range over the ranks (weak scaling:
+125 Mbases per GPU): every rank scatters its k-mer records, bucketed by hash prefix, into its own exported buffer and
+publishes a step counter; the owner of a bucket waits for the counters on the device and pulls the bucket's segments
+straight out of the peers' buffers over NVLink with TMA bulk copies inside its split kernel (the all-to-all is fused
+into the kernel), groups them in shared memory, publishes its vertex keys the same way; a pull kernel concatenates all
+ranks' keys (the all-gather, fused); local instance tables (sibelia_b200/distributed.py).  `value` = total bases /
+max-over-ranks step time; `alt` = the same on N random contigs of 100 MB (round 1's workload).  `result_digest` =
+sha256 over (vertex count, positive table, negative table) assembled on rank 0 outside the timed region.
 
 One JSON line is printed by rank 0 (see the task contract): value = device-resident throughput, e2e = the same
 metric through sibgpu_enumerate with pinned HOST buffers (H2D + D2H inside the timed region), roofline = dominant
@@ -33,7 +36,8 @@ import numpy as np  # noqa: E402
 
 METRIC = "Mbases/s indexed (k=25)"
 UNIT = "Mbases/s"
-REF_SAMPLE_BASES = 8_000_000
+CPU_SAMPLE_BASES = 16_000_000
+STRAIN_BASES = 125_000_000
 
 
 def genome(mbases, seed):
@@ -103,34 +107,63 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def workload(world, mbases):
+    """The chromosomes of the N-GPU workload and its description."""
+    from sibelia_b200 import synth
+    if world == 1:
+        return [genome(mbases, 12345)], ("synthetic %g MB random-ACGT single contig, numpy default_rng(12345) "
+                                         "(BASELINE configs[1])" % mbases)
+    return synth.strains(world, STRAIN_BASES), (
+        "SURVEY 8(d) strain recipe, %d strains x 125 MB (base default_rng(1000), strain s default_rng(2000+s): p_sub 0.002, "
+        "4 x 200 kb inversions, indels)%s, one genome sharded by text range over %d GPUs"
+        % (world, " = BASELINE configs[3]" if world == 8 else "", world))
+
+
+def result_digest(count, pos, neg):
+    import hashlib
+    h = hashlib.sha256()
+    h.update(np.uint64(count).tobytes())
+    h.update(np.ascontiguousarray(pos).tobytes())
+    h.update(np.ascontiguousarray(neg).tobytes())
+    return h.hexdigest()
+
+
 def run_reference(args, rank, world):
     """The reference's own CPU implementation of the path (oracle/_ref = unmodified /root/reference sources compiled
-    by oracle/Makefile), single thread (the reference has no threading), on a bounded sample of the same workload."""
+    by oracle/Makefile), single thread (the reference has no threading).  N=1: the FULL 100 MB workload, one step
+    (40-120 s; warm-up would only repeat it).  N>1: one rank's shard of the strain workload (strain 0, 125 MB): the
+    whole 10^9-base set needs ~40 GB and ~20 min per index on the CPU."""
     if rank != 0:
         return
     from oracle import ref
     if not ref.available():
         print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libsibelia_ref.so is not built"}))
         return
-    sample = min(REF_SAMPLE_BASES, int(args.mbases * 1_000_000))
-    g = genome(args.mbases, 12345)[:sample]
-    for _ in range(args.warmup_ref):
-        ref.index([g], args.k, dump=False)
+    if world == 1:
+        g = genome(args.mbases, 12345)
+        what = "synthetic %g MB random-ACGT single contig, numpy default_rng(12345), k=%d (BASELINE configs[1]), FULL size" % (args.mbases, args.k)
+        sample = "the whole workload genome (%d bases)" % len(g)
+    else:
+        from sibelia_b200 import synth
+        g = synth.strains(1, STRAIN_BASES)[0]
+        what = ("strain 0 (125 MB) of the %d-strain workload of the GPU arm, k=%d: one rank's shard" % (world, args.k))
+        sample = "strain 0 of the strain set (%d bases)" % len(g)
+    steps = max(1, min(args.steps, args.ref_steps))
     t = []
-    for _ in range(args.steps):
+    for _ in range(steps):
         t.append(ref.index([g], args.k, dump=False)["seconds"])
     sec = float(np.mean(t))
-    v = sample / 1e6 / sec
+    v = len(g) / 1e6 / sec
     line = {
-        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup_ref, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+        "warmup": 0, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": {"workload": "synthetic %g MB random-ACGT single contig, k=%d (BASELINE configs[1])" % (args.mbases, args.k),
-                   "k": args.k},
+        "config": {"workload": what, "k": args.k,
+                   "steps_note": "one index construction takes %.0f s on this host: %d step(s) run, no warm-up (requested "
+                                 "--steps %d --warmup %d)" % (sec, steps, args.steps, args.warmup)},
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": 1, "kind": "reference",
-                         "sample": "first %d bases of the workload genome, IndexedSequence ctor (in-RAM SA path), "
-                                   "libdivsufsort 32-bit, 1 thread (the reference is single-threaded); %d host cores present"
-                                   % (sample, os.cpu_count())},
+                         "sample": "%s, IndexedSequence ctor (in-RAM SA path), libdivsufsort 32-bit, 1 thread (the reference "
+                                   "is single-threaded); %d host cores present" % (sample, os.cpu_count())},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
@@ -145,8 +178,9 @@ def main():
     ap.add_argument("--mbases", type=float, default=100.0)
     ap.add_argument("--k", type=int, default=25)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ref-steps", type=int, default=1, help="steps the reference arm actually runs (each is 40-170 s)")
+    ap.add_argument("--no-alt", action="store_true", help="N>1: skip the random-contig line of round 1")
     args = ap.parse_args()
-    args.warmup_ref = min(args.warmup, 1)
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -170,7 +204,6 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    N = int(args.mbases * 1_000_000)
     ctx = sb.Context(local_rank)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 
@@ -178,104 +211,128 @@ def main():
         flush.fill_(1)
         torch.cuda.synchronize()
 
-    kstats = {}
+    def pinned(a):
+        t = torch.empty(len(a), dtype=torch.uint8, pin_memory=True)
+        t.numpy()[:] = a
+        return t
 
-    def add_stats():
-        for s in ctx.kernel_stats():
-            a = kstats.setdefault(s["name"], {"launches": 0, "ms": 0.0, "algo_bytes": 0})
-            a["launches"] += s["launches"]
-            a["ms"] += s["ms"]
-            a["algo_bytes"] += s["algo_bytes"]
+    def measure(chrs, profile):
+        """Device-resident and end-to-end arms on one workload (list of uint8 arrays, the same on every rank)."""
+        total = int(sum(len(c) for c in chrs))
+        kstats = {}
 
-    if world == 1:
-        g = genome(args.mbases, 12345)
-        host = torch.empty(N, dtype=torch.uint8, pin_memory=True)
-        host.numpy()[:] = g
-        hview = [host.numpy()]
-        ctx.upload(hview)
+        def add_stats():
+            for s in ctx.kernel_stats():
+                a = kstats.setdefault(s["name"], {"launches": 0, "ms": 0.0, "algo_bytes": 0})
+                a["launches"] += s["launches"]
+                a["ms"] += s["ms"]
+                a["algo_bytes"] += s["algo_bytes"]
 
-        def step_resident():
-            count, ninst = ctx.enumerate_resident(args.k)
-            return count, ninst, ctx.last_device_ms()
+        if world == 1:
+            keep = [pinned(c) for c in chrs]
+            hview = [t.numpy() for t in keep]
+            ctx.upload(hview)
 
-        def step_e2e():
-            c2, pos, neg = ctx.enumerate(hview, args.k)
-            return pos.nbytes + neg.nbytes + 64
-        h2d = N + 8
-    else:
-        from sibelia_b200 import distributed as D
-        hosts = []
-        for c in range(world):
-            h = torch.empty(N, dtype=torch.uint8, pin_memory=(c == rank))
-            h.numpy()[:] = genome(args.mbases, 12345 + c)
-            hosts.append(h)
-        hview = [h.numpy() for h in hosts]
-        g = hview[0]
-        shard = D.GpuShard(ctx)
+            def step_resident():
+                count, ninst = ctx.enumerate_resident(args.k)
+                return count, ninst, ctx.last_device_ms()
 
-        class Resident(D.GpuShard):
-            """the shard's text is already in HBM: skip the upload phase of enumerate_sharded"""
-            def upload(self, chrs, rank, world):
-                self._pending = None
-        resident = Resident(ctx)
-        ctx.dist_upload(hview, rank, world)
-        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            def step_e2e():
+                c2, pos, neg = ctx.enumerate(hview, args.k)
+                return c2, pos, neg
+            h2d = total + 8
+        else:
+            from sibelia_b200 import distributed as D
+            # a rank copies only the bytes of its own text range (+ halo): pin the chromosomes that range touches
+            starts = np.concatenate([[1], 1 + np.cumsum([len(c) + 1 for c in chrs])])[:-1]
+            M = total + len(chrs) + 1
+            lo, hi = M * rank // world - 8192, M * (rank + 1) // world + 8192
+            keep = [pinned(c) if (s < hi and s + len(c) > lo) else None for c, s in zip(chrs, starts)]
+            hview = [t.numpy() if t is not None else c for t, c in zip(keep, chrs)]
+            shard = D.GpuShard(ctx)
+            resident = D.GpuShard(ctx)
+            resident.resident = True                     # fused path: the text range stays in HBM
 
-        def step_resident():
-            torch.cuda.synchronize()
-            ev0.record()
-            count, pos, neg = D.enumerate_sharded(resident, hview, args.k)
-            torch.cuda.synchronize()
-            ev1.record()
-            ev1.synchronize()
-            return count, len(pos), ev0.elapsed_time(ev1)
+            def _skip_upload(chrs_, rank_, world_):      # phased paths: likewise
+                resident._pending = None
+            resident.upload = _skip_upload
+            ctx.dist_upload(hview, rank, world)
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 
-        def step_e2e():
-            count, pos, neg = D.enumerate_sharded(shard, hview, args.k)
-            return pos.nbytes + neg.nbytes + 64
-        h2d = N + 8
+            def step_resident():
+                torch.cuda.synchronize()
+                ev0.record()
+                count, pos, neg = D.enumerate_sharded(resident, hview, args.k)
+                torch.cuda.synchronize()
+                ev1.record()
+                ev1.synchronize()
+                return count, len(pos), ev0.elapsed_time(ev1)
 
-    # ---- device-resident arm: inputs already in HBM
-    ctx.set_profiling(True)
-    for _ in range(args.warmup):
-        count, ninst, _ms = step_resident()
-    sampler = ClockSampler(local_rank)
-    barrier()
-    sampler.start()
-    dev_ms, launches = 0.0, 0
-    wall0 = time.perf_counter()
-    for _ in range(args.steps):
-        l2_flush()
+            def step_e2e():
+                return D.enumerate_sharded(shard, hview, args.k)
+            h2d = (hi - lo if world > 1 else total) + 8
+
+        # ---- device-resident arm: inputs already in HBM
+        ctx.set_profiling(profile)
+        for _ in range(args.warmup):
+            count, ninst, _ms = step_resident()
+        sampler = ClockSampler(local_rank)
+        barrier()
+        sampler.start()
+        dev_ms, launches = 0.0, 0
+        wall0 = time.perf_counter()
+        for _ in range(args.steps):
+            l2_flush()
+            if world > 1:
+                dist.barrier()
+            count, ninst, ms = step_resident()
+            dev_ms += ms
+            launches += ctx.last_launches()
+            if profile:
+                add_stats()
+        barrier()
+        wall = time.perf_counter() - wall0
+        clocks = sampler.stop()
+        ctx.set_profiling(False)
+        t = torch.tensor([dev_ms], dtype=torch.float64, device="cuda")
         if world > 1:
-            dist.barrier()
-        count, ninst, ms = step_resident()
-        dev_ms += ms
-        launches += ctx.last_launches()
-        add_stats()
-    barrier()
-    wall = time.perf_counter() - wall0
-    clocks = sampler.stop()
-    ctx.set_profiling(False)
-    t = torch.tensor([dev_ms], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_per_step = float(t.item()) / args.steps
-    value = world * N / 1e6 / (ms_per_step / 1e3)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_per_step = float(t.item()) / args.steps
 
-    # ---- end-to-end arm: pinned host buffers in, host tables out, through the public API
-    for _ in range(2):
-        step_e2e()
-    barrier()
-    t0 = time.perf_counter()
-    d2h = 0
-    for _ in range(args.steps):
-        d2h = step_e2e()
-    barrier()
-    e2e_s = (time.perf_counter() - t0) / args.steps
-    te = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_value = world * N / 1e6 / float(te.item())
+        # ---- end-to-end arm: pinned host buffers in, host tables out, through the public API
+        for _ in range(2):
+            step_e2e()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            c2, pos, neg = step_e2e()
+        barrier()
+        e2e_s = (time.perf_counter() - t0) / args.steps
+        d2h = pos.nbytes + neg.nbytes + 64
+        te = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+        ti = torch.tensor([len(pos)], dtype=torch.int64, device="cuda")
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+            dist.all_reduce(ti, op=dist.ReduceOp.SUM)
+
+        # ---- result digest, outside every timed region: the full tables on rank 0
+        if world > 1:
+            c2, pos, neg = D.gather_tables_device(c2, pos, neg)
+        digest = result_digest(c2, pos, neg) if rank == 0 else None
+        return {"total": total, "ms_per_step": ms_per_step, "value": total / 1e6 / (ms_per_step / 1e3), "dev_ms": dev_ms,
+                "e2e_ms": float(te.item()) * 1e3, "e2e_value": total / 1e6 / float(te.item()), "h2d": int(h2d), "d2h": int(d2h),
+                "launches": int(launches), "count": int(c2), "ninst": int(ti.item()), "clocks": clocks, "wall": wall,
+                "kstats": kstats, "digest": digest, "strategy": getattr(shard, "last_strategy", None) if world > 1 else None}
+
+    chrs, what = workload(world, args.mbases)
+    r = measure(chrs, True)
+    alt = None
+    if world > 1 and not args.no_alt:
+        from sibelia_b200 import synth
+        a = measure([synth.random_genome(int(args.mbases * 1_000_000), 12345 + c) for c in range(world)], False)
+        alt = {"workload": "%d random-ACGT contigs x %g MB (default_rng(12345+c)): round 1's multi-GPU workload" % (world, args.mbases),
+               "value": a["value"], "ms_per_step": a["ms_per_step"], "e2e_value": a["e2e_value"], "e2e_ms_per_step": a["e2e_ms"],
+               "vertices": a["count"], "result_digest": a["digest"]}
 
     if rank != 0:
         if world > 1:
@@ -283,6 +340,7 @@ def main():
         return
 
     # ---- roofline of the dominant kernel (CUDA events on the library's stream, live over the timed steps)
+    kstats, dev_ms = r["kstats"], r["dev_ms"]
     peak, peak_src = peaks()
     dom = max(kstats.items(), key=lambda kv: kv[1]["ms"])
     dname, d = dom
@@ -296,36 +354,35 @@ def main():
                             for n, s in sorted(kstats.items(), key=lambda kv: -kv[1]["ms"])}}
     tr = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tr):
-        # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures
-        # (profiles/r1_ncu_*.txt); for the overlapped insert+scan phase: both kernels, all partitions of one step
+        # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of that kernel on this workload, from the committed
+        # `ncu --set full --cache-control all` captures (profiles/r2_ncu_*.txt)
         try:
             tj = json.load(open(tr))
-            if dname in tj:
+            if dname in tj and world == 1:
                 roofline["traffic"] = tj[dname]
-            elif dname == "k_insert+k_table_scan":
-                per_launch_records = 1048576.0      # the captures were taken with the default 1 Mi-record partitions
-                nrec = d["algo_bytes"] / 8.0 / args.steps
-                roofline["traffic"] = (tj["k_insert"] + tj["k_table_scan"]) * nrec / per_launch_records
-                roofline["traffic_note"] = ("whole phase per step = per-launch dram bytes of the two kernels (ncu --set full, warm L2: the "
-                                            "table and most of the freshly scattered records are L2-resident) x partitions per step")
         except Exception:
             pass
-    roofline["note"] = ("k_insert is bound by scattered L2 atomics, not by HBM: tools/ubench/atomics.cu measures 90-104 G CAS/s "
-                        "on this part for an L2-resident table; the phase issues ~1.5 CAS per record (linear probing at load 0.5)")
+    whole = sum(s["algo_bytes"] for s in kstats.values()) / 1e9 / (dev_ms / 1e3) if dev_ms else 0.0
+    roofline["whole_step_algo_GBps"] = whole
+    roofline["note"] = ("every kernel of the step is listed with its algorithmic bytes / its own device time; the scan kernels "
+                        "(k_scatter, k_mark) are instruction-issue bound (rolling canonical 2-bit k-mers, mixing, shared-memory "
+                        "counting sort), k_split / k_group move each 8-byte record once more")
 
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         from oracle import ref
+        g = chrs[0]
         if ref.available():
-            sample = min(REF_SAMPLE_BASES * 2, N)
+            sample = min(CPU_SAMPLE_BASES, len(g))
             sec = ref.index([g[:sample]], args.k, dump=False)["seconds"]
             cpu = {"value": sample / 1e6 / sec, "unit": UNIT, "cores": 1, "kind": "reference",
                    "sample": "first %d bases of the workload genome, unmodified reference IndexedSequence ctor "
-                             "(oracle/_ref, libdivsufsort in-RAM path), 1 thread of %d host cores, %.1f s"
+                             "(oracle/_ref, libdivsufsort in-RAM path), 1 thread of %d host cores, %.1f s; the reference gets "
+                             "slower per base with size (suffix sorting): the full-size figure is the --impl reference arm"
                              % (sample, os.cpu_count(), sec)}
         else:
             from oracle import restate
-            sample = min(2_000_000, N)
+            sample = min(2_000_000, len(g))
             t0 = time.perf_counter()
             restate.enumerate_bifurcations([g[:sample]], args.k)
             sec = time.perf_counter() - t0
@@ -333,26 +390,26 @@ def main():
                    "sample": "first %d bases, oracle/enum_restate.c (sort-based restatement), %.1f s" % (sample, sec)}
 
     line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u64", "data": "synthetic",
-        "config": {"workload": ("synthetic %g MB random-ACGT single contig, numpy default_rng(12345), k=%d (BASELINE configs[1])"
-                                % (args.mbases, args.k)) if world == 1 else
-                               ("one synthetic genome of %d random-ACGT contigs x %g MB (default_rng(12345+c)), k=%d, sharded by "
-                                "text range over %d GPUs; k-mer records exchanged by peer reads over NVLink fused into the "
-                                "grouping kernel (NCCL only for the bucket counts and the vertex keys)" % (world, args.mbases, args.k, world)),
-                   "k": args.k, "bases_per_gpu": N, "vertices": int(count), "instances_per_strand": int(ninst),
+        "config": {"workload": what + ", k=%d" % args.k, "k": args.k, "bases_total": r["total"], "bases_per_gpu": r["total"] // world,
+                   "vertices": r["count"], "instances_per_strand": r["ninst"], "exchange": r["strategy"],
                    "l2": "256 MB L2 flush between timed iterations (outside the event-timed region)",
                    "timing": ("CUDA events on the library stream around each whole step" if world == 1 else
-                              "CUDA events around each whole sharded step (device-synchronised on both sides)")
-                             + "; wall %.1f ms/step incl. flush" % (wall / args.steps * 1e3)},
-        "clocks": clocks,
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                "ms_per_step": float(te.item()) * 1e3},
-        "gpu_launches": int(launches),
+                              "CUDA events around each whole sharded step (device-synchronised on both sides), max over ranks")
+                             + "; wall %.1f ms/step incl. flush" % (r["wall"] / args.steps * 1e3)},
+        "clocks": r["clocks"],
+        "e2e": {"value": r["e2e_value"], "unit": UNIT, "h2d_bytes_per_step": r["h2d"], "d2h_bytes_per_step": r["d2h"],
+                "ms_per_step": r["e2e_ms"], "note": "pinned host buffers -> sibgpu_enumerate / the sharded step -> host tables; "
+                                                    "bytes are per rank"},
+        "gpu_launches": r["launches"],
+        "result_digest": r["digest"],
         "roofline": roofline,
         "cpu_baseline": cpu,
     }
+    if alt:
+        line["alt"] = alt
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -208,6 +208,32 @@ int sibgpu_dist_export_send(sibgpu_ctx *ctx, void *handle64);
 int sibgpu_dist_import_peers(sibgpu_ctx *ctx, const void *handles);
 int sibgpu_dist_group_peer(sibgpu_ctx *ctx, const uint64_t *counts, const uint64_t *seg_caps, uint64_t *nkeys_local);
 
+/* Fused variant (k <= 28): no collective and no host round trip inside a step.  Every rank owns one exported buffer
+ * [header | fill cursors | vertex keys | one fixed-capacity segment per global partition]; the peers map it once
+ * (CUDA IPC).  In a step a rank scatters its text range into its own segments and publishes a step counter in its
+ * header; the level-2 split kernel of the partition owner waits for the peers' counters on the device and pulls the
+ * segments with TMA bulk copies straight out of the peers' memory (the all-to-all, fused into the kernel); the vertex
+ * keys are published the same way and concatenated by a pull kernel (the all-gather, fused).
+ *
+ *   sibgpu_fused_plan           layout of this call (every rank passes the whole input).  *need_alloc: 0 = the live
+ *                               buffers fit, 1 = (re)allocation needed -- the SAME answer on every rank, the caller
+ *                               then runs, collectively: barrier, sibgpu_fused_release_peers, barrier,
+ *                               sibgpu_fused_alloc, all-gather of the 64-byte handles, sibgpu_fused_import;
+ *                               -1 = not applicable (k > 28, input beyond the bucket fan-out): use the phased API above.
+ *                               resident != 0: the text range is already in HBM (sibgpu_dist_upload).
+ *   sibgpu_fused_run            one step.  *status: 0 = done (sibgpu_download returns the LOCAL tables, text order);
+ *                               1 = a segment or bucket overflowed on some rank: every rank gets 1 and uses the phased
+ *                               API; 2 = a key region was too small: plan again (need_alloc will be 1) and rerun.
+ *                               A peer that never publishes makes the kernels give up after 4 s (SIBGPU_ERR_INTERNAL).
+ */
+int sibgpu_fused_plan(sibgpu_ctx *ctx, const char *const *chr, const uint64_t *len, uint32_t nchr, uint32_t rank, uint32_t world,
+	uint32_t k, int resident, int *need_alloc);
+int sibgpu_fused_release_peers(sibgpu_ctx *ctx);
+int sibgpu_fused_alloc(sibgpu_ctx *ctx, void *handle64);
+int sibgpu_fused_import(sibgpu_ctx *ctx, const void *handles);
+int sibgpu_fused_run(sibgpu_ctx *ctx, const char *const *chr, const uint64_t *len, uint32_t nchr, int resident, uint32_t *count,
+	uint64_t *ninst_local, int *status);
+
 /* Test hook (host only, no GPU needed): iteration order of the reference's boost::unordered_map<size_t, BranchData>
  * (Boost 1.54, src/bulgeremoval.cpp:168,203-215) after inserting n distinct keys in the given order, as restated in
  * sibelia_b200/csrc/boost_order.h.  out receives the n keys in begin()..end() order. */

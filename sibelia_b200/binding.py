@@ -18,6 +18,7 @@ SYMBOLS = [
     "sibgpu_kernel_stats", "sibgpu_last_launches", "sibgpu_partition_fallbacks", "sibgpu_bucket_fallbacks", "sibgpu_last_device_ms", "sibgpu_simplify", "sibgpu_debug_unordered_order", "sibgpu_debug_trim_from_tables", "sibgpu_dist_upload", "sibgpu_dist_scan", "sibgpu_dist_record_bytes",
     "sibgpu_dist_scatter", "sibgpu_dist_group", "sibgpu_dist_keys", "sibgpu_dist_finish",
     "sibgpu_dist_scatter_local", "sibgpu_dist_upload_scatter", "sibgpu_dist_export_send", "sibgpu_dist_import_peers", "sibgpu_dist_group_peer",
+    "sibgpu_fused_plan", "sibgpu_fused_release_peers", "sibgpu_fused_alloc", "sibgpu_fused_import", "sibgpu_fused_run",
 ]
 
 
@@ -258,6 +259,33 @@ class Context:
         _check(load().sibgpu_dist_group_peer(self._h, C.c_void_p(counts.ctypes.data), C.c_void_p(seg_caps.ctypes.data),
                                              C.byref(nkeys)))
         return nkeys.value
+
+    # -- fused variant: one exported buffer per rank, exchange inside the kernels (see include/sibgpu.h)
+    def dist2_plan(self, chrs, rank, world, k, resident=False):
+        bufs, ptrs, lens, n = _chr_args(chrs)
+        need = C.c_int()
+        _check(load().sibgpu_fused_plan(self._h, ptrs, lens, C.c_uint32(n), C.c_uint32(rank), C.c_uint32(world), C.c_uint32(k),
+                                        C.c_int(1 if resident else 0), C.byref(need)))
+        return need.value
+
+    def dist2_release_peers(self):
+        _check(load().sibgpu_fused_release_peers(self._h))
+
+    def dist2_alloc(self):
+        h = np.zeros(64, dtype=np.uint8)
+        _check(load().sibgpu_fused_alloc(self._h, C.c_void_p(h.ctypes.data)))
+        return h
+
+    def dist2_import(self, handles):
+        handles = np.ascontiguousarray(handles, dtype=np.uint8)
+        _check(load().sibgpu_fused_import(self._h, C.c_void_p(handles.ctypes.data)))
+
+    def dist2_run(self, chrs, resident=False):
+        bufs, ptrs, lens, n = _chr_args(chrs)
+        cnt, ninst, status = C.c_uint32(), C.c_uint64(), C.c_int()
+        _check(load().sibgpu_fused_run(self._h, ptrs, lens, C.c_uint32(n), C.c_int(1 if resident else 0), C.byref(cnt),
+                                       C.byref(ninst), C.byref(status)))
+        return status.value, cnt.value, ninst.value
 
     def dist_keys(self, keys_ptr):
         _check(load().sibgpu_dist_keys(self._h, C.c_void_p(keys_ptr)))

@@ -166,7 +166,12 @@ void sibgpu_destroy(sibgpu_ctx *c)
 	{
 		if(pp) cudaIpcCloseMemHandle(pp);
 	}
+	for(void *pp : c->peer_x)
+	{
+		if(pp) cudaIpcCloseMemHandle(pp);
+	}
 	c->d_keystage.release();
+	c->d_xbuf.release();
 	for(DevBuf *b : bufs) b->release();
 	for(cudaEvent_t e : c->event_pool) cudaEventDestroy(e);
 	if(c->h_scalars) cudaFreeHost(c->h_scalars);
@@ -252,8 +257,9 @@ int sibgpu_enumerate_resident(sibgpu_ctx *c, uint32_t k, uint64_t *ninst, uint32
 		set_error("invalid: NULL context or k == 0");
 		return SIBGPU_ERR_INVALID;
 	}
-	if(!c->have_text)
+	if(!c->have_text || c->dist_world > 1)
 	{
+		// after sibgpu_dist_upload only this rank's byte range of the text is resident
 		set_error("state: sibgpu_upload must precede sibgpu_enumerate_resident");
 		return SIBGPU_ERR_STATE;
 	}
@@ -682,6 +688,70 @@ int sibgpu_dist_group_peer(sibgpu_ctx *c, const uint64_t *counts, const uint64_t
 		return SIBGPU_ERR_INVALID;
 	}
 	return dist_group_peer(c, counts, seg_caps, nkeys_local);
+}
+
+// ---- fused sharded path
+int sibgpu_fused_plan(sibgpu_ctx *c, const char *const *chr, const uint64_t *len, uint32_t nchr, uint32_t rank, uint32_t world,
+	uint32_t k, int resident, int *need_alloc)
+{
+	if(!c || !need_alloc || k == 0)
+	{
+		set_error("invalid: NULL argument or k == 0");
+		return SIBGPU_ERR_INVALID;
+	}
+	if(resident)
+	{
+		if(!c->have_text || c->dist_world != world || c->dist_rank != rank)
+		{
+			set_error("state: resident sharded run needs sibgpu_dist_upload with the same rank / world first");
+			return SIBGPU_ERR_STATE;
+		}
+	}
+	else SIB_TRY(dist_layout(c, chr, len, nchr, rank, world));
+	return dist2_plan(c, k, need_alloc);
+}
+
+int sibgpu_fused_release_peers(sibgpu_ctx *c) { return c ? dist2_release_peers(c) : SIBGPU_ERR_INVALID; }
+
+int sibgpu_fused_alloc(sibgpu_ctx *c, void *handle64)
+{
+	if(!c || !handle64)
+	{
+		set_error("invalid: NULL argument");
+		return SIBGPU_ERR_INVALID;
+	}
+	return dist2_alloc(c, handle64);
+}
+
+int sibgpu_fused_import(sibgpu_ctx *c, const void *handles)
+{
+	if(!c || !handles)
+	{
+		set_error("invalid: NULL argument");
+		return SIBGPU_ERR_INVALID;
+	}
+	return dist2_import(c, handles);
+}
+
+int sibgpu_fused_run(sibgpu_ctx *c, const char *const *chr, const uint64_t *len, uint32_t nchr, int resident, uint32_t *count,
+	uint64_t *ninst_local, int *status)
+{
+	if(!c || !status || (!resident && nchr && (!chr || !len)))
+	{
+		set_error("invalid: NULL argument");
+		return SIBGPU_ERR_INVALID;
+	}
+	SIB_CUDA(cudaSetDevice(c->device));
+	HostSrc src = {chr, len};
+	SIB_CUDA(cudaEventRecord(c->ev_begin, c->stream));
+	SIB_TRY(dist2_run(c, resident ? nullptr : &src, status));
+	c->have_text = true;
+	SIB_CUDA(cudaEventRecord(c->ev_end, c->stream));
+	SIB_CUDA(cudaEventSynchronize(c->ev_end));
+	SIB_CUDA(cudaEventElapsedTime(&c->last_ms, c->ev_begin, c->ev_end));
+	if(ninst_local) *ninst_local = c->n_inst;
+	if(count) *count = c->n_vertices;
+	return SIBGPU_OK;
 }
 
 int sibgpu_set_profiling(sibgpu_ctx *c, int enabled)

@@ -54,6 +54,12 @@ struct sibgpu_ctx {
 	std::vector<void*> peer_ptr;                       // [world], nullptr for the own rank / not mapped
 	std::vector<std::vector<unsigned char>> peer_handle;
 	sibgpu::DevBuf d_keystage;                         // vertex keys of the owned partitions
+	// fused path (sibgpu_fused_*): ONE exported buffer per rank [header | cursors | vertex keys | segments]
+	sibgpu::DevBuf d_xbuf;
+	std::vector<void*> peer_x;                         // [world] mappings of the peers' exported buffers
+	uint64_t x_kc = 0, x_kc_live = 0, x_off_seg = 0, x_off_seg_plan = 0, x_seg_cap = 0, x_nrec = 0, x_bytes = 0;
+	uint32_t x_PL = 0, x_sub_bits = 0, x_k = 0;
+	unsigned long long dist_epoch = 0;                 // step counter, the same on all ranks
 	sibgpu::TextDesc dist_text = {};
 
 	// tunables (env SIBGPU_PART_RECORDS)
@@ -84,6 +90,7 @@ struct sibgpu_ctx {
 	// grouping of 8-byte records (k <= 28): 1 = buckets of ~1 Ki records grouped in shared memory (k_split + k_group),
 	// 0 = one L2-resident table per hash partition (k_insert + k_table_scan; also the fallback when a bucket overflows)
 	int group_smem = 1;                                // env SIBGPU_GROUP_SMEM
+	bool split_attr_done = false;
 	int split_stages = 2;                              // input tiles in flight per CTA of k_split (env SIBGPU_SPLIT_STAGES, dev)
 	uint64_t ckeys_init = 1u << 20;                    // initial capacity of the vertex-key list (env SIBGPU_CKEYS_INIT, tests)
 	uint64_t smem_fallbacks = 0;                       // times a bucket overflowed and the L2-table path took over
@@ -139,4 +146,9 @@ int dist_group(sibgpu_ctx *ctx, const void *recv_dev, const uint32_t *counts, ui
 int dist_finish(sibgpu_ctx *ctx, const void *allkeys_dev, uint64_t nkeys_total);
 int dist_scatter_local(sibgpu_ctx *ctx, uint32_t k, uint64_t *counts_out, uint64_t *seg_cap_out, int *overflow_out, const HostSrc *src);
 int dist_group_peer(sibgpu_ctx *ctx, const uint64_t *counts, const uint64_t *seg_caps, uint64_t *nkeys_local);
+int dist2_plan(sibgpu_ctx *ctx, uint32_t k, int *need_alloc);
+int dist2_release_peers(sibgpu_ctx *ctx);
+int dist2_alloc(sibgpu_ctx *ctx, void *handle64);
+int dist2_import(sibgpu_ctx *ctx, const void *handles);
+int dist2_run(sibgpu_ctx *ctx, const HostSrc *src, int *status);
 } // namespace sibgpu

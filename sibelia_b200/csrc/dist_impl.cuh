@@ -236,6 +236,65 @@ int dist_scan(sibgpu_ctx *ctx, uint32_t k, uint32_t *hist_out)
 // swap the per-segment counts (one small all-gather, which is also the barrier), and the owner of partition p reads
 // the W segments of p straight out of the W send buffers (CUDA IPC mappings, NVLink) inside its insert kernel.
 // ---------------------------------------------------------------------------------------------------------------
+// pack (when the own byte range is still on the host: pipelined with its upload) + scatter of the own tile range into PT
+// fixed-capacity segments of `cap` records at out_dev, fill cursors at cursor_dev (already initialised to p * cap)
+template<int MODE, bool MIXED>
+static int dist_scatter_core(sibgpu_ctx *ctx, uint32_t k, uint32_t PT, uint64_t cap, unsigned long long *cursor_dev,
+	typename RecT<MODE>::type *out_dev, const HostSrc *src)
+{
+	typedef typename RecT<MODE>::type Rec;
+	cudaStream_t st = ctx->stream;
+	uint64_t *ds = ctx->d_scalars.as<uint64_t>();
+	TextDesc t = ctx->dist_text;
+	const uint32_t ntiles = ctx->dist_tile_hi - ctx->dist_tile_lo;
+	if(!ntiles) return SIBGPU_OK;
+	size_t smem = sizeof(ScatterSmem<MODE>);
+	SIB_CUDA(cudaFuncSetAttribute(k_scatter<MODE, MIXED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+	// src: the own byte range is still on the host -- stream it in pieces of CHUNK_TILES tiles on the copy stream and
+	// pack + scatter every piece as it lands (same pipeline as sibgpu_enumerate, enumerate.cu)
+	const uint32_t nchunks = src ? (ntiles + CHUNK_TILES - 1) / CHUNK_TILES : 1;
+	auto piece_byte = [&](uint32_t c) -> uint64_t {               // first byte of piece c (multiples of 16)
+		if(c == 0) return ctx->dist_byte_lo;
+		if(c >= nchunks) return ctx->dist_byte_hi;
+		return (uint64_t)(ctx->dist_tile_lo + c * CHUNK_TILES) * TILE_POS;
+	};
+	if(src)
+	{
+		SIB_TRY(ctx->ensure_copy_stream(nchunks));
+		SIB_CUDA(cudaEventRecord(ctx->ev_fork_copy, st));
+		SIB_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_fork_copy, 0));
+		for(uint32_t c = 0; c < nchunks; c++)
+		{
+			SIB_TRY(copy_text_range(ctx, *src, piece_byte(c), piece_byte(c + 1), ctx->copy_stream));
+			SIB_CUDA(cudaEventRecord(ctx->ev_chunk[c], ctx->copy_stream));
+		}
+	}
+	uint32_t tiles_done = ctx->dist_tile_lo;                      // absolute tile index
+	for(uint32_t c = 0; c < nchunks; c++)
+	{
+		uint32_t tile_end = ctx->dist_tile_hi;
+		if(src)
+		{
+			const uint64_t w0 = piece_byte(c) / 16, w1 = (piece_byte(c + 1) + 15) / 16;
+			SIB_CUDA(cudaStreamWaitEvent(st, ctx->ev_chunk[c], 0));
+			if(w1 > w0) SIB_TRY(launch_pack(ctx, w0, w1));
+			if(c + 1 < nchunks) tile_end = (uint32_t)((w1 - (TILE_THREADS + 5)) / TILE_THREADS);   // staged words of these tiles are packed
+		}
+		if(tile_end > tiles_done)
+		{
+			const uint32_t nt = tile_end - tiles_done;
+			const uint32_t g = nt < (uint32_t)ctx->sm_count * 4 ? nt : (uint32_t)ctx->sm_count * 4;
+			TextDesc tc = t;
+			tc.tile0 = tiles_done;
+			ProfScope ps(ctx, "k_scatter", (uint64_t)nt * TILE_POS / 4 + (uint64_t)nt * TILE_POS * sizeof(Rec));
+			k_scatter<MODE, MIXED><<<g, TILE_THREADS, smem, st>>>(tc, nullptr, k, nt, PT, cursor_dev, out_dev, cap,
+				reinterpret_cast<uint32_t*>(ds + 10));
+			tiles_done = tile_end;
+		}
+	}
+	return SIBGPU_OK;
+}
+
 template<int MODE>
 static int dist_scatter_local_mode(sibgpu_ctx *ctx, uint32_t k, uint64_t *counts_out, uint64_t *seg_cap_out, int *overflow_out,
 	const HostSrc *src)
@@ -244,7 +303,6 @@ static int dist_scatter_local_mode(sibgpu_ctx *ctx, uint32_t k, uint64_t *counts
 	cudaStream_t st = ctx->stream;
 	uint64_t *hs = static_cast<uint64_t*>(ctx->h_scalars);
 	uint64_t *ds = ctx->d_scalars.as<uint64_t>();
-	TextDesc t = ctx->dist_text;
 	const uint32_t ntiles = ctx->dist_tile_hi - ctx->dist_tile_lo, PT = ctx->dist_P_total;
 	// at most one record per text position of the own range
 	const uint64_t mean = ((uint64_t)ntiles * TILE_POS + PT - 1) / PT;
@@ -255,53 +313,7 @@ static int dist_scatter_local_mode(sibgpu_ctx *ctx, uint32_t k, uint64_t *counts
 	std::vector<uint64_t> base(PT), cur((size_t)PT * CURSOR_STRIDE, 0);
 	for(uint32_t p = 0; p < PT; p++) cur[(size_t)p * CURSOR_STRIDE] = base[p] = (uint64_t)p * cap;
 	SIB_CUDA(cudaMemcpyAsync(ctx->d_cursor.p, cur.data(), sizeof(uint64_t) * cur.size(), cudaMemcpyHostToDevice, st));
-	if(ntiles)
-	{
-		size_t smem = sizeof(ScatterSmem<MODE>);
-		SIB_CUDA(cudaFuncSetAttribute(k_scatter<MODE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-		// src: the own byte range is still on the host -- stream it in pieces of CHUNK_TILES tiles on the copy stream and
-		// pack + scatter every piece as it lands (same pipeline as sibgpu_enumerate, enumerate.cu)
-		const uint32_t nchunks = src ? (ntiles + CHUNK_TILES - 1) / CHUNK_TILES : 1;
-		auto piece_byte = [&](uint32_t c) -> uint64_t {               // first byte of piece c (multiples of 16)
-			if(c == 0) return ctx->dist_byte_lo;
-			if(c >= nchunks) return ctx->dist_byte_hi;
-			return (uint64_t)(ctx->dist_tile_lo + c * CHUNK_TILES) * TILE_POS;
-		};
-		if(src)
-		{
-			SIB_TRY(ctx->ensure_copy_stream(nchunks));
-			SIB_CUDA(cudaEventRecord(ctx->ev_fork_copy, st));
-			SIB_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_fork_copy, 0));
-			for(uint32_t c = 0; c < nchunks; c++)
-			{
-				SIB_TRY(copy_text_range(ctx, *src, piece_byte(c), piece_byte(c + 1), ctx->copy_stream));
-				SIB_CUDA(cudaEventRecord(ctx->ev_chunk[c], ctx->copy_stream));
-			}
-		}
-		uint32_t tiles_done = ctx->dist_tile_lo;                      // absolute tile index
-		for(uint32_t c = 0; c < nchunks; c++)
-		{
-			uint32_t tile_end = ctx->dist_tile_hi;
-			if(src)
-			{
-				const uint64_t w0 = piece_byte(c) / 16, w1 = (piece_byte(c + 1) + 15) / 16;
-				SIB_CUDA(cudaStreamWaitEvent(st, ctx->ev_chunk[c], 0));
-				if(w1 > w0) SIB_TRY(launch_pack(ctx, w0, w1));
-				if(c + 1 < nchunks) tile_end = (uint32_t)((w1 - 261) / TILE_THREADS);   // staged words of these tiles are packed
-			}
-			if(tile_end > tiles_done)
-			{
-				const uint32_t nt = tile_end - tiles_done;
-				const uint32_t g = nt < (uint32_t)ctx->sm_count * 4 ? nt : (uint32_t)ctx->sm_count * 4;
-				TextDesc tc = t;
-				tc.tile0 = tiles_done;
-				ProfScope ps(ctx, "k_scatter", (uint64_t)nt * TILE_POS / 4 + (uint64_t)nt * TILE_POS * sizeof(Rec));
-				k_scatter<MODE, false><<<g, TILE_THREADS, smem, st>>>(tc, nullptr, k, nt, PT, ctx->d_cursor.as<unsigned long long>(),
-					ctx->d_records.as<Rec>(), cap, reinterpret_cast<uint32_t*>(ds + 10));
-				tiles_done = tile_end;
-			}
-		}
-	}
+	SIB_TRY((dist_scatter_core<MODE, false>(ctx, k, PT, cap, ctx->d_cursor.as<unsigned long long>(), ctx->d_records.as<Rec>(), src)));
 	SIB_CUDA(cudaMemcpyAsync(cur.data(), ctx->d_cursor.p, sizeof(uint64_t) * cur.size(), cudaMemcpyDeviceToHost, st));
 	SIB_CUDA(cudaMemcpyAsync(hs + 8, ds + 8, sizeof(uint64_t) * 3, cudaMemcpyDeviceToHost, st));
 	SIB_CUDA(cudaStreamSynchronize(st));
@@ -489,6 +501,291 @@ int dist_finish(sibgpu_ctx *ctx, const void *allkeys_dev, uint64_t nkeys_total)
 	int rc = ctx->last_k <= 28 ? dist_finish_mode<0>(ctx, ctx->last_k, allkeys_dev, nkeys_total)
 		: dist_finish_mode<1>(ctx, ctx->last_k, allkeys_dev, nkeys_total);
 	if(rc != SIBGPU_OK) return rc;
+	SIB_CUDA(cudaGetLastError());
+	ctx->have_result = true;
+	ctx->dist_result = true;
+	if(ctx->profiling) SIB_TRY(ctx->prof_collect());
+	return SIBGPU_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Fused path (k <= 28): no collective and no host round trip inside a step.  Every rank owns ONE exported buffer
+//     [DistHeader | fill cursors | vertex keys of the owned partitions | PT fixed-capacity segments]
+// mapped by all peers (CUDA IPC, once).  A step e:
+//   scatter   own text range -> own segments (mixed 8-byte records), then header.epoch_scatter = e
+//   k_split   for every owned partition and every source rank: wait for the source's epoch_scatter == e (device-side
+//             spin on the mapped header), read its fill cursor and bulk-copy (TMA) its segment tiles straight out of
+//             the peer's memory over NVLink -> local ~1 Ki-record buckets          [the all-to-all, fused]
+//   k_group   buckets -> vertex keys of the owned partitions in the own key region, then header.epoch_keys = e
+//   k_pull    wait for every rank's epoch_keys == e, concatenate all key regions    [the all-gather, fused]
+//   ids + instance tables of the own text range (ids_and_tables)
+// Reuse of a buffer for step e+1 is safe without any barrier: a rank starts e+1 after it has pulled every peer's keys
+// of step e, which a peer publishes only after its k_split of step e has consumed all segments; and a peer's pull of
+// step e precedes its scatter flag of step e+1, which this rank's k_split(e+1) awaits before k_group(e+1) rewrites keys.
+// Failures (segment / bucket / key-list overflow, illegal character) travel in the headers, so all ranks take the
+// same decision: status 1 = use the phased path, 2 = regrow the key regions (collectively) and run again.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr size_t XOFF_CURSOR = sizeof(DistHeader);
+constexpr size_t XOFF_KEYS = XOFF_CURSOR + sizeof(uint64_t) * MAX_PARTS * CURSOR_STRIDE;
+static_assert(sizeof(DistHeader) == 256, "header layout");
+
+__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v)
+{
+	asm volatile("st.release.sys.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
+}
+
+__global__ void k_init_cursors(unsigned long long *cursor, uint32_t PT, unsigned long long cap)
+{
+	const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+	if(p < PT) cursor[(size_t)p * CURSOR_STRIDE] = (unsigned long long)p * cap;
+}
+
+// scalars[8] bit 0 = illegal character, scalars[10] = a segment overflowed
+__global__ void k_publish_scatter(DistHeader *h, const uint64_t *scalars, unsigned long long epoch)
+{
+	h->scatter_flags = ((scalars[8] & 1u) ? 2u : 0u) | ((scalars[10] & 0xFFFFFFFFull) ? 1u : 0u);
+	__threadfence_system();
+	st_release_sys(&h->epoch_scatter, epoch);
+}
+
+__global__ void k_publish_keys(DistHeader *h, const uint32_t *nkeys, const uint32_t *grp_flags, uint32_t key_cap, unsigned long long epoch)
+{
+	h->nkeys = *nkeys;
+	h->key_flags = *grp_flags | (*nkeys > key_cap ? 16u : 0u);
+	__threadfence_system();
+	st_release_sys(&h->epoch_keys, epoch);
+}
+
+struct PullSrc { const DistHeader *header[SPLIT_MAX_SRC]; const unsigned long long *keys[SPLIT_MAX_SRC]; };
+// out[0] = total keys, out[1] = OR of all ranks' failure flags (bit 1 of the scatter flags -> 64: illegal character),
+// out[2] = largest per-rank key count
+__global__ void __launch_bounds__(256) k_pull_keys(const PullSrc src, uint32_t W, unsigned long long epoch, uint32_t key_cap,
+	uint64_t *__restrict__ allkeys, uint64_t allcap, uint64_t *__restrict__ out)
+{
+	__shared__ unsigned long long s_off, s_n, s_total, s_flags, s_max;
+	const uint32_t me = blockIdx.y;
+	if(threadIdx.x == 0)
+	{
+		unsigned long long off = 0, total = 0, flags = 0, mx = 0, mine = 0;
+		for(uint32_t r = 0; r < W; r++)
+		{
+			if(!wait_epoch(&src.header[r]->epoch_keys, epoch)) { flags |= GRP_TIMEOUT; break; }
+			const unsigned long long n = ld_relaxed_sys(&src.header[r]->nkeys);
+			flags |= ld_relaxed_sys(&src.header[r]->key_flags);
+			const unsigned long long sf = ld_relaxed_sys(&src.header[r]->scatter_flags);
+			flags |= (sf & 1u ? GRP_PEER_FAILED : 0u) | (sf & 2u ? 64u : 0u);
+			if(r < me) off += n;
+			if(r == me) mine = n;
+			total += n;
+			if(n > mx) mx = n;
+		}
+		if(total > allcap) flags |= 32u;
+		s_off = off; s_n = mine; s_total = total; s_flags = flags; s_max = mx;
+	}
+	__syncthreads();
+	if(me == 0 && blockIdx.x == 0 && threadIdx.x == 0) { out[0] = s_total; out[1] = s_flags; out[2] = s_max; }
+	if(s_flags) return;
+	const unsigned long long *k = src.keys[me];
+	for(uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < s_n; i += (uint64_t)gridDim.x * blockDim.x)
+	{
+		allkeys[s_off + i] = ld_relaxed_sys(k + i);
+	}
+}
+
+int dist2_plan(sibgpu_ctx *ctx, uint32_t k, int *need_alloc)
+{
+	*need_alloc = -1;
+	const uint32_t W = ctx->dist_world;
+	if(k > 28 || W > (uint32_t)SPLIT_MAX_SRC || !ctx->group_smem) return SIBGPU_OK;
+	uint64_t nrec = 0;
+	for(uint32_t c = 0; c < ctx->nchr; c++)
+	{
+		if(ctx->h_chr_len[c] >= k) nrec += ctx->h_chr_len[c] - k + 1;
+	}
+	const uint64_t part_rec = ctx->part_explicit ? ctx->part_target : (uint64_t)512 << 10;
+	uint64_t PL = ((nrec + W - 1) / W + part_rec - 1) / part_rec;
+	if(PL < 1) PL = 1;
+	if(PL > MAX_PARTS / W) PL = MAX_PARTS / W;
+	const uint32_t PT = (uint32_t)PL * W;
+	const uint64_t mean1 = (nrec + PT - 1) / PT;
+	uint32_t sub_bits = 0;
+	while(((mean1 + ((uint64_t)1 << sub_bits) - 1) >> sub_bits) > GROUP_MEAN) sub_bits++;
+	if(sub_bits > SUB_BITS_MAX) return SIBGPU_OK;
+	const uint64_t ntiles = (ctx->M + TILE_POS - 1) / TILE_POS;
+	const uint64_t tiles_max = ntiles / W + 1;             // no rank scans more tiles than this
+	const uint64_t mean_seg = (tiles_max * TILE_POS + PT - 1) / PT;
+	const uint64_t seg_cap = (mean_seg + mean_seg / 8 + ctx->part_slack + 31) / 32 * 32;
+	const uint64_t kc = std::max<uint64_t>(ctx->x_kc, std::max<uint64_t>(ctx->ckeys_init, 16));
+	const uint64_t off_seg = (XOFF_KEYS + kc * 8 + 255) / 256 * 256;
+	const uint64_t bytes = off_seg + (uint64_t)PT * seg_cap * 8 + 256;
+	ctx->x_PL = (uint32_t)PL;
+	ctx->x_sub_bits = sub_bits;
+	ctx->x_seg_cap = seg_cap;
+	ctx->x_nrec = nrec;
+	ctx->x_k = k;
+	ctx->x_bytes = bytes;
+	// the layout of a live buffer must not move (the peers computed their addresses from it): new key capacity or
+	// segment offset means a new buffer
+	*need_alloc = (ctx->d_xbuf.cap < bytes || ctx->x_off_seg != off_seg || ctx->x_kc_live != kc || ctx->peer_x.size() != W) ? 1 : 0;
+	ctx->x_kc = kc;
+	ctx->x_off_seg_plan = off_seg;
+	return SIBGPU_OK;
+}
+
+int dist2_release_peers(sibgpu_ctx *ctx)
+{
+	SIB_CUDA(cudaSetDevice(ctx->device));
+	SIB_CUDA(cudaStreamSynchronize(ctx->stream));
+	for(void *&pp : ctx->peer_x)
+	{
+		if(pp) cudaIpcCloseMemHandle(pp);
+		pp = nullptr;
+	}
+	ctx->peer_x.clear();
+	return SIBGPU_OK;
+}
+
+int dist2_alloc(sibgpu_ctx *ctx, void *handle64)
+{
+	SIB_CUDA(cudaSetDevice(ctx->device));
+	if(!ctx->peer_x.empty())
+	{
+		set_error("state: sibgpu_fused_release_peers must precede sibgpu_fused_alloc");
+		return SIBGPU_ERR_STATE;
+	}
+	ctx->d_xbuf.release();                                 // every peer has closed its mapping (collective protocol)
+	SIB_TRY(ctx->d_xbuf.ensure(ctx->x_bytes));
+	SIB_CUDA(cudaMemsetAsync(ctx->d_xbuf.p, 0, XOFF_KEYS, ctx->stream));
+	SIB_CUDA(cudaStreamSynchronize(ctx->stream));
+	ctx->x_off_seg = ctx->x_off_seg_plan;
+	ctx->x_kc_live = ctx->x_kc;
+	cudaIpcMemHandle_t h;
+	SIB_CUDA(cudaIpcGetMemHandle(&h, ctx->d_xbuf.p));
+	memcpy(handle64, &h, 64);
+	return SIBGPU_OK;
+}
+
+int dist2_import(sibgpu_ctx *ctx, const void *handles)
+{
+	SIB_CUDA(cudaSetDevice(ctx->device));
+	const uint32_t W = ctx->dist_world;
+	ctx->peer_x.assign(W, nullptr);
+	for(uint32_t s = 0; s < W; s++)
+	{
+		if(s == ctx->dist_rank) continue;
+		cudaIpcMemHandle_t ih;
+		memcpy(&ih, static_cast<const unsigned char*>(handles) + 64 * (size_t)s, 64);
+		SIB_CUDA(cudaIpcOpenMemHandle(&ctx->peer_x[s], ih, cudaIpcMemLazyEnablePeerAccess));
+	}
+	return SIBGPU_OK;
+}
+
+int dist2_run(sibgpu_ctx *ctx, const HostSrc *src, int *status)
+{
+	cudaStream_t st = ctx->stream;
+	const uint32_t W = ctx->dist_world, rank = ctx->dist_rank, k = ctx->x_k, PL = ctx->x_PL, PT = PL * W;
+	*status = 0;
+	if(ctx->peer_x.size() != W || !ctx->d_xbuf.p)
+	{
+		set_error("state: sibgpu_fused_alloc / sibgpu_fused_import must precede sibgpu_fused_run");
+		return SIBGPU_ERR_STATE;
+	}
+	const unsigned long long epoch = ++ctx->dist_epoch;
+	SIB_TRY(dist_prepare(ctx, k, src == nullptr));
+	ctx->dist_P_local = PL;
+	ctx->dist_P_total = PT;
+	uint64_t *hs = static_cast<uint64_t*>(ctx->h_scalars);
+	uint64_t *ds = ctx->d_scalars.as<uint64_t>();
+	unsigned char *xb = static_cast<unsigned char*>(ctx->d_xbuf.p);
+	DistHeader *hdr = reinterpret_cast<DistHeader*>(xb);
+	unsigned long long *cursor = reinterpret_cast<unsigned long long*>(xb + XOFF_CURSOR);
+	uint64_t *keys = reinterpret_cast<uint64_t*>(xb + XOFF_KEYS);
+	uint64_t *segs = reinterpret_cast<uint64_t*>(xb + ctx->x_off_seg);
+	const uint32_t key_cap = (uint32_t)std::min<uint64_t>(ctx->x_kc_live, 0xFFFFFFF0u);
+	// ---- scatter + publish
+	k_init_cursors<<<(PT + 255) / 256, 256, 0, st>>>(cursor, PT, ctx->x_seg_cap);
+	ctx->total_launches++;
+	SIB_TRY((dist_scatter_core<0, true>(ctx, k, PT, ctx->x_seg_cap, cursor, segs, src)));
+	k_publish_scatter<<<1, 1, 0, st>>>(hdr, ds, epoch);
+	// ---- fused exchange + split, group, publish
+	const uint32_t sub_bits = ctx->x_sub_bits, nbuckets = PL << sub_bits;
+	SIB_TRY(ctx->d_records2.ensure(sizeof(uint64_t) * (size_t)nbuckets * GROUP_CAP + 64));
+	SIB_TRY(ctx->d_cnt2.ensure(sizeof(uint32_t) * (size_t)nbuckets));
+	SIB_CUDA(cudaMemsetAsync(ctx->d_cnt2.p, 0, sizeof(uint32_t) * (size_t)nbuckets, st));
+	SplitSrc ssrc = {};
+	PullSrc psrc = {};
+	for(uint32_t s = 0; s < W; s++)
+	{
+		const unsigned char *b = s == rank ? xb : static_cast<const unsigned char*>(ctx->peer_x[s]);
+		ssrc.seg[s] = reinterpret_cast<const uint64_t*>(b + ctx->x_off_seg);
+		ssrc.cursor[s] = reinterpret_cast<const unsigned long long*>(b + XOFF_CURSOR);
+		ssrc.header[s] = s == rank ? nullptr : reinterpret_cast<const DistHeader*>(b);
+		psrc.header[s] = reinterpret_cast<const DistHeader*>(b);
+		psrc.keys[s] = reinterpret_cast<const unsigned long long*>(b + XOFF_KEYS);
+	}
+	ssrc.seg_cap = ctx->x_seg_cap;
+	ssrc.epoch = epoch;
+	ssrc.W = W;
+	ssrc.p0 = rank * PL;
+	const uint32_t tiles_per_seg = (uint32_t)((ctx->x_seg_cap + SPLIT_TILE - 1) / SPLIT_TILE);
+	uint32_t *d_flags = reinterpret_cast<uint32_t*>(ds + 11);
+	SIB_TRY(launch_split(ctx, ssrc, PL, tiles_per_seg, sub_bits, ctx->x_nrec / W, d_flags));
+	SIB_TRY(launch_group(ctx, nbuckets, ctx->x_nrec / W, d_flags, keys, key_cap, reinterpret_cast<uint32_t*>(ds + 2)));
+	k_publish_keys<<<1, 1, 0, st>>>(hdr, reinterpret_cast<uint32_t*>(ds + 2), d_flags, key_cap, epoch);
+	// ---- all ranks' keys
+	SIB_TRY(ctx->d_ckeys.ensure(sizeof(uint64_t) * std::max<uint64_t>(ctx->ckeys_init, 16)));
+	for(int attempt = 0; ; attempt++)
+	{
+		const uint64_t allcap = ctx->d_ckeys.cap / sizeof(uint64_t);
+		{
+			ProfScope ps(ctx, "k_pull_keys", 0);
+			k_pull_keys<<<dim3(8, W), 256, 0, st>>>(psrc, W, epoch, key_cap, ctx->d_ckeys.as<uint64_t>(), allcap, ds + 12);
+		}
+		ctx->total_launches += 2;
+		SIB_CUDA(cudaMemcpyAsync(hs + 8, ds + 8, sizeof(uint64_t) * 8, cudaMemcpyDeviceToHost, st));
+		SIB_CUDA(cudaStreamSynchronize(st));
+		const uint64_t flags = hs[13];
+		if(flags & GRP_TIMEOUT)
+		{
+			set_error("internal: a peer rank did not publish its step within 4 s");
+			return SIBGPU_ERR_INTERNAL;
+		}
+		if((hs[8] & 1u) || (flags & 64u)) return input_error();
+		if(flags & 16u)                                        // a rank's key region is too small: regrow collectively
+		{
+			ctx->x_kc = hs[14] + hs[14] / 4 + 1024;
+			*status = 2;
+			return SIBGPU_OK;
+		}
+		if(flags & (GRP_BUCKET_OVERFLOW | GRP_PEER_FAILED))
+		{
+			if(hs[10] & 0xFFFFFFFFull) ctx->hist_fallbacks++;
+			if(hs[11] & GRP_BUCKET_OVERFLOW) ctx->smem_fallbacks++;
+			*status = 1;
+			return SIBGPU_OK;
+		}
+		if(flags & 32u)                                        // the local list of all keys is too small: regrow, pull again
+		{
+			if(attempt) { set_error("internal: key list regrow failed"); return SIBGPU_ERR_INTERNAL; }
+			SIB_TRY(ctx->d_ckeys.ensure(sizeof(uint64_t) * hs[12]));
+			continue;
+		}
+		break;
+	}
+	const uint64_t Vc = hs[12];
+	const uint32_t ntiles = ctx->dist_tile_hi - ctx->dist_tile_lo;
+	ctx->n_inst = 0;
+	ctx->n_vertices = 0;
+	if(Vc)
+	{
+		if(2 * Vc > 0xFFFFFFF0ull)
+		{
+			set_error("invalid: more than 2^32 vertices");
+			return SIBGPU_ERR_INVALID;
+		}
+		bool collision = false;
+		SIB_TRY(ids_and_tables<0>(ctx, ctx->dist_text, k, ctx->d_ckeys.as<uint64_t>(), Vc, ntiles, nullptr, false, &collision));
+	}
 	SIB_CUDA(cudaGetLastError());
 	ctx->have_result = true;
 	ctx->dist_result = true;

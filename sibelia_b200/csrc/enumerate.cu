@@ -1155,6 +1155,43 @@ static int input_error()
 	return SIBGPU_ERR_INPUT;
 }
 
+// k_split over P1 owned partitions read from ssrc (single GPU: the own record buffer; sharded: all ranks' buffers)
+static int launch_split(sibgpu_ctx *ctx, const SplitSrc &ssrc, uint32_t P1, uint32_t tiles_per_seg, uint32_t sub_bits,
+	uint64_t nrec, uint32_t *d_flags)
+{
+	bool &attr_done = ctx->split_attr_done;
+	if(!attr_done)
+	{
+		SIB_CUDA(cudaFuncSetAttribute(k_split<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SplitSmem<1>)));
+		SIB_CUDA(cudaFuncSetAttribute(k_split<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SplitSmem<2>)));
+		SIB_CUDA(cudaFuncSetAttribute(k_group, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(GroupSmem)));
+		attr_done = true;
+	}
+	const uint64_t split_tiles = (uint64_t)P1 * ssrc.W * tiles_per_seg;
+	const uint64_t sms = (uint64_t)ctx->sm_count;
+	ProfScope ps(ctx, "k_split", nrec * 16);
+	if(ctx->split_stages == 1)
+	{
+		k_split<1><<<(uint32_t)std::min<uint64_t>(split_tiles, sms * 3), SPLIT_THREADS, sizeof(SplitSmem<1>), ctx->stream>>>(
+			ssrc, P1, tiles_per_seg, sub_bits, ctx->d_records2.as<uint64_t>(), ctx->d_cnt2.as<uint32_t>(), GROUP_CAP, d_flags);
+	}
+	else
+	{
+		k_split<2><<<(uint32_t)std::min<uint64_t>(split_tiles, sms * 2), SPLIT_THREADS, sizeof(SplitSmem<2>), ctx->stream>>>(
+			ssrc, P1, tiles_per_seg, sub_bits, ctx->d_records2.as<uint64_t>(), ctx->d_cnt2.as<uint32_t>(), GROUP_CAP, d_flags);
+	}
+	return SIBGPU_OK;
+}
+
+static int launch_group(sibgpu_ctx *ctx, uint32_t nbuckets, uint64_t nrec, uint32_t *d_flags, uint64_t *ckeys, uint32_t ckeys_cap,
+	uint32_t *d_nkeys)
+{
+	ProfScope ps(ctx, "k_group", nrec * 8);
+	k_group<<<std::min<uint32_t>(nbuckets, (uint32_t)ctx->sm_count * 4), GROUP_THREADS, sizeof(GroupSmem), ctx->stream>>>(
+		ctx->d_records2.as<uint64_t>(), ctx->d_cnt2.as<uint32_t>(), nbuckets, GROUP_CAP, d_flags, ckeys, ckeys_cap, d_nkeys);
+	return SIBGPU_OK;
+}
+
 // src != nullptr: the text is still on the host (sibgpu_enumerate); it is streamed in CHUNK_TILES-tile pieces on the
 // copy stream while the pack and scatter kernels of the previous pieces run (exact modes; the layout, the '$'
 // separators and the chromosome tables are already on the device).  src == nullptr: text resident and packed.
@@ -1249,7 +1286,7 @@ static int enumerate_mode(sibgpu_ctx *ctx, uint32_t k, uint64_t nrec, const Host
 					const uint64_t w1 = c + 1 == nchunks ? t.nwords : w0 + (uint64_t)CHUNK_TILES * TILE_THREADS;
 					SIB_CUDA(cudaStreamWaitEvent(st, ctx->ev_chunk[c], 0));
 					SIB_TRY(launch_pack(ctx, w0, w1));
-					if(c + 1 < nchunks) tile_hi = (uint32_t)((w1 - 261) / TILE_THREADS);
+					if(c + 1 < nchunks) tile_hi = (uint32_t)((w1 - (TILE_THREADS + 5)) / TILE_THREADS);
 				}
 				if(tile_hi > tiles_done)
 				{
@@ -1281,34 +1318,15 @@ static int enumerate_mode(sibgpu_ctx *ctx, uint32_t k, uint64_t nrec, const Host
 					SIB_TRY(ctx->d_ckeys.ensure(sizeof(uint64_t) * (ctx->ckeys_init ? ctx->ckeys_init : 1)));
 					ckeys_cap = (uint32_t)std::min<size_t>(ctx->d_ckeys.cap / sizeof(uint64_t), 0xFFFFFFF0u);
 					SIB_CUDA(cudaMemsetAsync(ctx->d_cnt2.p, 0, sizeof(uint32_t) * (size_t)nbuckets, st));
-					SIB_CUDA(cudaFuncSetAttribute(k_split<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SplitSmem<1>)));
-					SIB_CUDA(cudaFuncSetAttribute(k_split<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SplitSmem<2>)));
-					SIB_CUDA(cudaFuncSetAttribute(k_group, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(GroupSmem)));
-					const uint32_t tiles_per_part = (uint32_t)((cap + SPLIT_TILE - 1) / SPLIT_TILE);
-					const uint64_t split_tiles = (uint64_t)P * tiles_per_part;
-					{
-						ProfScope ps(ctx, "k_split", nrec * 16);
-						if(ctx->split_stages == 1)
-						{
-							k_split<1><<<(uint32_t)std::min<uint64_t>(split_tiles, (uint64_t)sms * 3), SPLIT_THREADS, sizeof(SplitSmem<1>), st>>>(
-								ctx->d_records.as<uint64_t>(), ctx->d_partoff.as<uint64_t>(), ctx->d_cursor.as<unsigned long long>(), P,
-								tiles_per_part, sub_bits, ctx->d_records2.as<uint64_t>(), ctx->d_cnt2.as<uint32_t>(), GROUP_CAP,
-								reinterpret_cast<uint32_t*>(ds + 11));
-						}
-						else
-						{
-							k_split<2><<<(uint32_t)std::min<uint64_t>(split_tiles, (uint64_t)sms * 2), SPLIT_THREADS, sizeof(SplitSmem<2>), st>>>(
-								ctx->d_records.as<uint64_t>(), ctx->d_partoff.as<uint64_t>(), ctx->d_cursor.as<unsigned long long>(), P,
-								tiles_per_part, sub_bits, ctx->d_records2.as<uint64_t>(), ctx->d_cnt2.as<uint32_t>(), GROUP_CAP,
-								reinterpret_cast<uint32_t*>(ds + 11));
-						}
-					}
-					{
-						ProfScope ps(ctx, "k_group", nrec * 8);
-						k_group<<<std::min<uint32_t>(nbuckets, (uint32_t)sms * 4), GROUP_THREADS, sizeof(GroupSmem), st>>>(
-							ctx->d_records2.as<uint64_t>(), ctx->d_cnt2.as<uint32_t>(), nbuckets, GROUP_CAP,
-							reinterpret_cast<uint32_t*>(ds + 11), ctx->d_ckeys.as<uint64_t>(), ckeys_cap, reinterpret_cast<uint32_t*>(ds + 2));
-					}
+					const uint32_t tiles_per_seg = (uint32_t)((cap + SPLIT_TILE - 1) / SPLIT_TILE);
+					SplitSrc ssrc = {};
+					ssrc.seg[0] = ctx->d_records.as<uint64_t>();
+					ssrc.cursor[0] = ctx->d_cursor.as<unsigned long long>();
+					ssrc.seg_cap = cap;
+					ssrc.W = 1;
+					SIB_TRY(launch_split(ctx, ssrc, P, tiles_per_seg, sub_bits, nrec, reinterpret_cast<uint32_t*>(ds + 11)));
+					SIB_TRY(launch_group(ctx, nbuckets, nrec, reinterpret_cast<uint32_t*>(ds + 11), ctx->d_ckeys.as<uint64_t>(), ckeys_cap,
+						reinterpret_cast<uint32_t*>(ds + 2)));
 					smem_launched = true;
 				}
 			}
@@ -1360,10 +1378,8 @@ static int enumerate_mode(sibgpu_ctx *ctx, uint32_t k, uint64_t nrec, const Host
 								// the key list was too small (k_group kept counting): regrow, group again -- the buckets are intact
 								SIB_TRY(ctx->d_ckeys.ensure(sizeof(uint64_t) * Vc));
 								SIB_CUDA(cudaMemsetAsync(ds + 2, 0, sizeof(uint64_t), st));
-								ProfScope ps(ctx, "k_group", nrec * 8);
-								k_group<<<std::min<uint32_t>(nbuckets, (uint32_t)sms * 4), GROUP_THREADS, sizeof(GroupSmem), st>>>(
-									ctx->d_records2.as<uint64_t>(), ctx->d_cnt2.as<uint32_t>(), nbuckets, GROUP_CAP,
-									reinterpret_cast<uint32_t*>(ds + 11), ctx->d_ckeys.as<uint64_t>(), (uint32_t)Vc, reinterpret_cast<uint32_t*>(ds + 2));
+								SIB_TRY(launch_group(ctx, nbuckets, nrec, reinterpret_cast<uint32_t*>(ds + 11), ctx->d_ckeys.as<uint64_t>(),
+									(uint32_t)Vc, reinterpret_cast<uint32_t*>(ds + 2)));
 								SIB_CUDA(cudaStreamSynchronize(st));
 							}
 						}

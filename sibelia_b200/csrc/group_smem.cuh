@@ -93,15 +93,69 @@ template<int STAGES> struct SplitSmem {
 	unsigned long long bar[STAGES];
 };
 
-// Level 2: partition p's records [partbase[p], cursor[p]) -> B2 buckets of fixed capacity cap2 at out[(p * B2 + b) * cap2].
-// A tile is 4096 consecutive records of one partition: TMA bulk copy into shared memory (STAGES tiles in flight: the
+// Where the level-1 partitions lie.  Single GPU: one source, the context's own record buffer.  Sharded: every rank
+// scatters the records of its text range into its own exported buffer (one fixed-capacity segment per GLOBAL partition)
+// and the owner of a partition reads that partition's segment out of every rank's buffer -- the exchange is fused into
+// this kernel: the TMA bulk copies read the peers' memory over NVLink (CUDA IPC mappings).
+constexpr int SPLIT_MAX_SRC = 16;
+constexpr uint32_t GRP_BUCKET_OVERFLOW = 1u, GRP_PEER_FAILED = 4u, GRP_TIMEOUT = 8u;
+struct DistHeader {                                    // first 256 bytes of a rank's exported buffer
+	unsigned long long epoch_scatter;                  // == e once the segments and fill cursors of step e are final
+	unsigned long long scatter_flags;                  // != 0: a segment overflowed / illegal input character (step failed)
+	unsigned long long epoch_keys;                     // == e once the vertex keys of step e are final
+	unsigned long long key_flags;                      // != 0: grouping failed on this rank (bucket overflow, peer failure)
+	unsigned long long nkeys;
+	unsigned long long pad[27];
+};
+struct SplitSrc {
+	const uint64_t *seg[SPLIT_MAX_SRC];                // records of source s; partition q lies at [q * seg_cap, ...)
+	const unsigned long long *cursor[SPLIT_MAX_SRC];   // fill cursors of source s (absolute record index, one per CURSOR_STRIDE)
+	const DistHeader *header[SPLIT_MAX_SRC];           // nullptr: no waiting (own buffer on a single GPU)
+	unsigned long long seg_cap;
+	unsigned long long epoch;
+	uint32_t W, p0;                                    // number of sources, first owned partition
+};
+
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p)
+{
+	unsigned long long v;
+	asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+	return v;
+}
+__device__ __forceinline__ unsigned long long ld_relaxed_sys(const unsigned long long *p)
+{
+	unsigned long long v;
+	asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+	return v;
+}
+__device__ __forceinline__ unsigned long long global_ns()
+{
+	unsigned long long t;
+	asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+	return t;
+}
+// spins until *flag == epoch (a peer publishes its step); false after ~4 s (the peer died: never hang the GPU)
+__device__ __forceinline__ bool wait_epoch(const unsigned long long *flag, unsigned long long epoch)
+{
+	if(ld_acquire_sys(flag) == epoch) return true;
+	const unsigned long long t0 = global_ns();
+	for(;;)
+	{
+		if(ld_acquire_sys(flag) == epoch) return true;
+		if(global_ns() - t0 > 4000000000ull) return false;
+		__nanosleep(200);
+	}
+}
+
+// Level 2: the records of owned partition p (from every source) -> B2 buckets of fixed capacity cap2 at
+// out[(p * B2 + b) * cap2].
+// A tile is 4096 consecutive records of one segment: TMA bulk copy into shared memory (STAGES tiles in flight: the
 // copies of the following tiles run while this one is sorted and written out), counting sort by bucket (rank =
 // returning shared atomic), coalesced copy-out of the runs; cnt2[p * B2 + b] is the bucket's fill count.  Consecutive
 // tile indices belong to different partitions, so concurrently running CTAs bump different bucket counters.
-// Partition bases must be 16-byte aligned.
+// Segments must be 16-byte aligned (seg_cap even).
 template<int STAGES>
-__global__ void __launch_bounds__(SPLIT_THREADS, STAGES == 1 ? 3 : 2) k_split(const uint64_t *__restrict__ recs,
-	const uint64_t *__restrict__ partbase, const unsigned long long *__restrict__ cursor, uint32_t P1, uint32_t tiles_per_part,
+__global__ void __launch_bounds__(SPLIT_THREADS, STAGES == 1 ? 3 : 2) k_split(const SplitSrc src, uint32_t P1, uint32_t tiles_per_seg,
 	uint32_t sub_bits, uint64_t *__restrict__ out, uint32_t *__restrict__ cnt2, uint32_t cap2, uint32_t *__restrict__ overflow)
 {
 	extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -109,7 +163,7 @@ __global__ void __launch_bounds__(SPLIT_THREADS, STAGES == 1 ? 3 : 2) k_split(co
 	typedef cub::BlockScan<uint32_t, SPLIT_THREADS> Scan;
 	__shared__ typename Scan::TempStorage scan_tmp;
 	const uint32_t B2 = 1u << sub_bits, sub_mask = B2 - 1u;
-	const uint32_t ntiles = P1 * tiles_per_part;
+	const uint32_t ntiles = P1 * src.W * tiles_per_seg;
 	if(threadIdx.x == 0)
 	{
 		for(int st = 0; st < STAGES; st++) mbar_init(&s.bar[st], 1);
@@ -117,21 +171,35 @@ __global__ void __launch_bounds__(SPLIT_THREADS, STAGES == 1 ? 3 : 2) k_split(co
 	}
 	__syncthreads();
 	// elected thread: first non-empty tile at or after t (stride gridDim.x); starts its bulk copy into stage st and
-	// publishes (n, p) there; n = 0: no tile left
+	// publishes (n, p) there; n = 0: no tile left.  Tile t = (partition t % P1, source (t / P1) % W, chunk t / P1 / W).
+	uint32_t seen = 0;                                 // sources whose step flag this CTA has already observed
 	auto fetch = [&](uint32_t t, int st) -> uint32_t {
 		for(; t < ntiles; t += gridDim.x)
 		{
-			const uint32_t p = t % P1, chunk = t / P1;
-			const uint64_t base = partbase[p];
-			uint64_t np = cursor[(size_t)p * CURSOR_STRIDE] - base;
-			const uint64_t room = partbase[p + 1] - base;
-			if(np > room) np = room;                   // an overflowed level-1 partition: the caller discards this run anyway
+			const uint32_t p = t % P1, x = t / P1, sidx = x % src.W, chunk = x / src.W;
+			if(src.header[sidx] && !((seen >> sidx) & 1u))
+			{
+				if(!wait_epoch(&src.header[sidx]->epoch_scatter, src.epoch))
+				{
+					atomicOr(overflow, GRP_TIMEOUT);
+					break;
+				}
+				if(ld_relaxed_sys(&src.header[sidx]->scatter_flags))
+				{
+					atomicOr(overflow, GRP_PEER_FAILED);
+					break;
+				}
+				seen |= 1u << sidx;
+			}
+			const uint64_t base = (uint64_t)(src.p0 + p) * src.seg_cap;
+			uint64_t np = ld_relaxed_sys(src.cursor[sidx] + (size_t)(src.p0 + p) * CURSOR_STRIDE) - base;
+			if(np > src.seg_cap) np = src.seg_cap;     // an overflowed segment: the caller discards this run anyway
 			const uint64_t first = (uint64_t)chunk * SPLIT_TILE;
 			if(first >= np) continue;
 			const uint32_t n = np - first < SPLIT_TILE ? (uint32_t)(np - first) : SPLIT_TILE;
 			s.tile_n[st] = n;
 			s.tile_p[st] = p;
-			bulk_load(s.in[st], recs + base + first, (n * 8u + 15u) & ~15u, &s.bar[st]);
+			bulk_load(s.in[st], src.seg[sidx] + base + first, (n * 8u + 15u) & ~15u, &s.bar[st]);
 			return t;
 		}
 		s.tile_n[st] = 0;
@@ -202,7 +270,7 @@ __global__ void __launch_bounds__(SPLIT_THREADS, STAGES == 1 ? 3 : 2) k_split(co
 				s.gbase[b] = b * cap2 + g[j] - (excl + (j ? c[0] : 0u));   // 32-bit wrap-around arithmetic: + local index >= offset
 				if(g[j] + c[j] > cap2)
 				{
-					*overflow = 1u;
+					atomicOr(overflow, GRP_BUCKET_OVERFLOW);
 					atomicOr(&s.dropmask[b >> 5], 1u << (b & 31u));
 					s.anydrop = 1u;
 				}

@@ -40,6 +40,47 @@ class GpuShard:
             self.ctx.dist_upload(*self._pending)
             self._pending = None
 
+    # -- fused strategy (k <= 28): the whole step is one C call, no collective inside (include/sibgpu.h, sibgpu_fused_*)
+    fused = os.environ.get("SIBGPU_DIST_FUSED", "1") != "0"
+    resident = False                                 # the text range is already in HBM (ctx.dist_upload)
+
+    def fused_enumerate(self, chrs, rank, world, k, group=None):
+        """(count, pos, negtext) through the fused path, or None when it does not apply here (k > 28, no peer access) or
+        asked every rank to take the phased path (a segment or bucket overflowed somewhere)."""
+        for _ in range(3):
+            need = self.ctx.dist2_plan(chrs, rank, world, k, self.resident)
+            if need < 0:
+                return None
+            if need:
+                # (re)allocation of the exported buffers: collective, and only when the input shape outgrows them
+                dist.barrier(group)
+                self.ctx.dist2_release_peers()
+                dist.barrier(group)
+                mine = torch.from_numpy(self.ctx.dist2_alloc().view(np.int64).copy()).to(self.device)
+                m = _comm(mine, group)
+                allh = torch.empty(world * 8, dtype=torch.int64, device=m.device)
+                dist.all_gather_into_tensor(allh, m, group=group)
+                handles = np.ascontiguousarray(allh.cpu().numpy()).view(np.uint8).reshape(world, 64)
+                ok = 1
+                try:
+                    self.ctx.dist2_import(handles)
+                except Exception as e:                   # noqa: BLE001 -- reported once, the phased paths take over
+                    print("sibelia_b200.distributed: peer mapping unavailable (%s); using the phased exchange" % e, flush=True)
+                    ok = 0
+                flag = _comm(torch.tensor([ok], dtype=torch.int64, device=self.device), group)
+                dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+                if not int(flag.cpu()[0]):
+                    self.ctx.dist2_release_peers()
+                    type(self).fused = False
+                    return None
+            status, count, ninst = self.ctx.dist2_run(chrs, self.resident)
+            if status == 0:
+                pos, negtext = self.ctx.download()
+                return count, pos, negtext
+            if status == 1:
+                return None
+        raise RuntimeError("sibelia_b200.distributed: the vertex key regions kept overflowing")
+
     # -- peer strategy
     peer = os.environ.get("SIBGPU_DIST_PEER", "1") != "0"
 
@@ -120,6 +161,12 @@ def enumerate_sharded(shard, chrs, k, group=None):
                 torch.cuda.synchronize()
             marks.append((what, time.perf_counter()))
     lap("start")
+    if getattr(shard, "fused", False) and world <= 16:
+        out = shard.fused_enumerate(chrs, rank, world, k, group)
+        if out is not None:
+            lap("fused step")
+            shard.last_strategy = "fused (device-side step counters, TMA peer pulls in k_split, key pull kernel; no collective)"
+            return out
     shard.upload(chrs, rank, world)
     lap("upload")
     keys = None
@@ -151,8 +198,10 @@ def enumerate_sharded(shard, chrs, k, group=None):
                 keys = shard.group_peer(allm[:, :nparts].astype(np.uint64), allm[:, nparts].astype(np.uint64))
                 lap("group (peer reads)")
                 words = shard.words
+                shard.last_strategy = "peer (counts all-gather, peer reads in the insert kernel, key all-gather)"
     if keys is None:
         keys, words, dev = _staged_exchange(shard, k, rank, world, group, lap)
+        shard.last_strategy = "staged (histogram, one all-to-all of the records, key all-gather)"
     # --- vertex keys of all ranks (variable sizes: pad to the maximum)
     nk = _comm(torch.tensor([keys.numel()], dtype=torch.int64, device=dev), group)
     all_nk = torch.empty(world, dtype=torch.int64, device=nk.device)
@@ -218,4 +267,42 @@ def gather_tables(count, pos_part, negtext_part, group=None):
     if rank != 0:
         return count, None, None
     pos, neg = assemble_tables([o[0] for o in objs], [o[1] for o in objs])
+    return count, pos, neg
+
+
+def gather_tables_device(count, pos_part, negtext_part, group=None):
+    """gather_tables for large tables under NCCL: the parts travel as byte tensors over NVLink (point to point to rank 0)
+    instead of pickled objects; the negative table is assembled per chromosome (descending text order inside each)."""
+    from .binding import INST_DTYPE
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    if dist.get_backend(group) != "nccl":
+        return gather_tables(count, pos_part, negtext_part, group)
+    dev = torch.device("cuda", torch.cuda.current_device())
+    n = torch.tensor([len(pos_part)], dtype=torch.int64, device=dev)
+    alln = torch.empty(world, dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(alln, n, group=group)
+    alln = [int(x) for x in alln.cpu()]
+
+    def as_bytes(a):
+        return torch.from_numpy(np.ascontiguousarray(a).view(np.uint8).reshape(-1).copy()).to(dev)
+    if rank != 0:
+        for part in (pos_part, negtext_part):
+            if len(part):
+                dist.send(as_bytes(part), dst=0, group=group)
+        return count, None, None
+    pos_parts, neg_parts = [pos_part], [negtext_part]
+    for src in range(1, world):
+        for parts in (pos_parts, neg_parts):
+            if alln[src]:
+                buf = torch.empty(alln[src] * INST_DTYPE.itemsize, dtype=torch.uint8, device=dev)
+                dist.recv(buf, src=src, group=group)
+                parts.append(buf.cpu().numpy().view(INST_DTYPE))
+            else:
+                parts.append(np.zeros(0, dtype=INST_DTYPE))
+    pos = np.concatenate(pos_parts)
+    negtext = np.concatenate(neg_parts)
+    # text order is ascending (chr, text position): reverse every chromosome's run
+    bounds = np.flatnonzero(np.diff(negtext["chr"].astype(np.int64))) + 1
+    edges = np.concatenate([[0], bounds, [len(negtext)]])
+    neg = np.concatenate([negtext[a:b][::-1] for a, b in zip(edges[:-1], edges[1:])]) if len(negtext) else negtext
     return count, pos, neg
