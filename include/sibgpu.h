@@ -111,6 +111,10 @@ float sibgpu_last_device_ms(sibgpu_ctx *ctx);
  *   seq[i] / origpos[i] / len[i]   rawSeq_[i], originalPos_[i] and their common length.  On success the three
  *                                  arrays are overwritten with library-allocated buffers of the new lengths
  *                                  (release with sibgpu_free); the caller keeps ownership of the old ones.
+ *                                  EXCEPT when the stage finds no bulge at all (*bulges == 0, decided on the device
+ *                                  from the resident enumeration: no host index is built): then seq / origpos / len
+ *                                  are left exactly as passed -- compare seq[i] with the pointer handed in before
+ *                                  adopting or freeing it.
  *   progress(done, state, user)    optional; same protocol as BlockFinder::ProgressCallBack (blockfinder.h:39):
  *                                  state 0 = start, 1 = run (<= 50 ticks), 2 = end
  *   *bulges                        the return value (cumulative number of collapsed bulges)

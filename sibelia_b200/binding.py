@@ -2,6 +2,7 @@
 import ctypes as C
 import os
 import subprocess
+import weakref
 
 import numpy as np
 
@@ -94,15 +95,16 @@ def _chr_args(chrs):
 
 
 def _take(ptr, n):
+    """The library's table as a numpy array WITHOUT a copy: the array owns the (pinned, pooled) buffer and hands it back
+    with sibgpu_free when the last view dies."""
     L = load()
     if n:
         buf = (C.c_char * (n * INST_DTYPE.itemsize)).from_address(ptr.value)
-        out = np.frombuffer(buf, dtype=INST_DTYPE, count=n).copy()
-    else:
-        out = np.zeros(0, dtype=INST_DTYPE)
+        weakref.finalize(buf, L.sibgpu_free, C.c_void_p(ptr.value))
+        return np.frombuffer(buf, dtype=INST_DTYPE, count=n)
     if ptr.value:
         L.sibgpu_free(ptr)
-    return out
+    return np.zeros(0, dtype=INST_DTYPE)
 
 
 class Context:
@@ -308,6 +310,11 @@ class Context:
         new_chrs, new_op = [], []
         for i in range(n):
             m = lens[i]
+            if seq[i] == (bufs[i].ctypes.data if len(bufs[i]) else None) or (not seq[i] and not len(bufs[i])):
+                # the stage found no bulge at all: the library left the caller's arrays untouched (include/sibgpu.h)
+                new_chrs.append(bufs[i].tobytes())
+                new_op.append(ops[i].copy())
+                continue
             sbuf = (C.c_char * m).from_address(seq[i]) if m else b""
             new_chrs.append(bytes(sbuf))
             obuf = (C.c_char * (4 * m)).from_address(op[i]) if m else b""

@@ -4,6 +4,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
+#include <vector>
 
 #include "context.h"
 
@@ -190,7 +191,73 @@ void sibgpu_destroy(sibgpu_ctx *c)
 	delete c;
 }
 
-void sibgpu_free(void *p) { free(p); }
+// Result buffers (instance tables) come from a small pool of pinned host blocks: the device-to-host copy of a table
+// then runs at PCIe speed straight into the buffer the caller receives, and a caller that frees a table before asking
+// for the next one (the reference binds one index at a time) gets the same pages back -- a fresh 50 MB malloc costs more
+// in page faults than the whole enumeration.  sibgpu_free recognises pool blocks; everything else is free()d.
+namespace {
+struct PinnedBlock { void *p; size_t cap; bool used; };
+std::mutex g_pool_mutex;
+std::vector<PinnedBlock> g_pool;
+const size_t POOL_MAX_BLOCKS = 8;
+
+void *pool_alloc(size_t bytes)
+{
+	if(bytes < (1u << 16)) return malloc(bytes ? bytes : 1);           // small tables: plain memory
+	std::lock_guard<std::mutex> lock(g_pool_mutex);
+	size_t best = g_pool.size();
+	for(size_t i = 0; i < g_pool.size(); i++)
+	{
+		if(!g_pool[i].used && g_pool[i].cap >= bytes && g_pool[i].cap <= 4 * bytes + (1u << 20) &&
+			(best == g_pool.size() || g_pool[i].cap < g_pool[best].cap)) best = i;
+	}
+	if(best < g_pool.size())
+	{
+		g_pool[best].used = true;
+		return g_pool[best].p;
+	}
+	if(g_pool.size() >= POOL_MAX_BLOCKS)
+	{
+		// drop the smallest idle block to make room; if all are in use fall back to plain memory
+		size_t idle = g_pool.size();
+		for(size_t i = 0; i < g_pool.size(); i++)
+		{
+			if(!g_pool[i].used && (idle == g_pool.size() || g_pool[i].cap < g_pool[idle].cap)) idle = i;
+		}
+		if(idle == g_pool.size()) return malloc(bytes);
+		cudaFreeHost(g_pool[idle].p);
+		g_pool.erase(g_pool.begin() + idle);
+	}
+	void *p = nullptr;
+	const size_t cap = bytes + bytes / 4;
+	if(cudaHostAlloc(&p, cap, cudaHostAllocPortable) != cudaSuccess)
+	{
+		cudaGetLastError();
+		return malloc(bytes);
+	}
+	g_pool.push_back(PinnedBlock{p, cap, true});
+	return p;
+}
+
+bool pool_release(void *p)
+{
+	std::lock_guard<std::mutex> lock(g_pool_mutex);
+	for(PinnedBlock &b : g_pool)
+	{
+		if(b.p == p)
+		{
+			b.used = false;
+			return true;
+		}
+	}
+	return false;
+}
+} // namespace
+
+void sibgpu_free(void *p)
+{
+	if(p && !pool_release(p)) free(p);
+}
 
 // Plans the text layout '$' chr0 '$' chr1 '$' ... '$' (the DNASequence layout, src/dnasequence.cpp:75-103), allocates,
 // fills the whole buffer with '$' and uploads the chromosome tables; the bases follow with copy_text_range.
@@ -240,6 +307,31 @@ static int upload_layout(sibgpu_ctx *c, const char *const *chr, const uint64_t *
 	return SIBGPU_OK;
 }
 
+} // extern "C"
+
+// sibgpu_enumerate without the download: host buffers in, result tables left in HBM (d_pos / d_neg, n_inst, n_vertices).
+// Upload, pack and partition are pipelined piece by piece (enumerate.cu); the context ends up in the same state as
+// after sibgpu_upload + sibgpu_enumerate_resident.
+int sibgpu::enumerate_keep(sibgpu_ctx *c, const char *const *chr, const uint64_t *len, uint32_t nchr, uint32_t k)
+{
+	if(!c || k == 0)
+	{
+		set_error("invalid: NULL context or k == 0");
+		return SIBGPU_ERR_INVALID;
+	}
+	SIB_TRY(upload_layout(c, chr, len, nchr));
+	HostSrc src = {chr, len};
+	SIB_CUDA(cudaEventRecord(c->ev_begin, c->stream));
+	SIB_TRY(enumerate_resident(c, k, &src));
+	c->have_text = true;
+	SIB_CUDA(cudaEventRecord(c->ev_end, c->stream));
+	SIB_CUDA(cudaEventSynchronize(c->ev_end));
+	SIB_CUDA(cudaEventElapsedTime(&c->last_ms, c->ev_begin, c->ev_end));
+	return SIBGPU_OK;
+}
+
+extern "C" {
+
 int sibgpu_upload(sibgpu_ctx *c, const char *const *chr, const uint64_t *len, uint32_t nchr)
 {
 	SIB_TRY(upload_layout(c, chr, len, nchr));
@@ -288,10 +380,13 @@ int sibgpu_download(sibgpu_ctx *c, sibgpu_inst **pos, uint64_t *npos, sibgpu_ins
 	}
 	SIB_CUDA(cudaSetDevice(c->device));
 	const uint64_t n = c->n_inst;
-	*pos = static_cast<sibgpu_inst*>(malloc(sizeof(sibgpu_inst) * (n + 1)));
-	*neg = static_cast<sibgpu_inst*>(malloc(sizeof(sibgpu_inst) * (n + 1)));
+	*pos = static_cast<sibgpu_inst*>(pool_alloc(sizeof(sibgpu_inst) * (n + 1)));
+	*neg = static_cast<sibgpu_inst*>(pool_alloc(sizeof(sibgpu_inst) * (n + 1)));
 	if(!*pos || !*neg)
 	{
+		sibgpu_free(*pos);
+		sibgpu_free(*neg);
+		*pos = *neg = nullptr;
 		set_error("invalid: host allocation failed");
 		return SIBGPU_ERR_INVALID;
 	}
@@ -309,23 +404,9 @@ int sibgpu_download(sibgpu_ctx *c, sibgpu_inst **pos, uint64_t *npos, sibgpu_ins
 int sibgpu_enumerate(sibgpu_ctx *c, const char *const *chr, const uint64_t *len, uint32_t nchr, uint32_t k,
 	sibgpu_inst **pos, uint64_t *npos, sibgpu_inst **neg, uint64_t *nneg, uint32_t *count)
 {
-	if(k == 0)
-	{
-		set_error("invalid: NULL context or k == 0");
-		return SIBGPU_ERR_INVALID;
-	}
-	// upload, pack and partition are pipelined piece by piece (enumerate.cu); the context ends up in the same state
-	// as after sibgpu_upload + sibgpu_enumerate_resident
 	static const bool trace = getenv("SIBGPU_TRACE") != nullptr;
 	const auto t0 = std::chrono::steady_clock::now();
-	SIB_TRY(upload_layout(c, chr, len, nchr));
-	HostSrc src = {chr, len};
-	SIB_CUDA(cudaEventRecord(c->ev_begin, c->stream));
-	SIB_TRY(enumerate_resident(c, k, &src));
-	c->have_text = true;
-	SIB_CUDA(cudaEventRecord(c->ev_end, c->stream));
-	SIB_CUDA(cudaEventSynchronize(c->ev_end));
-	SIB_CUDA(cudaEventElapsedTime(&c->last_ms, c->ev_begin, c->ev_end));
+	SIB_TRY(sibgpu::enumerate_keep(c, chr, len, nchr, k));
 	if(count) *count = c->n_vertices;
 	const int rc = sibgpu_download(c, pos, npos, neg, nneg);
 	if(trace)

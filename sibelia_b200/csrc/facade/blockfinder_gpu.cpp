@@ -79,6 +79,8 @@ namespace SyntenyFinder
 			len[chr] = record.size();
 		}
 
+		// IndexedSequence(rawSeq_, originalPos_, k, tempDir_, true): sanitise, then (file-backed variant only) the temp files
+		ConsumeTempFileSideEffects(tempDir_);
 		uint64_t bulges = 0;
 		ProgressThunk thunk;
 		thunk.f = f;
@@ -87,6 +89,12 @@ namespace SyntenyFinder
 			static_cast<uint32_t>(maxIterations), CallProgress, &thunk, &bulges));
 		for(size_t chr = 0; chr < chrNumber; chr++)
 		{
+			// a stage without any bulge leaves the arrays as they were handed in (include/sibgpu.h)
+			if(seq[chr] == (rawSeq_[chr].empty() ? 0 : &rawSeq_[chr][0]))
+			{
+				continue;
+			}
+
 			rawSeq_[chr].assign(seq[chr], seq[chr] + len[chr]);
 			originalPos_[chr].assign(pos[chr], pos[chr] + len[chr]);
 			sibgpu_free(seq[chr]);

@@ -32,6 +32,7 @@ LIST_EDGES = r'''			// sibgpu: index + ListEdges in one GPU call, no host-side I
 				chrLen[i] = record[i].size();
 			}
 
+			ConsumeTempFileSideEffects(tempDir_);           // IndexedSequence iseq(rawSeq_, originalPos_, k, tempDir_)
 			sibgpu_edge * gpuEdge = 0;
 			uint64_t gpuEdgeCount = 0;
 			GpuCheck(sibgpu_list_edges(GpuSession(), record.empty() ? 0 : &chrPtr[0], record.empty() ? 0 : &posPtr[0], record.empty() ? 0 : &chrLen[0],

@@ -60,8 +60,12 @@ namespace SyntenyFinder
 		return count;
 	}
 
-	size_t IndexedSequence::EnumerateBifurcationsSArray(const std::vector<std::string> & data, const std::string &, std::vector<BifurcationInstance> & positiveBif, std::vector<BifurcationInstance> & negativeBif)
+	size_t IndexedSequence::EnumerateBifurcationsSArray(const std::vector<std::string> & data, const std::string & tempDir, std::vector<BifurcationInstance> & positiveBif, std::vector<BifurcationInstance> & negativeBif)
 	{
+		// The file-backed variant of the reference creates the temp directory and two TempFiles (src/vertexenumeration.cpp:
+		// 187-188, 125-126, 101); each file name draws 12 values from the process-wide rand() stream (src/platform.cpp:50-58)
+		// that also replaces the non-ACGT characters of every later index: the side effects are kept, the files are not.
+		ConsumeTempFileSideEffects(tempDir);
 		return EnumerateBifurcationsSArrayInRAM(data, positiveBif, negativeBif);
 	}
 }

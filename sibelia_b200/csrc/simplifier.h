@@ -282,85 +282,6 @@ public:
 		std::fill(dirty.begin(), dirty.end(), 0);
 	}
 
-	// Renumbers the elements in sequence order so that element index == flat position again (start of a sweep).
-	void compact()
-	{
-		const size_t total = live;
-		std::vector<int32_t> newidx(ch.size(), -1);
-		HostChars ch2(total);
-		HostU32 op2(total), m0(total), m1(total);
-		HostI32 no0(total), no1(total);
-		size_t j = 0;
-		for(int32_t e = 0; e >= 0; e = nxt[e], j++)
-		{
-			newidx[e] = (int32_t)j;
-			ch2[j] = ch[e];
-			op2[j] = opos[e];
-			m0[j] = mark[0][e];
-			m1[j] = mark[1][e];
-			no0[j] = node_of[0][e];
-			no1[j] = node_of[1][e];
-		}
-		for(size_t n = 0; n < n_elem.size(); n++)
-		{
-			if(n_valid[n]) n_elem[n] = newidx[n_elem[n]];
-		}
-		for(size_t c = 0; c < chr_first_sep.size(); c++) chr_first_sep[c] = newidx[chr_first_sep[c]];
-		last_sep = newidx[last_sep];
-		ch.swap(ch2);
-		opos.swap(op2);
-		mark[0].swap(m0);
-		mark[1].swap(m1);
-		node_of[0].swap(no0);
-		node_of[1].swap(no1);
-		nxt.resize(total);
-		prv.resize(total);
-		for(size_t i = 0; i < total; i++)
-		{
-			nxt[i] = (int32_t)i + 1;
-			prv[i] = (int32_t)i - 1;
-		}
-		nxt[total - 1] = -1;
-	}
-
-	// Drops the list nodes that Cleanup already unlinked (keeps node indices small between sweeps).
-	void compact_nodes()
-	{
-		std::vector<int32_t> remap(n_elem.size(), -1);
-		size_t j = 0;
-		for(size_t n = 0; n < n_elem.size(); n++)
-		{
-			if(n_valid[n]) remap[n] = (int32_t)j++;
-		}
-		std::vector<int32_t> e2(j), nx2(j), pv2(j);
-		std::vector<uint8_t> s2(j), v2(j, 1);
-		std::vector<uint32_t> id2(j);
-		for(size_t n = 0; n < n_elem.size(); n++)
-		{
-			if(!n_valid[n]) continue;
-			const int32_t m = remap[n];
-			e2[m] = n_elem[n];
-			s2[m] = n_strand[n];
-			id2[m] = n_id[n];
-			nx2[m] = n_next[n] >= 0 ? remap[n_next[n]] : -1;
-			pv2[m] = n_prev[n] >= 0 ? remap[n_prev[n]] : -1;
-			node_of[s2[m]][e2[m]] = m;
-		}
-		for(int s = 0; s < 2; s++)
-		{
-			for(size_t id = 0; id < head[s].size(); id++)
-			{
-				if(head[s][id] >= 0) head[s][id] = remap[head[s][id]];
-			}
-		}
-		n_elem.swap(e2);
-		n_next.swap(nx2);
-		n_prev.swap(pv2);
-		n_strand.swap(s2);
-		n_valid.swap(v2);
-		n_id.swap(id2);
-	}
-
 	// =========================================================== DNASequence::Replace
 	int32_t new_element(char c)
 	{
@@ -622,6 +543,96 @@ public:
 		}
 		for(size_t i = 0; i < touched.size(); i++) slot_of[touched[i]] = -1;
 		return !bulges.empty();
+	}
+
+	// ---- read-only screen of the dirty vertices at the start of a sweep (all host threads)
+	struct ScreenScratch {
+		std::vector<int32_t> slot_of, start_kmer;
+		std::vector<uint32_t> touched;
+		std::vector<char> first_char, end_char;
+	};
+
+	// Would RemoveBulges(id) find a bulge in the CURRENT state?  Same walks as the existence pass of any_bulges, on
+	// scratch of the calling thread; touches no member.
+	bool exists_bulge(size_t id, ScreenScratch &sc) const
+	{
+		list_positions(id, sc.start_kmer);
+		if(sc.start_kmer.size() < 2) return false;
+		sc.end_char.assign(sc.start_kmer.size(), EMPTY);
+		for(size_t i = 0; i < sc.start_kmer.size(); i++)
+		{
+			const It it = node_it(sc.start_kmer[i]);
+			if(proper_kmer(it, k + 1)) sc.end_char[i] = deref(advance(it, k));
+		}
+		sc.touched.clear();
+		sc.first_char.clear();
+		bool conflict = false;
+		for(size_t i = 0; i < sc.start_kmer.size() && !conflict; i++)
+		{
+			if(sc.end_char[i] == EMPTY) continue;
+			It kmer = node_it(sc.start_kmer[i]);
+			const uint32_t start = get_bif(kmer);
+			inc(kmer);
+			for(size_t step = 1; step < D && at_valid(kmer); inc(kmer), step++)
+			{
+				const uint32_t b = get_bif(kmer);
+				if(b == start) break;
+				if(b != NO_BIF)
+				{
+					const int32_t sl = sc.slot_of[b];
+					if(sl < 0)
+					{
+						sc.slot_of[b] = (int32_t)sc.first_char.size();
+						sc.touched.push_back(b);
+						sc.first_char.push_back(sc.end_char[i]);
+					}
+					else if(sc.first_char[sl] != sc.end_char[i])
+					{
+						conflict = true;
+						break;
+					}
+				}
+			}
+		}
+		for(size_t i = 0; i < sc.touched.size(); i++) sc.slot_of[sc.touched[i]] = -1;
+		return conflict;
+	}
+
+	// Clears `dirty` for every dirty vertex whose RemoveBulges call would find nothing in the state as it is now (the
+	// start of a sweep): such a vertex needs the exact call only if a collapse of this sweep dirties it again.  Returns
+	// the number of vertices screened (0: too few to be worth the threads).
+	size_t screen_min = 4096;                           // fewer dirty vertices than this: not worth the threads
+	size_t screen_dirty()
+	{
+		std::vector<uint32_t> ids;
+		for(size_t id = 0; id < dirty.size(); id++)
+		{
+			if(dirty[id]) ids.push_back((uint32_t)id);
+		}
+		if(ids.size() < screen_min) return 0;
+		size_t nt = std::thread::hardware_concurrency();
+		nt = nt < 1 ? 1 : (nt > 16 ? 16 : nt);
+		std::vector<std::thread> th;
+		for(size_t t = 0; t < nt; t++)
+		{
+			th.emplace_back([this, &ids, t, nt]() {
+				ScreenScratch sc;
+				sc.slot_of.assign(dirty.size(), -1);
+				// interleaved blocks: neighbouring ids have neighbouring instances (ids are lexicographic ranks, not positions),
+				// the split only has to balance the work
+				const size_t block = 256;
+				for(size_t b = t * block; b < ids.size(); b += nt * block)
+				{
+					const size_t e = std::min(b + block, ids.size());
+					for(size_t i = b; i < e; i++)
+					{
+						if(!exists_bulge(ids[i], sc)) dirty[ids[i]] = 0;
+					}
+				}
+			});
+		}
+		for(std::thread &x : th) x.join();
+		return ids.size();
 	}
 
 	void update_bifurcations(const std::vector<int32_t> &start_kmer, VisitData source, VisitData target,

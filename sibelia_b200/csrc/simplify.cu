@@ -23,6 +23,8 @@
 #include <string>
 #include <thread>
 
+#include <cub/cub.cuh>
+
 #include "context.h"
 #include "simplifier.h"
 
@@ -109,6 +111,103 @@ __global__ void __launch_bounds__(DETECT_WARPS * 32) k_bulge_detect(const uint8_
 	}
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Device-resident stage front-end: everything k_bulge_detect needs is derived on the device from what the enumeration
+// left there -- the text IS the element array of a fresh DNASequence (element index = text position,
+// dnasequence.cpp:75-103), the two instance tables give the per-strand marks (IndexedSequence::Init,
+// indexedsequence.cpp:51-67) and, sorted by vertex id, the per-vertex instance lists.  No host state, no upload.
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_fill_marks(const sibgpu_inst *__restrict__ pos, const sibgpu_inst *__restrict__ neg, uint64_t n,
+	const uint32_t *__restrict__ chr_start, const uint32_t *__restrict__ chr_len, uint32_t *__restrict__ mark0,
+	uint32_t *__restrict__ mark1, uint32_t *__restrict__ keys, uint32_t *__restrict__ vals)
+{
+	for(uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
+	{
+		const sibgpu_inst p = pos[i], q = neg[i];
+		const uint32_t e0 = chr_start[p.chr] + p.pos;                               // element where the k-mer starts, + strand
+		const uint32_t e1 = chr_start[q.chr] + chr_len[q.chr] - 1u - q.pos;         // - strand: counted from the chromosome's end
+		mark0[e0] = p.bifId;
+		mark1[e1] = q.bifId;
+		keys[i] = p.bifId;
+		vals[i] = e0;
+		keys[n + i] = q.bifId;
+		vals[n + i] = e1 | 0x80000000u;
+	}
+}
+
+// inst_off[v] = first index of vertex v in the id-sorted instance list, for v in 0 .. nvert (nvert + 1 entries)
+__global__ void __launch_bounds__(256) k_inst_offsets(const uint32_t *__restrict__ sorted_keys, uint64_t n, uint32_t nvert,
+	uint64_t *__restrict__ inst_off)
+{
+	const uint32_t v = blockIdx.x * blockDim.x + threadIdx.x;
+	if(v > nvert) return;
+	uint64_t lo = 0, hi = n;
+	while(lo < hi)
+	{
+		const uint64_t mid = (lo + hi) >> 1;
+		if(sorted_keys[mid] < v) lo = mid + 1; else hi = mid;
+	}
+	inst_off[v] = lo;
+}
+
+__global__ void __launch_bounds__(256) k_count_flags(const uint8_t *__restrict__ flag, uint32_t n, unsigned long long *__restrict__ out)
+{
+	uint32_t c = 0;
+	for(uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) c += flag[i];
+	c = __reduce_add_sync(0xffffffffu, c);
+	if((threadIdx.x & 31u) == 0 && c) atomicAdd(out, (unsigned long long)c);
+}
+
+// Detection of every vertex of the stage's first sweep, from the enumeration result resident on `ctx`.
+// *nflag = number of flagged vertices; the flags stay in ctx->d_s_flag (max_id + 1 bytes).
+static int detect_resident(sibgpu_ctx *ctx, uint32_t k, uint32_t D, uint32_t max_id, uint64_t *nflag, float *ms)
+{
+	cudaStream_t st = ctx->stream;
+	const uint64_t total = ctx->M, n = ctx->n_inst;
+	const uint32_t nvert = max_id + 1;
+	DevBuf &d_m0 = ctx->d_s_m0, &d_m1 = ctx->d_s_m1, &d_off = ctx->d_s_off, &d_inst = ctx->d_s_inst, &d_flag = ctx->d_s_flag;
+	SIB_TRY(d_m0.ensure(total * 4));
+	SIB_TRY(d_m1.ensure(total * 4));
+	SIB_TRY(d_off.ensure(((size_t)nvert + 2) * 8));
+	SIB_TRY(d_inst.ensure(n * 8 + 8));
+	SIB_TRY(d_flag.ensure((size_t)nvert + 8));
+	SIB_TRY(ctx->d_vkeys.ensure(n * 16 + 16));             // id-sort workspace: keys | keys_alt
+	SIB_TRY(ctx->d_vkeys_alt.ensure(n * 8 + 8));           //                    vals_alt
+	uint32_t *keys = ctx->d_vkeys.as<uint32_t>(), *keys_alt = keys + n * 2;
+	uint32_t *vals = d_inst.as<uint32_t>(), *vals_alt = ctx->d_vkeys_alt.as<uint32_t>();
+	SIB_CUDA(cudaEventRecord(ctx->ev_begin, st));
+	SIB_CUDA(cudaMemsetAsync(d_m0.p, 0xFF, total * 4, st));
+	SIB_CUDA(cudaMemsetAsync(d_m1.p, 0xFF, total * 4, st));
+	SIB_CUDA(cudaMemsetAsync(ctx->d_scalars.as<uint64_t>() + 16, 0, 8, st));
+	const uint32_t grid = (uint32_t)ctx->sm_count * 8;
+	if(n)
+	{
+		k_fill_marks<<<grid, 256, 0, st>>>(ctx->d_pos.as<sibgpu_inst>(), ctx->d_neg.as<sibgpu_inst>(), n, ctx->d_chr_start.as<uint32_t>(),
+			ctx->d_chr_len.as<uint32_t>(), d_m0.as<uint32_t>(), d_m1.as<uint32_t>(), keys, vals);
+		int bits = 1;
+		while(bits < 32 && (1ull << bits) <= max_id) bits++;
+		cub::DoubleBuffer<uint32_t> kb(keys, keys_alt), vb(vals, vals_alt);
+		size_t tmp_bytes = 0;
+		SIB_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, kb, vb, (int)(2 * n), 0, bits, st));
+		SIB_TRY(ctx->d_cubtmp.ensure(tmp_bytes));
+		SIB_CUDA(cub::DeviceRadixSort::SortPairs(ctx->d_cubtmp.p, tmp_bytes, kb, vb, (int)(2 * n), 0, bits, st));
+		k_inst_offsets<<<(nvert + 1 + 255) / 256, 256, 0, st>>>(kb.Current(), 2 * n, nvert, d_off.as<uint64_t>());
+		uint32_t dgrid = (nvert + DETECT_WARPS - 1) / DETECT_WARPS;
+		if(dgrid > grid) dgrid = grid;
+		k_bulge_detect<<<dgrid, DETECT_WARPS * 32, 0, st>>>(ctx->d_text.as<uint8_t>(), d_m0.as<uint32_t>(), d_m1.as<uint32_t>(),
+			(uint32_t)total, d_off.as<uint64_t>(), vb.Current(), nvert, k, D, d_flag.as<uint8_t>());
+		k_count_flags<<<grid, 256, 0, st>>>(d_flag.as<uint8_t>(), nvert, ctx->d_scalars.as<unsigned long long>() + 16);
+		ctx->total_launches += 12;
+	}
+	SIB_CUDA(cudaEventRecord(ctx->ev_end, st));
+	uint64_t *hs = static_cast<uint64_t*>(ctx->h_scalars);
+	SIB_CUDA(cudaMemcpyAsync(hs + 16, ctx->d_scalars.as<uint64_t>() + 16, 8, cudaMemcpyDeviceToHost, st));
+	SIB_CUDA(cudaStreamSynchronize(st));
+	SIB_CUDA(cudaEventElapsedTime(ms, ctx->ev_begin, ctx->ev_end));
+	*nflag = n ? hs[16] : 0;
+	return SIBGPU_OK;
+}
+
 } // namespace sibgpu
 
 using namespace sibgpu;
@@ -132,14 +231,57 @@ extern "C" int sibgpu_simplify(sibgpu_ctx *ctx, char **seq, uint32_t **origpos, 
 			t_mark = t;
 		}
 	};
-	// ---- IndexedSequence(rawSeq_, originalPos_, k, tempDir_, true): the vertex tables come from the GPU enumerator
-	sibgpu_inst *pos = nullptr, *neg = nullptr;
-	uint64_t npos = 0, nneg = 0;
-	uint32_t count = 0;
-	SIB_TRY(sibgpu_enumerate(ctx, seq, len, nchr, k, &pos, &npos, &neg, &nneg, &count));
+	// ---- IndexedSequence(rawSeq_, originalPos_, k, tempDir_, true): the vertex tables come from the GPU enumerator and
+	// stay in HBM; the detection of the first sweep runs on them right away (no host state yet)
+	SIB_TRY(enumerate_keep(ctx, seq, len, nchr, k));
+	const uint32_t count = ctx->n_vertices;
 	uint64_t launches = ctx->total_launches;
 	float device_ms = ctx->last_ms;
 	lap("enumerate (host buffers)");
+	const size_t max_id = count;
+	uint64_t n_flag_dev = 0;
+	{
+		float ms = 0.f;
+		SIB_TRY(detect_resident(ctx, k, min_branch_size, count, &n_flag_dev, &ms));
+		device_ms += ms;
+		launches += ctx->total_launches - launches;
+	}
+	lap("marks + instance lists + k_bulge_detect");
+	const size_t PROGRESS_STRIDE = 50;
+	if(n_flag_dev == 0)
+	{
+		// No vertex has a bulge: the first sweep of SimplifyGraph (blockfinder.cpp:29-43) calls RemoveBulges for every id,
+		// all return 0, the loop ends, and the copy-back re-spells the unchanged sequence.  Nothing to build, nothing to
+		// copy: the caller's arrays stay as they are (only the progress protocol is replayed).
+		if(progress)
+		{
+			progress(0, 0, user);
+			const size_t threshold = (max_id * max_iterations) / PROGRESS_STRIDE;
+			size_t cnt = 0, total_progress = 0;
+			for(size_t id = 0; id <= max_id; id++)
+			{
+				if(++cnt >= threshold)
+				{
+					cnt = 0;
+					total_progress = std::min(total_progress + 1, PROGRESS_STRIDE);
+					progress(total_progress, 1, user);
+				}
+			}
+			progress(PROGRESS_STRIDE, 2, user);
+		}
+		if(trace) fprintf(stderr, "[sibgpu_simplify] sweep 1: %zu vertices, 0 flagged by the GPU: stage leaves the sequences untouched\n", max_id + 1);
+		ctx->total_launches = launches;
+		ctx->last_ms = device_ms;
+		*bulges = 0;
+		return SIBGPU_OK;
+	}
+	sibgpu_inst *pos = nullptr, *neg = nullptr;
+	uint64_t npos = 0, nneg = 0;
+	SIB_TRY(sibgpu_download(ctx, &pos, &npos, &neg, &nneg));
+	std::vector<uint8_t> flag(max_id + 1);
+	SIB_CUDA(cudaMemcpyAsync(flag.data(), ctx->d_s_flag.p, max_id + 1, cudaMemcpyDeviceToHost, ctx->stream));
+	SIB_CUDA(cudaStreamSynchronize(ctx->stream));
+	lap("download tables + flags");
 	Simplifier S;
 	auto recycle = [&]() {                              // swaps the big per-element arrays with the context's pool
 		S.ch.swap(ctx->pool_ch);
@@ -153,87 +295,31 @@ extern "C" int sibgpu_simplify(sibgpu_ctx *ctx, char **seq, uint32_t **origpos, 
 	};
 	recycle();
 	S.build(nchr, seq, origpos, len, k, min_branch_size, count, pos, npos, neg, nneg);
-	free(pos);
-	free(neg);
+	sibgpu_free(pos);
+	sibgpu_free(neg);
 	S.slot_of.assign((size_t)count + 1, -1);
 	lap("build host state");
 
 	// ---- SimplifyGraph, blockfinder.cpp:16-51
-	cudaStream_t st = ctx->stream;
-	DevBuf &d_ch = ctx->d_s_ch, &d_m0 = ctx->d_s_m0, &d_m1 = ctx->d_s_m1, &d_off = ctx->d_s_off, &d_inst = ctx->d_s_inst, &d_flag = ctx->d_s_flag;
-	auto release = [&]() {};   // the buffers live in the context (grow-only): no cudaMalloc/cudaFree per stage
-	const size_t PROGRESS_STRIDE = 50;
 	size_t cnt = 0, total_bulges = 0, iterations = 0, total_progress = 0;
 	if(progress) progress(total_progress, 0, user);
-	const size_t max_id = count;
 	const size_t threshold = (max_id * max_iterations) / PROGRESS_STRIDE;
-	std::vector<uint8_t> flag(max_id + 1);
-	std::vector<uint64_t> inst_off(max_id + 2);
-	std::vector<uint32_t> inst_elem;
-	std::vector<int32_t> tmp_nodes;
 	do
 	{
 		iterations++;
-		// ---- first sweep: snapshot of the initial state -> GPU detection of every vertex.  Later sweeps need no
-		// snapshot: `dirty` is cleared when a vertex is visited and set by every later change its walks can see, so a
-		// vertex that is clean at its next visit would repeat its last (empty) outcome -- RemoveBulges only changes
-		// state through collapses, and a call that collapsed something always dirties its own vertex.
-		int rc = SIBGPU_OK;
-		if(iterations == 1)
+		// ---- first sweep: the GPU decided every vertex against the initial state (flags above).  Later sweeps need no
+		// snapshot of everything: `dirty` is cleared when a vertex is visited and set by every later change its walks can
+		// see, so a vertex that is clean at its next visit would repeat its last (empty) outcome -- RemoveBulges only
+		// changes state through collapses, and a call that collapsed something always dirties its own vertex.  The dirty
+		// vertices of a later sweep are first screened against the sweep's initial state by all host threads (read-only
+		// existence test of AnyBulges); the survivors and everything dirtied during the sweep get the exact call.
+		if(iterations > 1)
 		{
-		const size_t total = S.ch.size();
-		inst_elem.clear();
-		for(size_t id = 0; id <= max_id; id++)
-		{
-			inst_off[id] = inst_elem.size();
-			for(int s = 0; s < 2; s++)
-			{
-				for(int32_t n = S.head[s][id]; n >= 0; n = S.n_next[n]) inst_elem.push_back((uint32_t)S.n_elem[n] | ((uint32_t)s << 31));
-			}
+			std::fill(flag.begin(), flag.end(), 0);
+			const size_t screened = S.screen_dirty();
+			if(trace) fprintf(stderr, "[sibgpu_simplify] sweep %zu: %zu dirty vertices screened in parallel\n", iterations, screened);
+			lap("parallel existence screen");
 		}
-		inst_off[max_id + 1] = inst_elem.size();
-		auto dev = [&]() -> int {
-			SIB_CUDA(cudaSetDevice(ctx->device));
-			SIB_TRY(d_ch.ensure(total));
-			SIB_TRY(d_m0.ensure(total * 4));
-			SIB_TRY(d_m1.ensure(total * 4));
-			SIB_TRY(d_off.ensure((max_id + 2) * 8));
-			SIB_TRY(d_inst.ensure(inst_elem.size() * 4 + 4));
-			SIB_TRY(d_flag.ensure(max_id + 1));
-			SIB_CUDA(cudaMemcpyAsync(d_ch.p, S.ch.data(), total, cudaMemcpyHostToDevice, st));
-			SIB_CUDA(cudaMemcpyAsync(d_m0.p, S.mark[0].data(), total * 4, cudaMemcpyHostToDevice, st));
-			SIB_CUDA(cudaMemcpyAsync(d_m1.p, S.mark[1].data(), total * 4, cudaMemcpyHostToDevice, st));
-			SIB_CUDA(cudaMemcpyAsync(d_off.p, inst_off.data(), (max_id + 2) * 8, cudaMemcpyHostToDevice, st));
-			if(!inst_elem.empty())
-			{
-				SIB_CUDA(cudaMemcpyAsync(d_inst.p, inst_elem.data(), inst_elem.size() * 4, cudaMemcpyHostToDevice, st));
-			}
-			SIB_CUDA(cudaEventRecord(ctx->ev_begin, st));
-			const uint32_t nvert = (uint32_t)(max_id + 1);
-			uint32_t grid = (nvert + DETECT_WARPS - 1) / DETECT_WARPS;
-			const uint32_t cap = (uint32_t)ctx->sm_count * 8;
-			if(grid > cap) grid = cap;
-			k_bulge_detect<<<grid, DETECT_WARPS * 32, 0, st>>>(d_ch.as<uint8_t>(), d_m0.as<uint32_t>(), d_m1.as<uint32_t>(),
-				(uint32_t)total, d_off.as<uint64_t>(), d_inst.as<uint32_t>(), nvert, k, min_branch_size, d_flag.as<uint8_t>());
-			SIB_CUDA(cudaEventRecord(ctx->ev_end, st));
-			SIB_CUDA(cudaMemcpyAsync(flag.data(), d_flag.p, max_id + 1, cudaMemcpyDeviceToHost, st));
-			SIB_CUDA(cudaStreamSynchronize(st));
-			float ms = 0.f;
-			SIB_CUDA(cudaEventElapsedTime(&ms, ctx->ev_begin, ctx->ev_end));
-			device_ms += ms;
-			launches++;
-			return SIBGPU_OK;
-		};
-		lap("instance CSR");
-		rc = dev();
-		}
-		else std::fill(flag.begin(), flag.end(), 0);
-		if(rc != SIBGPU_OK)
-		{
-			release();
-			return rc;
-		}
-		lap("upload + k_bulge_detect");
 		size_t n_flag = 0, n_calls = 0;
 		const size_t collapses_before = S.collapses;
 		// ---- the reference's sweep, skipping the vertices whose negative outcome is already known
@@ -282,13 +368,15 @@ extern "C" int sibgpu_simplify(sibgpu_ctx *ctx, char **seq, uint32_t **origpos, 
 	}
 	while(total_bulges > 0 && iterations < max_iterations);
 	if(progress) progress(PROGRESS_STRIDE, 2, user);
-	release();
 	ctx->total_launches = launches;
 	ctx->last_ms = device_ms;
 
-	// ---- copy-back, blockfinder.cpp:85-95 (one host thread per chromosome: the walks are independent)
+	// ---- copy-back, blockfinder.cpp:85-95 (one host thread per chromosome: the walks are independent).  The caller's
+	// arrays are only overwritten once every chromosome has its new buffers; on failure nothing is handed out.
 	{
-		std::vector<int> ok(nchr, 1);
+		std::vector<char*> new_seq(nchr, nullptr);
+		std::vector<uint32_t*> new_pos(nchr, nullptr);
+		std::vector<uint64_t> new_len(nchr, 0);
 		auto copy_chr = [&](uint32_t c) {
 			size_t n = 0;
 			for(int32_t e = S.nxt[S.chr_first_sep[c]]; S.ch[e] != SEP; e = S.nxt[e]) n++;
@@ -298,7 +386,6 @@ extern "C" int sibgpu_simplify(sibgpu_ctx *ctx, char **seq, uint32_t **origpos, 
 			{
 				free(out_seq);
 				free(out_pos);
-				ok[c] = 0;
 				return;
 			}
 			size_t j = 0;
@@ -307,9 +394,9 @@ extern "C" int sibgpu_simplify(sibgpu_ctx *ctx, char **seq, uint32_t **origpos, 
 				out_seq[j] = S.ch[e];
 				out_pos[j] = S.opos[e];
 			}
-			seq[c] = out_seq;
-			origpos[c] = out_pos;
-			len[c] = n;
+			new_seq[c] = out_seq;
+			new_pos[c] = out_pos;
+			new_len[c] = n;
 		};
 		std::vector<std::thread> th;
 		for(uint32_t c = 0; c < nchr; c += 16)
@@ -318,13 +405,24 @@ extern "C" int sibgpu_simplify(sibgpu_ctx *ctx, char **seq, uint32_t **origpos, 
 			for(uint32_t d = c; d < nchr && d < c + 16; d++) th.emplace_back(copy_chr, d);
 			for(std::thread &x : th) x.join();
 		}
+		bool ok = true;
+		for(uint32_t c = 0; c < nchr; c++) ok = ok && new_seq[c] && new_pos[c];
+		if(!ok)
+		{
+			for(uint32_t c = 0; c < nchr; c++)
+			{
+				free(new_seq[c]);
+				free(new_pos[c]);
+			}
+			recycle();
+			set_error("invalid: host allocation failed");
+			return SIBGPU_ERR_INVALID;
+		}
 		for(uint32_t c = 0; c < nchr; c++)
 		{
-			if(!ok[c])
-			{
-				set_error("invalid: host allocation failed");
-				return SIBGPU_ERR_INVALID;
-			}
+			seq[c] = new_seq[c];
+			origpos[c] = new_pos[c];
+			len[c] = new_len[c];
 		}
 	}
 	lap("copy-back");

@@ -44,9 +44,10 @@ class GpuShard:
     fused = os.environ.get("SIBGPU_DIST_FUSED", "1") != "0"
     resident = False                                 # the text range is already in HBM (ctx.dist_upload)
 
-    def fused_enumerate(self, chrs, rank, world, k, group=None):
+    def fused_enumerate(self, chrs, rank, world, k, group=None, download=True):
         """(count, pos, negtext) through the fused path, or None when it does not apply here (k > 28, no peer access) or
-        asked every rank to take the phased path (a segment or bucket overflowed somewhere)."""
+        asked every rank to take the phased path (a segment or bucket overflowed somewhere).  download=False leaves the
+        local tables in HBM (ctx.download() fetches them) and returns (count, local instance count, None)."""
         for _ in range(3):
             need = self.ctx.dist2_plan(chrs, rank, world, k, self.resident)
             if need < 0:
@@ -75,6 +76,8 @@ class GpuShard:
                     return None
             status, count, ninst = self.ctx.dist2_run(chrs, self.resident)
             if status == 0:
+                if not download:
+                    return count, ninst, None
                 pos, negtext = self.ctx.download()
                 return count, pos, negtext
             if status == 1:
@@ -149,9 +152,10 @@ def _comm(t, group):
     return t if dist.get_backend(group) == "nccl" else t.cpu()
 
 
-def enumerate_sharded(shard, chrs, k, group=None):
+def enumerate_sharded(shard, chrs, k, group=None, download=True):
     """Runs the sharded enumeration on every rank of `group`; returns (global vertex count, this rank's positive table,
-    this rank's negative table in TEXT order).  `shard` is a backend with upload/scan/scatter/group/finish."""
+    this rank's negative table in TEXT order).  `shard` is a backend with upload/scan/scatter/group/finish.
+    download=False (fused strategy only): the tables stay in HBM, the second item is the local instance count."""
     rank, world = dist.get_rank(group), dist.get_world_size(group)
     marks = []
 
@@ -162,7 +166,7 @@ def enumerate_sharded(shard, chrs, k, group=None):
             marks.append((what, time.perf_counter()))
     lap("start")
     if getattr(shard, "fused", False) and world <= 16:
-        out = shard.fused_enumerate(chrs, rank, world, k, group)
+        out = shard.fused_enumerate(chrs, rank, world, k, group, download)
         if out is not None:
             lap("fused step")
             shard.last_strategy = "fused (device-side step counters, TMA peer pulls in k_split, key pull kernel; no collective)"

@@ -70,6 +70,21 @@ def test_non_acgt_input_consumes_rand_like_the_reference(tmp_path):
     compare(["-s", "loose", "-m", "1000", "-r", fa], tmp_path)
 
 
+@pytest.mark.skipif(not have, reason="oracle/_ref/Sibelia{,_gpu} did not travel")
+def test_non_acgt_input_without_inram(tmp_path):
+    """Without --inram every index of the reference creates two temp files whose names draw 24 values from the same
+    rand() stream (platform.cpp:50-58) before the next index replaces its Ns: the GPU-served CLI builds no files but
+    must leave the stream in the same state (facade/gpu_session.h, ConsumeTempFileSideEffects)."""
+    rng = np.random.default_rng(6)
+    chrs = [c.copy() for c in helpers.strain_case(3, 60_000, p_sub=0.01, inv_len=5_000, seed=33)]
+    for c in chrs:
+        for o in rng.integers(0, len(c) - 50, 30):
+            c[o:o + int(rng.integers(1, 40))] = ord("N")
+    fa = str(tmp_path / "in.fasta")
+    write_fasta(fa, chrs)
+    compare(["-s", "loose", "-m", "1000", fa], tmp_path)
+
+
 @pytest.mark.skipif(not (have and os.path.exists(os.path.join(DATA, "Helicobacter_pylori.fasta"))),
                     reason="reference example genome did not travel")
 def test_helicobacter_pylori_loose(tmp_path):

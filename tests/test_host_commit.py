@@ -65,7 +65,7 @@ def assert_state_equal(got, want, what):
 FILES = sorted(glob.glob(os.path.join(GOLD, "simplify_*.npz")))
 
 
-@pytest.mark.parametrize("dirty_mode", [0, 1])
+@pytest.mark.parametrize("dirty_mode", [0, 1, 2])
 @pytest.mark.parametrize("path", FILES, ids=[os.path.basename(p)[:-4] for p in FILES])
 def test_golden_stages(hc, path, dirty_mode):
     z = np.load(path)
@@ -90,16 +90,18 @@ def test_random_small_against_reference(hc):
         iters = int(rng.integers(1, 5))
         D = int(rng.integers(k + 1, 50))
         want = ref.simplify(chrs, op, k, D, iters)[:3]
-        for dm in (0, 1):
+        for dm in (0, 1, 2):
             assert_state_equal(host_simplify(hc, chrs, op, k, D, iters, dm), want,
                                "case %d k=%d D=%d iters=%d dirty_mode=%d" % (it, k, D, iters, dm))
 
 
 @pytest.mark.skipif(not ref.available(), reason="oracle/_ref not built (needs /root/reference)")
-@pytest.mark.parametrize("dirty_mode,seed,ps", [(0, 91, 0.02), (1, 91, 0.02), (1, 92, 0.05), (1, 93, 0.005)])
+@pytest.mark.parametrize("dirty_mode,seed,ps", [(0, 91, 0.02), (1, 91, 0.02), (1, 92, 0.05), (1, 93, 0.005), (2, 91, 0.02), (2, 92, 0.05),
+                                                (2, 94, 0.01)])
 def test_strains_against_reference(hc, dirty_mode, seed, ps):
     """dirty_mode = 1 is the sweep policy of sibgpu_simplify: later sweeps visit only vertices dirtied since their
-    last visit (no snapshot, no renumbering); it must give the reference's result exactly like visiting everything."""
+    last visit (no snapshot, no renumbering); dirty_mode = 2 adds the parallel read-only screen of the dirty vertices at
+    the start of those sweeps; both must give the reference's result exactly like visiting everything."""
     chrs = [c.tobytes() for c in helpers.strain_case(4, 40_000, p_sub=ps, inv_len=3000, seed=seed)]
     op = [np.arange(len(c), dtype=np.uint32) for c in chrs]
     rc, ro = chrs, op
