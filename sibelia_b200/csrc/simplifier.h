@@ -598,39 +598,46 @@ public:
 		return conflict;
 	}
 
-	// Clears `dirty` for every dirty vertex whose RemoveBulges call would find nothing in the state as it is now (the
-	// start of a sweep): such a vertex needs the exact call only if a collapse of this sweep dirties it again.  Returns
-	// the number of vertices screened (0: too few to be worth the threads).
-	size_t screen_min = 4096;                           // fewer dirty vertices than this: not worth the threads
-	size_t screen_dirty()
+	// Screens the vertices of [lo, hi) that are due for an exact call (flagged by the GPU or dirty) against the state as
+	// it is NOW, with all host threads: a vertex whose RemoveBulges call would find nothing loses its flag and its dirty
+	// mark -- it needs the exact call only if a later collapse dirties it again (mark_dirty_around / add_point /
+	// erase_point do that).  Must not run concurrently with a mutation.  Returns the number of vertices screened
+	// (0: fewer than screen_min candidates, not worth the threads).
+	size_t screen_min = 2048;
+	std::vector<ScreenScratch> screen_scratch;          // one per thread, kept across calls (slot_of is max_id + 1 entries)
+	size_t screen_range(size_t lo, size_t hi, uint8_t *flag)
 	{
 		std::vector<uint32_t> ids;
-		for(size_t id = 0; id < dirty.size(); id++)
+		for(size_t id = lo; id < hi; id++)
 		{
-			if(dirty[id]) ids.push_back((uint32_t)id);
+			if(dirty[id] || (flag && flag[id])) ids.push_back((uint32_t)id);
 		}
-		if(ids.size() < screen_min) return 0;
+		if(ids.size() < screen_min || ids.empty()) return 0;
 		size_t nt = std::thread::hardware_concurrency();
 		nt = nt < 1 ? 1 : (nt > 16 ? 16 : nt);
-		std::vector<std::thread> th;
-		for(size_t t = 0; t < nt; t++)
-		{
-			th.emplace_back([this, &ids, t, nt]() {
-				ScreenScratch sc;
-				sc.slot_of.assign(dirty.size(), -1);
-				// interleaved blocks: neighbouring ids have neighbouring instances (ids are lexicographic ranks, not positions),
-				// the split only has to balance the work
-				const size_t block = 256;
-				for(size_t b = t * block; b < ids.size(); b += nt * block)
+		if(nt > (ids.size() + 255) / 256) nt = (ids.size() + 255) / 256;
+		if(screen_scratch.size() < nt) screen_scratch.resize(nt);
+		auto work = [this, &ids, flag, nt](size_t t) {
+			ScreenScratch &sc = screen_scratch[t];
+			if(sc.slot_of.size() != dirty.size()) sc.slot_of.assign(dirty.size(), -1);
+			// interleaved blocks: ids are lexicographic ranks, not positions; the split only has to balance the work
+			const size_t block = 256;
+			for(size_t b = t * block; b < ids.size(); b += nt * block)
+			{
+				const size_t e = std::min(b + block, ids.size());
+				for(size_t i = b; i < e; i++)
 				{
-					const size_t e = std::min(b + block, ids.size());
-					for(size_t i = b; i < e; i++)
+					if(!exists_bulge(ids[i], sc))
 					{
-						if(!exists_bulge(ids[i], sc)) dirty[ids[i]] = 0;
+						dirty[ids[i]] = 0;
+						if(flag) flag[ids[i]] = 0;
 					}
 				}
-			});
-		}
+			}
+		};
+		std::vector<std::thread> th;
+		for(size_t t = 1; t < nt; t++) th.emplace_back(work, t);
+		work(0);
 		for(std::thread &x : th) x.join();
 		return ids.size();
 	}

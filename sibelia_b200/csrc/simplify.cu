@@ -310,39 +310,40 @@ extern "C" int sibgpu_simplify(sibgpu_ctx *ctx, char **seq, uint32_t **origpos, 
 		// ---- first sweep: the GPU decided every vertex against the initial state (flags above).  Later sweeps need no
 		// snapshot of everything: `dirty` is cleared when a vertex is visited and set by every later change its walks can
 		// see, so a vertex that is clean at its next visit would repeat its last (empty) outcome -- RemoveBulges only
-		// changes state through collapses, and a call that collapsed something always dirties its own vertex.  The dirty
-		// vertices of a later sweep are first screened against the sweep's initial state by all host threads (read-only
-		// existence test of AnyBulges); the survivors and everything dirtied during the sweep get the exact call.
-		if(iterations > 1)
-		{
-			std::fill(flag.begin(), flag.end(), 0);
-			const size_t screened = S.screen_dirty();
-			if(trace) fprintf(stderr, "[sibgpu_simplify] sweep %zu: %zu dirty vertices screened in parallel\n", iterations, screened);
-			lap("parallel existence screen");
-		}
-		size_t n_flag = 0, n_calls = 0;
+		// changes state through collapses, and a call that collapsed something always dirties its own vertex.
+		// The ids are visited in the reference's order, in chunks: before a chunk all host threads screen its flagged and
+		// dirty vertices against the current state (read-only existence test of AnyBulges), so the strictly ordered part
+		// only pays for vertices that really have a bulge or are dirtied after the screen.
+		if(iterations > 1) std::fill(flag.begin(), flag.end(), 0);
+		size_t n_flag = 0, n_calls = 0, n_screened = 0;
 		const size_t collapses_before = S.collapses;
-		// ---- the reference's sweep, skipping the vertices whose negative outcome is already known
-		for(size_t id = 0; id <= max_id; id++)
+		const size_t CHUNK = (size_t)1 << 16;
+		for(size_t chunk_lo = 0; chunk_lo <= max_id; chunk_lo += CHUNK)
 		{
-			n_flag += flag[id];
-			if(flag[id] || S.dirty[id])
+			const size_t chunk_hi = std::min(max_id + 1, chunk_lo + CHUNK);
+			for(size_t id = chunk_lo; id < chunk_hi; id++) n_flag += flag[id];
+			n_screened += S.screen_range(chunk_lo, chunk_hi, flag.data());
+			// ---- the reference's sweep, skipping the vertices whose negative outcome is already known
+			for(size_t id = chunk_lo; id < chunk_hi; id++)
 			{
-				n_calls++;
-				S.dirty[id] = 0;                            // clean as of this visit; the call itself may dirty it again
-				total_bulges += S.remove_bulges(id);
-			}
-			if(++cnt >= threshold && progress)
-			{
-				cnt = 0;
-				total_progress = std::min(total_progress + 1, PROGRESS_STRIDE);
-				progress(total_progress, 1, user);
+				if(flag[id] || S.dirty[id])
+				{
+					n_calls++;
+					S.dirty[id] = 0;                        // clean as of this visit; the call itself may dirty it again
+					total_bulges += S.remove_bulges(id);
+				}
+				if(++cnt >= threshold && progress)
+				{
+					cnt = 0;
+					total_progress = std::min(total_progress + 1, PROGRESS_STRIDE);
+					progress(total_progress, 1, user);
+				}
 			}
 		}
 		if(trace)
 		{
-			fprintf(stderr, "[sibgpu_simplify] sweep %zu: %zu vertices, %zu flagged by the GPU, %zu exact calls, %zu collapses\n",
-				iterations, max_id + 1, n_flag, n_calls, S.collapses - collapses_before);
+			fprintf(stderr, "[sibgpu_simplify] sweep %zu: %zu vertices, %zu flagged by the GPU, %zu screened by the host threads, "
+				"%zu exact calls, %zu collapses\n", iterations, max_id + 1, n_flag, n_screened, n_calls, S.collapses - collapses_before);
 		}
 		lap("ordered host commit");
 		if(S.collapses == collapses_before)

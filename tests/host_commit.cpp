@@ -2,7 +2,8 @@
 // The vertex tables come from the caller (the tests pass the oracle's), and EVERY vertex is treated as flagged, i.e. the
 // exact RemoveBulges restatement runs for all ids in order -- which must reproduce the reference stage bit for bit.
 // With dirty_mode the later sweeps visit only the vertices dirtied since their last visit (the product's policy);
-// dirty_mode 2 additionally screens the dirty vertices in parallel at the start of those sweeps (Simplifier::screen_dirty).
+// dirty_mode 2 is the full product policy: chunks of ids are screened by all host threads against the current state
+// (Simplifier::screen_range) and only the survivors, plus whatever a collapse dirties afterwards, get the exact call.
 // Built by tests/test_host_commit.py into tests/_build/libhostcommit.so.
 #include <cstdlib>
 
@@ -110,16 +111,18 @@ extern "C" int host_simplify(uint32_t nchr, char **seq, uint32_t **origpos, uint
 			compact(S);
 			compact_nodes(S);
 		}
-		if(iterations > 1 && dirty_mode == 2)
-		{
-			S.screen_min = 1;
-			S.screen_dirty();
-		}
 		for(size_t id = 0; id <= count; id++)
 		{
+			// dirty_mode 2: the product's chunked screen (tiny chunks here so that it interleaves with the collapses)
+			if(dirty_mode == 2 && id % 64 == 0)
+			{
+				S.screen_min = 1;
+				if(iterations == 1) std::fill(S.dirty.begin() + id, S.dirty.begin() + std::min<size_t>(id + 64, (size_t)count + 1), 1);
+				S.screen_range(id, std::min<size_t>(id + 64, (size_t)count + 1), nullptr);
+			}
 			// dirty_mode = the sweep policy of sibgpu_simplify: every vertex in the first sweep (there the GPU flags a
 			// superset of the vertices with bulges), afterwards only the vertices dirtied since their last visit
-			if(dirty_mode && iterations > 1 && !S.dirty[id]) continue;
+			if(dirty_mode == 2 ? !S.dirty[id] : (dirty_mode && iterations > 1 && !S.dirty[id])) continue;
 			S.dirty[id] = 0;
 			total_bulges += S.remove_bulges(id);
 			calls++;
