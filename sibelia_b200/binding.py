@@ -312,8 +312,8 @@ class Context:
             m = lens[i]
             if seq[i] == (bufs[i].ctypes.data if len(bufs[i]) else None) or (not seq[i] and not len(bufs[i])):
                 # the stage found no bulge at all: the library left the caller's arrays untouched (include/sibgpu.h)
-                new_chrs.append(bufs[i].tobytes())
-                new_op.append(ops[i].copy())
+                new_chrs.append(chrs[i])
+                new_op.append(origpos[i])
                 continue
             sbuf = (C.c_char * m).from_address(seq[i]) if m else b""
             new_chrs.append(bytes(sbuf))

@@ -1,6 +1,7 @@
 // Shared host/device helpers of libsibgpu (sm_100a only).
 #pragma once
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>
 #include <stdint.h>
 #include <string>
 #include <vector>
@@ -26,6 +27,14 @@ void set_error(const std::string &msg);
 		int s__ = (expr);                                                                                       \
 		if(s__ != SIBGPU_OK) return s__;                                                                        \
 	} while(0)
+
+// NVTX range for the profilers' timelines (header-only NVTX 3: a no-op unless a tool is attached).
+struct NvtxRange {
+	explicit NvtxRange(const char *name) { nvtxRangePushA(name); }
+	~NvtxRange() { nvtxRangePop(); }
+	NvtxRange(const NvtxRange&) = delete;
+	NvtxRange &operator=(const NvtxRange&) = delete;
+};
 
 // Grow-only device buffer.
 struct DevBuf {

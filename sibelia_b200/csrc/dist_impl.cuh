@@ -682,6 +682,7 @@ int dist2_import(sibgpu_ctx *ctx, const void *handles)
 
 int dist2_run(sibgpu_ctx *ctx, const HostSrc *src, int *status)
 {
+	NvtxRange nvtx("sibgpu: fused sharded step");
 	cudaStream_t st = ctx->stream;
 	const uint32_t W = ctx->dist_world, rank = ctx->dist_rank, k = ctx->x_k, PL = ctx->x_PL, PT = PL * W;
 	*status = 0;

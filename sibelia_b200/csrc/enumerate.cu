@@ -991,6 +991,7 @@ static int ids_and_tables(sibgpu_ctx *ctx, const TextDesc &t, uint32_t k, const 
 	uint32_t ntiles, const Rec16 *fp, bool reverse_neg, bool *collision)
 {
 	typedef typename RecT<MODE>::type Rec;
+	NvtxRange nvtx("sibgpu: vertex ids + instance tables");
 	cudaStream_t st = ctx->stream;
 	const int sms = ctx->sm_count;
 	uint64_t *hs = static_cast<uint64_t*>(ctx->h_scalars);
@@ -1535,6 +1536,7 @@ static int enumerate_mode(sibgpu_ctx *ctx, uint32_t k, uint64_t nrec, const Host
 
 int enumerate_resident(sibgpu_ctx *ctx, uint32_t k, const HostSrc *src)
 {
+	NvtxRange nvtx("sibgpu: enumerate");
 	cudaStream_t st = ctx->stream;
 	ctx->have_result = false;
 	ctx->prof_reset();

@@ -162,6 +162,7 @@ __global__ void __launch_bounds__(256) k_count_flags(const uint8_t *__restrict__
 // *nflag = number of flagged vertices; the flags stay in ctx->d_s_flag (max_id + 1 bytes).
 static int detect_resident(sibgpu_ctx *ctx, uint32_t k, uint32_t D, uint32_t max_id, uint64_t *nflag, float *ms)
 {
+	NvtxRange nvtx("sibgpu: stage front-end (marks, instance lists, k_bulge_detect)");
 	cudaStream_t st = ctx->stream;
 	const uint64_t total = ctx->M, n = ctx->n_inst;
 	const uint32_t nvert = max_id + 1;
@@ -220,6 +221,7 @@ extern "C" int sibgpu_simplify(sibgpu_ctx *ctx, char **seq, uint32_t **origpos, 
 		set_error("invalid: NULL argument or k == 0");
 		return SIBGPU_ERR_INVALID;
 	}
+	NvtxRange nvtx_stage("sibgpu: simplify stage");
 	const bool trace = getenv("SIBGPU_TRACE") != nullptr;
 	auto now = []() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
 	double t_mark = now();
@@ -294,7 +296,10 @@ extern "C" int sibgpu_simplify(sibgpu_ctx *ctx, char **seq, uint32_t **origpos, 
 		S.node_of[1].swap(ctx->pool_i32[3]);
 	};
 	recycle();
-	S.build(nchr, seq, origpos, len, k, min_branch_size, count, pos, npos, neg, nneg);
+	{
+		NvtxRange nvtx("sibgpu: host state build");
+		S.build(nchr, seq, origpos, len, k, min_branch_size, count, pos, npos, neg, nneg);
+	}
 	sibgpu_free(pos);
 	sibgpu_free(neg);
 	S.slot_of.assign((size_t)count + 1, -1);
@@ -307,6 +312,7 @@ extern "C" int sibgpu_simplify(sibgpu_ctx *ctx, char **seq, uint32_t **origpos, 
 	do
 	{
 		iterations++;
+		NvtxRange nvtx_sweep("sibgpu: sweep (parallel screen + ordered commit)");
 		// ---- first sweep: the GPU decided every vertex against the initial state (flags above).  Later sweeps need no
 		// snapshot of everything: `dirty` is cleared when a vertex is visited and set by every later change its walks can
 		// see, so a vertex that is clean at its next visit would repeat its last (empty) outcome -- RemoveBulges only
@@ -375,6 +381,7 @@ extern "C" int sibgpu_simplify(sibgpu_ctx *ctx, char **seq, uint32_t **origpos, 
 	// ---- copy-back, blockfinder.cpp:85-95 (one host thread per chromosome: the walks are independent).  The caller's
 	// arrays are only overwritten once every chromosome has its new buffers; on failure nothing is handed out.
 	{
+		NvtxRange nvtx("sibgpu: copy-back");
 		std::vector<char*> new_seq(nchr, nullptr);
 		std::vector<uint32_t*> new_pos(nchr, nullptr);
 		std::vector<uint64_t> new_len(nchr, 0);
