@@ -1,16 +1,20 @@
 #!/usr/bin/env python
-"""Writes a copy of the reference's src/synteny.cpp with its two index-building sites bound to libsibgpu.so -- the
-change a maintainer of the reference would make by hand:
+"""Writes a copy of the reference's src/synteny.cpp (or src/serialization.cpp) with its index-building sites bound to
+libsibgpu.so -- the change a maintainer of the reference would make by hand:
 
   * BlockFinder::GenerateSyntenyBlocks (src/synteny.cpp:238-241): `IndexedSequence iseq(...); ListEdges(...)`
     becomes one sibgpu_list_edges call;
   * BlockFinder::TrimBlocks (src/synteny.cpp:31-122): `IndexedSequence iseq(blockSeq, trimK, "")` and the walk over all
     vertex marks become one sibgpu_trim_blocks call, the final size test / Edge construction (:105-116) is kept.
 
+  * BlockFinder::SerializeCondensedGraph (src/serialization.cpp:88-94, the -g output): the same
+    `IndexedSequence iseq(...); ListEdges(...)` pair becomes the same sibgpu_list_edges call.
+
 The reference source is read where it lies and edited by anchors; nothing of it is stored in this repository and the
 output (a file in the build directory of whoever links the bound CLI) is a build artefact.
 
     python patch_synteny.py /root/reference/src/synteny.cpp out.cpp
+    python patch_synteny.py /root/reference/src/serialization.cpp out.cpp
 """
 import sys
 
@@ -106,6 +110,16 @@ def between(text, start_anchor, end_anchor, replacement, what):
 def main(src, dst):
     s = open(src).read()
     s = s.replace('#include "blockfinder.h"\n', '#include "blockfinder.h"\n#include "gpu_session.h"\n', 1)
+    if src.endswith("serialization.cpp"):
+        # SerializeCondensedGraph: drop the host-side index, list the edges on the GPU
+        a = s.find("\tvoid BlockFinder::SerializeCondensedGraph(")
+        if a < 0 or s.find("\t\tIndexedSequence iseq(rawSeq_, originalPos_, k, tempDir_);\n", a) < 0:
+            sys.exit("patch_synteny: anchor for SerializeCondensedGraph not found -- the reference changed")
+        head, tail = s[:a], s[a:]
+        tail = tail.replace("\t\tIndexedSequence iseq(rawSeq_, originalPos_, k, tempDir_);\n", "", 1)
+        tail = tail.replace("\t\tListEdges(iseq.Sequence(), iseq.BifStorage(), k, edge);\n", LIST_EDGES, 1)
+        open(dst, "w").write(head + tail)
+        return
     # TrimBlocks: everything from the sentinel constant to the final swap
     s = between(s, "\t\tconst size_t oo = UINT_MAX;", "\t\tblock.swap(ret);", TRIM, "TrimBlocks")
     s = s.replace("\t\tsize_t pos = 0;\n\t\tbool drop = false;", "\t\tbool drop = false;", 1)

@@ -85,6 +85,24 @@ def test_non_acgt_input_without_inram(tmp_path):
     compare(["-s", "loose", "-m", "1000", fa], tmp_path)
 
 
+@pytest.mark.skipif(not have, reason="oracle/_ref/Sibelia{,_gpu} did not travel")
+def test_condensed_graph_output(tmp_path):
+    """-g: BlockFinder::SerializeCondensedGraph (serialization.cpp:88-110) writes the condensed de Bruijn graph of every
+    stage and of the final index; in the bound CLI its index + ListEdges pair is one sibgpu_list_edges call."""
+    chrs = helpers.strain_case(3, 80_000, p_sub=0.01, inv_len=8_000, seed=34)
+    fa = str(tmp_path / "in.fasta")
+    write_fasta(fa, chrs)
+    args = ["-s", "loose", "-m", "1000", "-g", fa]
+    run(REF_BIN, args, str(tmp_path / "ref"))
+    run(GPU_BIN, args, str(tmp_path / "gpu"))
+    dots = sorted(f for f in os.listdir(str(tmp_path / "ref")) if f.endswith(".dot"))
+    assert len(dots) >= 2
+    for f in dots:
+        want = open(os.path.join(str(tmp_path / "ref"), f), "rb").read()
+        got = open(os.path.join(str(tmp_path / "gpu"), f), "rb").read()
+        assert got == want, "%s differs" % f
+
+
 @pytest.mark.skipif(not (have and os.path.exists(os.path.join(DATA, "Helicobacter_pylori.fasta"))),
                     reason="reference example genome did not travel")
 def test_helicobacter_pylori_loose(tmp_path):
