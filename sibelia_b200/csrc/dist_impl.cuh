@@ -585,11 +585,17 @@ __global__ void __launch_bounds__(256) k_pull_keys(const PullSrc src, uint32_t W
 	__syncthreads();
 	if(me == 0 && blockIdx.x == 0 && threadIdx.x == 0) { out[0] = s_total; out[1] = s_flags; out[2] = s_max; }
 	if(s_flags) return;
+	// 16-byte loads over NVLink (the key regions are 16-byte aligned), the odd last key on its own
 	const unsigned long long *k = src.keys[me];
-	for(uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < s_n; i += (uint64_t)gridDim.x * blockDim.x)
+	const uint64_t pairs = s_n / 2;
+	for(uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < pairs; i += (uint64_t)gridDim.x * blockDim.x)
 	{
-		allkeys[s_off + i] = ld_relaxed_sys(k + i);
+		unsigned long long a, b;
+		asm volatile("ld.relaxed.sys.global.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(k + 2 * i) : "memory");
+		allkeys[s_off + 2 * i] = a;
+		allkeys[s_off + 2 * i + 1] = b;
 	}
+	if((s_n & 1u) && blockIdx.x == 0 && threadIdx.x == 0) allkeys[s_off + s_n - 1] = ld_relaxed_sys(k + s_n - 1);
 }
 
 int dist2_plan(sibgpu_ctx *ctx, uint32_t k, int *need_alloc)
@@ -740,7 +746,7 @@ int dist2_run(sibgpu_ctx *ctx, const HostSrc *src, int *status)
 		const uint64_t allcap = ctx->d_ckeys.cap / sizeof(uint64_t);
 		{
 			ProfScope ps(ctx, "k_pull_keys", 0);
-			k_pull_keys<<<dim3(8, W), 256, 0, st>>>(psrc, W, epoch, key_cap, ctx->d_ckeys.as<uint64_t>(), allcap, ds + 12);
+			k_pull_keys<<<dim3(32, W), 256, 0, st>>>(psrc, W, epoch, key_cap, ctx->d_ckeys.as<uint64_t>(), allcap, ds + 12);
 		}
 		ctx->total_launches += 2;
 		SIB_CUDA(cudaMemcpyAsync(hs + 8, ds + 8, sizeof(uint64_t) * 8, cudaMemcpyDeviceToHost, st));

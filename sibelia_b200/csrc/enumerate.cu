@@ -1022,11 +1022,13 @@ static int ids_and_tables(sibgpu_ctx *ctx, const TextDesc &t, uint32_t k, const 
 		}
 		size_t tmp_bytes = 0;
 		cub::DoubleBuffer<uint64_t> dbuf(ctx->d_vkeys.as<uint64_t>(), ctx->d_vkeys_alt.as<uint64_t>());
-		SIB_CUDA(cub::DeviceRadixSort::SortKeys(nullptr, tmp_bytes, dbuf, (int)(2 * Vc), 0, 64, st));
+		// keys have 2k significant bits; the palindrome sentinel (all ones) must still sort last: one more bit
+		const int sort_bits = 2 * k + 1 < 64 ? (int)(2 * k + 1) : 64;
+		SIB_CUDA(cub::DeviceRadixSort::SortKeys(nullptr, tmp_bytes, dbuf, (int)(2 * Vc), 0, sort_bits, st));
 		SIB_TRY(ctx->d_cubtmp.ensure(tmp_bytes));
 		{
 			ProfScope ps(ctx, "cub_sort_vertex_keys", 2 * Vc * 8 * 2, 8);
-			SIB_CUDA(cub::DeviceRadixSort::SortKeys(ctx->d_cubtmp.p, tmp_bytes, dbuf, (int)(2 * Vc), 0, 64, st));
+			SIB_CUDA(cub::DeviceRadixSort::SortKeys(ctx->d_cubtmp.p, tmp_bytes, dbuf, (int)(2 * Vc), 0, sort_bits, st));
 		}
 		{
 			// V = 2 Vc - #palindromes is read by the kernel from the device counter; the host learns it with the final sync
