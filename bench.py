@@ -311,6 +311,16 @@ def main():
         barrier()
         e2e_s = (time.perf_counter() - t0) / args.steps
         d2h = pos.nbytes + neg.nbytes + 64
+        pageable_s = None
+        if world == 1:
+            # the same call from PAGEABLE host memory -- what the C++ facade hands over (std::string::data(),
+            # sibelia_b200/csrc/facade/vertexenumeration_gpu.cpp): the driver stages the copy through its own pinned buffer
+            for _ in range(2):
+                ctx.enumerate(chrs, args.k)
+            t0 = time.perf_counter()
+            for _ in range(args.steps):
+                ctx.enumerate(chrs, args.k)
+            pageable_s = (time.perf_counter() - t0) / args.steps
         te = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
         ti = torch.tensor([len(pos)], dtype=torch.int64, device="cuda")
         if world > 1:
@@ -323,6 +333,7 @@ def main():
         digest = result_digest(c2, pos, neg) if rank == 0 else None
         return {"total": total, "ms_per_step": ms_per_step, "value": total / 1e6 / (ms_per_step / 1e3), "dev_ms": dev_ms,
                 "e2e_ms": float(te.item()) * 1e3, "e2e_value": total / 1e6 / float(te.item()), "h2d": int(h2d), "d2h": int(d2h),
+                "pageable_ms": pageable_s * 1e3 if pageable_s else None,
                 "launches": int(launches), "count": int(c2), "ninst": int(ti.item()), "clocks": clocks, "wall": wall,
                 "kstats": kstats, "digest": digest, "strategy": getattr(shard, "last_strategy", None) if world > 1 else None}
 
@@ -404,7 +415,10 @@ def main():
         "clocks": r["clocks"],
         "e2e": {"value": r["e2e_value"], "unit": UNIT, "h2d_bytes_per_step": r["h2d"], "d2h_bytes_per_step": r["d2h"],
                 "ms_per_step": r["e2e_ms"], "note": "pinned host buffers -> sibgpu_enumerate / the sharded step -> host tables; "
-                                                    "bytes are per rank"},
+                                                    "bytes are per rank",
+                "pageable_ms_per_step": r["pageable_ms"],
+                "pageable_value": (r["total"] / 1e6 / (r["pageable_ms"] / 1e3)) if r["pageable_ms"] else None,
+                "pageable_note": "same call from pageable host memory, as the C++ facade of the reference CLI passes it"},
         "gpu_launches": r["launches"],
         "result_digest": r["digest"],
         "roofline": roofline,

@@ -767,7 +767,13 @@ __device__ __forceinline__ uint32_t lower_bound_u64(const uint64_t *__restrict__
 	return lo;
 }
 
-// vertex map: canonical key -> (id of the canonical k-mer, id of its reverse complement); 32-byte slots
+// vertex map: canonical key -> (id of the canonical k-mer, id of its reverse complement); 32-byte slots.
+// The one-hash bit filter in front of it is tested for EVERY text position by k_mark, so its index is a single
+// multiplicative hash (top bits of the low product word), not the full mix the map slot uses.
+__device__ __forceinline__ uint32_t filter_bit(unsigned long long a, unsigned long long b, uint32_t fshift)
+{
+	return (uint32_t)(((a ^ (b * 0xD6E8FEB86659FD93ull)) * 0x9E3779B97F4A7C15ull) >> fshift);
+}
 
 __device__ __forceinline__ void map_insert(MapSlot *map, uint32_t Tm, uint32_t *filter, uint32_t fshift,
 	unsigned long long a, unsigned long long b, uint32_t idc, uint32_t idr, uint32_t cls)
@@ -784,7 +790,7 @@ __device__ __forceinline__ void map_insert(MapSlot *map, uint32_t Tm, uint32_t *
 	map[slot].idc = idc;
 	map[slot].idr = idr;
 	map[slot].cls = cls;
-	uint32_t bit = (uint32_t)(h >> fshift);
+	const uint32_t bit = filter_bit(a, b, fshift);
 	atomicOr(&filter[bit >> 5], 1u << (bit & 31u));
 }
 
@@ -812,9 +818,9 @@ __global__ void __launch_bounds__(256) k_build_map(const typename RecT<MODE>::ty
 __device__ __forceinline__ bool map_lookup(const MapSlot *__restrict__ map, uint32_t Tm, const uint32_t *__restrict__ filter,
 	uint32_t fshift, unsigned long long a, unsigned long long b, uint32_t &idc, uint32_t &idr, uint32_t &cls)
 {
-	uint64_t h = rec_hash(a, b);
-	uint32_t bit = (uint32_t)(h >> fshift);
+	const uint32_t bit = filter_bit(a, b, fshift);
 	if(!((__ldg(filter + (bit >> 5)) >> (bit & 31u)) & 1u)) return false;
+	uint64_t h = rec_hash(a, b);
 	uint32_t slot = __umulhi((uint32_t)h, Tm);
 	for(;;)
 	{

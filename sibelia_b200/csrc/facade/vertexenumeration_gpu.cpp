@@ -47,13 +47,10 @@ namespace SyntenyFinder
 		std::vector<BifurcationInstance> * ret[] = {&positiveBif, &negativeBif};
 		for(size_t strand = 0; strand < 2; strand++)
 		{
-			ret[strand]->clear();
-			ret[strand]->reserve(size[strand]);
-			for(uint64_t i = 0; i < size[strand]; i++)
-			{
-				ret[strand]->push_back(BifurcationInstance(table[strand][i].bifId, table[strand][i].chr, table[strand][i].pos));
-			}
-
+			// BifurcationInstance (src/indexedsequence.h:57-68) and sibgpu_inst are the same three 32-bit fields: one bulk copy
+			static_assert(sizeof(BifurcationInstance) == sizeof(sibgpu_inst), "BifurcationInstance layout");
+			const BifurcationInstance * first = reinterpret_cast<const BifurcationInstance*>(table[strand]);
+			ret[strand]->assign(first, first + size[strand]);
 			sibgpu_free(table[strand]);
 		}
 
