@@ -164,6 +164,30 @@ int sibgpu_trim_blocks(sibgpu_ctx *ctx, const char *const *seq, const uint64_t *
 	uint32_t nchr, uint32_t trim_k, sibgpu_trim *out);
 
 /* ---------------------------------------------------------------------------------------------------------------
+ * sibgpu_fasta_parse: replaces
+ *     size_t FASTAReader::GetSequences(std::vector<FASTARecord> & record)            src/fasta.cpp:22-73
+ * (with ValidateHeader :75-90 and ValidateSequence :92-106) on the bytes of a whole FASTA file: line splitting, trimming,
+ * '>' records (description = text up to the first blank), upper-casing and validation against "ACGTURYKMSWBDHWNX-",
+ * all on the GPU, independent of how the sequence is wrapped.  Quirks kept: sequence lines before the first header are
+ * glued to the first record; no header at all = one record with an empty description.
+ *   data, nbytes     the file as read from disk (any line ending)
+ *   out              nrec records {name (NUL-terminated), name_len, seq (NOT NUL-terminated), len}; the sequences are
+ *                    slices of one pinned block; release everything with sibgpu_fasta_free
+ *   *err_line        on SIBGPU_ERR_INPUT: the reference's line counter (non-empty lines, 1-based); sibgpu_last_error()
+ *                    is the reference's `what` ("empty sequence", "empty header", "illegal character: x"), so that
+ *                    "parse error in <file> on line <err_line>: <what>" is the reference's exception text
+ */
+typedef struct sibgpu_fasta_record { const char *name; uint64_t name_len; const char *seq; uint64_t len; } sibgpu_fasta_record;
+typedef struct sibgpu_fasta {
+	uint32_t nrec;
+	sibgpu_fasta_record *rec;
+	void *text_block, *name_block;                     /* owned storage behind the records */
+	uint64_t total;                                    /* sum of the sequence lengths */
+} sibgpu_fasta;
+int sibgpu_fasta_parse(sibgpu_ctx *ctx, const char *data, uint64_t nbytes, sibgpu_fasta *out, uint64_t *err_line);
+void sibgpu_fasta_free(sibgpu_fasta *f);
+
+/* ---------------------------------------------------------------------------------------------------------------
  * Sharded enumeration over `world` GPUs of one box, ONE PROCESS PER GPU (k <= 32).  The concatenated genome is split
  * into `world` contiguous text ranges; records are bucketed by hash prefix so that partition p belongs to rank
  * p / (nparts_total / world); the caller moves them with one all-to-all (NCCL) between two device buffers it owns,

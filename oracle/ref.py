@@ -160,3 +160,27 @@ def boost_order(keys):
     out = np.zeros(len(keys), dtype=np.uint64)
     lib().ref_boost_order(C.c_void_p(keys.ctypes.data), C.c_uint64(len(keys)), C.c_void_p(out.ctypes.data))
     return out
+
+
+def fasta_parse(path):
+    """FASTAReader(path).GetSequences of the reference.  Returns ([(description bytes, sequence bytes)], seconds) or raises
+    RuntimeError with the reference's exception text."""
+    L = lib()
+    L.ref_fasta_parse.restype = C.c_int
+    nrec, nb = C.c_uint32(), C.c_uint64()
+    names, seqs, lens, sec = C.c_void_p(), C.c_void_p(), C.POINTER(C.c_uint64)(), C.c_double()
+    rc = L.ref_fasta_parse(C.c_char_p(path.encode()), C.byref(nrec), C.byref(names), C.byref(nb), C.byref(seqs), C.byref(lens),
+                           C.byref(sec))
+    if rc != 0:
+        raise RuntimeError(L.ref_last_error().decode("latin-1"))
+    out, na, sa = [], 0, 0
+    nbuf = C.string_at(names, nb.value)
+    for i in range(nrec.value):
+        end = nbuf.index(b"\0", na)
+        n = lens[i]
+        out.append((nbuf[na:end], C.string_at(seqs.value + sa, n)))
+        na = end + 1
+        sa += n
+    for p in (names, seqs, C.cast(lens, C.c_void_p)):
+        L.ref_free(p)
+    return out, sec.value

@@ -301,4 +301,46 @@ int ref_trim_blocks(uint32_t nchr, const char* const* seq, const uint64_t* len, 
 	}
 }
 
+
+// FASTAReader(path).GetSequences (src/fasta.cpp:22-73).  Returns 0 and the records packed as
+//   names: nrec NUL-terminated descriptions back to back, seqs: the sequences back to back, lens[nrec];
+// or 1 with the exception text in ref_last_error() ("parse error in <path> on line N: what").
+int ref_fasta_parse(const char* path, uint32_t* nrec, char** names, uint64_t* names_bytes, char** seqs, uint64_t** lens, double* seconds)
+{
+	try
+	{
+		const double t0 = now_s();
+		FASTAReader reader(path);
+		if(!reader.IsOk()) throw std::runtime_error(std::string("Cannot open file ") + path);
+		std::vector<FASTARecord> rec;
+		reader.GetSequences(rec);
+		*seconds = now_s() - t0;
+		uint64_t nb = 0, sb = 0;
+		for(size_t i = 0; i < rec.size(); i++)
+		{
+			nb += rec[i].GetDescription().size() + 1;
+			sb += rec[i].GetSequence().size();
+		}
+		*nrec = static_cast<uint32_t>(rec.size());
+		*names = static_cast<char*>(malloc(nb + 1));
+		*seqs = static_cast<char*>(malloc(sb + 1));
+		*lens = static_cast<uint64_t*>(malloc(sizeof(uint64_t) * (rec.size() + 1)));
+		*names_bytes = nb;
+		uint64_t na = 0, sa = 0;
+		for(size_t i = 0; i < rec.size(); i++)
+		{
+			memcpy(*names + na, rec[i].GetDescription().c_str(), rec[i].GetDescription().size() + 1);
+			na += rec[i].GetDescription().size() + 1;
+			memcpy(*seqs + sa, rec[i].GetSequence().data(), rec[i].GetSequence().size());
+			sa += rec[i].GetSequence().size();
+			(*lens)[i] = rec[i].GetSequence().size();
+		}
+		return 0;
+	}
+	catch(const std::exception & e)
+	{
+		g_err = e.what();
+		return 1;
+	}
+}
 }

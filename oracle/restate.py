@@ -140,3 +140,50 @@ def list_edges(chrs, origpos, k):
         e["original_length"] = np.maximum(o1, o2) + 1 - np.minimum(o1, o2)
         out.append(e)
     return np.concatenate(out) if out else np.zeros(0, dtype=EDGE_DTYPE)
+
+
+_FASTA_WS = b" \t\n\v\f\r"
+_FASTA_VALID = set(b"ACGTURYKMSWBDHWNX-")
+
+
+class FastaError(Exception):
+    def __init__(self, line, what):
+        super().__init__("on line %d: %s" % (line, what))
+        self.line, self.what = line, what
+
+
+def fasta_get_sequences(data):
+    """FASTAReader::GetSequences restated (/root/reference/src/fasta.cpp:22-106): list of (description, sequence) bytes, or
+    FastaError(line, what) with the reference's line counter (non-empty lines) and message.  Pure Python: small inputs."""
+    header, sequence, line, out = b"", bytearray(), 1, []
+    for buf in data.split(b"\n"):                        # std::getline; a trailing newline yields one more, empty, line
+        buf = buf.strip(_FASTA_WS)                       # boost::algorithm::trim (C locale)
+        if not buf:
+            continue
+        if buf[:1] == b">":
+            if header:
+                if not sequence:
+                    raise FastaError(line, "empty sequence")
+                out.append((header, bytes(sequence)))
+                sequence = bytearray()
+                header = b""
+            delim = buf.find(b" ")                       # ValidateHeader :75-90
+            delim = len(buf) - 1 if delim < 0 else delim - 1
+            name = buf[1:1 + delim] if delim > 0 else b""
+            if not name:
+                raise FastaError(line, "empty header")
+            header = name
+        else:
+            up = bytearray(buf)
+            for i, c in enumerate(buf):                  # ValidateSequence :92-106
+                u = c - 32 if 97 <= c <= 122 else c
+                if u not in _FASTA_VALID:
+                    # the reference builds the message through c_str(): a NUL byte ends it
+                    raise FastaError(line, "illegal character: " + (chr(c) if c else ""))
+                up[i] = u
+            sequence += up
+        line += 1
+    if not sequence:
+        raise FastaError(line, "empty sequence")
+    out.append((header, bytes(sequence)))
+    return out

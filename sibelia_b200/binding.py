@@ -19,6 +19,7 @@ SYMBOLS = [
     "sibgpu_kernel_stats", "sibgpu_last_launches", "sibgpu_partition_fallbacks", "sibgpu_bucket_fallbacks", "sibgpu_last_device_ms", "sibgpu_simplify", "sibgpu_debug_unordered_order", "sibgpu_debug_trim_from_tables", "sibgpu_dist_upload", "sibgpu_dist_scan", "sibgpu_dist_record_bytes",
     "sibgpu_dist_scatter", "sibgpu_dist_group", "sibgpu_dist_keys", "sibgpu_dist_finish",
     "sibgpu_dist_scatter_local", "sibgpu_dist_upload_scatter", "sibgpu_dist_export_send", "sibgpu_dist_import_peers", "sibgpu_dist_group_peer",
+    "sibgpu_fasta_parse", "sibgpu_fasta_free",
     "sibgpu_fused_plan", "sibgpu_fused_release_peers", "sibgpu_fused_alloc", "sibgpu_fused_import", "sibgpu_fused_run",
 ]
 
@@ -27,6 +28,23 @@ class SibgpuError(RuntimeError):
     def __init__(self, status, msg):
         super().__init__("sibgpu status %d: %s" % (status, msg))
         self.status = status
+
+
+class _FastaRec(C.Structure):
+    _fields_ = [("name", C.c_char_p), ("name_len", C.c_uint64), ("seq", C.c_void_p), ("len", C.c_uint64)]
+
+
+class _Fasta(C.Structure):
+    _fields_ = [("nrec", C.c_uint32), ("rec", C.POINTER(_FastaRec)), ("text_block", C.c_void_p), ("name_block", C.c_void_p),
+                ("total", C.c_uint64)]
+
+
+class FastaParseError(RuntimeError):
+    """The reference's ParseException: `line` is its line counter, `what` its message (fasta.cpp:66-70)."""
+    def __init__(self, line, what):
+        super().__init__("parse error on line %d: %s" % (line, what))
+        self.line = line
+        self.what = what
 
 
 class _KStat(C.Structure):
@@ -296,6 +314,25 @@ class Context:
         ninst, cnt = C.c_uint64(), C.c_uint32()
         _check(load().sibgpu_dist_finish(self._h, C.c_void_p(allkeys_ptr), C.c_uint64(nkeys_total), C.byref(ninst), C.byref(cnt)))
         return cnt.value, ninst.value
+
+    # -- sibgpu_fasta_parse: FASTAReader::GetSequences on the GPU
+    def fasta_parse(self, data):
+        """bytes of a FASTA file -> list of (description: bytes, sequence: uint8 array); raises FastaParseError."""
+        L = load()
+        data = bytes(data)
+        f = _Fasta()
+        line = C.c_uint64()
+        rc = L.sibgpu_fasta_parse(self._h, C.c_char_p(data), C.c_uint64(len(data)), C.byref(f), C.byref(line))
+        if rc == 3:
+            raise FastaParseError(line.value, L.sibgpu_last_error().decode("latin-1"))
+        _check(rc)
+        out = []
+        for i in range(f.nrec):
+            r = f.rec[i]
+            seq = np.frombuffer((C.c_char * r.len).from_address(r.seq), dtype=np.uint8).copy() if r.len else np.zeros(0, np.uint8)
+            out.append((C.string_at(r.name, r.name_len), seq))
+        L.sibgpu_fasta_free(C.byref(f))
+        return out
 
     # -- sibgpu_simplify: one PerformGraphSimplifications stage
     def simplify(self, chrs, origpos, k, min_branch_size, max_iterations=4):

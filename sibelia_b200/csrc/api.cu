@@ -191,6 +191,8 @@ void sibgpu_destroy(sibgpu_ctx *c)
 	delete c;
 }
 
+} // extern "C"
+
 // Result buffers (instance tables) come from a small pool of pinned host blocks: the device-to-host copy of a table
 // then runs at PCIe speed straight into the buffer the caller receives, and a caller that frees a table before asking
 // for the next one (the reference binds one index at a time) gets the same pages back -- a fresh 50 MB malloc costs more
@@ -200,8 +202,9 @@ struct PinnedBlock { void *p; size_t cap; bool used; };
 std::mutex g_pool_mutex;
 std::vector<PinnedBlock> g_pool;
 const size_t POOL_MAX_BLOCKS = 8;
+} // namespace
 
-void *pool_alloc(size_t bytes)
+void *sibgpu::pool_alloc(size_t bytes)
 {
 	if(bytes < (1u << 16)) return malloc(bytes ? bytes : 1);           // small tables: plain memory
 	std::lock_guard<std::mutex> lock(g_pool_mutex);
@@ -239,6 +242,7 @@ void *pool_alloc(size_t bytes)
 	return p;
 }
 
+namespace {
 bool pool_release(void *p)
 {
 	std::lock_guard<std::mutex> lock(g_pool_mutex);
@@ -253,6 +257,8 @@ bool pool_release(void *p)
 	return false;
 }
 } // namespace
+
+extern "C" {
 
 void sibgpu_free(void *p)
 {

@@ -139,6 +139,7 @@ struct ProfScope {
 struct HostSrc { const char *const *chr; const uint64_t *len; };
 int copy_text_range(sibgpu_ctx *ctx, const HostSrc &src, uint64_t lo, uint64_t hi, cudaStream_t st);
 int enumerate_resident(sibgpu_ctx *ctx, uint32_t k, const HostSrc *src);
+void *pool_alloc(size_t bytes);                        // api.cu: pinned, pooled result buffer (release with sibgpu_free)
 int enumerate_keep(sibgpu_ctx *ctx, const char *const *chr, const uint64_t *len, uint32_t nchr, uint32_t k);   // api.cu
 int list_edges_device(sibgpu_ctx *ctx, uint32_t k, sibgpu_edge **edges_out, uint64_t *nedges_out);   // edges.cu
 int dist_scan(sibgpu_ctx *ctx, uint32_t k, uint32_t *hist_out);

@@ -86,6 +86,21 @@ def test_non_acgt_input_without_inram(tmp_path):
 
 
 @pytest.mark.skipif(not have, reason="oracle/_ref/Sibelia{,_gpu} did not travel")
+@pytest.mark.parametrize("defect", [b">a\nACGT\nACJT\n", b">a\n>b\nACGT\n", b"> x\nACGT\n"])
+def test_cli_reports_parse_errors_like_the_reference(tmp_path, defect):
+    """the bound CLI reads its FASTA files through sibgpu_fasta_parse (facade/fasta_gpu.cpp): same exception text, same
+    exit code as FASTAReader::GetSequences"""
+    fa = str(tmp_path / "bad.fasta")
+    with open(fa, "wb") as f:
+        f.write(b">ok\n" + b"ACGT" * 500 + b"\n" + defect)
+    outs = []
+    for binary in (REF_BIN, GPU_BIN):
+        p = subprocess.run([binary, "-s", "loose", "-o", str(tmp_path / "o"), fa], stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=300)
+        outs.append((p.returncode, [ln for ln in (p.stdout + p.stderr).splitlines() if b"parse error" in ln]))
+    assert outs[0] == outs[1] and outs[0][0] != 0 and outs[0][1], outs
+
+
+@pytest.mark.skipif(not have, reason="oracle/_ref/Sibelia{,_gpu} did not travel")
 def test_condensed_graph_output(tmp_path):
     """-g: BlockFinder::SerializeCondensedGraph (serialization.cpp:88-110) writes the condensed de Bruijn graph of every
     stage and of the final index; in the bound CLI its index + ListEdges pair is one sibgpu_list_edges call."""
