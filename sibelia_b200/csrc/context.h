@@ -66,11 +66,11 @@ struct sibgpu_ctx {
 	uint64_t part_target = 1u << 20;                   // records per partition for 8-byte table slots ...
 	bool part_explicit = false;                        // ... scaled down for wider slots unless the env var pins it
 	// records per hash partition such that one partition's table (table_factor slots per record) stays near 16 MB and
-	// the tables of the overlapped streams stay L2-resident: 8-byte slots (k <= 26) 1 Mi, 16-byte (k <= 32) 512 Ki, 32-byte 256 Ki
+	// the tables of the overlapped streams stay L2-resident: 8-byte slots (k <= 26) 1 Mi, 16-byte slots (all other k) 512 Ki
 	uint64_t part_records(uint32_t k) const
 	{
 		if(part_explicit) return part_target;
-		const uint64_t slot = k <= 26 ? 8 : (k <= 32 ? 16 : 32);
+		const uint64_t slot = k <= 26 ? 8 : 16;
 		const uint64_t r = part_target * 8 / slot;
 		return r < 65536 ? 65536 : r;
 	}
@@ -90,7 +90,7 @@ struct sibgpu_ctx {
 	// grouping of 8-byte records (k <= 28): 1 = buckets of ~1 Ki records grouped in shared memory (k_split + k_group),
 	// 0 = one L2-resident table per hash partition (k_insert + k_table_scan; also the fallback when a bucket overflows)
 	int group_smem = 1;                                // env SIBGPU_GROUP_SMEM
-	bool split_attr_done = false;
+	bool split_attr_done[2] = {false, false};
 	int split_stages = 2;                              // input tiles in flight per CTA of k_split (env SIBGPU_SPLIT_STAGES, dev)
 	uint64_t ckeys_init = 1u << 20;                    // initial capacity of the vertex-key list (env SIBGPU_CKEYS_INIT, tests)
 	uint64_t smem_fallbacks = 0;                       // times a bucket overflowed and the L2-table path took over

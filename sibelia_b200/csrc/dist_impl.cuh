@@ -95,7 +95,7 @@ static int dist_group_mode(sibgpu_ctx *ctx, uint32_t k, const void *recv_dev, co
 	}
 	const uint32_t T = (uint32_t)T64;
 	const bool compact = MODE == 0 && k <= COMPACT_MAX_K;
-	const size_t slot_bytes = compact ? 8 : (MODE <= 1 ? sizeof(Slot8) : sizeof(Slot16));
+	const size_t slot_bytes = compact ? 8 : sizeof(Slot8);
 	SIB_TRY(ctx->d_table.ensure(slot_bytes * T));
 	SIB_CUDA(cudaMemsetAsync(ctx->d_table.p, 0xFF, slot_bytes * T, st));
 	SIB_TRY(ctx->d_records.ensure(sizeof(Rec) * recv_total));          // staging area of the vertex keys, per partition
@@ -368,7 +368,7 @@ static int dist_group_peer_mode(sibgpu_ctx *ctx, uint32_t k, const uint64_t *cou
 	}
 	const uint32_t T = (uint32_t)T64;
 	const bool compact = MODE == 0 && k <= COMPACT_MAX_K;
-	const size_t slot_bytes = compact ? 8 : (MODE <= 1 ? sizeof(Slot8) : sizeof(Slot16));
+	const size_t slot_bytes = compact ? 8 : sizeof(Slot8);
 	const uint32_t S = ctx->n_streams < 1 ? 1 : (ctx->n_streams > 8 ? 8 : ctx->n_streams);
 	const size_t table_bytes = (slot_bytes * T + 255) / 256 * 256;
 	SIB_TRY(ctx->d_table.ensure(table_bytes * S));
@@ -734,10 +734,10 @@ int dist2_run(sibgpu_ctx *ctx, const HostSrc *src, int *status)
 	ssrc.epoch = epoch;
 	ssrc.W = W;
 	ssrc.p0 = rank * PL;
-	const uint32_t tiles_per_seg = (uint32_t)((ctx->x_seg_cap + SPLIT_TILE - 1) / SPLIT_TILE);
+	const uint32_t tiles_per_seg = (uint32_t)((ctx->x_seg_cap + RecOps<uint64_t>::TILE - 1) / RecOps<uint64_t>::TILE);
 	uint32_t *d_flags = reinterpret_cast<uint32_t*>(ds + 11);
-	SIB_TRY(launch_split(ctx, ssrc, PL, tiles_per_seg, sub_bits, ctx->x_nrec / W, d_flags));
-	SIB_TRY(launch_group(ctx, nbuckets, ctx->x_nrec / W, d_flags, keys, key_cap, reinterpret_cast<uint32_t*>(ds + 2)));
+	SIB_TRY(launch_split<uint64_t>(ctx, ssrc, PL, tiles_per_seg, sub_bits, ctx->x_nrec / W, d_flags));
+	SIB_TRY(launch_group<uint64_t>(ctx, nbuckets, ctx->x_nrec / W, d_flags, keys, key_cap, reinterpret_cast<uint32_t*>(ds + 2)));
 	k_publish_keys<<<1, 1, 0, st>>>(hdr, reinterpret_cast<uint32_t*>(ds + 2), d_flags, key_cap, epoch);
 	// ---- all ranks' keys
 	SIB_TRY(ctx->d_ckeys.ensure(sizeof(uint64_t) * std::max<uint64_t>(ctx->ckeys_init, 16)));

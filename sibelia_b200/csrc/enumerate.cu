@@ -18,6 +18,7 @@
 // min(w, revcomp(w)) and the neighbour symbols re-expressed in the canonical orientation, so the class of w and the
 // class of revcomp(w) (which the reference enumerates separately and symmetrically) are decided once.
 #include <algorithm>
+#include <type_traits>
 #include <cub/cub.cuh>
 
 #include "enum_common.cuh"
@@ -220,8 +221,8 @@ template<> struct ScatterSmem<2> : ScatterSmem<1> {};
 // cap != 0: partition b owns the fixed region [b * cap, (b + 1) * cap) of `out` and cursor[b] starts at b * cap (no
 // histogram pass needed); a run that does not fit raises *overflow and is dropped -- the host then redoes the
 // partitioning with exact sizes (k_scan_hist + k_part_offsets, cap == 0).
-// MIXED (8-byte records only): the record carries mix56(key) instead of the key and the partition is a bit field of it
-// (group_smem.cuh)
+// MIXED: the record carries mix56(key) (8-byte records) / mix64(key) (16-byte records) instead of the key and the
+// partition is a bit field of it (group_smem.cuh)
 template<int MODE, bool MIXED>
 __global__ void __launch_bounds__(TILE_THREADS, MODE == 0 ? 4 : 2) k_scatter(TextDesc t, const Rec16 *__restrict__ fp, uint32_t k,
 	uint32_t ntiles, uint32_t P, unsigned long long *__restrict__ cursor, typename RecT<MODE>::type *__restrict__ out,
@@ -245,8 +246,9 @@ __global__ void __launch_bounds__(TILE_THREADS, MODE == 0 ? 4 : 2) k_scatter(Tex
 		uint32_t binrank[POS_PER_THREAD];
 		uint32_t valid = 0;
 		scan16<MODE>(t, fp, s.sw, t.tile0 + tile, k, [&](int i, uint64_t a, uint64_t b, uint32_t ctx) {
-			if(MIXED) a = mix56(a);
-			uint32_t bin = MIXED ? mixed_part(a, P) : __umulhi((uint32_t)(rec_hash(a, b) >> 32), P);
+			if(MIXED) a = MODE == 0 ? mix56(a) : mix64(a);
+			uint32_t bin = MIXED ? (MODE == 0 ? mixed_part(a, P) : __umulhi((uint32_t)(a >> 32), P))
+				: __umulhi((uint32_t)(rec_hash(a, b) >> 32), P);
 			uint32_t rank = atomicAdd(&s.cnt[bin], 1u);
 			binrank[i] = (bin << 16) | rank;             // rank < 4096, bin < 1024
 			valid |= 1u << i;
@@ -314,7 +316,7 @@ __global__ void __launch_bounds__(TILE_THREADS, MODE == 0 ? 4 : 2) k_scatter(Tex
 		for(uint32_t l = threadIdx.x; l < n; l += TILE_THREADS)
 		{
 			const uint64_t a = s.a[l];
-			const uint32_t bin = MIXED ? mixed_part(a >> 7, P) : s.bin_of[l];
+			const uint32_t bin = MIXED ? (MODE == 0 ? mixed_part(a >> 7, P) : __umulhi((uint32_t)(a >> 32), P)) : s.bin_of[l];
 			if(drops && ((s.dropmask[bin >> 5] >> (bin & 31u)) & 1u)) continue;
 			unsigned long long gi = s.gbase[bin] + l;
 			if(MODE == 0) { reinterpret_cast<uint64_t*>(out)[gi] = a; }
@@ -328,7 +330,6 @@ __global__ void __launch_bounds__(TILE_THREADS, MODE == 0 ? 4 : 2) k_scatter(Tex
 // K3: insert one partition into the L2-resident table.   K4: predicate + reset.
 // ---------------------------------------------------------------------------------------------------------------
 struct Slot8 { unsigned long long key; uint32_t pay; uint32_t pad; };             // 16 B
-struct Slot16 { unsigned long long a, b; uint32_t pay; uint32_t pad[3]; };        // 32 B
 
 // one occurrence into the 16-byte (MODE 0) / 32-byte (MODE 1, 2) slot tables
 template<int MODE> struct RecVal { typedef ulonglong2 type; };
@@ -362,40 +363,11 @@ __device__ __forceinline__ void insert_slot8(unsigned long long key, uint32_t ct
 	}
 }
 
-// 32-byte slots {a, b, payload}: 117-bit fingerprints (k > 32)
-__device__ __forceinline__ void insert_slot16(ulonglong2 rec, void *__restrict__ table, uint32_t T)
-{
-	{
-		Slot16 *tab = static_cast<Slot16*>(table);
-		const unsigned long long a = rec.x, b = rec.y >> 8;    // b < 2^56, never the "unclaimed" sentinel
-		const uint32_t ctx = (uint32_t)rec.y & 127u;
-		uint32_t slot = __umulhi((uint32_t)rec_hash(a, b), T);
-		uint32_t bits = payload_bits(ctx);
-		for(;;)
-		{
-			unsigned long long oa = atomicCAS(&tab[slot].a, EMPTY64, a);
-			if(oa == EMPTY64 || oa == a)
-			{
-				// second word: claimed by whoever CASes it first; a different b means another class
-				unsigned long long ob = atomicCAS(&tab[slot].b, EMPTY64, b);
-				if(ob == EMPTY64 || ob == b)
-				{
-					if(ob == b) bits |= PAY_MULTI;
-					atomicAnd(&tab[slot].pay, ~bits);
-					break;
-				}
-			}
-			slot = slot + 1 == T ? 0 : slot + 1;
-		}
-	}
-}
-
 template<int MODE>
 __device__ __forceinline__ void insert_wide_rec(typename RecVal<MODE>::type rec, void *__restrict__ table, uint32_t T)
 {
 	if constexpr(MODE == 0) insert_slot8(rec >> 7, (uint32_t)rec & 127u, table, T);
-	else if constexpr(MODE == 1) insert_slot8(rec.x, (uint32_t)rec.y & 127u, table, T);
-	else insert_slot16(rec, table, T);
+	else insert_slot8(rec.x, (uint32_t)rec.y & 127u, table, T);      // exact 64-bit key, or the 61-bit fingerprint
 }
 
 template<int MODE>
@@ -422,7 +394,6 @@ __global__ void __launch_bounds__(256) k_table_scan(void *__restrict__ table, ui
 		unsigned long long a = 0, b = 0;
 		if(sidx < T)
 		{
-			if(MODE <= 1)
 			{
 				Slot8 *tab = static_cast<Slot8*>(table);
 				a = tab[sidx].key;
@@ -430,19 +401,6 @@ __global__ void __launch_bounds__(256) k_table_scan(void *__restrict__ table, ui
 				{
 					bif = is_bifurcation(~tab[sidx].pay);
 					tab[sidx].key = EMPTY64;
-					tab[sidx].pay = ~0u;
-				}
-			}
-			else
-			{
-				Slot16 *tab = static_cast<Slot16*>(table);
-				a = tab[sidx].a;
-				if(a != EMPTY64)
-				{
-					b = tab[sidx].b;
-					bif = is_bifurcation(~tab[sidx].pay);
-					tab[sidx].a = EMPTY64;
-					tab[sidx].b = EMPTY64;
 					tab[sidx].pay = ~0u;
 				}
 			}
@@ -1164,40 +1122,43 @@ static int input_error()
 	return SIBGPU_ERR_INPUT;
 }
 
-// k_split over P1 owned partitions read from ssrc (single GPU: the own record buffer; sharded: all ranks' buffers)
+// k_split over P1 owned partitions read from ssrc (single GPU: the own record buffer; sharded: all ranks' buffers);
+// R = uint64_t (8-byte records) or ulonglong2 (16-byte records)
+template<class R>
 static int launch_split(sibgpu_ctx *ctx, const SplitSrc &ssrc, uint32_t P1, uint32_t tiles_per_seg, uint32_t sub_bits,
 	uint64_t nrec, uint32_t *d_flags)
 {
-	bool &attr_done = ctx->split_attr_done;
+	bool &attr_done = ctx->split_attr_done[sizeof(R) == 8 ? 0 : 1];
 	if(!attr_done)
 	{
-		SIB_CUDA(cudaFuncSetAttribute(k_split<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SplitSmem<1>)));
-		SIB_CUDA(cudaFuncSetAttribute(k_split<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SplitSmem<2>)));
-		SIB_CUDA(cudaFuncSetAttribute(k_group, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(GroupSmem)));
+		SIB_CUDA(cudaFuncSetAttribute(k_split<1, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SplitSmem<1, R>)));
+		SIB_CUDA(cudaFuncSetAttribute(k_split<2, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SplitSmem<2, R>)));
+		SIB_CUDA(cudaFuncSetAttribute(k_group<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(GroupSmem<R>)));
 		attr_done = true;
 	}
 	const uint64_t split_tiles = (uint64_t)P1 * ssrc.W * tiles_per_seg;
 	const uint64_t sms = (uint64_t)ctx->sm_count;
-	ProfScope ps(ctx, "k_split", nrec * 16);
+	ProfScope ps(ctx, "k_split", nrec * 2 * sizeof(R));
 	if(ctx->split_stages == 1)
 	{
-		k_split<1><<<(uint32_t)std::min<uint64_t>(split_tiles, sms * 3), SPLIT_THREADS, sizeof(SplitSmem<1>), ctx->stream>>>(
-			ssrc, P1, tiles_per_seg, sub_bits, ctx->d_records2.as<uint64_t>(), ctx->d_cnt2.as<uint32_t>(), GROUP_CAP, d_flags);
+		k_split<1, R><<<(uint32_t)std::min<uint64_t>(split_tiles, sms * 3), SPLIT_THREADS, sizeof(SplitSmem<1, R>), ctx->stream>>>(
+			ssrc, P1, tiles_per_seg, sub_bits, ctx->d_records2.as<R>(), ctx->d_cnt2.as<uint32_t>(), GROUP_CAP, d_flags);
 	}
 	else
 	{
-		k_split<2><<<(uint32_t)std::min<uint64_t>(split_tiles, sms * 2), SPLIT_THREADS, sizeof(SplitSmem<2>), ctx->stream>>>(
-			ssrc, P1, tiles_per_seg, sub_bits, ctx->d_records2.as<uint64_t>(), ctx->d_cnt2.as<uint32_t>(), GROUP_CAP, d_flags);
+		k_split<2, R><<<(uint32_t)std::min<uint64_t>(split_tiles, sms * 2), SPLIT_THREADS, sizeof(SplitSmem<2, R>), ctx->stream>>>(
+			ssrc, P1, tiles_per_seg, sub_bits, ctx->d_records2.as<R>(), ctx->d_cnt2.as<uint32_t>(), GROUP_CAP, d_flags);
 	}
 	return SIBGPU_OK;
 }
 
-static int launch_group(sibgpu_ctx *ctx, uint32_t nbuckets, uint64_t nrec, uint32_t *d_flags, uint64_t *ckeys, uint32_t ckeys_cap,
+template<class R>
+static int launch_group(sibgpu_ctx *ctx, uint32_t nbuckets, uint64_t nrec, uint32_t *d_flags, R *ckeys, uint32_t ckeys_cap,
 	uint32_t *d_nkeys)
 {
-	ProfScope ps(ctx, "k_group", nrec * 8);
-	k_group<<<std::min<uint32_t>(nbuckets, (uint32_t)ctx->sm_count * 4), GROUP_THREADS, sizeof(GroupSmem), ctx->stream>>>(
-		ctx->d_records2.as<uint64_t>(), ctx->d_cnt2.as<uint32_t>(), nbuckets, GROUP_CAP, d_flags, ckeys, ckeys_cap, d_nkeys);
+	ProfScope ps(ctx, "k_group", nrec * sizeof(R));
+	k_group<R><<<std::min<uint32_t>(nbuckets, (uint32_t)ctx->sm_count * (sizeof(R) == 8 ? 4 : 2)), GROUP_THREADS, sizeof(GroupSmem<R>),
+		ctx->stream>>>(ctx->d_records2.as<R>(), ctx->d_cnt2.as<uint32_t>(), nbuckets, GROUP_CAP, d_flags, ckeys, ckeys_cap, d_nkeys);
 	return SIBGPU_OK;
 }
 
@@ -1224,9 +1185,10 @@ static int enumerate_mode(sibgpu_ctx *ctx, uint32_t k, uint64_t nrec, const Host
 	t.nwords = (uint32_t)((ctx->M + 15) / 16) + 8;
 	t.tile0 = 0;
 	const uint32_t ntiles = (uint32_t)((ctx->M + TILE_POS - 1) / TILE_POS);
+	typedef typename std::conditional<MODE == 0, uint64_t, ulonglong2>::type SR;   // record type of the shared-memory path
 	const size_t scatter_smem = sizeof(ScatterSmem<MODE>);
 	SIB_CUDA(cudaFuncSetAttribute(k_scatter<MODE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scatter_smem));
-	if(MODE == 0) SIB_CUDA(cudaFuncSetAttribute(k_scatter<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScatterSmem<0>)));
+	SIB_CUDA(cudaFuncSetAttribute(k_scatter<MODE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scatter_smem));
 
 	for(uint32_t attempt = 0; ; attempt++)
 	{
@@ -1234,9 +1196,9 @@ static int enumerate_mode(sibgpu_ctx *ctx, uint32_t k, uint64_t nrec, const Host
 		const Rec16 *fp = ctx->d_fp.as<Rec16>();
 
 		// ---- partition plan
-		// 8-byte records: level-1 partitions of 512 Ki records, split into ~1 Ki-record buckets and grouped in shared
-		// memory (group_smem.cuh); otherwise one L2-resident table per partition
-		const bool smem_group = MODE == 0 && ctx->group_smem && !ctx->exact_hist;
+		// level-1 partitions of 512 Ki records, split into ~1 Ki-record buckets and grouped in shared memory
+		// (group_smem.cuh); otherwise (SIBGPU_GROUP_SMEM=0, fallbacks) one L2-resident table per partition
+		const bool smem_group = ctx->group_smem && !ctx->exact_hist;
 		const uint64_t part_rec = smem_group && !ctx->part_explicit ? (uint64_t)512 << 10 : ctx->part_records(k);
 		uint64_t P64 = (nrec + part_rec - 1) / part_rec;
 		const uint32_t P = (uint32_t)(P64 < 1 ? 1 : (P64 > MAX_PARTS ? MAX_PARTS : P64));
@@ -1305,8 +1267,8 @@ static int enumerate_mode(sibgpu_ctx *ctx, uint32_t k, uint64_t nrec, const Host
 					tc.tile0 = tiles_done;
 					ProfScope ps(ctx, "k_scatter", (MODE == 2 ? (uint64_t)nt * TILE_POS * 16 : (uint64_t)nt * TILE_POS / 4)
 						+ nrec * sizeof(Rec) * nt / ntiles);
-					if(mixed) k_scatter<0, true><<<g, TILE_THREADS, sizeof(ScatterSmem<0>), st>>>(tc, fp, k, nt, P,
-						ctx->d_cursor.as<unsigned long long>(), ctx->d_records.as<uint64_t>(), cap, d_overflow);
+					if(mixed) k_scatter<MODE, true><<<g, TILE_THREADS, scatter_smem, st>>>(tc, fp, k, nt, P,
+						ctx->d_cursor.as<unsigned long long>(), ctx->d_records.as<Rec>(), cap, d_overflow);
 					else k_scatter<MODE, false><<<g, TILE_THREADS, scatter_smem, st>>>(tc, fp, k, nt, P, ctx->d_cursor.as<unsigned long long>(),
 						ctx->d_records.as<Rec>(), cap, d_overflow);
 					tiles_done = tile_hi;
@@ -1317,27 +1279,24 @@ static int enumerate_mode(sibgpu_ctx *ctx, uint32_t k, uint64_t nrec, const Host
 			bool smem_launched = false;
 			uint32_t nbuckets = 0;
 			uint32_t ckeys_cap = 0;
-			if constexpr(MODE == 0)
+			if(mixed)
 			{
-				if(mixed)
-				{
-					nbuckets = P << sub_bits;
-					SIB_TRY(ctx->d_records2.ensure(sizeof(uint64_t) * (size_t)nbuckets * GROUP_CAP + 64));
-					SIB_TRY(ctx->d_cnt2.ensure(sizeof(uint32_t) * (size_t)nbuckets));
-					SIB_TRY(ctx->d_ckeys.ensure(sizeof(uint64_t) * (ctx->ckeys_init ? ctx->ckeys_init : 1)));
-					ckeys_cap = (uint32_t)std::min<size_t>(ctx->d_ckeys.cap / sizeof(uint64_t), 0xFFFFFFF0u);
-					SIB_CUDA(cudaMemsetAsync(ctx->d_cnt2.p, 0, sizeof(uint32_t) * (size_t)nbuckets, st));
-					const uint32_t tiles_per_seg = (uint32_t)((cap + SPLIT_TILE - 1) / SPLIT_TILE);
-					SplitSrc ssrc = {};
-					ssrc.seg[0] = ctx->d_records.as<uint64_t>();
-					ssrc.cursor[0] = ctx->d_cursor.as<unsigned long long>();
-					ssrc.seg_cap = cap;
-					ssrc.W = 1;
-					SIB_TRY(launch_split(ctx, ssrc, P, tiles_per_seg, sub_bits, nrec, reinterpret_cast<uint32_t*>(ds + 11)));
-					SIB_TRY(launch_group(ctx, nbuckets, nrec, reinterpret_cast<uint32_t*>(ds + 11), ctx->d_ckeys.as<uint64_t>(), ckeys_cap,
-						reinterpret_cast<uint32_t*>(ds + 2)));
-					smem_launched = true;
-				}
+				nbuckets = P << sub_bits;
+				SIB_TRY(ctx->d_records2.ensure(sizeof(SR) * (size_t)nbuckets * GROUP_CAP + 64));
+				SIB_TRY(ctx->d_cnt2.ensure(sizeof(uint32_t) * (size_t)nbuckets));
+				SIB_TRY(ctx->d_ckeys.ensure(sizeof(SR) * (ctx->ckeys_init ? ctx->ckeys_init : 1)));
+				ckeys_cap = (uint32_t)std::min<size_t>(ctx->d_ckeys.cap / sizeof(SR), 0xFFFFFFF0u);
+				SIB_CUDA(cudaMemsetAsync(ctx->d_cnt2.p, 0, sizeof(uint32_t) * (size_t)nbuckets, st));
+				const uint32_t tiles_per_seg = (uint32_t)((cap + RecOps<SR>::TILE - 1) / RecOps<SR>::TILE);
+				SplitSrc ssrc = {};
+				ssrc.seg[0] = ctx->d_records.p;
+				ssrc.cursor[0] = ctx->d_cursor.as<unsigned long long>();
+				ssrc.seg_cap = cap;
+				ssrc.W = 1;
+				SIB_TRY(launch_split<SR>(ctx, ssrc, P, tiles_per_seg, sub_bits, nrec, reinterpret_cast<uint32_t*>(ds + 11)));
+				SIB_TRY(launch_group<SR>(ctx, nbuckets, nrec, reinterpret_cast<uint32_t*>(ds + 11), ctx->d_ckeys.as<SR>(), ckeys_cap,
+					reinterpret_cast<uint32_t*>(ds + 2)));
+				smem_launched = true;
 			}
 			SIB_CUDA(cudaMemcpyAsync(cur.data(), ctx->d_cursor.p, sizeof(uint64_t) * cur.size(), cudaMemcpyDeviceToHost, st));
 			SIB_CUDA(cudaMemcpyAsync(hs + 8, ds + 8, sizeof(uint64_t) * 4, cudaMemcpyDeviceToHost, st));
@@ -1380,17 +1339,14 @@ static int enumerate_mode(sibgpu_ctx *ctx, uint32_t k, uint64_t nrec, const Host
 					else
 					{
 						Vc = hs[2] & 0xFFFFFFFFull;
-						if constexpr(MODE == 0)
+						if(Vc > ckeys_cap)
 						{
-							if(Vc > ckeys_cap)
-							{
-								// the key list was too small (k_group kept counting): regrow, group again -- the buckets are intact
-								SIB_TRY(ctx->d_ckeys.ensure(sizeof(uint64_t) * Vc));
-								SIB_CUDA(cudaMemsetAsync(ds + 2, 0, sizeof(uint64_t), st));
-								SIB_TRY(launch_group(ctx, nbuckets, nrec, reinterpret_cast<uint32_t*>(ds + 11), ctx->d_ckeys.as<uint64_t>(),
-									(uint32_t)Vc, reinterpret_cast<uint32_t*>(ds + 2)));
-								SIB_CUDA(cudaStreamSynchronize(st));
-							}
+							// the key list was too small (k_group kept counting): regrow, group again -- the buckets are intact
+							SIB_TRY(ctx->d_ckeys.ensure(sizeof(SR) * Vc));
+							SIB_CUDA(cudaMemsetAsync(ds + 2, 0, sizeof(uint64_t), st));
+							SIB_TRY(launch_group<SR>(ctx, nbuckets, nrec, reinterpret_cast<uint32_t*>(ds + 11), ctx->d_ckeys.as<SR>(),
+								(uint32_t)Vc, reinterpret_cast<uint32_t*>(ds + 2)));
+							SIB_CUDA(cudaStreamSynchronize(st));
 						}
 						grouped = true;
 					}
@@ -1451,7 +1407,7 @@ static int enumerate_mode(sibgpu_ctx *ctx, uint32_t k, uint64_t nrec, const Host
 		}
 		const uint32_t T = (uint32_t)T64;
 		const bool compact = MODE == 0 && k <= COMPACT_MAX_K && !mixed;   // a mixed key needs all 56 bits
-		const size_t slot_bytes = compact ? 8 : (MODE <= 1 ? sizeof(Slot8) : sizeof(Slot16));
+		const size_t slot_bytes = compact ? 8 : sizeof(Slot8);
 		// S independent tables on S streams: consecutive partitions overlap, so the ramp-up / tail of one partition's
 		// kernels is filled by its neighbours (with S = 1 everything runs on the main stream and is timed per launch)
 		const uint32_t S = ctx->n_streams < 1 ? 1 : (ctx->n_streams > 8 ? 8 : ctx->n_streams);
@@ -1524,7 +1480,7 @@ static int enumerate_mode(sibgpu_ctx *ctx, uint32_t k, uint64_t nrec, const Host
 			dim3 g(8, P);
 			k_gather_keys<MODE><<<g, 256, 0, st>>>(ctx->d_records.as<Rec>(), ctx->d_partoff.as<uint64_t>(),
 				ctx->d_partcnt.as<uint32_t>(), ctx->d_keyoff.as<uint64_t>(), ctx->d_ckeys.as<Rec>());
-			if(mixed) k_unmix<<<(uint32_t)((Vc + 255) / 256), 256, 0, st>>>(ctx->d_ckeys.as<uint64_t>(), Vc);
+			if(mixed) k_unmix<SR><<<(uint32_t)((Vc + 255) / 256), 256, 0, st>>>(ctx->d_ckeys.as<SR>(), Vc);
 		}
 
 		bool collision = false;

@@ -1,6 +1,9 @@
-// k > 32: the k-mer no longer fits a 64-bit word, so classes are found on 117-bit fingerprints
-//   a = polynomial hash mod 2^61-1,  b = top 56 bits of a polynomial hash mod 2^64  (both rolled along the text),
-// the canonical form being the smaller of the fingerprints of w and revcomp(w).  Vertex ids still have to be the
+// k > 32: the k-mer no longer fits a 64-bit word, so classes are found on a 61-bit fingerprint
+//   a = polynomial hash mod 2^61-1, rolled along the text,
+// the canonical form being the smaller of the fingerprints of w and revcomp(w); the record {a, context} then takes the
+// same path as the exact 16-byte records of k = 29..32.  Two different k-mers share a fingerprint with probability
+// ~ n^2 / 2^62 per run (0.05 for 5 * 10^8 distinct k-mers); a false merge can only ADD symbols to a class, i.e. turn a
+// non-vertex into a vertex, and that is caught below.  Vertex ids still have to be the
 // lexicographic ranks of the actual k-mers (vertexenumeration.cpp:350), so the (few) vertex classes are ranked by
 // comparing the strings they spell in the packed text, and every emitted instance is verified against its class
 // representative (k_emit) -- a collision that could alter the result forces a re-run with other bases.
@@ -84,18 +87,16 @@ __global__ void __launch_bounds__(128) k_fingerprint(TextDesc t, uint32_t k, uin
 	if(start64 >= t.M) return;
 	const uint32_t start = (uint32_t)start64;
 	const uint32_t end = start + L < t.M ? start + L : t.M;
-	uint64_t hf1 = 0, hf2 = 0, hr1 = 0, hr2 = 0;
+	uint64_t hf1 = 0, hr1 = 0;
 	for(uint32_t j = 0; j < k; j++)
 	{
 		const uint32_t c = code_at(t, start + j);
 		hf1 = addmod61(mulmod61(hf1, prm.B1), c + 1);
-		hf2 = hf2 * prm.B2 + (c + 1);
 	}
 	for(uint32_t j = k; j-- > 0; )
 	{
 		const uint32_t c = code_at(t, start + j);
 		hr1 = addmod61(mulmod61(hr1, prm.B1), 4 - c);
-		hr2 = hr2 * prm.B2 + (4 - c);
 	}
 	ChrCursor cur;
 	cur.init(t, start);
@@ -111,19 +112,16 @@ __global__ void __launch_bounds__(128) k_fingerprint(TextDesc t, uint32_t k, uin
 		{
 			const uint32_t ps = p == cur.cs ? 4u : prevc;
 			const uint32_t ns = p + k == cur.ce ? 4u : cin;
-			const uint64_t f2 = hf2 >> 8, r2 = hr2 >> 8;
-			const bool pal = hf1 == hr1 && f2 == r2;
-			const bool fw = hf1 < hr1 || (hf1 == hr1 && f2 <= r2);
+			const bool pal = hf1 == hr1;
+			const bool fw = hf1 <= hr1;
 			uint32_t ctx = fw ? ((ps << 3) | ns) : ((comp_sym(ns) << 3) | comp_sym(ps));
 			ctx |= (pal ? 64u : 0u) | (fw ? 128u : 0u);
 			out.a = fw ? hf1 : hr1;
-			out.b = ((fw ? f2 : r2) << 8) | ctx;
+			out.b = ctx;
 		}
 		fp[p] = out;
 		hf1 = addmod61(mulmod61(addmod61(hf1, P61 - prm.T1f[cout]), prm.B1), cin + 1);
-		hf2 = (hf2 - prm.T2f[cout]) * prm.B2 + (cin + 1);
 		hr1 = addmod61(mulmod61(addmod61(hr1, P61 - (4 - cout)), prm.invB1), prm.T1r[cin]);
-		hr2 = (hr2 - (4 - cout)) * prm.invB2 + prm.T2r[cin];
 		prevc = cout;
 	}
 }

@@ -45,9 +45,36 @@ __host__ __device__ __forceinline__ uint64_t unmix56(uint64_t x)
 // bit fields of a mixed key m:  level-1 partition = top bits, bucket = bits 0-9, table slot = bits 10-21, tag = bits 22-41
 __device__ __forceinline__ uint32_t mixed_part(uint64_t m, uint32_t P) { return __umulhi((uint32_t)(m >> 24), P); }
 
+// Wide records (16 bytes: k = 29..32 exact keys, k > 32 fingerprints) carry mix64(key), the murmur3 finaliser, which is a
+// bijection of the 64-bit words: xor-shift by 33 is an involution, the multipliers are odd.
+constexpr uint64_t MIX64_I1 = 0x4f74430c22a54005ull, MIX64_I2 = 0x9cb4b2f8129337dbull;   // inverses of the two multipliers mod 2^64
+__host__ __device__ __forceinline__ uint64_t unmix64(uint64_t x)
+{
+	x ^= x >> 33;
+	x *= MIX64_I2;
+	x ^= x >> 33;
+	x *= MIX64_I1;
+	x ^= x >> 33;
+	return x;
+}
+
+// Record formats of the shared-memory path.  narrow: (mixed 56-bit key << 7) | context;  wide: {mixed 64-bit key, context}.
+// Bit fields of the mixed key: bucket = bits 0-9, table slot = bits 10-21, tag = bits 22-41, partition = top bits.
+template<class R> struct RecOps;
+template<> struct RecOps<uint64_t> {
+	static constexpr int TILE = 4096;                  // records per k_split tile (32 KB)
+	static __device__ __forceinline__ uint64_t key(uint64_t r) { return r >> 7; }
+	static __device__ __forceinline__ uint32_t ctx(uint64_t r) { return (uint32_t)r & 127u; }
+	static __device__ __forceinline__ bool same_key(uint64_t a, uint64_t b) { return (a >> 7) == (b >> 7); }
+};
+template<> struct RecOps<ulonglong2> {
+	static constexpr int TILE = 2048;
+	static __device__ __forceinline__ uint64_t key(const ulonglong2 &r) { return r.x; }
+	static __device__ __forceinline__ uint32_t ctx(const ulonglong2 &r) { return (uint32_t)r.y & 127u; }
+	static __device__ __forceinline__ bool same_key(const ulonglong2 &a, const ulonglong2 &b) { return a.x == b.x; }
+};
+
 constexpr int SPLIT_THREADS = 512;
-constexpr int SPLIT_TILE = 4096;                       // records per tile
-constexpr int SPLIT_PER_THREAD = SPLIT_TILE / SPLIT_THREADS;
 constexpr int SPLIT_MAX_BINS = 1024;
 constexpr uint32_t GROUP_THREADS = 256;
 constexpr uint32_t GROUP_SLOTS = 4096;                 // shared-memory table slots (load <= 0.41)
@@ -82,9 +109,9 @@ __device__ __forceinline__ void bulk_load(void *dst, const void *src, uint32_t b
 	}
 }
 
-template<int STAGES> struct SplitSmem {
-	uint64_t in[STAGES][SPLIT_TILE];                   // tiles as they lie in the partition (TMA destinations)
-	uint64_t sorted[SPLIT_TILE];                       // the current tile ordered by bucket
+template<int STAGES, class R> struct SplitSmem {
+	R in[STAGES][RecOps<R>::TILE];                     // tiles as they lie in the partition (TMA destinations)
+	R sorted[RecOps<R>::TILE];                         // the current tile ordered by bucket
 	uint32_t cnt[SPLIT_MAX_BINS];                      // per-bin count of this tile, then exclusive local offset
 	uint32_t gbase[SPLIT_MAX_BINS];                    // index of the bin's run in the partition's level-2 region minus the local offset
 	uint32_t dropmask[SPLIT_MAX_BINS / 32];            // bins whose run did not fit (overflow: the caller discards the run)
@@ -108,7 +135,7 @@ struct DistHeader {                                    // first 256 bytes of a r
 	unsigned long long pad[27];
 };
 struct SplitSrc {
-	const uint64_t *seg[SPLIT_MAX_SRC];                // records of source s; partition q lies at [q * seg_cap, ...)
+	const void *seg[SPLIT_MAX_SRC];                    // records of source s; partition q lies at [q * seg_cap, ...)
 	const unsigned long long *cursor[SPLIT_MAX_SRC];   // fill cursors of source s (absolute record index, one per CURSOR_STRIDE)
 	const DistHeader *header[SPLIT_MAX_SRC];           // nullptr: no waiting (own buffer on a single GPU)
 	unsigned long long seg_cap;
@@ -149,17 +176,19 @@ __device__ __forceinline__ bool wait_epoch(const unsigned long long *flag, unsig
 
 // Level 2: the records of owned partition p (from every source) -> B2 buckets of fixed capacity cap2 at
 // out[(p * B2 + b) * cap2].
-// A tile is 4096 consecutive records of one segment: TMA bulk copy into shared memory (STAGES tiles in flight: the
+// A tile is 32 KB of consecutive records of one segment: TMA bulk copy into shared memory (STAGES tiles in flight: the
 // copies of the following tiles run while this one is sorted and written out), counting sort by bucket (rank =
 // returning shared atomic), coalesced copy-out of the runs; cnt2[p * B2 + b] is the bucket's fill count.  Consecutive
 // tile indices belong to different partitions, so concurrently running CTAs bump different bucket counters.
 // Segments must be 16-byte aligned (seg_cap even).
-template<int STAGES>
+template<int STAGES, class R>
 __global__ void __launch_bounds__(SPLIT_THREADS, STAGES == 1 ? 3 : 2) k_split(const SplitSrc src, uint32_t P1, uint32_t tiles_per_seg,
-	uint32_t sub_bits, uint64_t *__restrict__ out, uint32_t *__restrict__ cnt2, uint32_t cap2, uint32_t *__restrict__ overflow)
+	uint32_t sub_bits, R *__restrict__ out, uint32_t *__restrict__ cnt2, uint32_t cap2, uint32_t *__restrict__ overflow)
 {
 	extern __shared__ __align__(16) unsigned char smem_raw[];
-	SplitSmem<STAGES> &s = *reinterpret_cast<SplitSmem<STAGES>*>(smem_raw);
+	SplitSmem<STAGES, R> &s = *reinterpret_cast<SplitSmem<STAGES, R>*>(smem_raw);
+	constexpr uint32_t SPLIT_TILE = RecOps<R>::TILE;
+	constexpr int SPLIT_PER_THREAD = SPLIT_TILE / SPLIT_THREADS;
 	typedef cub::BlockScan<uint32_t, SPLIT_THREADS> Scan;
 	__shared__ typename Scan::TempStorage scan_tmp;
 	const uint32_t B2 = 1u << sub_bits, sub_mask = B2 - 1u;
@@ -199,7 +228,7 @@ __global__ void __launch_bounds__(SPLIT_THREADS, STAGES == 1 ? 3 : 2) k_split(co
 			const uint32_t n = np - first < SPLIT_TILE ? (uint32_t)(np - first) : SPLIT_TILE;
 			s.tile_n[st] = n;
 			s.tile_p[st] = p;
-			bulk_load(s.in[st], src.seg[sidx] + base + first, (n * 8u + 15u) & ~15u, &s.bar[st]);
+			bulk_load(s.in[st], static_cast<const R*>(src.seg[sidx]) + base + first, (n * (uint32_t)sizeof(R) + 15u) & ~15u, &s.bar[st]);
 			return t;
 		}
 		s.tile_n[st] = 0;
@@ -221,14 +250,14 @@ __global__ void __launch_bounds__(SPLIT_THREADS, STAGES == 1 ? 3 : 2) k_split(co
 		const uint32_t n = s.tile_n[stage], p = s.tile_p[stage];
 		if(n == 0) break;
 		mbar_wait(&s.bar[stage], phase);
-		const uint64_t *in = s.in[stage];
+		const R *in = s.in[stage];
 
 		uint32_t rank[SPLIT_PER_THREAD];
 #pragma unroll
 		for(int j = 0; j < SPLIT_PER_THREAD; j++)
 		{
 			const uint32_t i = j * SPLIT_THREADS + threadIdx.x;
-			if(i < n) rank[j] = atomicAdd(&s.cnt[(uint32_t)(in[i] >> 7) & sub_mask], 1u);
+			if(i < n) rank[j] = atomicAdd(&s.cnt[(uint32_t)RecOps<R>::key(in[i]) & sub_mask], 1u);
 		}
 		__syncthreads();
 
@@ -257,8 +286,8 @@ __global__ void __launch_bounds__(SPLIT_THREADS, STAGES == 1 ? 3 : 2) k_split(co
 			const uint32_t i = j * SPLIT_THREADS + threadIdx.x;
 			if(i < n)
 			{
-				const uint64_t rec = in[i];
-				s.sorted[s.cnt[(uint32_t)(rec >> 7) & sub_mask] + rank[j]] = rec;
+				const R rec = in[i];
+				s.sorted[s.cnt[(uint32_t)RecOps<R>::key(rec) & sub_mask] + rank[j]] = rec;
 			}
 		}
 #pragma unroll
@@ -279,12 +308,12 @@ __global__ void __launch_bounds__(SPLIT_THREADS, STAGES == 1 ? 3 : 2) k_split(co
 		__syncthreads();                               // this stage's input is consumed: the tile after the ones in flight may land
 		if(threadIdx.x == 0) t_cur = fetch(t_cur + gridDim.x, stage);
 
-		uint64_t *dst = out + (uint64_t)p * B2 * cap2;
+		R *dst = out + (uint64_t)p * B2 * cap2;
 		const bool drops = s.anydrop != 0;
 		for(uint32_t l = threadIdx.x; l < n; l += SPLIT_THREADS)
 		{
-			const uint64_t rec = s.sorted[l];
-			const uint32_t bin = (uint32_t)(rec >> 7) & sub_mask;
+			const R rec = s.sorted[l];
+			const uint32_t bin = (uint32_t)RecOps<R>::key(rec) & sub_mask;
 			if(!drops || !((s.dropmask[bin >> 5] >> (bin & 31u)) & 1u)) dst[s.gbase[bin] + l] = rec;
 		}
 		if(++stage == STAGES) { stage = 0; phase ^= 1u; }
@@ -295,8 +324,8 @@ __global__ void __launch_bounds__(SPLIT_THREADS, STAGES == 1 ? 3 : 2) k_split(co
 constexpr uint32_t GROUP_WARPS = GROUP_THREADS / 32;
 constexpr uint32_t GROUP_DEFER_CAP = (GROUP_CAP + GROUP_THREADS - 1) / GROUP_THREADS * 32;   // records one warp handles per bucket
 
-struct GroupSmem {
-	unsigned long long stage[GROUP_STAGES][GROUP_CAP];
+template<class R> struct GroupSmem {
+	R stage[GROUP_STAGES][GROUP_CAP];
 	uint32_t tab[GROUP_SLOTS];                         // {tag : 20, index of the class's first record : 12} or EMPTY32
 	uint32_t pay[GROUP_CAP];                           // payload of the class whose first record has this index (else 0)
 	uint16_t defer[GROUP_WARPS][GROUP_DEFER_CAP];      // per warp: records whose home slot holds another key
@@ -307,12 +336,13 @@ struct GroupSmem {
 
 // Level 3: one bucket at a time per CTA (persistent grid, GROUP_STAGES buckets in flight per CTA through the TMA ring).
 // nkeys counts every bifurcation class even when the key list is full (the caller then regrows it and runs again).
-__global__ void __launch_bounds__(GROUP_THREADS, 4) k_group(const uint64_t *__restrict__ recs2, const uint32_t *__restrict__ cnt2,
-	uint32_t nbuckets, uint32_t cap2, const uint32_t *__restrict__ overflow, uint64_t *__restrict__ ckeys, uint32_t ckeys_cap,
+template<class R>
+__global__ void __launch_bounds__(GROUP_THREADS, sizeof(R) == 8 ? 4 : 2) k_group(const R *__restrict__ recs2, const uint32_t *__restrict__ cnt2,
+	uint32_t nbuckets, uint32_t cap2, const uint32_t *__restrict__ overflow, R *__restrict__ ckeys, uint32_t ckeys_cap,
 	uint32_t *__restrict__ nkeys)
 {
 	extern __shared__ __align__(16) unsigned char smem_raw[];
-	GroupSmem &s = *reinterpret_cast<GroupSmem*>(smem_raw);
+	GroupSmem<R> &s = *reinterpret_cast<GroupSmem<R>*>(smem_raw);
 	if(*overflow) return;                                  // a bucket outgrew its region: the caller takes the L2-table path
 	for(uint32_t i = threadIdx.x; i < GROUP_SLOTS; i += GROUP_THREADS) s.tab[i] = EMPTY32;
 	for(uint32_t i = threadIdx.x; i < GROUP_CAP; i += GROUP_THREADS) s.pay[i] = 0u;
@@ -325,7 +355,7 @@ __global__ void __launch_bounds__(GROUP_THREADS, 4) k_group(const uint64_t *__re
 	__syncthreads();
 	auto issue = [&](uint32_t q, uint32_t n, uint32_t st) {
 		s.n_stage[st] = n;
-		bulk_load(s.stage[st], recs2 + (uint64_t)q * cap2, (n * 8u + 15u) & ~15u, &s.bar[st]);
+		bulk_load(s.stage[st], recs2 + (uint64_t)q * cap2, (n * (uint32_t)sizeof(R) + 15u) & ~15u, &s.bar[st]);
 	};
 	uint32_t n_ahead = 0;                                  // thread 0: fill count of the bucket it will issue next
 	if(threadIdx.x == 0)
@@ -340,7 +370,7 @@ __global__ void __launch_bounds__(GROUP_THREADS, 4) k_group(const uint64_t *__re
 	{
 		mbar_wait(&s.bar[stage], phase);
 		const uint32_t n = s.n_stage[stage];
-		const unsigned long long *w = s.stage[stage];
+		const R *w = s.stage[stage];
 		// the bucket after the next: its count is fetched now and used when this stage is refilled below
 		const uint64_t qn = (uint64_t)q + (uint64_t)GROUP_STAGES * gridDim.x;
 		const uint32_t n_next = n_ahead;
@@ -357,16 +387,16 @@ __global__ void __launch_bounds__(GROUP_THREADS, 4) k_group(const uint64_t *__re
 			bool later = false;
 			if(i < n)
 			{
-				const unsigned long long rec = w[i];
-				const unsigned long long m = rec >> 7;
+				const R rec = w[i];
+				const unsigned long long m = RecOps<R>::key(rec);
 				const uint32_t slot = ((uint32_t)m >> SUB_BITS_MAX) & (GROUP_SLOTS - 1u);
 				const uint32_t entry = ((uint32_t)(m >> 22) << 12) | i;
-				uint32_t bits = s.lut[(uint32_t)rec & 127u], target = i;
+				uint32_t bits = s.lut[RecOps<R>::ctx(rec)], target = i;
 				const uint32_t old = atomicCAS(&s.tab[slot], EMPTY32, entry);
 				if(old != EMPTY32)
 				{
 					const uint32_t j = old & 4095u;
-					if((old ^ entry) < 4096u && (w[j] >> 7) == m)      // same tag, same key
+					if((old ^ entry) < 4096u && RecOps<R>::key(w[j]) == m)   // same tag, same key
 					{
 						target = j;
 						bits |= PAY_MULTI;
@@ -383,11 +413,11 @@ __global__ void __launch_bounds__(GROUP_THREADS, 4) k_group(const uint64_t *__re
 		for(uint32_t d = lane; d < ndef; d += 32)
 		{
 			const uint32_t i = s.defer[warp][d];
-			const unsigned long long rec = w[i];
-			const unsigned long long m = rec >> 7;
+			const R rec = w[i];
+			const unsigned long long m = RecOps<R>::key(rec);
 			uint32_t slot = ((uint32_t)m >> SUB_BITS_MAX) & (GROUP_SLOTS - 1u);
 			const uint32_t entry = ((uint32_t)(m >> 22) << 12) | i;
-			uint32_t bits = s.lut[(uint32_t)rec & 127u], target = i;
+			uint32_t bits = s.lut[RecOps<R>::ctx(rec)], target = i;
 			for(;;)
 			{
 				slot = (slot + 1u) & (GROUP_SLOTS - 1u);
@@ -396,7 +426,7 @@ __global__ void __launch_bounds__(GROUP_THREADS, 4) k_group(const uint64_t *__re
 				if((old ^ entry) < 4096u)                      // same tag: compare the keys
 				{
 					const uint32_t j = old & 4095u;
-					if((w[j] >> 7) == m)
+					if(RecOps<R>::key(w[j]) == m)
 					{
 						target = j;
 						bits |= PAY_MULTI;
@@ -431,7 +461,11 @@ __global__ void __launch_bounds__(GROUP_THREADS, 4) k_group(const uint64_t *__re
 				if(lane == (uint32_t)(__ffs(mk) - 1)) base = atomicAdd(nkeys, (uint32_t)__popc(mk));
 				base = __shfl_sync(0xffffffffu, base, __ffs(mk) - 1);
 				const uint32_t idx = base + __popc(mk & ((1u << lane) - 1u));
-				if(bif && idx < ckeys_cap) ckeys[idx] = unmix56(w[i] >> 7);
+				if(bif && idx < ckeys_cap)
+				{
+					if constexpr(sizeof(R) == 8) ckeys[idx] = unmix56(RecOps<R>::key(w[i]));
+					else ckeys[idx] = make_ulonglong2(unmix64(RecOps<R>::key(w[i])), 0ull);
+				}
 			}
 		}
 		__syncthreads();                                       // stage consumed, table and payloads clean
@@ -441,10 +475,13 @@ __global__ void __launch_bounds__(GROUP_THREADS, 4) k_group(const uint64_t *__re
 }
 
 // vertex keys of the L2-table fallback on mixed records -> plain canonical keys
-__global__ void __launch_bounds__(256) k_unmix(uint64_t *__restrict__ keys, uint64_t n)
+template<class R>
+__global__ void __launch_bounds__(256) k_unmix(R *__restrict__ keys, uint64_t n)
 {
 	const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
-	if(i < n) keys[i] = unmix56(keys[i]);
+	if(i >= n) return;
+	if constexpr(sizeof(R) == 8) keys[i] = unmix56(keys[i]);
+	else keys[i].x = unmix64(keys[i].x);
 }
 
 } // namespace sibgpu
