@@ -161,7 +161,7 @@ void sibgpu_destroy(sibgpu_ctx *c)
 	DevBuf *bufs[] = {&c->d_text, &c->d_packed, &c->d_chr_start, &c->d_chr_len, &c->d_hist, &c->d_partoff, &c->d_cursor,
 		&c->d_records, &c->d_table, &c->d_partcnt, &c->d_keyoff, &c->d_ckeys, &c->d_vkeys, &c->d_vkeys_alt, &c->d_cubtmp,
 		&c->d_map, &c->d_filter, &c->d_hitmask, &c->d_tilecnt, &c->d_tileoff, &c->d_pos, &c->d_negtmp, &c->d_neg,
-		&c->d_chrinst, &c->d_scalars, &c->d_fp, &c->d_rep, &c->d_order, &c->d_s_ch, &c->d_s_m0, &c->d_s_m1, &c->d_s_off,
+		&c->d_chrinst, &c->d_scalars, &c->d_fp, &c->d_fpprm, &c->d_rep, &c->d_order, &c->d_s_ch, &c->d_s_m0, &c->d_s_m1, &c->d_s_off,
 		&c->d_s_inst, &c->d_s_flag, &c->d_edges, &c->d_edge_skip, &c->d_records2, &c->d_cnt2};
 	for(void *pp : c->peer_ptr)
 	{

@@ -36,7 +36,7 @@ struct sibgpu_ctx {
 	// enumeration workspace
 	sibgpu::DevBuf d_hist, d_partoff, d_cursor, d_records, d_table, d_partcnt, d_keyoff, d_ckeys, d_vkeys, d_vkeys_alt,
 		d_cubtmp, d_map, d_filter, d_hitmask, d_tilecnt, d_tileoff, d_pos, d_negtmp, d_neg, d_chrinst, d_scalars,
-		d_fp, d_rep, d_order, d_records2, d_cnt2, d_s_ch, d_s_m0, d_s_m1, d_s_off, d_s_inst, d_s_flag, d_edges, d_edge_skip;
+		d_fp, d_fpprm, d_rep, d_order, d_records2, d_cnt2, d_s_ch, d_s_m0, d_s_m1, d_s_off, d_s_inst, d_s_flag, d_edges, d_edge_skip;
 	void *h_scalars = nullptr;                         // pinned, 64 x u64
 
 	// last result
@@ -90,7 +90,7 @@ struct sibgpu_ctx {
 	// grouping of 8-byte records (k <= 28): 1 = buckets of ~1 Ki records grouped in shared memory (k_split + k_group),
 	// 0 = one L2-resident table per hash partition (k_insert + k_table_scan; also the fallback when a bucket overflows)
 	int group_smem = 1;                                // env SIBGPU_GROUP_SMEM
-	bool split_attr_done[2] = {false, false};
+	bool split_attr_done[2] = {false, false}, group_attr_done[4] = {false, false, false, false};
 	int split_stages = 2;                              // input tiles in flight per CTA of k_split (env SIBGPU_SPLIT_STAGES, dev)
 	uint64_t ckeys_init = 1u << 20;                    // initial capacity of the vertex-key list (env SIBGPU_CKEYS_INIT, tests)
 	uint64_t smem_fallbacks = 0;                       // times a bucket overflowed and the L2-table path took over

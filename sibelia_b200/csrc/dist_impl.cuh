@@ -26,7 +26,7 @@ static int dist_scan_mode(sibgpu_ctx *ctx, uint32_t k, uint32_t *hist_out)
 	{
 		const uint32_t g = ntiles < (uint32_t)ctx->sm_count * 8 ? ntiles : (uint32_t)ctx->sm_count * 8;
 		ProfScope ps(ctx, "k_scan_hist", (uint64_t)ntiles * TILE_POS / 4);
-		k_scan_hist<MODE><<<g, TILE_THREADS, 0, st>>>(t, nullptr, k, ntiles, ctx->dist_P_total, ctx->d_hist.as<uint32_t>());
+		k_scan_hist<MODE><<<g, TILE_THREADS, 0, st>>>(t, FpView{}, k, ntiles, ctx->dist_P_total, ctx->d_hist.as<uint32_t>());
 	}
 	SIB_CUDA(cudaMemcpyAsync(hist_out, ctx->d_hist.p, sizeof(uint32_t) * ctx->dist_P_total, cudaMemcpyDeviceToHost, st));
 	SIB_CUDA(cudaStreamSynchronize(st));
@@ -51,7 +51,7 @@ static int dist_scatter_mode(sibgpu_ctx *ctx, uint32_t k, void *send_dev)
 		SIB_CUDA(cudaFuncSetAttribute(k_scatter<MODE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 		const uint32_t g = ntiles < (uint32_t)ctx->sm_count * 4 ? ntiles : (uint32_t)ctx->sm_count * 4;
 		ProfScope ps(ctx, "k_scatter", (uint64_t)ntiles * TILE_POS / 4 + ctx->dist_nrec_local * sizeof(Rec));
-		k_scatter<MODE, false><<<g, TILE_THREADS, smem, st>>>(t, nullptr, k, ntiles, ctx->dist_P_total,
+		k_scatter<MODE, false><<<g, TILE_THREADS, smem, st>>>(t, FpView{}, k, ntiles, ctx->dist_P_total,
 			ctx->d_cursor.as<unsigned long long>(), static_cast<Rec*>(send_dev), 0ull, nullptr);
 	}
 	SIB_CUDA(cudaStreamSynchronize(st));
@@ -165,7 +165,7 @@ static int dist_finish_mode(sibgpu_ctx *ctx, uint32_t k, const void *allkeys_dev
 	}
 	bool collision = false;
 	return ids_and_tables<MODE>(ctx, ctx->dist_text, k, static_cast<const Rec*>(allkeys_dev), nkeys_total,
-		ntiles ? ntiles : 0, nullptr, false, &collision);
+		ntiles ? ntiles : 0, FpView{}, 0u, false, &collision);
 }
 
 // pack the words of the own range (+ halo) unless the caller pipelines that with the upload, partition plan, text descriptor
@@ -287,7 +287,7 @@ static int dist_scatter_core(sibgpu_ctx *ctx, uint32_t k, uint32_t PT, uint64_t 
 			TextDesc tc = t;
 			tc.tile0 = tiles_done;
 			ProfScope ps(ctx, "k_scatter", (uint64_t)nt * TILE_POS / 4 + (uint64_t)nt * TILE_POS * sizeof(Rec));
-			k_scatter<MODE, MIXED><<<g, TILE_THREADS, smem, st>>>(tc, nullptr, k, nt, PT, cursor_dev, out_dev, cap,
+			k_scatter<MODE, MIXED><<<g, TILE_THREADS, smem, st>>>(tc, FpView{}, k, nt, PT, cursor_dev, out_dev, cap,
 				reinterpret_cast<uint32_t*>(ds + 10));
 			tiles_done = tile_end;
 		}
@@ -737,7 +737,7 @@ int dist2_run(sibgpu_ctx *ctx, const HostSrc *src, int *status)
 	const uint32_t tiles_per_seg = (uint32_t)((ctx->x_seg_cap + RecOps<uint64_t>::TILE - 1) / RecOps<uint64_t>::TILE);
 	uint32_t *d_flags = reinterpret_cast<uint32_t*>(ds + 11);
 	SIB_TRY(launch_split<uint64_t>(ctx, ssrc, PL, tiles_per_seg, sub_bits, ctx->x_nrec / W, d_flags));
-	SIB_TRY(launch_group<uint64_t>(ctx, nbuckets, ctx->x_nrec / W, d_flags, keys, key_cap, reinterpret_cast<uint32_t*>(ds + 2)));
+	SIB_TRY(launch_group<uint64_t>(ctx, nbuckets, sub_bits, ctx->x_nrec / W, d_flags, keys, key_cap, reinterpret_cast<uint32_t*>(ds + 2)));
 	k_publish_keys<<<1, 1, 0, st>>>(hdr, reinterpret_cast<uint32_t*>(ds + 2), d_flags, key_cap, epoch);
 	// ---- all ranks' keys
 	SIB_TRY(ctx->d_ckeys.ensure(sizeof(uint64_t) * std::max<uint64_t>(ctx->ckeys_init, 16)));
@@ -791,7 +791,7 @@ int dist2_run(sibgpu_ctx *ctx, const HostSrc *src, int *status)
 			return SIBGPU_ERR_INVALID;
 		}
 		bool collision = false;
-		SIB_TRY(ids_and_tables<0>(ctx, ctx->dist_text, k, ctx->d_ckeys.as<uint64_t>(), Vc, ntiles, nullptr, false, &collision));
+		SIB_TRY(ids_and_tables<0>(ctx, ctx->dist_text, k, ctx->d_ckeys.as<uint64_t>(), Vc, ntiles, FpView{}, 0u, false, &collision));
 	}
 	SIB_CUDA(cudaGetLastError());
 	ctx->have_result = true;

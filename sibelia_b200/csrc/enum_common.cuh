@@ -28,9 +28,64 @@ struct Rec16 { uint64_t a, b; };
 
 // MODE 0: k <= 28, record = key << 7 | ctx[6:0] in one 64-bit word
 // MODE 1: k <= 32, record = {key, ctx}
-// MODE 2: k  > 32, record = {fingerprint a, fingerprint b << 8 | ctx}, read from the per-position array d_fp
-template<int MODE> struct RecT { typedef Rec16 type; };
-template<> struct RecT<0> { typedef uint64_t type; };
+// MODE 2: k  > 32, record = 56-bit fingerprint << 7 | ctx[6:0]; the hash partition comes from a second fingerprint and
+//         belongs to the key (a vertex class is {fingerprint, partition}: 16-byte entries in the key list)
+template<int MODE> struct RecT { typedef uint64_t type; };
+template<> struct RecT<1> { typedef Rec16 type; };
+template<int MODE> struct KeyT { typedef typename RecT<MODE>::type type; };     // entry of the vertex-key list
+template<> struct KeyT<2> { typedef Rec16 type; };
+
+// ---------------------------------------------------------------------------------------------------------------
+// rolling fingerprints (k > 32)
+// ---------------------------------------------------------------------------------------------------------------
+constexpr uint64_t P61 = (1ull << 61) - 1;
+
+// a * b + c mod 2^61-1 for a, b < 2^61, c < 2^61; result fully reduced
+__host__ __device__ __forceinline__ uint64_t muladdmod61(uint64_t a, uint64_t b, uint64_t c)
+{
+#ifdef __CUDA_ARCH__
+	const uint64_t hi = __umul64hi(a, b), lo = a * b;
+#else
+	const unsigned __int128 z = (unsigned __int128)a * b;
+	const uint64_t hi = (uint64_t)(z >> 64), lo = (uint64_t)z;
+#endif
+	uint64_t r = (lo & P61) + (lo >> 61) + (hi << 3) + c;      // 2^61 = 1 (mod p); hi < 2^58: the sum stays below 2^63
+	r = (r & P61) + (r >> 61);
+	return r >= P61 ? r - P61 : r;
+}
+__host__ __device__ __forceinline__ uint64_t mulmod61(uint64_t a, uint64_t b) { return muladdmod61(a, b, 0); }
+__host__ __device__ __forceinline__ uint64_t addmod61(uint64_t a, uint64_t b)
+{
+	uint64_t r = a + b;
+	return r >= P61 ? r - P61 : r;
+}
+
+// D[h][out * 4 + in]: what one rolling step adds to hash h (0: h1 forward, 1: h1 reverse, 2: h2 forward, 3: h2 reverse)
+// after the multiplication by the base (forward) / its inverse (reverse)
+struct FpBases { uint64_t B1, invB1, B2, invB2; };
+struct FpParams { uint64_t D[4][16]; FpBases b; };
+struct FpCk { uint64_t hf1, hr1, hf2, hr2; };          // the four hashes of the k-mer starting at a position = 0 (mod 16)
+typedef FpCk FpState;
+struct FpView { const FpCk *ck; const FpParams *prm; };
+
+// sD = FpParams in shared memory (the lanes of a warp index the tables with different symbols: shared memory serves
+// distinct 8-byte entries from distinct banks, a constant bank would replay per distinct address)
+constexpr int FP_SMEM_WORDS = sizeof(FpParams) / 8;
+__device__ __forceinline__ void fp_stage_params(const FpParams *__restrict__ prm, uint64_t *sD)
+{
+	for(uint32_t i = threadIdx.x; i < FP_SMEM_WORDS; i += blockDim.x) sD[i] = __ldg(reinterpret_cast<const uint64_t*>(prm) + i);
+}
+__device__ __forceinline__ FpBases fp_bases(const uint64_t *sD) { return FpBases{sD[64], sD[65], sD[66], sD[67]}; }
+__device__ __forceinline__ void fp_roll(FpState &h, const uint64_t *sD, const FpBases &b, uint32_t idx)
+{
+	h.hf1 = muladdmod61(h.hf1, b.B1, sD[idx]);
+	h.hr1 = muladdmod61(h.hr1, b.invB1, sD[16 + idx]);
+	h.hf2 = h.hf2 * b.B2 + sD[32 + idx];
+	h.hr2 = h.hr2 * b.invB2 + sD[48 + idx];
+}
+// canonical orientation = the smaller (h1, h2) pair; equal pairs = the k-mer is its own reverse complement
+__device__ __forceinline__ bool fp_forward(const FpState &h) { return h.hf1 < h.hr1 || (h.hf1 == h.hr1 && h.hf2 <= h.hr2); }
+__device__ __forceinline__ bool fp_palindrome(const FpState &h) { return h.hf1 == h.hr1 && h.hf2 == h.hr2; }
 
 __device__ __forceinline__ uint64_t rec_hash(uint64_t a, uint64_t b_fp)
 {

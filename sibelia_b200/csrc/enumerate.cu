@@ -134,49 +134,113 @@ __device__ __forceinline__ void scan16_exact(const TextDesc &t, const uint32_t *
 	}
 }
 
-// MODE 2: the per-position canonical fingerprints were precomputed by k_fingerprint (fingerprint.cu)
+// MODE 2 (k > 32): the four rolling hashes start from the checkpoint of the thread's word (k_fp_ckpt, fingerprint.cu)
+// and advance one position at a time; f(i, a, hb, ctx): a = 56-bit fingerprint of the canonical orientation, hb = the
+// 32 bits of the second hash that choose the hash partition (the partition index is part of the class key)
 template<class F>
-__device__ __forceinline__ void scan16_fp(const TextDesc &t, const Rec16 *__restrict__ fp, uint32_t tile, F f_emit)
+__device__ __forceinline__ void scan16_fp(const TextDesc &t, const FpView &fv, const uint32_t *sw, const uint64_t *sD,
+	uint32_t tile, uint32_t k, F f_emit)
 {
-	const uint32_t p0 = tile * TILE_POS + threadIdx.x * POS_PER_THREAD;
+	const uint32_t tid = threadIdx.x;
+	const uint32_t p0 = tile * TILE_POS + tid * POS_PER_THREAD;
+	if(p0 >= t.M) return;
+	const uint32_t wm1 = sw[tid], w0 = sw[tid + 1];
+	// the symbols entering the window: text positions p0 + k ... p0 + k + 15
+	const uint32_t wi = (p0 + k) >> 4;
+	const uint32_t in_lo = wi < t.nwords ? __ldg(t.packed + wi) : 0u, in_hi = wi + 1 < t.nwords ? __ldg(t.packed + wi + 1) : 0u;
+	const uint32_t win = __funnelshift_l(in_hi, in_lo, 2u * (k & 15u));
+	const FpBases bs = fp_bases(sD);
+	FpState h;
+	{
+		const ulonglong2 *c = reinterpret_cast<const ulonglong2*>(fv.ck + (p0 >> 4));
+		const ulonglong2 c0 = __ldg(c), c1 = __ldg(c + 1);
+		h.hf1 = c0.x; h.hr1 = c0.y; h.hf2 = c1.x; h.hr2 = c1.y;
+	}
+	uint32_t prevc = wm1 & 3u;
+	ChrCursor cur;
+	cur.init(t, p0);
+	const bool interior = p0 > cur.cs && (uint64_t)p0 + (POS_PER_THREAD - 1) + k < cur.ce;
 #pragma unroll
 	for(int i = 0; i < POS_PER_THREAD; i++)
 	{
 		const uint32_t p = p0 + i;
-		if(p < t.M)
+		const uint32_t outc = (w0 >> (30 - 2 * i)) & 3u, nextc = (win >> (30 - 2 * i)) & 3u;
+		bool valid = true;
+		uint32_t ps = prevc, ns = nextc;
+		if(!interior)
 		{
-			Rec16 v = fp[p];
-			if(v.a != EMPTY64) f_emit(i, v.a, v.b >> 8, (uint32_t)(v.b & 255u));
+			cur.advance(t, p);
+			valid = p >= cur.cs && p + k <= cur.ce;
+			if(p == cur.cs) ps = 4u;
+			if(p + k == cur.ce) ns = 4u;
 		}
+		if(valid)
+		{
+			const bool fw = fp_forward(h);
+			uint32_t ctx = fw ? ((ps << 3) | ns) : ((comp_sym(ns) << 3) | comp_sym(ps));
+			ctx |= (fp_palindrome(h) ? 64u : 0u) | (fw ? 128u : 0u);
+			f_emit(i, (fw ? h.hf1 : h.hr1) & MIX_MASK, (fw ? h.hf2 : h.hr2) >> 32, ctx);
+		}
+		prevc = outc;
+		fp_roll(h, sD, bs, (outc << 2) | nextc);
 	}
 }
 
-template<int MODE, class F>
-__device__ __forceinline__ void scan16(const TextDesc &t, const Rec16 *fp, const uint32_t *sw, uint32_t tile, uint32_t k,
-	F f_emit)
+// the same for ONE text position (k_emit: only the hit positions are revisited)
+__device__ __forceinline__ void fp_at(const TextDesc &t, const FpView &fv, const uint64_t *sD, uint32_t p, uint32_t k,
+	uint64_t &a, uint64_t &hb, bool &fw)
 {
-	if(MODE == 2) scan16_fp(t, fp, tile, f_emit);
+	const uint32_t w = p >> 4, wi = w + (k >> 4);
+	const uint32_t w0 = __ldg(t.packed + w);
+	const uint32_t in_lo = wi < t.nwords ? __ldg(t.packed + wi) : 0u, in_hi = wi + 1 < t.nwords ? __ldg(t.packed + wi + 1) : 0u;
+	const uint32_t win = __funnelshift_l(in_hi, in_lo, 2u * (k & 15u));
+	const FpBases bs = fp_bases(sD);
+	const ulonglong2 *c = reinterpret_cast<const ulonglong2*>(fv.ck + w);
+	const ulonglong2 c0 = __ldg(c), c1 = __ldg(c + 1);
+	FpState h = {c0.x, c0.y, c1.x, c1.y};
+	for(uint32_t i = 0; i < (p & 15u); i++) fp_roll(h, sD, bs, (((w0 >> (30 - 2 * i)) & 3u) << 2) | ((win >> (30 - 2 * i)) & 3u));
+	fw = fp_forward(h);
+	a = (fw ? h.hf1 : h.hr1) & MIX_MASK;
+	hb = (fw ? h.hf2 : h.hr2) >> 32;
+}
+
+template<int MODE, class F>
+__device__ __forceinline__ void scan16(const TextDesc &t, const FpView &fv, const uint32_t *sw, const uint64_t *sD, uint32_t tile,
+	uint32_t k, F f_emit)
+{
+	if(MODE == 2) scan16_fp(t, fv, sw, sD, tile, k, f_emit);
 	else scan16_exact(t, sw, tile, k, f_emit);
+}
+
+// hash partition of a record: plain records hash the key, mixed records (group_smem.cuh) read a bit field of it;
+// fingerprint records (MODE 2) take it from the second hash (b = its top 32 bits)
+template<int MODE, bool MIXED>
+__device__ __forceinline__ uint32_t part_of(uint64_t a, uint64_t b, uint32_t P)
+{
+	if(MODE == 2) return __umulhi((uint32_t)b, P);
+	if(MIXED) return MODE == 0 ? mixed_part(a, P) : __umulhi((uint32_t)(a >> 32), P);
+	return __umulhi((uint32_t)(rec_hash(a, b) >> 32), P);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
 // K1: scan + partition histogram
 // ---------------------------------------------------------------------------------------------------------------
 template<int MODE>
-__global__ void __launch_bounds__(TILE_THREADS) k_scan_hist(TextDesc t, const Rec16 *__restrict__ fp, uint32_t k,
+__global__ void __launch_bounds__(TILE_THREADS) k_scan_hist(TextDesc t, const FpView fv, uint32_t k,
 	uint32_t ntiles, uint32_t P, uint32_t *__restrict__ ghist)
 {
 	__shared__ uint32_t sw[TILE_THREADS + 5];
 	__shared__ uint32_t shist[MAX_PARTS];
+	__shared__ uint64_t sD[MODE == 2 ? FP_SMEM_WORDS : 1];
+	if(MODE == 2) fp_stage_params(fv.prm, sD);
 	for(uint32_t b = threadIdx.x; b < P; b += TILE_THREADS) shist[b] = 0;
 	for(uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x)
 	{
 		__syncthreads();
-		if(MODE != 2) stage_tile(t, t.tile0 + tile, sw);
+		stage_tile(t, t.tile0 + tile, sw);
 		__syncthreads();
-		scan16<MODE>(t, fp, sw, t.tile0 + tile, k, [&](int, uint64_t a, uint64_t b, uint32_t) {
-			uint32_t bin = __umulhi((uint32_t)(rec_hash(a, b) >> 32), P);
-			atomicAdd(&shist[bin], 1u);
+		scan16<MODE>(t, fv, sw, sD, t.tile0 + tile, k, [&](int, uint64_t a, uint64_t b, uint32_t) {
+			atomicAdd(&shist[part_of<MODE, false>(a, b, P)], 1u);
 		});
 	}
 	__syncthreads();
@@ -216,15 +280,16 @@ template<int MODE> struct ScatterSmem {
 	uint16_t bin_of[TILE_POS];         // bin of the record at each sorted local index (plain records only)
 };
 template<> struct ScatterSmem<1> : ScatterSmem<0> { uint64_t b[TILE_POS]; };
-template<> struct ScatterSmem<2> : ScatterSmem<1> {};
+template<> struct ScatterSmem<2> : ScatterSmem<0> { uint64_t sD[FP_SMEM_WORDS]; };
 
 // cap != 0: partition b owns the fixed region [b * cap, (b + 1) * cap) of `out` and cursor[b] starts at b * cap (no
 // histogram pass needed); a run that does not fit raises *overflow and is dropped -- the host then redoes the
 // partitioning with exact sizes (k_scan_hist + k_part_offsets, cap == 0).
 // MIXED: the record carries mix56(key) (8-byte records) / mix64(key) (16-byte records) instead of the key and the
-// partition is a bit field of it (group_smem.cuh)
+// partition is a bit field of it (group_smem.cuh); fingerprint records (MODE 2) are mixed the same way but take their
+// partition from the second hash
 template<int MODE, bool MIXED>
-__global__ void __launch_bounds__(TILE_THREADS, MODE == 0 ? 4 : 2) k_scatter(TextDesc t, const Rec16 *__restrict__ fp, uint32_t k,
+__global__ void __launch_bounds__(TILE_THREADS, MODE == 0 ? 4 : (MODE == 1 ? 2 : 3)) k_scatter(TextDesc t, const FpView fv, uint32_t k,
 	uint32_t ntiles, uint32_t P, unsigned long long *__restrict__ cursor, typename RecT<MODE>::type *__restrict__ out,
 	unsigned long long cap, uint32_t *__restrict__ overflow)
 {
@@ -233,26 +298,33 @@ __global__ void __launch_bounds__(TILE_THREADS, MODE == 0 ? 4 : 2) k_scatter(Tex
 	typedef cub::BlockScan<uint32_t, TILE_THREADS> Scan;
 	__shared__ typename Scan::TempStorage scan_tmp;
 	constexpr int BINS_PER_THREAD = MAX_PARTS / TILE_THREADS;
+	constexpr bool NARROW = MODE != 1;                     // 8-byte records
+	constexpr bool KEEP_BIN = !MIXED || MODE == 2;         // the partition cannot be read back from the record
+	uint64_t *sD = nullptr;
+	if constexpr(MODE == 2)
+	{
+		sD = s.sD;
+		fp_stage_params(fv.prm, sD);
+	}
 
 	for(uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x)
 	{
 		for(uint32_t b = threadIdx.x; b < P; b += TILE_THREADS) s.cnt[b] = 0;
 		if(threadIdx.x < MAX_PARTS / 32) s.dropmask[threadIdx.x] = 0;
 		if(threadIdx.x == 0) s.anydrop = 0;
-		if(MODE != 2) stage_tile(t, t.tile0 + tile, s.sw);
+		stage_tile(t, t.tile0 + tile, s.sw);
 		__syncthreads();
 
-		uint64_t ra[POS_PER_THREAD], rb[POS_PER_THREAD];
+		uint64_t ra[POS_PER_THREAD], rb[NARROW ? 1 : POS_PER_THREAD];
 		uint32_t binrank[POS_PER_THREAD];
 		uint32_t valid = 0;
-		scan16<MODE>(t, fp, s.sw, t.tile0 + tile, k, [&](int i, uint64_t a, uint64_t b, uint32_t ctx) {
-			if(MIXED) a = MODE == 0 ? mix56(a) : mix64(a);
-			uint32_t bin = MIXED ? (MODE == 0 ? mixed_part(a, P) : __umulhi((uint32_t)(a >> 32), P))
-				: __umulhi((uint32_t)(rec_hash(a, b) >> 32), P);
+		scan16<MODE>(t, fv, s.sw, sD, t.tile0 + tile, k, [&](int i, uint64_t a, uint64_t b, uint32_t ctx) {
+			if(MIXED) a = NARROW ? mix56(a) : mix64(a);
+			const uint32_t bin = part_of<MODE, MIXED>(a, b, P);
 			uint32_t rank = atomicAdd(&s.cnt[bin], 1u);
 			binrank[i] = (bin << 16) | rank;             // rank < 4096, bin < 1024
 			valid |= 1u << i;
-			if(MODE == 0) { ra[i] = (a << 7) | (ctx & 127u); }
+			if(NARROW) { ra[i] = (a << 7) | (ctx & 127u); }
 			else { ra[i] = a; rb[i] = (b << 8) | ctx; }
 		});
 		__syncthreads();
@@ -289,8 +361,8 @@ __global__ void __launch_bounds__(TILE_THREADS, MODE == 0 ? 4 : 2) k_scatter(Tex
 			{
 				const uint32_t bin = binrank[i] >> 16, l = s.cnt[bin] + (binrank[i] & 0xFFFFu);
 				s.a[l] = ra[i];
-				if(MODE != 0) static_cast<ScatterSmem<1>&>(s).b[l] = rb[i];
-				if(!MIXED) s.bin_of[l] = (uint16_t)bin;
+				if constexpr(!NARROW) s.b[l] = rb[i];
+				if(KEEP_BIN) s.bin_of[l] = (uint16_t)bin;
 			}
 		}
 #pragma unroll
@@ -316,11 +388,11 @@ __global__ void __launch_bounds__(TILE_THREADS, MODE == 0 ? 4 : 2) k_scatter(Tex
 		for(uint32_t l = threadIdx.x; l < n; l += TILE_THREADS)
 		{
 			const uint64_t a = s.a[l];
-			const uint32_t bin = MIXED ? (MODE == 0 ? mixed_part(a >> 7, P) : __umulhi((uint32_t)(a >> 32), P)) : s.bin_of[l];
+			const uint32_t bin = KEEP_BIN ? s.bin_of[l] : (MODE == 0 ? mixed_part(a >> 7, P) : __umulhi((uint32_t)(a >> 32), P));
 			if(drops && ((s.dropmask[bin >> 5] >> (bin & 31u)) & 1u)) continue;
 			unsigned long long gi = s.gbase[bin] + l;
-			if(MODE == 0) { reinterpret_cast<uint64_t*>(out)[gi] = a; }
-			else reinterpret_cast<ulonglong2*>(out)[gi] = make_ulonglong2(a, static_cast<ScatterSmem<1>&>(s).b[l]);
+			if constexpr(NARROW) { reinterpret_cast<uint64_t*>(out)[gi] = a; }
+			else reinterpret_cast<ulonglong2*>(out)[gi] = make_ulonglong2(a, s.b[l]);
 		}
 		__syncthreads();
 	}
@@ -332,8 +404,8 @@ __global__ void __launch_bounds__(TILE_THREADS, MODE == 0 ? 4 : 2) k_scatter(Tex
 struct Slot8 { unsigned long long key; uint32_t pay; uint32_t pad; };             // 16 B
 
 // one occurrence into the 16-byte (MODE 0) / 32-byte (MODE 1, 2) slot tables
-template<int MODE> struct RecVal { typedef ulonglong2 type; };
-template<> struct RecVal<0> { typedef unsigned long long type; };
+template<int MODE> struct RecVal { typedef unsigned long long type; };
+template<> struct RecVal<1> { typedef ulonglong2 type; };
 template<int MODE>
 __device__ __forceinline__ typename RecVal<MODE>::type load_rec(const void *__restrict__ recs, uint64_t i)
 {
@@ -366,8 +438,8 @@ __device__ __forceinline__ void insert_slot8(unsigned long long key, uint32_t ct
 template<int MODE>
 __device__ __forceinline__ void insert_wide_rec(typename RecVal<MODE>::type rec, void *__restrict__ table, uint32_t T)
 {
-	if constexpr(MODE == 0) insert_slot8(rec >> 7, (uint32_t)rec & 127u, table, T);
-	else insert_slot8(rec.x, (uint32_t)rec.y & 127u, table, T);      // exact 64-bit key, or the 61-bit fingerprint
+	if constexpr(MODE != 1) insert_slot8(rec >> 7, (uint32_t)rec & 127u, table, T);   // 56-bit key or fingerprint
+	else insert_slot8(rec.x, (uint32_t)rec.y & 127u, table, T);      // exact 64-bit key
 }
 
 template<int MODE>
@@ -416,7 +488,7 @@ __global__ void __launch_bounds__(256) k_table_scan(void *__restrict__ table, ui
 			if(bif)
 			{
 				uint32_t idx = base + __popc(m & ((1u << lane) - 1));
-				if(MODE == 0) reinterpret_cast<uint64_t*>(out)[idx] = a;
+				if(MODE != 1) reinterpret_cast<uint64_t*>(out)[idx] = a;
 				else reinterpret_cast<ulonglong2*>(out)[idx] = make_ulonglong2(a, b);
 			}
 		}
@@ -698,11 +770,25 @@ __global__ void __launch_bounds__(256) k_gather_keys(const typename RecT<MODE>::
 	for(uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) dst[i] = src[i];
 }
 
+// fingerprint classes (MODE 2): key list entry = {fingerprint, partition}
+__global__ void __launch_bounds__(256) k_gather_keys_fp(const uint64_t *__restrict__ recs, const uint64_t *__restrict__ partoff,
+	const uint32_t *__restrict__ cnt, const uint64_t *__restrict__ keyoff, Rec16 *__restrict__ ckeys, int mixed)
+{
+	const uint32_t p = blockIdx.y;
+	const uint32_t n = cnt[p];
+	const uint64_t *src = recs + partoff[p];
+	Rec16 *dst = ckeys + keyoff[p];
+	for(uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+	{
+		dst[i] = Rec16{mixed ? unmix56(src[i]) : src[i], (uint64_t)p};
+	}
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // K5: vertex ids (exact modes): the vertex k-mers are {c, revcomp(c)}; id = rank in the sorted array
 // ---------------------------------------------------------------------------------------------------------------
 template<int MODE>
-__global__ void __launch_bounds__(256) k_expand(const typename RecT<MODE>::type *__restrict__ ckeys, uint64_t n, uint32_t k,
+__global__ void __launch_bounds__(256) k_expand(const typename KeyT<MODE>::type *__restrict__ ckeys, uint64_t n, uint32_t k,
 	uint64_t *__restrict__ vkeys, uint32_t *__restrict__ npal)
 {
 	uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
@@ -753,7 +839,7 @@ __device__ __forceinline__ void map_insert(MapSlot *map, uint32_t Tm, uint32_t *
 }
 
 template<int MODE>
-__global__ void __launch_bounds__(256) k_build_map(const typename RecT<MODE>::type *__restrict__ ckeys, uint64_t n, uint32_t k,
+__global__ void __launch_bounds__(256) k_build_map(const typename KeyT<MODE>::type *__restrict__ ckeys, uint64_t n, uint32_t k,
 	const uint64_t *__restrict__ vsorted, const uint32_t *__restrict__ npal, MapSlot *__restrict__ map, uint32_t Tm,
 	uint32_t *__restrict__ filter, uint32_t fshift)
 {
@@ -800,21 +886,24 @@ __device__ __forceinline__ bool map_lookup(const MapSlot *__restrict__ map, uint
 // K6: mark vertex positions.   K7: emit the instance tables in text order.
 // ---------------------------------------------------------------------------------------------------------------
 template<int MODE>
-__global__ void __launch_bounds__(TILE_THREADS) k_mark(TextDesc t, const Rec16 *__restrict__ fp, uint32_t k, uint32_t ntiles,
+__global__ void __launch_bounds__(TILE_THREADS) k_mark(TextDesc t, const FpView fv, uint32_t P, uint32_t k, uint32_t ntiles,
 	const MapSlot *__restrict__ map, uint32_t Tm, const uint32_t *__restrict__ filter, uint32_t fshift,
 	uint16_t *__restrict__ hitmask, uint64_t *__restrict__ tilecnt, unsigned long long *__restrict__ rep)
 {
 	__shared__ uint32_t sw[TILE_THREADS + 5];
+	__shared__ uint64_t sD[MODE == 2 ? FP_SMEM_WORDS : 1];
 	typedef cub::BlockReduce<uint32_t, TILE_THREADS> Red;
 	__shared__ typename Red::TempStorage red_tmp;
+	if(MODE == 2) fp_stage_params(fv.prm, sD);
 	for(uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x)
 	{
 		__syncthreads();
-		if(MODE != 2) stage_tile(t, t.tile0 + tile, sw);
+		stage_tile(t, t.tile0 + tile, sw);
 		__syncthreads();
 		uint32_t mask = 0;
-		scan16<MODE>(t, fp, sw, t.tile0 + tile, k, [&](int i, uint64_t a, uint64_t b, uint32_t ctx) {
+		scan16<MODE>(t, fv, sw, sD, t.tile0 + tile, k, [&](int i, uint64_t a, uint64_t b, uint32_t ctx) {
 			uint32_t idc, idr, cls;
+			if(MODE == 2) b = __umulhi((uint32_t)b, P);    // class key = {fingerprint, partition}
 			if(map_lookup(map, Tm, filter, fshift, a, b, idc, idr, cls))
 			{
 				mask |= 1u << i;
@@ -833,7 +922,7 @@ __global__ void __launch_bounds__(TILE_THREADS) k_mark(TextDesc t, const Rec16 *
 }
 
 template<int MODE>
-__global__ void __launch_bounds__(TILE_THREADS) k_emit(TextDesc t, const Rec16 *__restrict__ fp, uint32_t k, uint32_t ntiles,
+__global__ void __launch_bounds__(TILE_THREADS) k_emit(TextDesc t, const FpView fv, uint32_t P, uint32_t k, uint32_t ntiles,
 	const MapSlot *__restrict__ map, uint32_t Tm, const uint32_t *__restrict__ filter, uint32_t fshift,
 	const uint16_t *__restrict__ hitmask, const uint64_t *__restrict__ tileoff,
 	sibgpu_inst *__restrict__ pos_out, sibgpu_inst *__restrict__ neg_tmp, uint64_t inst_cap,
@@ -841,6 +930,8 @@ __global__ void __launch_bounds__(TILE_THREADS) k_emit(TextDesc t, const Rec16 *
 {
 	typedef cub::BlockScan<uint32_t, TILE_THREADS> Scan;
 	__shared__ typename Scan::TempStorage scan_tmp;
+	__shared__ uint64_t sD[MODE == 2 ? FP_SMEM_WORDS : 1];
+	if(MODE == 2) fp_stage_params(fv.prm, sD);
 	for(uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x)
 	{
 		uint32_t mask = hitmask[(uint64_t)tile * TILE_THREADS + threadIdx.x];
@@ -858,8 +949,10 @@ __global__ void __launch_bounds__(TILE_THREADS) k_emit(TextDesc t, const Rec16 *
 			bool fw;
 			if(MODE == 2)
 			{
-				Rec16 v = fp[p];
-				a = v.a; b = v.b >> 8; fw = (v.b & 128u) != 0;
+				uint64_t fa, hb;
+				fp_at(t, fv, sD, p, k, fa, hb, fw);
+				a = fa;
+				b = __umulhi((uint32_t)hb, P);
 			}
 			else
 			{
@@ -951,10 +1044,10 @@ static inline uint32_t grid_for(uint64_t work_items, int threads, int sm_count, 
 // Vertex ids, vertex map and the two instance tables for the text tiles [t.tile0, t.tile0 + ntiles), given the
 // canonical keys of ALL vertex classes (`ckeys`, Vc of them).  Shared by the single-GPU path and the sharded path.
 template<int MODE>
-static int ids_and_tables(sibgpu_ctx *ctx, const TextDesc &t, uint32_t k, const typename RecT<MODE>::type *ckeys_in, uint64_t Vc,
-	uint32_t ntiles, const Rec16 *fp, bool reverse_neg, bool *collision)
+static int ids_and_tables(sibgpu_ctx *ctx, const TextDesc &t, uint32_t k, const typename KeyT<MODE>::type *ckeys_in, uint64_t Vc,
+	uint32_t ntiles, const FpView fp, uint32_t P, bool reverse_neg, bool *collision)
 {
-	typedef typename RecT<MODE>::type Rec;
+	typedef typename KeyT<MODE>::type Rec;
 	NvtxRange nvtx("sibgpu: vertex ids + instance tables");
 	cudaStream_t st = ctx->stream;
 	const int sms = ctx->sm_count;
@@ -1025,8 +1118,8 @@ static int ids_and_tables(sibgpu_ctx *ctx, const TextDesc &t, uint32_t k, const 
 	SIB_TRY(ctx->d_tilecnt.ensure(sizeof(uint64_t) * ntiles));
 	SIB_TRY(ctx->d_tileoff.ensure(sizeof(uint64_t) * (ntiles + 1)));
 	{
-		ProfScope ps(ctx, "k_mark", (MODE == 2 ? ctx->M * 16 : ctx->M / 4) + ctx->M / 8);
-		k_mark<MODE><<<scan_grid, TILE_THREADS, 0, st>>>(t, fp, k, ntiles, ctx->d_map.as<MapSlot>(), Tm,
+		ProfScope ps(ctx, "k_mark", (MODE == 2 ? ctx->M / 2 + ctx->M * 2 : ctx->M / 4) + ctx->M / 8);
+		k_mark<MODE><<<scan_grid, TILE_THREADS, 0, st>>>(t, fp, P, k, ntiles, ctx->d_map.as<MapSlot>(), Tm,
 			ctx->d_filter.as<uint32_t>(), fshift, ctx->d_hitmask.as<uint16_t>(), ctx->d_tilecnt.as<uint64_t>(),
 			ctx->d_rep.as<unsigned long long>());
 	}
@@ -1052,7 +1145,7 @@ static int ids_and_tables(sibgpu_ctx *ctx, const TextDesc &t, uint32_t k, const 
 		const uint64_t inst_cap = std::min(std::min(ctx->d_pos.cap, ctx->d_negtmp.cap), ctx->d_neg.cap) / sizeof(sibgpu_inst);
 		{
 			ProfScope ps(ctx, "k_emit", ctx->M / 8 + I * 24);
-			k_emit<MODE><<<scan_grid, TILE_THREADS, 0, st>>>(t, fp, k, ntiles, ctx->d_map.as<MapSlot>(), Tm,
+			k_emit<MODE><<<scan_grid, TILE_THREADS, 0, st>>>(t, fp, P, k, ntiles, ctx->d_map.as<MapSlot>(), Tm,
 				ctx->d_filter.as<uint32_t>(), fshift, ctx->d_hitmask.as<uint16_t>(), ctx->d_tileoff.as<uint64_t>(),
 				ctx->d_pos.as<sibgpu_inst>(), ctx->d_negtmp.as<sibgpu_inst>(), inst_cap, ctx->d_rep.as<unsigned long long>(),
 				reinterpret_cast<uint32_t*>(ds + 9));
@@ -1133,7 +1226,6 @@ static int launch_split(sibgpu_ctx *ctx, const SplitSrc &ssrc, uint32_t P1, uint
 	{
 		SIB_CUDA(cudaFuncSetAttribute(k_split<1, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SplitSmem<1, R>)));
 		SIB_CUDA(cudaFuncSetAttribute(k_split<2, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SplitSmem<2, R>)));
-		SIB_CUDA(cudaFuncSetAttribute(k_group<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(GroupSmem<R>)));
 		attr_done = true;
 	}
 	const uint64_t split_tiles = (uint64_t)P1 * ssrc.W * tiles_per_seg;
@@ -1152,13 +1244,20 @@ static int launch_split(sibgpu_ctx *ctx, const SplitSrc &ssrc, uint32_t P1, uint
 	return SIBGPU_OK;
 }
 
-template<class R>
-static int launch_group(sibgpu_ctx *ctx, uint32_t nbuckets, uint64_t nrec, uint32_t *d_flags, R *ckeys, uint32_t ckeys_cap,
-	uint32_t *d_nkeys)
+// PKEY: the key list takes {key, partition} (fingerprint classes) instead of the bare key
+template<class R, bool PKEY = false>
+static int launch_group(sibgpu_ctx *ctx, uint32_t nbuckets, uint32_t sub_bits, uint64_t nrec, uint32_t *d_flags,
+	typename GroupKey<R, PKEY>::type *ckeys, uint32_t ckeys_cap, uint32_t *d_nkeys)
 {
+	bool &attr_done = ctx->group_attr_done[(sizeof(R) == 8 ? 0 : 1) + (PKEY ? 2 : 0)];
+	if(!attr_done)
+	{
+		SIB_CUDA(cudaFuncSetAttribute(k_group<R, PKEY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(GroupSmem<R>)));
+		attr_done = true;
+	}
 	ProfScope ps(ctx, "k_group", nrec * sizeof(R));
-	k_group<R><<<std::min<uint32_t>(nbuckets, (uint32_t)ctx->sm_count * (sizeof(R) == 8 ? 4 : 2)), GROUP_THREADS, sizeof(GroupSmem<R>),
-		ctx->stream>>>(ctx->d_records2.as<R>(), ctx->d_cnt2.as<uint32_t>(), nbuckets, GROUP_CAP, d_flags, ckeys, ckeys_cap, d_nkeys);
+	k_group<R, PKEY><<<std::min<uint32_t>(nbuckets, (uint32_t)ctx->sm_count * (sizeof(R) == 8 ? 4 : 2)), GROUP_THREADS, sizeof(GroupSmem<R>),
+		ctx->stream>>>(ctx->d_records2.as<R>(), ctx->d_cnt2.as<uint32_t>(), nbuckets, sub_bits, GROUP_CAP, d_flags, ckeys, ckeys_cap, d_nkeys);
 	return SIBGPU_OK;
 }
 
@@ -1185,15 +1284,17 @@ static int enumerate_mode(sibgpu_ctx *ctx, uint32_t k, uint64_t nrec, const Host
 	t.nwords = (uint32_t)((ctx->M + 15) / 16) + 8;
 	t.tile0 = 0;
 	const uint32_t ntiles = (uint32_t)((ctx->M + TILE_POS - 1) / TILE_POS);
-	typedef typename std::conditional<MODE == 0, uint64_t, ulonglong2>::type SR;   // record type of the shared-memory path
+	typedef typename std::conditional<MODE != 1, uint64_t, ulonglong2>::type SR;   // record type of the shared-memory path
+	typedef typename KeyT<MODE>::type Key;                 // entry of the vertex-key list
+	constexpr bool FP = MODE == 2;
 	const size_t scatter_smem = sizeof(ScatterSmem<MODE>);
 	SIB_CUDA(cudaFuncSetAttribute(k_scatter<MODE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scatter_smem));
 	SIB_CUDA(cudaFuncSetAttribute(k_scatter<MODE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scatter_smem));
 
 	for(uint32_t attempt = 0; ; attempt++)
 	{
-		if(MODE == 2) SIB_TRY(fingerprint_positions(ctx, t, k, attempt));
-		const Rec16 *fp = ctx->d_fp.as<Rec16>();
+		if(FP) SIB_TRY(fingerprint_positions(ctx, t, k, attempt));
+		const FpView fp = {ctx->d_fp.as<FpCk>(), ctx->d_fpprm.as<FpParams>()};
 
 		// ---- partition plan
 		// level-1 partitions of 512 Ki records, split into ~1 Ki-record buckets and grouped in shared memory
@@ -1265,7 +1366,7 @@ static int enumerate_mode(sibgpu_ctx *ctx, uint32_t k, uint64_t nrec, const Host
 					const uint32_t g = nt < (uint32_t)sms * 4 ? nt : (uint32_t)sms * 4;
 					TextDesc tc = t;
 					tc.tile0 = tiles_done;
-					ProfScope ps(ctx, "k_scatter", (MODE == 2 ? (uint64_t)nt * TILE_POS * 16 : (uint64_t)nt * TILE_POS / 4)
+					ProfScope ps(ctx, "k_scatter", (FP ? (uint64_t)nt * TILE_POS / 2 + (uint64_t)nt * TILE_POS * 2 : (uint64_t)nt * TILE_POS / 4)
 						+ nrec * sizeof(Rec) * nt / ntiles);
 					if(mixed) k_scatter<MODE, true><<<g, TILE_THREADS, scatter_smem, st>>>(tc, fp, k, nt, P,
 						ctx->d_cursor.as<unsigned long long>(), ctx->d_records.as<Rec>(), cap, d_overflow);
@@ -1284,8 +1385,8 @@ static int enumerate_mode(sibgpu_ctx *ctx, uint32_t k, uint64_t nrec, const Host
 				nbuckets = P << sub_bits;
 				SIB_TRY(ctx->d_records2.ensure(sizeof(SR) * (size_t)nbuckets * GROUP_CAP + 64));
 				SIB_TRY(ctx->d_cnt2.ensure(sizeof(uint32_t) * (size_t)nbuckets));
-				SIB_TRY(ctx->d_ckeys.ensure(sizeof(SR) * (ctx->ckeys_init ? ctx->ckeys_init : 1)));
-				ckeys_cap = (uint32_t)std::min<size_t>(ctx->d_ckeys.cap / sizeof(SR), 0xFFFFFFF0u);
+				SIB_TRY(ctx->d_ckeys.ensure(sizeof(Key) * (ctx->ckeys_init ? ctx->ckeys_init : 1)));
+				ckeys_cap = (uint32_t)std::min<size_t>(ctx->d_ckeys.cap / sizeof(Key), 0xFFFFFFF0u);
 				SIB_CUDA(cudaMemsetAsync(ctx->d_cnt2.p, 0, sizeof(uint32_t) * (size_t)nbuckets, st));
 				const uint32_t tiles_per_seg = (uint32_t)((cap + RecOps<SR>::TILE - 1) / RecOps<SR>::TILE);
 				SplitSrc ssrc = {};
@@ -1294,8 +1395,8 @@ static int enumerate_mode(sibgpu_ctx *ctx, uint32_t k, uint64_t nrec, const Host
 				ssrc.seg_cap = cap;
 				ssrc.W = 1;
 				SIB_TRY(launch_split<SR>(ctx, ssrc, P, tiles_per_seg, sub_bits, nrec, reinterpret_cast<uint32_t*>(ds + 11)));
-				SIB_TRY(launch_group<SR>(ctx, nbuckets, nrec, reinterpret_cast<uint32_t*>(ds + 11), ctx->d_ckeys.as<SR>(), ckeys_cap,
-					reinterpret_cast<uint32_t*>(ds + 2)));
+				SIB_TRY((launch_group<SR, FP>(ctx, nbuckets, sub_bits, nrec, reinterpret_cast<uint32_t*>(ds + 11), ctx->d_ckeys.as<typename GroupKey<SR, FP>::type>(), ckeys_cap,
+					reinterpret_cast<uint32_t*>(ds + 2))));
 				smem_launched = true;
 			}
 			SIB_CUDA(cudaMemcpyAsync(cur.data(), ctx->d_cursor.p, sizeof(uint64_t) * cur.size(), cudaMemcpyDeviceToHost, st));
@@ -1342,10 +1443,10 @@ static int enumerate_mode(sibgpu_ctx *ctx, uint32_t k, uint64_t nrec, const Host
 						if(Vc > ckeys_cap)
 						{
 							// the key list was too small (k_group kept counting): regrow, group again -- the buckets are intact
-							SIB_TRY(ctx->d_ckeys.ensure(sizeof(SR) * Vc));
+							SIB_TRY(ctx->d_ckeys.ensure(sizeof(Key) * Vc));
 							SIB_CUDA(cudaMemsetAsync(ds + 2, 0, sizeof(uint64_t), st));
-							SIB_TRY(launch_group<SR>(ctx, nbuckets, nrec, reinterpret_cast<uint32_t*>(ds + 11), ctx->d_ckeys.as<SR>(),
-								(uint32_t)Vc, reinterpret_cast<uint32_t*>(ds + 2)));
+							SIB_TRY((launch_group<SR, FP>(ctx, nbuckets, sub_bits, nrec, reinterpret_cast<uint32_t*>(ds + 11), ctx->d_ckeys.as<typename GroupKey<SR, FP>::type>(),
+								(uint32_t)Vc, reinterpret_cast<uint32_t*>(ds + 2))));
 							SIB_CUDA(cudaStreamSynchronize(st));
 						}
 						grouped = true;
@@ -1370,7 +1471,7 @@ static int enumerate_mode(sibgpu_ctx *ctx, uint32_t k, uint64_t nrec, const Host
 			SIB_CUDA(cudaMemsetAsync(ctx->d_hist.p, 0, sizeof(uint32_t) * MAX_PARTS, st));
 			const uint32_t scan_grid = ntiles < (uint32_t)sms * 8 ? ntiles : (uint32_t)sms * 8;
 			{
-				ProfScope ps(ctx, "k_scan_hist", MODE == 2 ? ctx->M * 16 : ctx->M / 4);
+				ProfScope ps(ctx, "k_scan_hist", FP ? ctx->M / 2 + ctx->M * 2 : ctx->M / 4);
 				k_scan_hist<MODE><<<scan_grid, TILE_THREADS, 0, st>>>(t, fp, k, ntiles, P, ctx->d_hist.as<uint32_t>());
 			}
 			{
@@ -1390,7 +1491,7 @@ static int enumerate_mode(sibgpu_ctx *ctx, uint32_t k, uint64_t nrec, const Host
 			for(uint32_t p = 0; p < P; p++) part_cnt[p] = part_base[p + 1] - part_base[p];
 			{
 				const uint32_t g = ntiles < (uint32_t)sms * 4 ? ntiles : (uint32_t)sms * 4;
-				ProfScope ps(ctx, "k_scatter", (MODE == 2 ? ctx->M * 16 : ctx->M / 4) + nrec * sizeof(Rec));
+				ProfScope ps(ctx, "k_scatter", (FP ? ctx->M / 2 + ctx->M * 2 : ctx->M / 4) + nrec * sizeof(Rec));
 				k_scatter<MODE, false><<<g, TILE_THREADS, scatter_smem, st>>>(t, fp, k, ntiles, P, ctx->d_cursor.as<unsigned long long>(),
 					ctx->d_records.as<Rec>(), 0ull, nullptr);
 			}
@@ -1475,16 +1576,24 @@ static int enumerate_mode(sibgpu_ctx *ctx, uint32_t k, uint64_t nrec, const Host
 		}
 		if(!grouped)
 		{
-			SIB_TRY(ctx->d_ckeys.ensure(sizeof(Rec) * Vc));
-			ProfScope ps(ctx, "k_gather_keys", 2 * Vc * sizeof(Rec));
+			SIB_TRY(ctx->d_ckeys.ensure(sizeof(Key) * Vc));
+			ProfScope ps(ctx, "k_gather_keys", Vc * (sizeof(Rec) + sizeof(Key)));
 			dim3 g(8, P);
-			k_gather_keys<MODE><<<g, 256, 0, st>>>(ctx->d_records.as<Rec>(), ctx->d_partoff.as<uint64_t>(),
-				ctx->d_partcnt.as<uint32_t>(), ctx->d_keyoff.as<uint64_t>(), ctx->d_ckeys.as<Rec>());
-			if(mixed) k_unmix<SR><<<(uint32_t)((Vc + 255) / 256), 256, 0, st>>>(ctx->d_ckeys.as<SR>(), Vc);
+			if constexpr(FP)
+			{
+				k_gather_keys_fp<<<g, 256, 0, st>>>(ctx->d_records.as<uint64_t>(), ctx->d_partoff.as<uint64_t>(),
+					ctx->d_partcnt.as<uint32_t>(), ctx->d_keyoff.as<uint64_t>(), ctx->d_ckeys.as<Rec16>(), mixed ? 1 : 0);
+			}
+			else
+			{
+				k_gather_keys<MODE><<<g, 256, 0, st>>>(ctx->d_records.as<Rec>(), ctx->d_partoff.as<uint64_t>(),
+					ctx->d_partcnt.as<uint32_t>(), ctx->d_keyoff.as<uint64_t>(), ctx->d_ckeys.as<Rec>());
+				if(mixed) k_unmix<SR><<<(uint32_t)((Vc + 255) / 256), 256, 0, st>>>(ctx->d_ckeys.as<SR>(), Vc);
+			}
 		}
 
 		bool collision = false;
-		SIB_TRY(ids_and_tables<MODE>(ctx, t, k, ctx->d_ckeys.as<Rec>(), Vc, ntiles, fp, true, &collision));
+		SIB_TRY(ids_and_tables<MODE>(ctx, t, k, ctx->d_ckeys.as<Key>(), Vc, ntiles, fp, P, true, &collision));
 		if(collision)
 		{
 			if(attempt >= 2)

@@ -1,38 +1,24 @@
-// k > 32: the k-mer no longer fits a 64-bit word, so classes are found on a 61-bit fingerprint
-//   a = polynomial hash mod 2^61-1, rolled along the text,
-// the canonical form being the smaller of the fingerprints of w and revcomp(w); the record {a, context} then takes the
-// same path as the exact 16-byte records of k = 29..32.  Two different k-mers share a fingerprint with probability
-// ~ n^2 / 2^62 per run (0.05 for 5 * 10^8 distinct k-mers); a false merge can only ADD symbols to a class, i.e. turn a
-// non-vertex into a vertex, and that is caught below.  Vertex ids still have to be the
-// lexicographic ranks of the actual k-mers (vertexenumeration.cpp:350), so the (few) vertex classes are ranked by
-// comparing the strings they spell in the packed text, and every emitted instance is verified against its class
-// representative (k_emit) -- a collision that could alter the result forces a re-run with other bases.
+// k > 32: the k-mer no longer fits a 64-bit word, so classes are found on fingerprints.  Two polynomial hashes are
+// rolled along the text for the k-mer w and for revcomp(w):
+//   h1 mod 2^61-1 (random base; 56 of its bits are the key an 8-byte record carries)
+//   h2 mod 2^64   (its top bits choose the hash partition and are NOT stored: the partition index is part of the key)
+// the canonical orientation being the one with the smaller h1.  The record then takes the path of the exact 8-byte
+// records of k <= 28 (k_scatter -> k_split -> k_group in shared memory).  Two different k-mers are merged only if they
+// agree in the 56 stored bits AND fall into the same partition: ~ n * (records per partition) / 2^57 per run (0.002 for
+// 5 * 10^8 distinct k-mers); a false merge can only ADD symbols to a class, i.e. turn a non-vertex into a vertex, and
+// that is caught: vertex ids have to be the lexicographic ranks of the actual k-mers (vertexenumeration.cpp:350), so the
+// (few) vertex classes are ranked by comparing the strings they spell in the packed text, and every emitted instance
+// is verified against its class representative (k_emit) -- a collision that could alter the result forces a re-run
+// with other bases.
+//
+// The hashes are not materialised per position.  k_fp_ckpt stores them for every 16th position (32 bytes per packed
+// word = 2 B/base); the scan kernels (k_scatter, k_mark: scan16_fp in enumerate.cu) start from the checkpoint of their
+// word and roll 16 positions in registers.
 #include <cub/cub.cuh>
 
 #include "enum_common.cuh"
 
 namespace sibgpu {
-
-constexpr uint64_t P61 = (1ull << 61) - 1;
-
-__host__ __device__ __forceinline__ uint64_t mulmod61(uint64_t a, uint64_t b)
-{
-#ifdef __CUDA_ARCH__
-	const uint64_t hi = __umul64hi(a, b), lo = a * b;
-#else
-	const unsigned __int128 z = (unsigned __int128)a * b;
-	const uint64_t hi = (uint64_t)(z >> 64), lo = (uint64_t)z;
-#endif
-	uint64_t r = (lo & P61) + (lo >> 61) + (hi << 3);      // 2^61 = 1 (mod p); a, b < 2^61 so hi < 2^58
-	r = (r & P61) + (r >> 61);
-	return r >= P61 ? r - P61 : r;
-}
-
-__host__ __device__ __forceinline__ uint64_t addmod61(uint64_t a, uint64_t b)
-{
-	uint64_t r = a + b;
-	return r >= P61 ? r - P61 : r;
-}
 
 static uint64_t powmod61(uint64_t b, uint64_t e)
 {
@@ -65,64 +51,77 @@ static uint64_t inv64(uint64_t b)                       // inverse of an odd num
 	return x;
 }
 
-struct FpParams {
-	uint64_t B1, invB1, B2, invB2;
-	uint64_t T1f[4], T1r[4], T2f[4], T2r[4];              // (c+1) B^(k-1) and (4-c) B^(k-1) for both hashes
-};
-
-__device__ __forceinline__ uint32_t code_at(const TextDesc &t, uint32_t j)
-{
-	const uint32_t w = j >> 4;
-	if(w >= t.nwords) return 0u;
-	return (__ldg(t.packed + w) >> (30u - 2u * (j & 15u))) & 3u;
-}
-
-// One thread rolls both fingerprints over a run of L consecutive text positions (O(k) warm-up, O(1) per position).
+// One thread computes the checkpoints of a run of L consecutive text positions (L a multiple of 16): Horner warm-up
+// over the k bases of its first k-mer (forward for w, backward for revcomp(w)), then one rolling step per position.
 //   Hf(i) = sum_j (c[i+j]+1) B^(k-1-j)        fingerprint of the k-mer at i
 //   Hr(i) = sum_m (4-c[i+m]) B^m              the same polynomial evaluated on its reverse complement
-__global__ void __launch_bounds__(128) k_fingerprint(TextDesc t, uint32_t k, uint32_t L, FpParams prm, Rec16 *__restrict__ fp)
+__global__ void __launch_bounds__(128) k_fp_ckpt(TextDesc t, uint32_t k, uint32_t L, FpParams prm, FpCk *__restrict__ ck)
 {
+	__shared__ uint64_t sD[64];
+	for(uint32_t i = threadIdx.x; i < 64; i += blockDim.x) sD[i] = prm.D[i >> 4][i & 15];
+	__syncthreads();
+	const FpBases b = prm.b;
 	const uint64_t g = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
 	const uint64_t start64 = g * L;
 	if(start64 >= t.M) return;
 	const uint32_t start = (uint32_t)start64;
-	const uint32_t end = start + L < t.M ? start + L : t.M;
-	uint64_t hf1 = 0, hr1 = 0;
-	for(uint32_t j = 0; j < k; j++)
+	const uint32_t w_first = start >> 4;
+	const uint32_t w_end = (uint32_t)((t.M + 15) >> 4);                 // checkpoints exist for words [0, w_end)
+	const uint32_t w_last = w_first + L / 16 < w_end ? w_first + L / 16 : w_end;
+	auto word = [&](uint32_t w) -> uint32_t { return w < t.nwords ? __ldg(t.packed + w) : 0u; };
+	FpState h = {0, 0, 0, 0};
+	const uint32_t kw = k >> 4, kt = k & 15u;
+	for(uint32_t wi = 0; wi < kw; wi++)
 	{
-		const uint32_t c = code_at(t, start + j);
-		hf1 = addmod61(mulmod61(hf1, prm.B1), c + 1);
-	}
-	for(uint32_t j = k; j-- > 0; )
-	{
-		const uint32_t c = code_at(t, start + j);
-		hr1 = addmod61(mulmod61(hr1, prm.B1), 4 - c);
-	}
-	ChrCursor cur;
-	cur.init(t, start);
-	uint32_t prevc = start ? code_at(t, start - 1) : 0u;
-	for(uint32_t p = start; p < end; p++)
-	{
-		const uint32_t cout = code_at(t, p), cin = code_at(t, p + k);
-		cur.advance(t, p);
-		Rec16 out;
-		out.a = EMPTY64;
-		out.b = 0;
-		if(p >= cur.cs && p + k <= cur.ce)
+		const uint32_t x = word(w_first + wi);
+#pragma unroll
+		for(int i = 0; i < 16; i++)
 		{
-			const uint32_t ps = p == cur.cs ? 4u : prevc;
-			const uint32_t ns = p + k == cur.ce ? 4u : cin;
-			const bool pal = hf1 == hr1;
-			const bool fw = hf1 <= hr1;
-			uint32_t ctx = fw ? ((ps << 3) | ns) : ((comp_sym(ns) << 3) | comp_sym(ps));
-			ctx |= (pal ? 64u : 0u) | (fw ? 128u : 0u);
-			out.a = fw ? hf1 : hr1;
-			out.b = ctx;
+			const uint32_t c = (x >> (30 - 2 * i)) & 3u;
+			h.hf1 = muladdmod61(h.hf1, b.B1, c + 1);
+			h.hf2 = h.hf2 * b.B2 + (c + 1);
 		}
-		fp[p] = out;
-		hf1 = addmod61(mulmod61(addmod61(hf1, P61 - prm.T1f[cout]), prm.B1), cin + 1);
-		hr1 = addmod61(mulmod61(addmod61(hr1, P61 - (4 - cout)), prm.invB1), prm.T1r[cin]);
-		prevc = cout;
+	}
+	{
+		const uint32_t x = word(w_first + kw);
+		for(uint32_t i = 0; i < kt; i++)
+		{
+			const uint32_t c = (x >> (30 - 2 * i)) & 3u;
+			h.hf1 = muladdmod61(h.hf1, b.B1, c + 1);
+			h.hf2 = h.hf2 * b.B2 + (c + 1);
+		}
+		for(uint32_t i = kt; i-- > 0; )
+		{
+			const uint32_t c = (x >> (30 - 2 * i)) & 3u;
+			h.hr1 = muladdmod61(h.hr1, b.B1, 4 - c);
+			h.hr2 = h.hr2 * b.B2 + (4 - c);
+		}
+	}
+	for(uint32_t wi = kw; wi-- > 0; )
+	{
+		const uint32_t x = word(w_first + wi);
+#pragma unroll
+		for(int i = 15; i >= 0; i--)
+		{
+			const uint32_t c = (x >> (30 - 2 * i)) & 3u;
+			h.hr1 = muladdmod61(h.hr1, b.B1, 4 - c);
+			h.hr2 = h.hr2 * b.B2 + (4 - c);
+		}
+	}
+	const uint32_t sh = 2 * kt;
+	uint32_t in_lo = word(w_first + kw);
+	for(uint32_t w = w_first; w < w_last; w++)
+	{
+		ck[w] = FpCk{h.hf1, h.hr1, h.hf2, h.hr2};
+		const uint32_t wout = word(w), in_hi = word(w + kw + 1);
+		const uint32_t win = __funnelshift_l(in_hi, in_lo, sh);       // the codes of positions 16 w + k ... + 15
+		in_lo = in_hi;
+#pragma unroll
+		for(int i = 0; i < 16; i++)
+		{
+			const uint32_t idx = (((wout >> (30 - 2 * i)) & 3u) << 2) | ((win >> (30 - 2 * i)) & 3u);
+			fp_roll(h, sD, b, idx);
+		}
 	}
 }
 
@@ -131,23 +130,33 @@ int fingerprint_positions(sibgpu_ctx *ctx, const TextDesc &t, uint32_t k, uint32
 	static const uint64_t B1S[3] = {0x0F3A5C7E9B1D2E4Full, 0x1B2D4F6A8C0E1357ull, 0x0A9C8E7F6D5B4A39ull};
 	static const uint64_t B2S[3] = {0x9E3779B97F4A7C15ull, 0xC2B2AE3D27D4EB4Full, 0xD6E8FEB86659FD93ull};
 	FpParams prm;
-	prm.B1 = B1S[attempt % 3] % P61;
-	prm.B2 = B2S[attempt % 3] | 1ull;
-	prm.invB1 = powmod61(prm.B1, P61 - 2);
-	prm.invB2 = inv64(prm.B2);
-	const uint64_t top1 = powmod61(prm.B1, k - 1), top2 = pow64(prm.B2, k - 1);
-	for(uint32_t c = 0; c < 4; c++)
+	FpBases &b = prm.b;
+	b.B1 = B1S[attempt % 3] % P61;
+	b.B2 = B2S[attempt % 3] | 1ull;
+	b.invB1 = powmod61(b.B1, P61 - 2);
+	b.invB2 = inv64(b.B2);
+	// rolling step: Hf' = Hf B - (out+1) B^k + (in+1);   Hr' = Hr / B - (4-out) / B + (4-in) B^(k-1)
+	const uint64_t top1 = powmod61(b.B1, k - 1), top2 = pow64(b.B2, k - 1);
+	const uint64_t full1 = mulmod61(top1, b.B1), full2 = top2 * b.B2;
+	for(uint32_t co = 0; co < 4; co++)
 	{
-		prm.T1f[c] = mulmod61(c + 1, top1);
-		prm.T1r[c] = mulmod61(4 - c, top1);
-		prm.T2f[c] = (c + 1) * top2;
-		prm.T2r[c] = (4 - c) * top2;
+		for(uint32_t ci = 0; ci < 4; ci++)
+		{
+			const uint32_t i = co * 4 + ci;
+			prm.D[0][i] = addmod61(ci + 1, P61 - mulmod61(co + 1, full1));
+			prm.D[1][i] = addmod61(mulmod61(4 - ci, top1), P61 - mulmod61(4 - co, b.invB1));
+			prm.D[2][i] = (ci + 1) - (co + 1) * full2;
+			prm.D[3][i] = (4 - ci) * top2 - (4 - co) * b.invB2;
+		}
 	}
-	SIB_TRY(ctx->d_fp.ensure(sizeof(Rec16) * (size_t)t.M));
-	uint32_t L = k < 128 ? 128 : ((k + 15) / 16) * 16;
+	const uint32_t nck = (uint32_t)((t.M + 15) >> 4);
+	SIB_TRY(ctx->d_fp.ensure(sizeof(FpCk) * (size_t)nck));
+	SIB_TRY(ctx->d_fpprm.ensure(sizeof(FpParams)));
+	SIB_CUDA(cudaMemcpyAsync(ctx->d_fpprm.p, &prm, sizeof(FpParams), cudaMemcpyHostToDevice, ctx->stream));
+	const uint32_t L = k < 128 ? 128 : ((k + 15) / 16) * 16;
 	const uint64_t threads = (t.M + L - 1) / L;
-	ProfScope ps(ctx, "k_fingerprint", (uint64_t)t.M / 4 * 2 + (uint64_t)t.M * 16);
-	k_fingerprint<<<(uint32_t)((threads + 127) / 128), 128, 0, ctx->stream>>>(t, k, L, prm, ctx->d_fp.as<Rec16>());
+	ProfScope ps(ctx, "k_fp_ckpt", (uint64_t)t.M / 4 * 2 + (uint64_t)nck * sizeof(FpCk));
+	k_fp_ckpt<<<(uint32_t)((threads + 127) / 128), 128, 0, ctx->stream>>>(t, k, L, prm, ctx->d_fp.as<FpCk>());
 	return SIBGPU_OK;
 }
 

@@ -336,10 +336,15 @@ template<class R> struct GroupSmem {
 
 // Level 3: one bucket at a time per CTA (persistent grid, GROUP_STAGES buckets in flight per CTA through the TMA ring).
 // nkeys counts every bifurcation class even when the key list is full (the caller then regrows it and runs again).
-template<class R>
+// PKEY (fingerprint records): a class is {56-bit fingerprint, level-1 partition} -- the partition was chosen by a second
+// hash that the record does not carry -- and the key list takes 16-byte entries {fingerprint, partition}.
+template<class R, bool PKEY> struct GroupKey { typedef R type; };
+template<> struct GroupKey<uint64_t, true> { typedef Rec16 type; };
+
+template<class R, bool PKEY = false>
 __global__ void __launch_bounds__(GROUP_THREADS, sizeof(R) == 8 ? 4 : 2) k_group(const R *__restrict__ recs2, const uint32_t *__restrict__ cnt2,
-	uint32_t nbuckets, uint32_t cap2, const uint32_t *__restrict__ overflow, R *__restrict__ ckeys, uint32_t ckeys_cap,
-	uint32_t *__restrict__ nkeys)
+	uint32_t nbuckets, uint32_t sub_bits, uint32_t cap2, const uint32_t *__restrict__ overflow,
+	typename GroupKey<R, PKEY>::type *__restrict__ ckeys, uint32_t ckeys_cap, uint32_t *__restrict__ nkeys)
 {
 	extern __shared__ __align__(16) unsigned char smem_raw[];
 	GroupSmem<R> &s = *reinterpret_cast<GroupSmem<R>*>(smem_raw);
@@ -463,7 +468,8 @@ __global__ void __launch_bounds__(GROUP_THREADS, sizeof(R) == 8 ? 4 : 2) k_group
 				const uint32_t idx = base + __popc(mk & ((1u << lane) - 1u));
 				if(bif && idx < ckeys_cap)
 				{
-					if constexpr(sizeof(R) == 8) ckeys[idx] = unmix56(RecOps<R>::key(w[i]));
+					if constexpr(PKEY) ckeys[idx] = Rec16{unmix56(RecOps<R>::key(w[i])), (uint64_t)(q >> sub_bits)};
+					else if constexpr(sizeof(R) == 8) ckeys[idx] = unmix56(RecOps<R>::key(w[i]));
 					else ckeys[idx] = make_ulonglong2(unmix64(RecOps<R>::key(w[i])), 0ull);
 				}
 			}

@@ -103,19 +103,24 @@ def test_cli_reports_parse_errors_like_the_reference(tmp_path, defect):
 @pytest.mark.skipif(not have, reason="oracle/_ref/Sibelia{,_gpu} did not travel")
 def test_condensed_graph_output(tmp_path):
     """-g: BlockFinder::SerializeCondensedGraph (serialization.cpp:88-110) writes the condensed de Bruijn graph of every
-    stage and of the final index; in the bound CLI its index + ListEdges pair is one sibgpu_list_edges call."""
+    stage (--allstages, sibelia.cpp:256-262) and of the final index (:333-344); in the bound CLI its index + ListEdges
+    pair is one sibgpu_list_edges call."""
     chrs = helpers.strain_case(3, 80_000, p_sub=0.01, inv_len=8_000, seed=34)
     fa = str(tmp_path / "in.fasta")
     write_fasta(fa, chrs)
-    args = ["-s", "loose", "-m", "1000", "-g", fa]
-    run(REF_BIN, args, str(tmp_path / "ref"))
-    run(GPU_BIN, args, str(tmp_path / "gpu"))
-    dots = sorted(f for f in os.listdir(str(tmp_path / "ref")) if f.endswith(".dot"))
-    assert len(dots) >= 2
-    for f in dots:
-        want = open(os.path.join(str(tmp_path / "ref"), f), "rb").read()
-        got = open(os.path.join(str(tmp_path / "gpu"), f), "rb").read()
-        assert got == want, "%s differs" % f
+    for sub, extra in (("one", []), ("all", ["--allstages"])):
+        outs = {}
+        for name, binary in (("ref", REF_BIN), ("gpu", GPU_BIN)):
+            outs[name] = str(tmp_path / sub / name)
+            os.makedirs(outs[name], exist_ok=True)
+            subprocess.run([binary, "-s", "loose", "-m", "1000", "-g"] + extra + [fa, "-o", outs[name]], check=True,
+                           stdout=subprocess.PIPE, stderr=subprocess.STDOUT, timeout=1500)
+        names = sorted(f for f in os.listdir(outs["ref"]) if f.endswith(".dot") or f.startswith("blocks_coords"))
+        assert sum(f.endswith(".dot") for f in names) == (5 if extra else 1), names
+        for f in names:
+            want = open(os.path.join(outs["ref"], f), "rb").read()
+            got = open(os.path.join(outs["gpu"], f), "rb").read()
+            assert got == want, "%s differs" % f
 
 
 @pytest.mark.skipif(not (have and os.path.exists(os.path.join(DATA, "Helicobacter_pylori.fasta"))),
