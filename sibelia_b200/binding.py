@@ -52,7 +52,8 @@ class _KStat(C.Structure):
 
 
 def lib_path():
-    return os.path.join(_HERE, "libsibgpu.so")
+    # SIBGPU_LIB: a differently compiled build of the same sources (tools/build_variant.sh, kernel tuning only)
+    return os.environ.get("SIBGPU_LIB") or os.path.join(_HERE, "libsibgpu.so")
 
 
 def build(verbose=False):

@@ -137,7 +137,9 @@ __device__ __forceinline__ void scan16_exact(const TextDesc &t, const uint32_t *
 // MODE 2 (k > 32): the four rolling hashes start from the checkpoint of the thread's word (k_fp_ckpt, fingerprint.cu)
 // and advance one position at a time; f(i, a, hb, ctx): a = 56-bit fingerprint of the canonical orientation, hb = the
 // 32 bits of the second hash that choose the hash partition (the partition index is part of the class key)
-template<class F>
+// UNROLL < 16 for callers whose per-position work is large and divergent (k_mark: map probes): the fully unrolled body
+// would be 16 copies of the rolling step + the caller's code
+template<int UNROLL, class F>
 __device__ __forceinline__ void scan16_fp(const TextDesc &t, const FpView &fv, const uint32_t *sw, const uint64_t *sD,
 	uint32_t tile, uint32_t k, F f_emit)
 {
@@ -160,7 +162,7 @@ __device__ __forceinline__ void scan16_fp(const TextDesc &t, const FpView &fv, c
 	ChrCursor cur;
 	cur.init(t, p0);
 	const bool interior = p0 > cur.cs && (uint64_t)p0 + (POS_PER_THREAD - 1) + k < cur.ce;
-#pragma unroll
+#pragma unroll UNROLL
 	for(int i = 0; i < POS_PER_THREAD; i++)
 	{
 		const uint32_t p = p0 + i;
@@ -204,11 +206,11 @@ __device__ __forceinline__ void fp_at(const TextDesc &t, const FpView &fv, const
 	hb = (fw ? h.hf2 : h.hr2) >> 32;
 }
 
-template<int MODE, class F>
+template<int MODE, int UNROLL = POS_PER_THREAD, class F>
 __device__ __forceinline__ void scan16(const TextDesc &t, const FpView &fv, const uint32_t *sw, const uint64_t *sD, uint32_t tile,
 	uint32_t k, F f_emit)
 {
-	if(MODE == 2) scan16_fp(t, fv, sw, sD, tile, k, f_emit);
+	if(MODE == 2) scan16_fp<UNROLL>(t, fv, sw, sD, tile, k, f_emit);
 	else scan16_exact(t, sw, tile, k, f_emit);
 }
 
@@ -885,6 +887,10 @@ __device__ __forceinline__ bool map_lookup(const MapSlot *__restrict__ map, uint
 // ---------------------------------------------------------------------------------------------------------------
 // K6: mark vertex positions.   K7: emit the instance tables in text order.
 // ---------------------------------------------------------------------------------------------------------------
+#ifndef SIBGPU_MARK_UNROLL
+#define SIBGPU_MARK_UNROLL 2
+#endif
+constexpr int MARK_UNROLL = SIBGPU_MARK_UNROLL;
 template<int MODE>
 __global__ void __launch_bounds__(TILE_THREADS) k_mark(TextDesc t, const FpView fv, uint32_t P, uint32_t k, uint32_t ntiles,
 	const MapSlot *__restrict__ map, uint32_t Tm, const uint32_t *__restrict__ filter, uint32_t fshift,
@@ -901,7 +907,7 @@ __global__ void __launch_bounds__(TILE_THREADS) k_mark(TextDesc t, const FpView 
 		stage_tile(t, t.tile0 + tile, sw);
 		__syncthreads();
 		uint32_t mask = 0;
-		scan16<MODE>(t, fv, sw, sD, t.tile0 + tile, k, [&](int i, uint64_t a, uint64_t b, uint32_t ctx) {
+		scan16<MODE, MARK_UNROLL>(t, fv, sw, sD, t.tile0 + tile, k, [&](int i, uint64_t a, uint64_t b, uint32_t ctx) {
 			uint32_t idc, idr, cls;
 			if(MODE == 2) b = __umulhi((uint32_t)b, P);    // class key = {fingerprint, partition}
 			if(map_lookup(map, Tm, filter, fshift, a, b, idc, idr, cls))
@@ -931,20 +937,29 @@ __global__ void __launch_bounds__(TILE_THREADS) k_emit(TextDesc t, const FpView 
 	typedef cub::BlockScan<uint32_t, TILE_THREADS> Scan;
 	__shared__ typename Scan::TempStorage scan_tmp;
 	__shared__ uint64_t sD[MODE == 2 ? FP_SMEM_WORDS : 1];
+	__shared__ uint16_t hits[TILE_POS];                    // tile-local positions of the hits, in text order
 	if(MODE == 2) fp_stage_params(fv.prm, sD);
 	for(uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x)
 	{
+		// The hits of the tile are listed in shared memory first and then dealt out one per thread: the work per hit
+		// (key or fingerprint, map probe, string verification) is long and the hits cluster, so a thread that walked
+		// the hits of its own 16 positions would hold up its whole warp; consecutive hits also write consecutive rows.
 		uint32_t mask = hitmask[(uint64_t)tile * TILE_THREADS + threadIdx.x];
-		uint32_t rank;
+		uint32_t rank, total;
 		__syncthreads();
-		Scan(scan_tmp).ExclusiveSum((uint32_t)__popc(mask), rank);
-		uint64_t o = tileoff[tile] + rank;
-		const uint32_t p0 = (t.tile0 + tile) * TILE_POS + threadIdx.x * POS_PER_THREAD;
+		Scan(scan_tmp).ExclusiveSum((uint32_t)__popc(mask), rank, total);
 		while(mask)
 		{
-			const uint32_t i = __ffs(mask) - 1;
+			hits[rank++] = (uint16_t)(threadIdx.x * POS_PER_THREAD + __ffs(mask) - 1);
 			mask &= mask - 1;
-			const uint32_t p = p0 + i;
+		}
+		__syncthreads();
+		const uint32_t tile_p0 = (t.tile0 + tile) * TILE_POS;
+		const uint64_t o0 = tileoff[tile];
+		for(uint32_t h = threadIdx.x; h < total; h += TILE_THREADS)
+		{
+			const uint32_t p = tile_p0 + hits[h];
+			const uint64_t o = o0 + h;
 			unsigned long long a, b = 0;
 			bool fw;
 			if(MODE == 2)
@@ -985,7 +1000,6 @@ __global__ void __launch_bounds__(TILE_THREADS) k_emit(TextDesc t, const FpView 
 				pos_out[o] = ip;
 				neg_tmp[o] = in;
 			}
-			o++;
 		}
 	}
 }

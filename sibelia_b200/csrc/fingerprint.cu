@@ -163,19 +163,22 @@ int fingerprint_positions(sibgpu_ctx *ctx, const TextDesc &t, uint32_t k, uint32
 // ---------------------------------------------------------------------------------------------------------------
 // lexicographic ranking of the vertex k-mers
 // ---------------------------------------------------------------------------------------------------------------
-// item key = text position << 1 | dir (dir = 1: the k-mer at that position, dir = 0: its reverse complement);
-// item value = class << 1 | (1 if the item is the reverse complement of the class's canonical string)
-__global__ void __launch_bounds__(256) k_make_items(const unsigned long long *__restrict__ rep, uint64_t Vc,
-	unsigned long long *__restrict__ keys, uint32_t *__restrict__ vals, uint32_t *__restrict__ npal)
+// item = text position << 1 | dir (dir = 1: the k-mer at that position, dir = 0: its reverse complement), carried with
+// the first 32 bases of the string it spells: almost every comparison of the sort is decided on that prefix, without
+// touching the text;  item value = class << 1 | (1 if the item is the reverse complement of the class's canonical string)
+struct VItem { unsigned long long prefix, item; };
+
+__global__ void __launch_bounds__(256) k_make_items(TextDesc t, uint32_t k, const unsigned long long *__restrict__ rep, uint64_t Vc,
+	VItem *__restrict__ keys, uint32_t *__restrict__ vals, uint32_t *__restrict__ npal)
 {
 	uint64_t j = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
 	if(j >= Vc) return;
 	const unsigned long long R = rep[j];
 	const unsigned long long p = R >> 2;
 	const uint32_t pal = (uint32_t)(R >> 1) & 1u, fw = (uint32_t)R & 1u;
-	keys[2 * j] = (p << 1) | fw;
+	keys[2 * j] = VItem{vstr_chunk(t, (uint32_t)p, fw, 0, k), (p << 1) | fw};
 	vals[2 * j] = (uint32_t)(j << 1);
-	keys[2 * j + 1] = pal ? EMPTY64 : ((p << 1) | (fw ^ 1u));
+	keys[2 * j + 1] = pal ? VItem{EMPTY64, EMPTY64} : VItem{vstr_chunk(t, (uint32_t)p, fw ^ 1u, 0, k), (p << 1) | (fw ^ 1u)};
 	vals[2 * j + 1] = (uint32_t)(j << 1) | 1u;
 	if(pal) atomicAdd(npal, 1u);
 }
@@ -183,11 +186,12 @@ __global__ void __launch_bounds__(256) k_make_items(const unsigned long long *__
 struct VStrLess {
 	TextDesc t;
 	uint32_t k;
-	__device__ bool operator()(const unsigned long long &x, const unsigned long long &y) const
+	__device__ bool operator()(const VItem &x, const VItem &y) const
 	{
-		if(x == EMPTY64 || y == EMPTY64) return x != EMPTY64 && y == EMPTY64;   // palindrome placeholders sort last
-		const uint32_t px = (uint32_t)(x >> 1), dx = (uint32_t)x & 1u, py = (uint32_t)(y >> 1), dy = (uint32_t)y & 1u;
-		for(uint32_t m = 0; m * 32 < k; m++)
+		if(x.item == EMPTY64 || y.item == EMPTY64) return x.item != EMPTY64 && y.item == EMPTY64;   // palindrome placeholders sort last
+		if(x.prefix != y.prefix) return x.prefix < y.prefix;
+		const uint32_t px = (uint32_t)(x.item >> 1), dx = (uint32_t)x.item & 1u, py = (uint32_t)(y.item >> 1), dy = (uint32_t)y.item & 1u;
+		for(uint32_t m = 1; m * 32 < k; m++)
 		{
 			const uint64_t cx = vstr_chunk(t, px, dx, m, k), cy = vstr_chunk(t, py, dy, m, k);
 			if(cx != cy) return cx < cy;
@@ -196,11 +200,11 @@ struct VStrLess {
 	}
 };
 
-__global__ void __launch_bounds__(256) k_assign_class_ids(const unsigned long long *__restrict__ keys,
+__global__ void __launch_bounds__(256) k_assign_class_ids(const VItem *__restrict__ keys,
 	const uint32_t *__restrict__ vals, uint64_t n, const unsigned long long *__restrict__ rep, uint32_t *__restrict__ classids)
 {
 	uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
-	if(i >= n || keys[i] == EMPTY64) return;
+	if(i >= n || keys[i].item == EMPTY64) return;
 	const uint32_t v = vals[i], cls = v >> 1;
 	classids[2 * cls + (v & 1u)] = (uint32_t)i;
 	if(!(v & 1u) && ((rep[cls] >> 1) & 1ull)) classids[2 * cls + 1] = (uint32_t)i;   // palindrome: one vertex
@@ -220,15 +224,15 @@ int rank_fingerprint_vertices(sibgpu_ctx *ctx, const TextDesc &t, uint32_t k, ui
 	cudaStream_t st = ctx->stream;
 	uint64_t *hs = static_cast<uint64_t*>(ctx->h_scalars);
 	uint64_t *ds = ctx->d_scalars.as<uint64_t>();
-	SIB_TRY(ctx->d_vkeys.ensure(sizeof(uint64_t) * 2 * Vc));
+	SIB_TRY(ctx->d_vkeys.ensure(sizeof(VItem) * 2 * Vc));
 	SIB_TRY(ctx->d_vkeys_alt.ensure(sizeof(uint32_t) * 2 * Vc));
 	SIB_TRY(ctx->d_order.ensure(sizeof(uint32_t) * 2 * Vc));
-	unsigned long long *keys = ctx->d_vkeys.as<unsigned long long>();
+	VItem *keys = ctx->d_vkeys.as<VItem>();
 	uint32_t *vals = ctx->d_vkeys_alt.as<uint32_t>();
 	SIB_CUDA(cudaMemsetAsync(ds + 3, 0, sizeof(uint64_t), st));
 	{
-		ProfScope ps(ctx, "k_make_items", Vc * 32);
-		k_make_items<<<(uint32_t)((Vc + 255) / 256), 256, 0, st>>>(ctx->d_rep.as<unsigned long long>(), Vc, keys, vals,
+		ProfScope ps(ctx, "k_make_items", Vc * 48);
+		k_make_items<<<(uint32_t)((Vc + 255) / 256), 256, 0, st>>>(t, k, ctx->d_rep.as<unsigned long long>(), Vc, keys, vals,
 			reinterpret_cast<uint32_t*>(ds + 3));
 	}
 	VStrLess less;
@@ -238,7 +242,7 @@ int rank_fingerprint_vertices(sibgpu_ctx *ctx, const TextDesc &t, uint32_t k, ui
 	SIB_CUDA(cub::DeviceMergeSort::SortPairs(nullptr, tmp_bytes, keys, vals, (int)(2 * Vc), less, st));
 	SIB_TRY(ctx->d_cubtmp.ensure(tmp_bytes));
 	{
-		ProfScope ps(ctx, "cub_merge_sort_vertex_strings", 2 * Vc * 12 * 2, 8);
+		ProfScope ps(ctx, "cub_merge_sort_vertex_strings", 2 * Vc * 20 * 2, 8);
 		SIB_CUDA(cub::DeviceMergeSort::SortPairs(ctx->d_cubtmp.p, tmp_bytes, keys, vals, (int)(2 * Vc), less, st));
 	}
 	{

@@ -17,12 +17,12 @@ ctx.upload(chrs)
 ctx.set_profiling(True)
 print("# %d strains x %d bases = %d bases; device-resident text; ms = CUDA events around the whole enumeration" % (n_strains, base_len, N))
 print("# %6s %10s %12s %9s %10s %9s  top kernels (ms)" % ("k", "vertices", "instances", "ms", "Gbases/s", "algoGB/s"))
-for k in (15, 25, 100, 500, 5000):
+for k in [int(x) for x in os.environ.get("KSWEEP_K", "15,25,100,500,5000").split(",")]:
     for rep in range(2):
         count, ninst = ctx.enumerate_resident(k)
     ms = ctx.last_device_ms()
     st = ctx.kernel_stats()
     algo = sum(s["algo_bytes"] for s in st)
-    top = sorted(st, key=lambda s: -s["ms"])[:5]
+    top = sorted(st, key=lambda s: -s["ms"])[:int(os.environ.get("KSWEEP_TOP", "5"))]
     print("  %6d %10d %12d %9.2f %10.2f %9.0f  %s" % (k, count, ninst, ms, N / ms / 1e6, algo / ms / 1e6,
           ", ".join("%s %.2f" % (s["name"], s["ms"]) for s in top)), flush=True)
