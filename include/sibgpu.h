@@ -236,7 +236,7 @@ int sibgpu_dist_export_send(sibgpu_ctx *ctx, void *handle64);
 int sibgpu_dist_import_peers(sibgpu_ctx *ctx, const void *handles);
 int sibgpu_dist_group_peer(sibgpu_ctx *ctx, const uint64_t *counts, const uint64_t *seg_caps, uint64_t *nkeys_local);
 
-/* Fused variant (k <= 28): no collective and no host round trip inside a step.  Every rank owns one exported buffer
+/* Fused variant (k <= 28, and k > 32 through sibgpu_fused_run_fp): no collective and no host round trip inside a step.  Every rank owns one exported buffer
  * [header | fill cursors | vertex keys | one fixed-capacity segment per global partition]; the peers map it once
  * (CUDA IPC).  In a step a rank scatters its text range into its own segments and publishes a step counter in its
  * header; the level-2 split kernel of the partition owner waits for the peers' counters on the device and pulls the
@@ -247,7 +247,7 @@ int sibgpu_dist_group_peer(sibgpu_ctx *ctx, const uint64_t *counts, const uint64
  *                               buffers fit, 1 = (re)allocation needed -- the SAME answer on every rank, the caller
  *                               then runs, collectively: barrier, sibgpu_fused_release_peers, barrier,
  *                               sibgpu_fused_alloc, all-gather of the 64-byte handles, sibgpu_fused_import;
- *                               -1 = not applicable (k > 28, input beyond the bucket fan-out): use the phased API above.
+ *                               -1 = not applicable (k = 29..32, input beyond the bucket fan-out): use the phased API above.
  *                               resident != 0: the text range is already in HBM (sibgpu_dist_upload).
  *   sibgpu_fused_run            one step.  *status: 0 = done (sibgpu_download returns the LOCAL tables, text order);
  *                               1 = a segment or bucket overflowed on some rank: every rank gets 1 and uses the phased
@@ -261,6 +261,24 @@ int sibgpu_fused_alloc(sibgpu_ctx *ctx, void *handle64);
 int sibgpu_fused_import(sibgpu_ctx *ctx, const void *handles);
 int sibgpu_fused_run(sibgpu_ctx *ctx, const char *const *chr, const uint64_t *len, uint32_t nchr, int resident, uint32_t *count,
 	uint64_t *ninst_local, int *status);
+
+/* k > 32 (fingerprint classes, the -s loose stages k = 100, 1000, 5000 of src/util.cpp:50-61) on the same exported buffers.
+ * The packed text is made complete on every rank by peer pulls (the rolling hashes, the string ranking of the vertex
+ * classes and the verification of the instances read it beyond the own range); a class is {fingerprint, partition}.
+ * The step has two halves because the representative occurrence of a class is its smallest text position over ALL ranks:
+ *
+ *   sibgpu_fused_run_fp         scatter, fused exchange, grouping, key pull, map, marking of the own range.
+ *                               *status as sibgpu_fused_run (1: no phased API exists for k > 32 -- the caller lets every
+ *                               rank run sibgpu_enumerate on the whole input and keeps its own range).
+ *                               *rep_dev = device array of *nclasses 64-bit words: the caller min-reduces it over the
+ *                               ranks in place (signed or unsigned: all values are < 2^63), e.g. ncclAllReduce(ncclMin)
+ *   sibgpu_fused_finish_fp      string ranking (every rank ranks all classes), instance tables of the own range with
+ *                               verification.  *collision != 0 on any rank (the caller max-reduces it): two different
+ *                               k-mers shared a fingerprint inside a vertex class -- run both halves again with attempt + 1.
+ */
+int sibgpu_fused_run_fp(sibgpu_ctx *ctx, const char *const *chr, const uint64_t *len, uint32_t nchr, int resident, uint32_t attempt,
+	uint64_t *nclasses, void **rep_dev, int *status);
+int sibgpu_fused_finish_fp(sibgpu_ctx *ctx, uint32_t *count, uint64_t *ninst_local, int *collision);
 
 /* Test hook (host only, no GPU needed): iteration order of the reference's boost::unordered_map<size_t, BranchData>
  * (Boost 1.54, src/bulgeremoval.cpp:168,203-215) after inserting n distinct keys in the given order, as restated in

@@ -308,6 +308,19 @@ class Context:
                                        C.byref(ninst), C.byref(status)))
         return status.value, cnt.value, ninst.value
 
+    def dist2_run_fp(self, chrs, resident=False, attempt=0):
+        """k > 32, first half: (status, classes, device pointer of the class representatives to min-reduce)"""
+        bufs, ptrs, lens, n = _chr_args(chrs)
+        ncls, rep, status = C.c_uint64(), C.c_void_p(), C.c_int()
+        _check(load().sibgpu_fused_run_fp(self._h, ptrs, lens, C.c_uint32(n), C.c_int(1 if resident else 0), C.c_uint32(attempt),
+                                          C.byref(ncls), C.byref(rep), C.byref(status)))
+        return status.value, ncls.value, rep.value or 0
+
+    def dist2_finish_fp(self):
+        cnt, ninst, coll = C.c_uint32(), C.c_uint64(), C.c_int()
+        _check(load().sibgpu_fused_finish_fp(self._h, C.byref(cnt), C.byref(ninst), C.byref(coll)))
+        return cnt.value, ninst.value, coll.value
+
     def dist_keys(self, keys_ptr):
         _check(load().sibgpu_dist_keys(self._h, C.c_void_p(keys_ptr)))
 

@@ -841,6 +841,41 @@ int sibgpu_fused_run(sibgpu_ctx *c, const char *const *chr, const uint64_t *len,
 	return SIBGPU_OK;
 }
 
+int sibgpu_fused_run_fp(sibgpu_ctx *c, const char *const *chr, const uint64_t *len, uint32_t nchr, int resident, uint32_t attempt,
+	uint64_t *nclasses, void **rep_dev, int *status)
+{
+	if(!c || !status || !nclasses || !rep_dev || (!resident && nchr && (!chr || !len)))
+	{
+		set_error("invalid: NULL argument");
+		return SIBGPU_ERR_INVALID;
+	}
+	SIB_CUDA(cudaSetDevice(c->device));
+	HostSrc src = {chr, len};
+	SIB_CUDA(cudaEventRecord(c->ev_begin, c->stream));
+	SIB_TRY(dist2_run_fp(c, resident ? nullptr : &src, attempt, status));
+	c->have_text = true;
+	*nclasses = c->x_Vc;
+	*rep_dev = c->x_Vc ? c->d_rep.p : nullptr;
+	return SIBGPU_OK;
+}
+
+int sibgpu_fused_finish_fp(sibgpu_ctx *c, uint32_t *count, uint64_t *ninst_local, int *collision)
+{
+	if(!c || !collision)
+	{
+		set_error("invalid: NULL argument");
+		return SIBGPU_ERR_INVALID;
+	}
+	SIB_CUDA(cudaSetDevice(c->device));
+	SIB_TRY(dist2_finish_fp(c, collision));
+	SIB_CUDA(cudaEventRecord(c->ev_end, c->stream));
+	SIB_CUDA(cudaEventSynchronize(c->ev_end));
+	SIB_CUDA(cudaEventElapsedTime(&c->last_ms, c->ev_begin, c->ev_end));
+	if(ninst_local) *ninst_local = c->n_inst;
+	if(count) *count = c->n_vertices;
+	return SIBGPU_OK;
+}
+
 int sibgpu_set_profiling(sibgpu_ctx *c, int enabled)
 {
 	if(!c) return SIBGPU_ERR_INVALID;

@@ -58,6 +58,9 @@ struct sibgpu_ctx {
 	sibgpu::DevBuf d_xbuf;
 	std::vector<void*> peer_x;                         // [world] mappings of the peers' exported buffers
 	uint64_t x_kc = 0, x_kc_live = 0, x_off_seg = 0, x_off_seg_plan = 0, x_seg_cap = 0, x_nrec = 0, x_bytes = 0;
+	uint64_t x_off_pk = 0, x_off_pk_plan = 0;             // k > 32: packed words of the own text range, pulled by the peers
+	uint64_t x_Vc = 0;                                    // k > 32: classes of the step between its two phases
+	uint32_t x_attempt = 0;
 	uint32_t x_PL = 0, x_sub_bits = 0, x_k = 0;
 	unsigned long long dist_epoch = 0;                 // step counter, the same on all ranks
 	sibgpu::TextDesc dist_text = {};
@@ -153,4 +156,6 @@ int dist2_release_peers(sibgpu_ctx *ctx);
 int dist2_alloc(sibgpu_ctx *ctx, void *handle64);
 int dist2_import(sibgpu_ctx *ctx, const void *handles);
 int dist2_run(sibgpu_ctx *ctx, const HostSrc *src, int *status);
+int dist2_run_fp(sibgpu_ctx *ctx, const HostSrc *src, uint32_t attempt, int *status);
+int dist2_finish_fp(sibgpu_ctx *ctx, int *collision);
 } // namespace sibgpu

@@ -240,7 +240,7 @@ int dist_scan(sibgpu_ctx *ctx, uint32_t k, uint32_t *hist_out)
 // fixed-capacity segments of `cap` records at out_dev, fill cursors at cursor_dev (already initialised to p * cap)
 template<int MODE, bool MIXED>
 static int dist_scatter_core(sibgpu_ctx *ctx, uint32_t k, uint32_t PT, uint64_t cap, unsigned long long *cursor_dev,
-	typename RecT<MODE>::type *out_dev, const HostSrc *src)
+	typename RecT<MODE>::type *out_dev, const HostSrc *src, const FpView fv = FpView{})
 {
 	typedef typename RecT<MODE>::type Rec;
 	cudaStream_t st = ctx->stream;
@@ -286,8 +286,8 @@ static int dist_scatter_core(sibgpu_ctx *ctx, uint32_t k, uint32_t PT, uint64_t 
 			const uint32_t g = nt < (uint32_t)ctx->sm_count * 4 ? nt : (uint32_t)ctx->sm_count * 4;
 			TextDesc tc = t;
 			tc.tile0 = tiles_done;
-			ProfScope ps(ctx, "k_scatter", (uint64_t)nt * TILE_POS / 4 + (uint64_t)nt * TILE_POS * sizeof(Rec));
-			k_scatter<MODE, MIXED><<<g, TILE_THREADS, smem, st>>>(tc, FpView{}, k, nt, PT, cursor_dev, out_dev, cap,
+			ProfScope ps(ctx, "k_scatter", (uint64_t)nt * TILE_POS / 4 * (MODE == 2 ? 10 : 1) + (uint64_t)nt * TILE_POS * sizeof(Rec));
+			k_scatter<MODE, MIXED><<<g, TILE_THREADS, smem, st>>>(tc, fv, k, nt, PT, cursor_dev, out_dev, cap,
 				reinterpret_cast<uint32_t*>(ds + 10));
 			tiles_done = tile_end;
 		}
@@ -559,6 +559,8 @@ __global__ void k_publish_keys(DistHeader *h, const uint32_t *nkeys, const uint3
 struct PullSrc { const DistHeader *header[SPLIT_MAX_SRC]; const unsigned long long *keys[SPLIT_MAX_SRC]; };
 // out[0] = total keys, out[1] = OR of all ranks' failure flags (bit 1 of the scatter flags -> 64: illegal character),
 // out[2] = largest per-rank key count
+// WPK = 64-bit words per key (2: fingerprint classes {fingerprint, partition})
+template<int WPK>
 __global__ void __launch_bounds__(256) k_pull_keys(const PullSrc src, uint32_t W, unsigned long long epoch, uint32_t key_cap,
 	uint64_t *__restrict__ allkeys, uint64_t allcap, uint64_t *__restrict__ out)
 {
@@ -587,22 +589,23 @@ __global__ void __launch_bounds__(256) k_pull_keys(const PullSrc src, uint32_t W
 	if(s_flags) return;
 	// 16-byte loads over NVLink (the key regions are 16-byte aligned), the odd last key on its own
 	const unsigned long long *k = src.keys[me];
-	const uint64_t pairs = s_n / 2;
+	const uint64_t nw = s_n * WPK, ow = s_off * WPK, pairs = nw / 2;
 	for(uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < pairs; i += (uint64_t)gridDim.x * blockDim.x)
 	{
 		unsigned long long a, b;
 		asm volatile("ld.relaxed.sys.global.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(k + 2 * i) : "memory");
-		allkeys[s_off + 2 * i] = a;
-		allkeys[s_off + 2 * i + 1] = b;
+		allkeys[ow + 2 * i] = a;
+		allkeys[ow + 2 * i + 1] = b;
 	}
-	if((s_n & 1u) && blockIdx.x == 0 && threadIdx.x == 0) allkeys[s_off + s_n - 1] = ld_relaxed_sys(k + s_n - 1);
+	if((nw & 1u) && blockIdx.x == 0 && threadIdx.x == 0) allkeys[ow + nw - 1] = ld_relaxed_sys(k + nw - 1);
 }
 
 int dist2_plan(sibgpu_ctx *ctx, uint32_t k, int *need_alloc)
 {
 	*need_alloc = -1;
 	const uint32_t W = ctx->dist_world;
-	if(k > 28 || W > (uint32_t)SPLIT_MAX_SRC || !ctx->group_smem) return SIBGPU_OK;
+	if((k > 28 && k <= 32) || W > (uint32_t)SPLIT_MAX_SRC || !ctx->group_smem) return SIBGPU_OK;
+	const bool fp = k > 32;                                // fingerprint classes: 16-byte keys, packed text replicated by peer pulls
 	uint64_t nrec = 0;
 	for(uint32_t c = 0; c < ctx->nchr; c++)
 	{
@@ -622,8 +625,10 @@ int dist2_plan(sibgpu_ctx *ctx, uint32_t k, int *need_alloc)
 	const uint64_t mean_seg = (tiles_max * TILE_POS + PT - 1) / PT;
 	const uint64_t seg_cap = (mean_seg + mean_seg / 8 + ctx->part_slack + 31) / 32 * 32;
 	const uint64_t kc = std::max<uint64_t>(ctx->x_kc, std::max<uint64_t>(ctx->ckeys_init, 16));
-	const uint64_t off_seg = (XOFF_KEYS + kc * 8 + 255) / 256 * 256;
-	const uint64_t bytes = off_seg + (uint64_t)PT * seg_cap * 8 + 256;
+	const uint64_t off_seg = (XOFF_KEYS + kc * (fp ? 16 : 8) + 255) / 256 * 256;
+	const uint64_t off_pk = fp ? (off_seg + (uint64_t)PT * seg_cap * 8 + 255) / 256 * 256 : 0;
+	const uint64_t nwords_all = (ctx->M + 15) / 16 + 8;
+	const uint64_t bytes = (fp ? off_pk + nwords_all * 4 : off_seg + (uint64_t)PT * seg_cap * 8) + 256;
 	ctx->x_PL = (uint32_t)PL;
 	ctx->x_sub_bits = sub_bits;
 	ctx->x_seg_cap = seg_cap;
@@ -632,9 +637,11 @@ int dist2_plan(sibgpu_ctx *ctx, uint32_t k, int *need_alloc)
 	ctx->x_bytes = bytes;
 	// the layout of a live buffer must not move (the peers computed their addresses from it): new key capacity or
 	// segment offset means a new buffer
-	*need_alloc = (ctx->d_xbuf.cap < bytes || ctx->x_off_seg != off_seg || ctx->x_kc_live != kc || ctx->peer_x.size() != W) ? 1 : 0;
+	*need_alloc = (ctx->d_xbuf.cap < bytes || ctx->x_off_seg != off_seg || ctx->x_off_pk != off_pk || ctx->x_kc_live != kc ||
+		ctx->peer_x.size() != W) ? 1 : 0;
 	ctx->x_kc = kc;
 	ctx->x_off_seg_plan = off_seg;
+	ctx->x_off_pk_plan = off_pk;
 	return SIBGPU_OK;
 }
 
@@ -664,6 +671,7 @@ int dist2_alloc(sibgpu_ctx *ctx, void *handle64)
 	SIB_CUDA(cudaMemsetAsync(ctx->d_xbuf.p, 0, XOFF_KEYS, ctx->stream));
 	SIB_CUDA(cudaStreamSynchronize(ctx->stream));
 	ctx->x_off_seg = ctx->x_off_seg_plan;
+	ctx->x_off_pk = ctx->x_off_pk_plan;
 	ctx->x_kc_live = ctx->x_kc;
 	cudaIpcMemHandle_t h;
 	SIB_CUDA(cudaIpcGetMemHandle(&h, ctx->d_xbuf.p));
@@ -746,7 +754,7 @@ int dist2_run(sibgpu_ctx *ctx, const HostSrc *src, int *status)
 		const uint64_t allcap = ctx->d_ckeys.cap / sizeof(uint64_t);
 		{
 			ProfScope ps(ctx, "k_pull_keys", 0);
-			k_pull_keys<<<dim3(32, W), 256, 0, st>>>(psrc, W, epoch, key_cap, ctx->d_ckeys.as<uint64_t>(), allcap, ds + 12);
+			k_pull_keys<1><<<dim3(32, W), 256, 0, st>>>(psrc, W, epoch, key_cap, ctx->d_ckeys.as<uint64_t>(), allcap, ds + 12);
 		}
 		ctx->total_launches += 2;
 		SIB_CUDA(cudaMemcpyAsync(hs + 8, ds + 8, sizeof(uint64_t) * 8, cudaMemcpyDeviceToHost, st));
@@ -792,6 +800,238 @@ int dist2_run(sibgpu_ctx *ctx, const HostSrc *src, int *status)
 		}
 		bool collision = false;
 		SIB_TRY(ids_and_tables<0>(ctx, ctx->dist_text, k, ctx->d_ckeys.as<uint64_t>(), Vc, ntiles, FpView{}, 0u, false, &collision));
+	}
+	SIB_CUDA(cudaGetLastError());
+	ctx->have_result = true;
+	ctx->dist_result = true;
+	if(ctx->profiling) SIB_TRY(ctx->prof_collect());
+	return SIBGPU_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Fused path, k > 32 (fingerprint classes).  Same exchange as above on 8-byte fingerprint records; what is new:
+//   * the rolling hashes of a position read the text up to k bases ahead, the string ranking of the vertex classes and
+//     the verification of every instance read it at arbitrary positions: the PACKED text (2 bits per base) is made
+//     complete on every rank first -- each rank packs its own range, copies it into its exported buffer, publishes
+//     epoch_packed, and k_pull_packed copies the peers' ranges over NVLink (the all-gather, fused)
+//   * a class is {fingerprint, GLOBAL partition}: 16-byte entries in the key regions
+//   * the representative of a class is its smallest text position over ALL ranks: the step stops after k_mark
+//     (dist2_run_fp), the caller min-reduces the representatives (one all-reduce), dist2_finish_fp ranks the strings
+//     (every rank ranks all classes: same ids everywhere) and emits + verifies the instances of the own range.
+// A verification failure anywhere (the caller max-reduces the flag) repeats the step with other hash bases.
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void k_publish_packed(DistHeader *h, unsigned long long epoch)
+{
+	__threadfence_system();
+	st_release_sys(&h->epoch_packed, epoch);
+}
+
+struct PackedSrc {
+	const DistHeader *header[SPLIT_MAX_SRC];
+	const uint32_t *pk[SPLIT_MAX_SRC];                 // exported packed region of rank s (word w at pk[s] + w)
+	uint32_t w_lo[SPLIT_MAX_SRC], w_hi[SPLIT_MAX_SRC]; // the words rank s owns (w_lo is a multiple of 256)
+};
+// blockIdx.y = source rank
+__global__ void __launch_bounds__(256) k_pull_packed(const PackedSrc src, uint32_t me, unsigned long long epoch,
+	uint32_t *__restrict__ packed, uint32_t *__restrict__ flags)
+{
+	const uint32_t s = blockIdx.y;
+	if(s == me || src.w_hi[s] <= src.w_lo[s]) return;
+	__shared__ uint32_t ok;
+	if(threadIdx.x == 0)
+	{
+		ok = wait_epoch(&src.header[s]->epoch_packed, epoch) ? 1u : 0u;
+		if(!ok) atomicOr(flags, GRP_TIMEOUT);
+	}
+	__syncthreads();
+	if(!ok) return;
+	const uint32_t w_lo = src.w_lo[s], n = src.w_hi[s] - w_lo;
+	const unsigned long long *from = reinterpret_cast<const unsigned long long*>(src.pk[s] + w_lo);
+	unsigned long long *to = reinterpret_cast<unsigned long long*>(packed + w_lo);
+	const uint32_t quads = n / 4;
+	for(uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < quads; i += gridDim.x * blockDim.x)
+	{
+		unsigned long long a, b;
+		asm volatile("ld.relaxed.sys.global.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(from + 2 * i) : "memory");
+		to[2 * i] = a;
+		to[2 * i + 1] = b;
+	}
+	if(blockIdx.x == 0 && threadIdx.x < (n & 3u))
+	{
+		const uint32_t w = w_lo + quads * 4 + threadIdx.x;
+		uint32_t v;
+		asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(src.pk[s] + w) : "memory");
+		packed[w] = v;
+	}
+}
+
+int dist2_run_fp(sibgpu_ctx *ctx, const HostSrc *src, uint32_t attempt, int *status)
+{
+	NvtxRange nvtx("sibgpu: fused sharded step, k > 32 (front)");
+	cudaStream_t st = ctx->stream;
+	const uint32_t W = ctx->dist_world, rank = ctx->dist_rank, k = ctx->x_k, PL = ctx->x_PL, PT = PL * W;
+	*status = 0;
+	if(ctx->peer_x.size() != W || !ctx->d_xbuf.p || !ctx->x_off_pk || k <= 32)
+	{
+		set_error("state: sibgpu_fused_plan (k > 32) / sibgpu_fused_alloc / sibgpu_fused_import must precede sibgpu_fused_run_fp");
+		return SIBGPU_ERR_STATE;
+	}
+	const unsigned long long epoch = ++ctx->dist_epoch;
+	SIB_TRY(dist_prepare(ctx, k, src == nullptr));
+	ctx->dist_P_local = PL;
+	ctx->dist_P_total = PT;
+	ctx->x_attempt = attempt;
+	ctx->x_Vc = 0;
+	uint64_t *hs = static_cast<uint64_t*>(ctx->h_scalars);
+	uint64_t *ds = ctx->d_scalars.as<uint64_t>();
+	unsigned char *xb = static_cast<unsigned char*>(ctx->d_xbuf.p);
+	DistHeader *hdr = reinterpret_cast<DistHeader*>(xb);
+	unsigned long long *cursor = reinterpret_cast<unsigned long long*>(xb + XOFF_CURSOR);
+	Rec16 *keys = reinterpret_cast<Rec16*>(xb + XOFF_KEYS);
+	uint64_t *segs = reinterpret_cast<uint64_t*>(xb + ctx->x_off_seg);
+	uint32_t *xpk = reinterpret_cast<uint32_t*>(xb + ctx->x_off_pk);
+	const uint32_t key_cap = (uint32_t)std::min<uint64_t>(ctx->x_kc_live, 0xFFFFFFF0u);
+	uint32_t *d_flags = reinterpret_cast<uint32_t*>(ds + 11);
+	// ---- the packed text: own range (uploaded here unless resident), exported, the peers' ranges pulled
+	if(src && ctx->dist_byte_hi > ctx->dist_byte_lo)
+	{
+		SIB_TRY(copy_text_range(ctx, *src, ctx->dist_byte_lo, ctx->dist_byte_hi, st));
+		SIB_TRY(launch_pack(ctx, ctx->dist_byte_lo / 16, (ctx->dist_byte_hi + 15) / 16));
+	}
+	const uint32_t nwords_all = ctx->dist_text.nwords;
+	const uint64_t ntiles_all = (ctx->M + TILE_POS - 1) / TILE_POS;
+	PackedSrc ksrc = {};
+	for(uint32_t s = 0; s < W; s++)
+	{
+		const uint64_t tlo = ntiles_all * s / W, thi = ntiles_all * (s + 1) / W;
+		uint64_t lo = tlo * TILE_THREADS, hi = s + 1 == W ? nwords_all : thi * TILE_THREADS;
+		if(hi > nwords_all) hi = nwords_all;
+		if(lo > hi) lo = hi;
+		ksrc.w_lo[s] = (uint32_t)lo;
+		ksrc.w_hi[s] = (uint32_t)hi;
+		const unsigned char *b = s == rank ? xb : static_cast<const unsigned char*>(ctx->peer_x[s]);
+		ksrc.header[s] = reinterpret_cast<const DistHeader*>(b);
+		ksrc.pk[s] = reinterpret_cast<const uint32_t*>(b + ctx->x_off_pk);
+	}
+	if(ksrc.w_hi[rank] > ksrc.w_lo[rank])
+	{
+		SIB_CUDA(cudaMemcpyAsync(xpk + ksrc.w_lo[rank], ctx->d_packed.as<uint32_t>() + ksrc.w_lo[rank],
+			sizeof(uint32_t) * (size_t)(ksrc.w_hi[rank] - ksrc.w_lo[rank]), cudaMemcpyDeviceToDevice, st));
+	}
+	k_publish_packed<<<1, 1, 0, st>>>(hdr, epoch);
+	if(W > 1)
+	{
+		ProfScope ps(ctx, "k_pull_packed", (uint64_t)nwords_all * 4);
+		k_pull_packed<<<dim3(64, W), 256, 0, st>>>(ksrc, rank, epoch, ctx->d_packed.as<uint32_t>(), d_flags);
+	}
+	ctx->total_launches += 2;
+	// ---- checkpoints of the own words, scatter + publish
+	const uint32_t w_ck_stop = (uint32_t)std::min<uint64_t>(ksrc.w_hi[rank], (ctx->M + 15) >> 4);
+	SIB_TRY(fingerprint_positions(ctx, ctx->dist_text, k, attempt, ksrc.w_lo[rank], w_ck_stop));
+	const FpView fv = {ctx->d_fp.as<FpCk>(), ctx->d_fpprm.as<FpParams>()};
+	k_init_cursors<<<(PT + 255) / 256, 256, 0, st>>>(cursor, PT, ctx->x_seg_cap);
+	ctx->total_launches++;
+	SIB_TRY((dist_scatter_core<2, true>(ctx, k, PT, ctx->x_seg_cap, cursor, segs, nullptr, fv)));
+	k_publish_scatter<<<1, 1, 0, st>>>(hdr, ds, epoch);
+	// ---- fused exchange + split, group, publish
+	const uint32_t sub_bits = ctx->x_sub_bits, nbuckets = PL << sub_bits;
+	SIB_TRY(ctx->d_records2.ensure(sizeof(uint64_t) * (size_t)nbuckets * GROUP_CAP + 64));
+	SIB_TRY(ctx->d_cnt2.ensure(sizeof(uint32_t) * (size_t)nbuckets));
+	SIB_CUDA(cudaMemsetAsync(ctx->d_cnt2.p, 0, sizeof(uint32_t) * (size_t)nbuckets, st));
+	SplitSrc ssrc = {};
+	PullSrc psrc = {};
+	for(uint32_t s = 0; s < W; s++)
+	{
+		const unsigned char *b = s == rank ? xb : static_cast<const unsigned char*>(ctx->peer_x[s]);
+		ssrc.seg[s] = reinterpret_cast<const uint64_t*>(b + ctx->x_off_seg);
+		ssrc.cursor[s] = reinterpret_cast<const unsigned long long*>(b + XOFF_CURSOR);
+		ssrc.header[s] = s == rank ? nullptr : reinterpret_cast<const DistHeader*>(b);
+		psrc.header[s] = reinterpret_cast<const DistHeader*>(b);
+		psrc.keys[s] = reinterpret_cast<const unsigned long long*>(b + XOFF_KEYS);
+	}
+	ssrc.seg_cap = ctx->x_seg_cap;
+	ssrc.epoch = epoch;
+	ssrc.W = W;
+	ssrc.p0 = rank * PL;
+	const uint32_t tiles_per_seg = (uint32_t)((ctx->x_seg_cap + RecOps<uint64_t>::TILE - 1) / RecOps<uint64_t>::TILE);
+	SIB_TRY(launch_split<uint64_t>(ctx, ssrc, PL, tiles_per_seg, sub_bits, ctx->x_nrec / W, d_flags));
+	SIB_TRY((launch_group<uint64_t, true>(ctx, nbuckets, sub_bits, ctx->x_nrec / W, d_flags, keys, key_cap,
+		reinterpret_cast<uint32_t*>(ds + 2), rank * PL)));
+	k_publish_keys<<<1, 1, 0, st>>>(hdr, reinterpret_cast<uint32_t*>(ds + 2), d_flags, key_cap, epoch);
+	// ---- all ranks' keys
+	SIB_TRY(ctx->d_ckeys.ensure(sizeof(Rec16) * std::max<uint64_t>(ctx->ckeys_init, 16)));
+	for(int pass = 0; ; pass++)
+	{
+		const uint64_t allcap = ctx->d_ckeys.cap / sizeof(Rec16);
+		{
+			ProfScope ps(ctx, "k_pull_keys", 0);
+			k_pull_keys<2><<<dim3(32, W), 256, 0, st>>>(psrc, W, epoch, key_cap, ctx->d_ckeys.as<uint64_t>(), allcap, ds + 12);
+		}
+		ctx->total_launches += 2;
+		SIB_CUDA(cudaMemcpyAsync(hs + 8, ds + 8, sizeof(uint64_t) * 8, cudaMemcpyDeviceToHost, st));
+		SIB_CUDA(cudaStreamSynchronize(st));
+		const uint64_t flags = hs[13] | (hs[11] & GRP_TIMEOUT);
+		if(flags & GRP_TIMEOUT)
+		{
+			set_error("internal: a peer rank did not publish its step within 4 s");
+			return SIBGPU_ERR_INTERNAL;
+		}
+		if((hs[8] & 1u) || (flags & 64u)) return input_error();
+		if(flags & 16u)                                        // a rank's key region is too small: regrow collectively
+		{
+			ctx->x_kc = hs[14] + hs[14] / 4 + 1024;
+			*status = 2;
+			return SIBGPU_OK;
+		}
+		if(flags & (GRP_BUCKET_OVERFLOW | GRP_PEER_FAILED))
+		{
+			if(hs[10] & 0xFFFFFFFFull) ctx->hist_fallbacks++;
+			if(hs[11] & GRP_BUCKET_OVERFLOW) ctx->smem_fallbacks++;
+			*status = 1;
+			return SIBGPU_OK;
+		}
+		if(flags & 32u)                                        // the local list of all keys is too small: regrow, pull again
+		{
+			if(pass) { set_error("internal: key list regrow failed"); return SIBGPU_ERR_INTERNAL; }
+			SIB_TRY(ctx->d_ckeys.ensure(sizeof(Rec16) * hs[12]));
+			continue;
+		}
+		break;
+	}
+	const uint64_t Vc = hs[12];
+	ctx->n_inst = 0;
+	ctx->n_vertices = 0;
+	ctx->x_Vc = Vc;
+	if(Vc)
+	{
+		if(2 * Vc > 0xFFFFFFF0ull)
+		{
+			set_error("invalid: more than 2^32 vertices");
+			return SIBGPU_ERR_INVALID;
+		}
+		bool collision = false;
+		const uint32_t ntiles = ctx->dist_tile_hi - ctx->dist_tile_lo;
+		SIB_TRY(ids_and_tables<2>(ctx, ctx->dist_text, k, ctx->d_ckeys.as<Rec16>(), Vc, ntiles, fv, PT, false, &collision, 1));
+		SIB_CUDA(cudaStreamSynchronize(st));
+	}
+	SIB_CUDA(cudaGetLastError());
+	return SIBGPU_OK;
+}
+
+// second half of the k > 32 step, after the caller's min-reduction of the class representatives (d_rep, x_Vc entries)
+int dist2_finish_fp(sibgpu_ctx *ctx, int *collision_out)
+{
+	NvtxRange nvtx("sibgpu: fused sharded step, k > 32 (back)");
+	*collision_out = 0;
+	const uint64_t Vc = ctx->x_Vc;
+	if(Vc)
+	{
+		bool collision = false;
+		const uint32_t ntiles = ctx->dist_tile_hi - ctx->dist_tile_lo;
+		const FpView fv = {ctx->d_fp.as<FpCk>(), ctx->d_fpprm.as<FpParams>()};
+		SIB_TRY(ids_and_tables<2>(ctx, ctx->dist_text, ctx->x_k, ctx->d_ckeys.as<Rec16>(), Vc, ntiles, fv, ctx->dist_P_total, false,
+			&collision, 2));
+		*collision_out = collision ? 1 : 0;
 	}
 	SIB_CUDA(cudaGetLastError());
 	ctx->have_result = true;

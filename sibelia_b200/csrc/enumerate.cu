@@ -1044,7 +1044,7 @@ __global__ void __launch_bounds__(256) k_reverse_neg(const sibgpu_inst *__restri
 // ---------------------------------------------------------------------------------------------------------------
 // host orchestration
 // ---------------------------------------------------------------------------------------------------------------
-int fingerprint_positions(sibgpu_ctx *ctx, const TextDesc &t, uint32_t k, uint32_t attempt);            // fingerprint.cu
+int fingerprint_positions(sibgpu_ctx *ctx, const TextDesc &t, uint32_t k, uint32_t attempt, uint32_t w_begin, uint32_t w_stop);   // fingerprint.cu
 int rank_fingerprint_vertices(sibgpu_ctx *ctx, const TextDesc &t, uint32_t k, uint64_t Vc, uint32_t Tm, uint32_t *V_out);   // fingerprint.cu
 
 static inline uint32_t grid_for(uint64_t work_items, int threads, int sm_count, int waves = 8)
@@ -1057,9 +1057,11 @@ static inline uint32_t grid_for(uint64_t work_items, int threads, int sm_count, 
 
 // Vertex ids, vertex map and the two instance tables for the text tiles [t.tile0, t.tile0 + ntiles), given the
 // canonical keys of ALL vertex classes (`ckeys`, Vc of them).  Shared by the single-GPU path and the sharded path.
+// phase 0 = everything.  Sharded fingerprint runs (MODE 2) stop after k_mark (phase 1): the class representatives found
+// in the own text range are then min-reduced over the ranks by the caller, and phase 2 resumes with the ranking.
 template<int MODE>
 static int ids_and_tables(sibgpu_ctx *ctx, const TextDesc &t, uint32_t k, const typename KeyT<MODE>::type *ckeys_in, uint64_t Vc,
-	uint32_t ntiles, const FpView fp, uint32_t P, bool reverse_neg, bool *collision)
+	uint32_t ntiles, const FpView fp, uint32_t P, bool reverse_neg, bool *collision, int phase = 0)
 {
 	typedef typename KeyT<MODE>::type Rec;
 	NvtxRange nvtx("sibgpu: vertex ids + instance tables");
@@ -1076,12 +1078,17 @@ static int ids_and_tables(sibgpu_ctx *ctx, const TextDesc &t, uint32_t k, const 
 	uint32_t fbits_log = 16;
 	while((1ull << fbits_log) < 32 * Vc && fbits_log < 32) fbits_log++;
 	const uint32_t fshift = 64 - fbits_log;
-	SIB_TRY(ctx->d_map.ensure(sizeof(MapSlot) * (size_t)Tm));
-	SIB_TRY(ctx->d_filter.ensure((1ull << fbits_log) / 8));
-	SIB_CUDA(cudaMemsetAsync(ctx->d_map.p, 0xFF, sizeof(MapSlot) * (size_t)Tm, st));
-	SIB_CUDA(cudaMemsetAsync(ctx->d_filter.p, 0, (1ull << fbits_log) / 8, st));
 	uint32_t V = 0;
-	if(MODE != 2)
+	const bool front = phase != 2, back = phase != 1;
+	if(front)
+	{
+		SIB_TRY(ctx->d_map.ensure(sizeof(MapSlot) * (size_t)Tm));
+		SIB_TRY(ctx->d_filter.ensure((1ull << fbits_log) / 8));
+		SIB_CUDA(cudaMemsetAsync(ctx->d_map.p, 0xFF, sizeof(MapSlot) * (size_t)Tm, st));
+		SIB_CUDA(cudaMemsetAsync(ctx->d_filter.p, 0, (1ull << fbits_log) / 8, st));
+	}
+	if(!front) {}
+	else if(MODE != 2)
 	{
 		SIB_TRY(ctx->d_vkeys.ensure(sizeof(uint64_t) * 2 * Vc));
 		SIB_TRY(ctx->d_vkeys_alt.ensure(sizeof(uint64_t) * 2 * Vc));
@@ -1110,9 +1117,10 @@ static int ids_and_tables(sibgpu_ctx *ctx, const TextDesc &t, uint32_t k, const 
 	}
 	else
 	{
-		// classes only; the ids follow once every class has a representative occurrence (after k_mark)
+		// classes only; the ids follow once every class has a representative occurrence (after k_mark).  "No occurrence
+		// yet" = 0x7F7F...: larger than any {position, flags} word, also as the signed number an all-reduce takes it for
 		SIB_TRY(ctx->d_rep.ensure(sizeof(uint64_t) * Vc));
-		SIB_CUDA(cudaMemsetAsync(ctx->d_rep.p, 0xFF, sizeof(uint64_t) * Vc, st));
+		SIB_CUDA(cudaMemsetAsync(ctx->d_rep.p, 0x7F, sizeof(uint64_t) * Vc, st));
 		ProfScope ps(ctx, "k_build_map", Vc * (sizeof(Rec) + sizeof(MapSlot)));
 		k_build_map<MODE><<<(uint32_t)((Vc + 255) / 256), 256, 0, st>>>(ckeys, Vc, k, nullptr, nullptr,
 			ctx->d_map.as<MapSlot>(), Tm, ctx->d_filter.as<uint32_t>(), fshift);
@@ -1121,6 +1129,8 @@ static int ids_and_tables(sibgpu_ctx *ctx, const TextDesc &t, uint32_t k, const 
 	if(ntiles == 0)
 	{
 		// a rank without text (tiny input, many ranks) still reports the global vertex count
+		if(!back) return SIBGPU_OK;
+		if(MODE == 2) SIB_TRY(rank_fingerprint_vertices(ctx, t, k, Vc, Tm, &V));
 		SIB_CUDA(cudaMemcpyAsync(hs + 3, ds + 3, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
 		SIB_CUDA(cudaStreamSynchronize(st));
 		ctx->n_inst = 0;
@@ -1128,15 +1138,17 @@ static int ids_and_tables(sibgpu_ctx *ctx, const TextDesc &t, uint32_t k, const 
 		return SIBGPU_OK;
 	}
 	// ---- instance tables
-	SIB_TRY(ctx->d_hitmask.ensure(sizeof(uint16_t) * (size_t)ntiles * TILE_THREADS));
-	SIB_TRY(ctx->d_tilecnt.ensure(sizeof(uint64_t) * ntiles));
-	SIB_TRY(ctx->d_tileoff.ensure(sizeof(uint64_t) * (ntiles + 1)));
+	if(front)
 	{
-		ProfScope ps(ctx, "k_mark", (MODE == 2 ? ctx->M / 2 + ctx->M * 2 : ctx->M / 4) + ctx->M / 8);
+		SIB_TRY(ctx->d_hitmask.ensure(sizeof(uint16_t) * (size_t)ntiles * TILE_THREADS));
+		SIB_TRY(ctx->d_tilecnt.ensure(sizeof(uint64_t) * ntiles));
+		SIB_TRY(ctx->d_tileoff.ensure(sizeof(uint64_t) * (ntiles + 1)));
+		ProfScope ps(ctx, "k_mark", (MODE == 2 ? ctx->M / 2 + ctx->M * 2 : ctx->M / 4) * ntiles / ((ctx->M + TILE_POS - 1) / TILE_POS) + ctx->M / 8);
 		k_mark<MODE><<<scan_grid, TILE_THREADS, 0, st>>>(t, fp, P, k, ntiles, ctx->d_map.as<MapSlot>(), Tm,
 			ctx->d_filter.as<uint32_t>(), fshift, ctx->d_hitmask.as<uint16_t>(), ctx->d_tilecnt.as<uint64_t>(),
 			ctx->d_rep.as<unsigned long long>());
 	}
+	if(!back) return SIBGPU_OK;
 	if(MODE == 2) SIB_TRY(rank_fingerprint_vertices(ctx, t, k, Vc, Tm, &V));
 	{
 		size_t tmp_bytes = 0;
@@ -1261,7 +1273,7 @@ static int launch_split(sibgpu_ctx *ctx, const SplitSrc &ssrc, uint32_t P1, uint
 // PKEY: the key list takes {key, partition} (fingerprint classes) instead of the bare key
 template<class R, bool PKEY = false>
 static int launch_group(sibgpu_ctx *ctx, uint32_t nbuckets, uint32_t sub_bits, uint64_t nrec, uint32_t *d_flags,
-	typename GroupKey<R, PKEY>::type *ckeys, uint32_t ckeys_cap, uint32_t *d_nkeys)
+	typename GroupKey<R, PKEY>::type *ckeys, uint32_t ckeys_cap, uint32_t *d_nkeys, uint32_t part0 = 0)
 {
 	bool &attr_done = ctx->group_attr_done[(sizeof(R) == 8 ? 0 : 1) + (PKEY ? 2 : 0)];
 	if(!attr_done)
@@ -1271,7 +1283,7 @@ static int launch_group(sibgpu_ctx *ctx, uint32_t nbuckets, uint32_t sub_bits, u
 	}
 	ProfScope ps(ctx, "k_group", nrec * sizeof(R));
 	k_group<R, PKEY><<<std::min<uint32_t>(nbuckets, (uint32_t)ctx->sm_count * (sizeof(R) == 8 ? 4 : 2)), GROUP_THREADS, sizeof(GroupSmem<R>),
-		ctx->stream>>>(ctx->d_records2.as<R>(), ctx->d_cnt2.as<uint32_t>(), nbuckets, sub_bits, GROUP_CAP, d_flags, ckeys, ckeys_cap, d_nkeys);
+		ctx->stream>>>(ctx->d_records2.as<R>(), ctx->d_cnt2.as<uint32_t>(), nbuckets, sub_bits, part0, GROUP_CAP, d_flags, ckeys, ckeys_cap, d_nkeys);
 	return SIBGPU_OK;
 }
 
@@ -1307,7 +1319,7 @@ static int enumerate_mode(sibgpu_ctx *ctx, uint32_t k, uint64_t nrec, const Host
 
 	for(uint32_t attempt = 0; ; attempt++)
 	{
-		if(FP) SIB_TRY(fingerprint_positions(ctx, t, k, attempt));
+		if(FP) SIB_TRY(fingerprint_positions(ctx, t, k, attempt, 0u, (uint32_t)((ctx->M + 15) >> 4)));
 		const FpView fp = {ctx->d_fp.as<FpCk>(), ctx->d_fpprm.as<FpParams>()};
 
 		// ---- partition plan

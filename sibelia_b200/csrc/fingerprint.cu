@@ -55,19 +55,19 @@ static uint64_t inv64(uint64_t b)                       // inverse of an odd num
 // over the k bases of its first k-mer (forward for w, backward for revcomp(w)), then one rolling step per position.
 //   Hf(i) = sum_j (c[i+j]+1) B^(k-1-j)        fingerprint of the k-mer at i
 //   Hr(i) = sum_m (4-c[i+m]) B^m              the same polynomial evaluated on its reverse complement
-__global__ void __launch_bounds__(128) k_fp_ckpt(TextDesc t, uint32_t k, uint32_t L, FpParams prm, FpCk *__restrict__ ck)
+// Checkpoints of the words [w_begin, w_stop) (sharded runs: the own text range).
+__global__ void __launch_bounds__(128) k_fp_ckpt(TextDesc t, uint32_t k, uint32_t L, FpParams prm, FpCk *__restrict__ ck,
+	uint32_t w_begin, uint32_t w_stop)
 {
 	__shared__ uint64_t sD[64];
 	for(uint32_t i = threadIdx.x; i < 64; i += blockDim.x) sD[i] = prm.D[i >> 4][i & 15];
 	__syncthreads();
 	const FpBases b = prm.b;
 	const uint64_t g = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
-	const uint64_t start64 = g * L;
-	if(start64 >= t.M) return;
-	const uint32_t start = (uint32_t)start64;
-	const uint32_t w_first = start >> 4;
-	const uint32_t w_end = (uint32_t)((t.M + 15) >> 4);                 // checkpoints exist for words [0, w_end)
-	const uint32_t w_last = w_first + L / 16 < w_end ? w_first + L / 16 : w_end;
+	const uint64_t w64 = w_begin + g * (L / 16);
+	if(w64 >= w_stop) return;
+	const uint32_t w_first = (uint32_t)w64;
+	const uint32_t w_last = w_first + L / 16 < w_stop ? w_first + L / 16 : w_stop;
 	auto word = [&](uint32_t w) -> uint32_t { return w < t.nwords ? __ldg(t.packed + w) : 0u; };
 	FpState h = {0, 0, 0, 0};
 	const uint32_t kw = k >> 4, kt = k & 15u;
@@ -125,7 +125,7 @@ __global__ void __launch_bounds__(128) k_fp_ckpt(TextDesc t, uint32_t k, uint32_
 	}
 }
 
-int fingerprint_positions(sibgpu_ctx *ctx, const TextDesc &t, uint32_t k, uint32_t attempt)
+int fingerprint_positions(sibgpu_ctx *ctx, const TextDesc &t, uint32_t k, uint32_t attempt, uint32_t w_begin, uint32_t w_stop)
 {
 	static const uint64_t B1S[3] = {0x0F3A5C7E9B1D2E4Full, 0x1B2D4F6A8C0E1357ull, 0x0A9C8E7F6D5B4A39ull};
 	static const uint64_t B2S[3] = {0x9E3779B97F4A7C15ull, 0xC2B2AE3D27D4EB4Full, 0xD6E8FEB86659FD93ull};
@@ -153,10 +153,11 @@ int fingerprint_positions(sibgpu_ctx *ctx, const TextDesc &t, uint32_t k, uint32
 	SIB_TRY(ctx->d_fp.ensure(sizeof(FpCk) * (size_t)nck));
 	SIB_TRY(ctx->d_fpprm.ensure(sizeof(FpParams)));
 	SIB_CUDA(cudaMemcpyAsync(ctx->d_fpprm.p, &prm, sizeof(FpParams), cudaMemcpyHostToDevice, ctx->stream));
+	if(w_stop <= w_begin) return SIBGPU_OK;
 	const uint32_t L = k < 128 ? 128 : ((k + 15) / 16) * 16;
-	const uint64_t threads = (t.M + L - 1) / L;
-	ProfScope ps(ctx, "k_fp_ckpt", (uint64_t)t.M / 4 * 2 + (uint64_t)nck * sizeof(FpCk));
-	k_fp_ckpt<<<(uint32_t)((threads + 127) / 128), 128, 0, ctx->stream>>>(t, k, L, prm, ctx->d_fp.as<FpCk>());
+	const uint64_t threads = ((uint64_t)(w_stop - w_begin) * 16 + L - 1) / L;
+	ProfScope ps(ctx, "k_fp_ckpt", (uint64_t)(w_stop - w_begin) * (8 + sizeof(FpCk)));
+	k_fp_ckpt<<<(uint32_t)((threads + 127) / 128), 128, 0, ctx->stream>>>(t, k, L, prm, ctx->d_fp.as<FpCk>(), w_begin, w_stop);
 	return SIBGPU_OK;
 }
 

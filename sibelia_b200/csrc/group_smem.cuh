@@ -132,7 +132,8 @@ struct DistHeader {                                    // first 256 bytes of a r
 	unsigned long long epoch_keys;                     // == e once the vertex keys of step e are final
 	unsigned long long key_flags;                      // != 0: grouping failed on this rank (bucket overflow, peer failure)
 	unsigned long long nkeys;
-	unsigned long long pad[27];
+	unsigned long long epoch_packed;                   // == e once the packed words of the own text range are final (k > 32)
+	unsigned long long pad[26];
 };
 struct SplitSrc {
 	const void *seg[SPLIT_MAX_SRC];                    // records of source s; partition q lies at [q * seg_cap, ...)
@@ -341,9 +342,10 @@ template<class R> struct GroupSmem {
 template<class R, bool PKEY> struct GroupKey { typedef R type; };
 template<> struct GroupKey<uint64_t, true> { typedef Rec16 type; };
 
+// part0 = global index of the first partition grouped here (sharded runs: the first owned partition)
 template<class R, bool PKEY = false>
 __global__ void __launch_bounds__(GROUP_THREADS, sizeof(R) == 8 ? 4 : 2) k_group(const R *__restrict__ recs2, const uint32_t *__restrict__ cnt2,
-	uint32_t nbuckets, uint32_t sub_bits, uint32_t cap2, const uint32_t *__restrict__ overflow,
+	uint32_t nbuckets, uint32_t sub_bits, uint32_t part0, uint32_t cap2, const uint32_t *__restrict__ overflow,
 	typename GroupKey<R, PKEY>::type *__restrict__ ckeys, uint32_t ckeys_cap, uint32_t *__restrict__ nkeys)
 {
 	extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -468,7 +470,7 @@ __global__ void __launch_bounds__(GROUP_THREADS, sizeof(R) == 8 ? 4 : 2) k_group
 				const uint32_t idx = base + __popc(mk & ((1u << lane) - 1u));
 				if(bif && idx < ckeys_cap)
 				{
-					if constexpr(PKEY) ckeys[idx] = Rec16{unmix56(RecOps<R>::key(w[i])), (uint64_t)(q >> sub_bits)};
+					if constexpr(PKEY) ckeys[idx] = Rec16{unmix56(RecOps<R>::key(w[i])), (uint64_t)(part0 + (q >> sub_bits))};
 					else if constexpr(sizeof(R) == 8) ckeys[idx] = unmix56(RecOps<R>::key(w[i]));
 					else ckeys[idx] = make_ulonglong2(unmix64(RecOps<R>::key(w[i])), 0ull);
 				}

@@ -74,6 +74,11 @@ class GpuShard:
                     self.ctx.dist2_release_peers()
                     type(self).fused = False
                     return None
+            if k > 32:
+                out = self._fused_fp(chrs, group, download)
+                if out != "regrow":
+                    return out
+                continue
             status, count, ninst = self.ctx.dist2_run(chrs, self.resident)
             if status == 0:
                 if not download:
@@ -83,6 +88,35 @@ class GpuShard:
             if status == 1:
                 return None
         raise RuntimeError("sibelia_b200.distributed: the vertex key regions kept overflowing")
+
+    def _fused_fp(self, chrs, group, download):
+        """k > 32: the two halves of the fingerprint step with the min-reduction of the class representatives between
+        them and the max-reduction of the verification flag behind them (include/sibgpu.h, sibgpu_fused_run_fp)."""
+        for attempt in range(3):
+            status, ncls, rep_ptr = self.ctx.dist2_run_fp(chrs, self.resident, attempt)
+            if status == 2:
+                return "regrow"
+            if status == 1:
+                return None
+            if ncls:
+                rep = torch.as_tensor(_DeviceArray(rep_ptr, ncls), device=self.device)
+                if dist.get_backend(group) == "nccl":
+                    dist.all_reduce(rep, op=dist.ReduceOp.MIN, group=group)
+                else:
+                    h = rep.cpu()
+                    dist.all_reduce(h, op=dist.ReduceOp.MIN, group=group)
+                    rep.copy_(h)
+                torch.cuda.synchronize(self.device)
+            count, ninst, collision = self.ctx.dist2_finish_fp()
+            flag = _comm(torch.tensor([collision], dtype=torch.int64, device=self.device), group)
+            dist.all_reduce(flag, op=dist.ReduceOp.MAX, group=group)
+            if int(flag.cpu()[0]):
+                continue                                 # a fingerprint collision inside a vertex class: other hash bases
+            if not download:
+                return count, ninst, None
+            pos, negtext = self.ctx.download()
+            return count, pos, negtext
+        raise RuntimeError("sibelia_b200.distributed: fingerprint verification failed three times")
 
     # -- peer strategy
     peer = os.environ.get("SIBGPU_DIST_PEER", "1") != "0"
@@ -147,6 +181,13 @@ class GpuShard:
         return count, pos, negtext
 
 
+class _DeviceArray:
+    """n int64 words of library-owned device memory, as torch.as_tensor takes it (zero copy)."""
+
+    def __init__(self, ptr, n):
+        self.__cuda_array_interface__ = {"shape": (int(n),), "typestr": "<i8", "data": (int(ptr), False), "version": 2}
+
+
 def _comm(t, group):
     """Tensor as the process group wants it: device tensors for NCCL, host tensors for gloo."""
     return t if dist.get_backend(group) == "nccl" else t.cpu()
@@ -169,8 +210,17 @@ def enumerate_sharded(shard, chrs, k, group=None, download=True):
         out = shard.fused_enumerate(chrs, rank, world, k, group, download)
         if out is not None:
             lap("fused step")
-            shard.last_strategy = "fused (device-side step counters, TMA peer pulls in k_split, key pull kernel; no collective)"
+            shard.last_strategy = ("fused (device-side step counters, TMA peer pulls in k_split, key pull kernel; no collective)"
+                                   if k <= 32 else
+                                   "fused (k > 32: packed text, k-mer records and keys pulled from the peers' buffers; one "
+                                   "all-reduce of the class representatives)")
             return out
+    if k > 32:
+        # no phased exchange exists for fingerprint classes: a segment or bucket overflowed (a k-mer repeated hundreds of
+        # times) or peer mappings are unavailable -- every rank indexes the whole input and keeps its own text range
+        out = _replicated(shard, chrs, k, rank, world)
+        shard.last_strategy = "replicated (k > 32 fallback: every rank runs the single-GPU enumeration, keeps its range)"
+        return out
     shard.upload(chrs, rank, world)
     lap("upload")
     keys = None
@@ -225,6 +275,21 @@ def enumerate_sharded(shard, chrs, k, group=None, download=True):
         print("[sharded] " + "  ".join("%s %.2f ms" % (marks[i][0], (marks[i][1] - marks[i - 1][1]) * 1e3)
                                        for i in range(1, len(marks))), flush=True)
     return out
+
+
+def _replicated(shard, chrs, k, rank, world):
+    """(count, pos rows of the own tile range, neg rows of the own tile range in text order) from a full enumeration"""
+    count, pos, neg = shard.ctx.enumerate(chrs, k)
+    lens = np.array([len(c) for c in chrs], dtype=np.int64)
+    start = 1 + np.concatenate([[0], np.cumsum(lens + 1)])[:-1] if len(chrs) else np.zeros(0, dtype=np.int64)
+    M = int(lens.sum()) + len(chrs) + 1
+    ntiles = (M + 4095) // 4096
+    lo, hi = ntiles * rank // world * 4096, ntiles * (rank + 1) // world * 4096
+    tp = start[pos["chr"]] + pos["pos"] if len(pos) else np.zeros(0, dtype=np.int64)
+    tn = start[neg["chr"]] + (lens[neg["chr"]] - neg["pos"] - k) if len(neg) else np.zeros(0, dtype=np.int64)
+    keep_n = np.flatnonzero((tn >= lo) & (tn < hi))
+    keep_n = keep_n[np.argsort(tn[keep_n], kind="stable")]
+    return count, pos[(tp >= lo) & (tp < hi)], neg[keep_n]
 
 
 def _staged_exchange(shard, k, rank, world, group, lap):

@@ -98,6 +98,22 @@ def test_sharded_enumeration_matches_oracle(built, world, k, seed, big, part):
     assert _run(world, k, seed, big, part, want="fused" if k <= 28 else "peer") == 0
 
 
+@pytest.mark.parametrize("world,k,seed,big,part", [
+    (2, 33, 11, False, 0), (3, 100, 12, False, 0), (2, 64, 13, True, 65536), (4, 500, 14, True, 0), (2, 5000, 15, True, 0),
+])
+def test_sharded_fingerprint_k(built, world, k, seed, big, part):
+    """k > 32 (the later -s loose stages) through the fused path: packed text replicated by peer pulls, fingerprint
+    records exchanged like the exact ones, class representatives min-reduced, ids = string ranks on every rank"""
+    assert _run(world, k, seed, big, part, want="fused") == 0
+
+
+def test_sharded_fingerprint_k_falls_back_to_replicas(built):
+    """no phased exchange exists for k > 32: without the fused path (here: switched off; in production: a bucket
+    overflow or missing peer access) every rank indexes the whole input and keeps the rows of its own text range"""
+    _run(2, 64, 16, False, 0, {"SIBGPU_DIST_FUSED": "0"}, want="replicated")
+    _run(2, 40, 7, "poly", 4096, {"SIBGPU_PART_SLACK": "16"}, want="replicated")
+
+
 @pytest.mark.parametrize("world,k,seed,big,part", [(2, 25, 2, False, 0), (4, 9, 6, False, 0), (2, 25, 4, True, 65536)])
 def test_sharded_peer_strategy(built, world, k, seed, big, part):
     assert _run(world, k, seed, big, part, {"SIBGPU_DIST_FUSED": "0"}, want="peer") == 0
@@ -119,10 +135,10 @@ def test_fused_key_regions_regrow(built):
     _run(2, 25, 8, True, 0, {"SIBGPU_CKEYS_INIT": "16"}, want="fused")
 
 
-@pytest.mark.parametrize("world,k,seed,big,part", [(2, 25, 9, True, 0), (2, 31, 10, True, 0)])
+@pytest.mark.parametrize("world,k,seed,big,part", [(2, 25, 9, True, 0), (2, 31, 10, True, 0), (2, 100, 17, True, 0)])
 def test_sharded_on_separate_gpus(built, world, k, seed, big, part):
     """one GPU per rank, NCCL for the set-up, NVLink for the pulls (needs gpurun --gpus 2)"""
     import torch
     if torch.cuda.device_count() < world:
         pytest.skip("needs %d GPUs" % world)
-    _run(world, k, seed, big, part, own_gpu=True, want="fused" if k <= 28 else "peer")
+    _run(world, k, seed, big, part, own_gpu=True, want="peer" if 28 < k <= 32 else "fused")
