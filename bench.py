@@ -14,7 +14,9 @@ publishes a step counter; the owner of a bucket waits for the counters on the de
 straight out of the peers' buffers over NVLink with TMA bulk copies inside its split kernel (the all-to-all is fused
 into the kernel), groups them in shared memory, publishes its vertex keys the same way; a pull kernel concatenates all
 ranks' keys (the all-gather, fused); local instance tables (sibelia_b200/distributed.py).  `value` = total bases /
-max-over-ranks step time; `alt` = the same on N random contigs of 100 MB (round 1's workload).  `result_digest` =
+max-over-ranks step time; `same_workload_1gpu` = the same genome indexed by rank 0 alone (the denominator for the
+speed-up of N GPUs on THIS workload: the N=1 line of a scaling run is the 100 MB random contig); `alt` = the same on
+N random contigs of 100 MB (round 1's workload, the N-fold of the N=1 line: weak scaling against it).  `result_digest` =
 sha256 over (vertex count, positive table, negative table) assembled on rank 0 outside the timed region.
 
 One JSON line is printed by rank 0 (see the task contract): value = device-resident throughput, e2e = the same
@@ -180,6 +182,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--ref-steps", type=int, default=1, help="steps the reference arm actually runs (each is 40-170 s)")
     ap.add_argument("--no-alt", action="store_true", help="N>1: skip the random-contig line of round 1")
+    ap.add_argument("--no-single", action="store_true", help="N>1: skip the one-GPU run of the same genome on rank 0")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -339,6 +342,24 @@ def main():
 
     chrs, what = workload(world, args.mbases)
     r = measure(chrs, True)
+    same1 = None
+    if world > 1 and not args.no_single:
+        # the denominator the N-GPU figure should be read against: the SAME genome indexed by ONE GPU (rank 0 alone, the
+        # others wait): N=1 of the driver's scaling run is the 100 MB random contig, which has almost no vertices
+        if rank == 0:
+            ctx.upload(chrs)
+            for _ in range(2):
+                ctx.enumerate_resident(args.k)
+            ms1 = []
+            for _ in range(3):
+                l2_flush()
+                ctx.enumerate_resident(args.k)
+                ms1.append(ctx.last_device_ms())
+            t1 = float(np.mean(ms1))
+            same1 = {"workload": "the same %d-strain genome on ONE GPU (rank 0, device-resident, 3 steps)" % world,
+                     "ms_per_step": t1, "value": r["total"] / 1e6 / (t1 / 1e3), "speedup_of_n_gpus": t1 / r["ms_per_step"],
+                     "parallel_efficiency": t1 / r["ms_per_step"] / world}
+        barrier()
     alt = None
     if world > 1 and not args.no_alt:
         from sibelia_b200 import synth
@@ -424,6 +445,8 @@ def main():
         "roofline": roofline,
         "cpu_baseline": cpu,
     }
+    if same1:
+        line["same_workload_1gpu"] = same1
     if alt:
         line["alt"] = alt
     print(json.dumps(line))

@@ -24,6 +24,10 @@
 #include "enum_common.cuh"
 #include "group_smem.cuh"
 
+#ifndef SIBGPU_SMEM_PART_KI
+#define SIBGPU_SMEM_PART_KI 256                       // Ki records per level-1 partition of the shared-memory grouping
+#endif
+
 namespace sibgpu {
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -1264,7 +1268,7 @@ static int launch_split(sibgpu_ctx *ctx, const SplitSrc &ssrc, uint32_t P1, uint
 	}
 	else
 	{
-		k_split<2, R><<<(uint32_t)std::min<uint64_t>(split_tiles, sms * 2), SPLIT_THREADS, sizeof(SplitSmem<2, R>), ctx->stream>>>(
+		k_split<2, R><<<(uint32_t)std::min<uint64_t>(split_tiles, sms * (sizeof(R) == 8 ? SPLIT_OCC : 2)), SPLIT_THREADS, sizeof(SplitSmem<2, R>), ctx->stream>>>(
 			ssrc, P1, tiles_per_seg, sub_bits, ctx->d_records2.as<R>(), ctx->d_cnt2.as<uint32_t>(), GROUP_CAP, d_flags);
 	}
 	return SIBGPU_OK;
@@ -1326,7 +1330,7 @@ static int enumerate_mode(sibgpu_ctx *ctx, uint32_t k, uint64_t nrec, const Host
 		// level-1 partitions of 512 Ki records, split into ~1 Ki-record buckets and grouped in shared memory
 		// (group_smem.cuh); otherwise (SIBGPU_GROUP_SMEM=0, fallbacks) one L2-resident table per partition
 		const bool smem_group = ctx->group_smem && !ctx->exact_hist;
-		const uint64_t part_rec = smem_group && !ctx->part_explicit ? (uint64_t)512 << 10 : ctx->part_records(k);
+		const uint64_t part_rec = smem_group && !ctx->part_explicit ? (uint64_t)SIBGPU_SMEM_PART_KI << 10 : ctx->part_records(k);
 		uint64_t P64 = (nrec + part_rec - 1) / part_rec;
 		const uint32_t P = (uint32_t)(P64 < 1 ? 1 : (P64 > MAX_PARTS ? MAX_PARTS : P64));
 		bool mixed = false;                                // the records carry mix56(key) (shared-memory path)

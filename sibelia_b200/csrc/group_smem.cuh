@@ -61,8 +61,11 @@ __host__ __device__ __forceinline__ uint64_t unmix64(uint64_t x)
 // Record formats of the shared-memory path.  narrow: (mixed 56-bit key << 7) | context;  wide: {mixed 64-bit key, context}.
 // Bit fields of the mixed key: bucket = bits 0-9, table slot = bits 10-21, tag = bits 22-41, partition = top bits.
 template<class R> struct RecOps;
+constexpr int SPLIT_OCC = 2;                           // CTAs per SM of the two-stage k_split
 template<> struct RecOps<uint64_t> {
-	static constexpr int TILE = 4096;                  // records per k_split tile (32 KB)
+	// records per k_split tile (32 KB).  Measured: 2048-record tiles at 3 CTAs per SM are slower (0.76 vs 0.59 ms per
+	// 10^8 records): the runs a tile contributes to a bucket halve and the writes fall below a sector pair
+	static constexpr int TILE = 4096;
 	static __device__ __forceinline__ uint64_t key(uint64_t r) { return r >> 7; }
 	static __device__ __forceinline__ uint32_t ctx(uint64_t r) { return (uint32_t)r & 127u; }
 	static __device__ __forceinline__ bool same_key(uint64_t a, uint64_t b) { return (a >> 7) == (b >> 7); }
@@ -183,7 +186,7 @@ __device__ __forceinline__ bool wait_epoch(const unsigned long long *flag, unsig
 // tile indices belong to different partitions, so concurrently running CTAs bump different bucket counters.
 // Segments must be 16-byte aligned (seg_cap even).
 template<int STAGES, class R>
-__global__ void __launch_bounds__(SPLIT_THREADS, STAGES == 1 ? 3 : 2) k_split(const SplitSrc src, uint32_t P1, uint32_t tiles_per_seg,
+__global__ void __launch_bounds__(SPLIT_THREADS, STAGES == 1 ? 3 : (sizeof(R) == 8 ? SPLIT_OCC : 2)) k_split(const SplitSrc src, uint32_t P1, uint32_t tiles_per_seg,
 	uint32_t sub_bits, R *__restrict__ out, uint32_t *__restrict__ cnt2, uint32_t cap2, uint32_t *__restrict__ overflow)
 {
 	extern __shared__ __align__(16) unsigned char smem_raw[];
