@@ -356,9 +356,13 @@ def main():
                 ctx.enumerate_resident(args.k)
                 ms1.append(ctx.last_device_ms())
             t1 = float(np.mean(ms1))
+            c1, _n1 = ctx.enumerate_resident(args.k)
+            p1, n1 = ctx.download()
+            d1 = result_digest(c1, p1, n1)               # outside every timed region
             same1 = {"workload": "the same %d-strain genome on ONE GPU (rank 0, device-resident, 3 steps)" % world,
                      "ms_per_step": t1, "value": r["total"] / 1e6 / (t1 / 1e3), "speedup_of_n_gpus": t1 / r["ms_per_step"],
-                     "parallel_efficiency": t1 / r["ms_per_step"] / world}
+                     "parallel_efficiency": t1 / r["ms_per_step"] / world,
+                     "result_digest": d1, "digest_equals_n_gpu_result": d1 == r["digest"]}
         barrier()
     alt = None
     if world > 1 and not args.no_alt:
