@@ -4,20 +4,21 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--mbases 100] [--k 25]
 
 A "step" is one construction of the de Bruijn-graph index of one synthetic genome: sibgpu_enumerate_resident
-(pack -> scan/histogram -> scatter -> L2-resident hash grouping -> vertex ranking -> instance tables), the GPU
+(pack -> scan + hash partition -> bucket split -> shared-memory grouping -> vertex ranking -> instance tables), the GPU
 replacement of IndexedSequence's EnumerateBifurcationsSArrayInRAM (/root/reference/src/vertexenumeration.cpp:263-364).
 Workload at N=1 is BASELINE.json configs[1]: 100 MB random-ACGT single contig, numpy default_rng(12345), k=25.
-With N>1 ranks (torchrun, one process per GPU) the workload is the SURVEY 8(d) strain recipe with N strains of 125 MB
-(N = 8: BASELINE configs[3], 10^9 bases), ONE genome sharded by contiguous text range over the ranks (weak scaling:
-125 Mbases per GPU): every rank scatters its k-mer records, bucketed by hash prefix, into its own exported buffer and
-publishes a step counter; the owner of a bucket waits for the counters on the device and pulls the bucket's segments
-straight out of the peers' buffers over NVLink with TMA bulk copies inside its split kernel (the all-to-all is fused
-into the kernel), groups them in shared memory, publishes its vertex keys the same way; a pull kernel concatenates all
-ranks' keys (the all-gather, fused); local instance tables (sibelia_b200/distributed.py).  `value` = total bases /
-max-over-ranks step time; `same_workload_1gpu` = the same genome indexed by rank 0 alone (the denominator for the
-speed-up of N GPUs on THIS workload: the N=1 line of a scaling run is the 100 MB random contig); `alt` = the same on
-N random contigs of 100 MB (round 1's workload, the N-fold of the N=1 line: weak scaling against it).  `result_digest` =
-sha256 over (vertex count, positive table, negative table) assembled on rank 0 outside the timed region.
+With N>1 ranks (torchrun, one process per GPU) the headline workload is its N-fold -- ONE random-ACGT genome of N contigs
+x 100 MB sharded by contiguous text range over the ranks (weak scaling: 100 Mbases per GPU): every rank scatters its
+k-mer records, bucketed by hash prefix, into its own exported buffer and publishes a step counter; the owner of a
+bucket waits for the counters on the device and pulls the bucket's segments straight out of the peers' buffers over
+NVLink with TMA bulk copies inside its split kernel (the all-to-all is fused into the kernel), groups them in shared
+memory, publishes its vertex keys the same way; a pull kernel concatenates all ranks' keys (the all-gather, fused);
+local instance tables (sibelia_b200/distributed.py).  `value` = total bases / max-over-ranks step time.
+`c4` (N>1) = the same measurement on the SURVEY 8(d) strain recipe with N strains of 125 MB (N = 8: BASELINE
+configs[3], 10^9 bases; millions of vertices, so the id ranking and the instance tables count), with
+`same_genome_on_1_gpu`: that genome indexed by rank 0 alone (speed-up of N GPUs on it, and the check that N GPUs produced
+the same tables).  `result_digest` = sha256 over (vertex count, positive table, negative table) assembled on rank 0
+outside the timed region.
 
 One JSON line is printed by rank 0 (see the task contract): value = device-resident throughput, e2e = the same
 metric through sibgpu_enumerate with pinned HOST buffers (H2D + D2H inside the timed region), roofline = dominant
@@ -110,11 +111,20 @@ class ClockSampler:
 
 
 def workload(world, mbases):
-    """The chromosomes of the N-GPU workload and its description."""
-    from sibelia_b200 import synth
+    """The chromosomes of the N-GPU headline workload and its description: N random contigs of `mbases` MB, i.e. the
+    N-fold of the N=1 workload (weak scaling; north_star: "throughput on a synthetic random-ACGT genome ... at 1, 2, 4 and
+    8 GPUs")."""
     if world == 1:
         return [genome(mbases, 12345)], ("synthetic %g MB random-ACGT single contig, numpy default_rng(12345) "
                                          "(BASELINE configs[1])" % mbases)
+    from sibelia_b200 import synth
+    return [synth.random_genome(int(mbases * 1_000_000), 12345 + c) for c in range(world)], (
+        "synthetic random-ACGT genome of %d contigs x %g MB (default_rng(12345 + c); contig 0 = BASELINE configs[1]), one "
+        "genome sharded by text range over %d GPUs" % (world, mbases, world))
+
+
+def strain_workload(world):
+    from sibelia_b200 import synth
     return synth.strains(world, STRAIN_BASES), (
         "SURVEY 8(d) strain recipe, %d strains x 125 MB (base default_rng(1000), strain s default_rng(2000+s): p_sub 0.002, "
         "4 x 200 kb inversions, indels)%s, one genome sharded by text range over %d GPUs"
@@ -133,8 +143,8 @@ def result_digest(count, pos, neg):
 def run_reference(args, rank, world):
     """The reference's own CPU implementation of the path (oracle/_ref = unmodified /root/reference sources compiled
     by oracle/Makefile), single thread (the reference has no threading).  N=1: the FULL 100 MB workload, one step
-    (40-120 s; warm-up would only repeat it).  N>1: one rank's shard of the strain workload (strain 0, 125 MB): the
-    whole 10^9-base set needs ~40 GB and ~20 min per index on the CPU."""
+    (40-120 s; warm-up would only repeat it).  N>1: one rank's shard of the N-contig genome (contig 0, 100 MB): the
+    whole set needs tens of GB and ~N x 45 s (and more: suffix sorting is superlinear) per index on the CPU."""
     if rank != 0:
         return
     from oracle import ref
@@ -146,10 +156,10 @@ def run_reference(args, rank, world):
         what = "synthetic %g MB random-ACGT single contig, numpy default_rng(12345), k=%d (BASELINE configs[1]), FULL size" % (args.mbases, args.k)
         sample = "the whole workload genome (%d bases)" % len(g)
     else:
-        from sibelia_b200 import synth
-        g = synth.strains(1, STRAIN_BASES)[0]
-        what = ("strain 0 (125 MB) of the %d-strain workload of the GPU arm, k=%d: one rank's shard" % (world, args.k))
-        sample = "strain 0 of the strain set (%d bases)" % len(g)
+        g = genome(args.mbases, 12345)
+        what = ("contig 0 (%g MB, = the N=1 workload) of the %d-contig random-ACGT genome of the GPU arm, k=%d: one rank's "
+                "shard -- a bounded sample, the reference gets slower per base with size" % (args.mbases, world, args.k))
+        sample = "contig 0 of the %d-contig genome (%d bases)" % (world, len(g))
     steps = max(1, min(args.steps, args.ref_steps))
     t = []
     for _ in range(steps):
@@ -181,8 +191,8 @@ def main():
     ap.add_argument("--k", type=int, default=25)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--ref-steps", type=int, default=1, help="steps the reference arm actually runs (each is 40-170 s)")
-    ap.add_argument("--no-alt", action="store_true", help="N>1: skip the random-contig line of round 1")
-    ap.add_argument("--no-single", action="store_true", help="N>1: skip the one-GPU run of the same genome on rank 0")
+    ap.add_argument("--no-c4", action="store_true", help="N>1: skip the strain-set workload (BASELINE configs[3] at N = 8)")
+    ap.add_argument("--no-single", action="store_true", help="N>1: skip the one-GPU run of the strain set on rank 0")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -342,12 +352,18 @@ def main():
 
     chrs, what = workload(world, args.mbases)
     r = measure(chrs, True)
-    same1 = None
-    if world > 1 and not args.no_single:
-        # the denominator the N-GPU figure should be read against: the SAME genome indexed by ONE GPU (rank 0 alone, the
-        # others wait): N=1 of the driver's scaling run is the 100 MB random contig, which has almost no vertices
-        if rank == 0:
-            ctx.upload(chrs)
+    c4 = None
+    if world > 1 and not args.no_c4:
+        # BASELINE configs[3] (N = 8: 10^9 bases) and its smaller siblings: N strains x 125 MB, with the output check
+        schrs, swhat = strain_workload(world)
+        a = measure(schrs, False)
+        c4 = {"workload": swhat + ", k=%d" % args.k, "value": a["value"], "ms_per_step": a["ms_per_step"], "e2e_value": a["e2e_value"],
+              "e2e_ms_per_step": a["e2e_ms"], "vertices": a["count"], "instances_per_strand": a["ninst"], "exchange": a["strategy"],
+              "result_digest": a["digest"]}
+        # the denominator this figure should be read against: the SAME genome indexed by ONE GPU (rank 0 alone, the others
+        # wait), and the proof that N GPUs computed the same tables
+        if rank == 0 and not args.no_single:
+            ctx.upload(schrs)
             for _ in range(2):
                 ctx.enumerate_resident(args.k)
             ms1 = []
@@ -359,18 +375,10 @@ def main():
             c1, _n1 = ctx.enumerate_resident(args.k)
             p1, n1 = ctx.download()
             d1 = result_digest(c1, p1, n1)               # outside every timed region
-            same1 = {"workload": "the same %d-strain genome on ONE GPU (rank 0, device-resident, 3 steps)" % world,
-                     "ms_per_step": t1, "value": r["total"] / 1e6 / (t1 / 1e3), "speedup_of_n_gpus": t1 / r["ms_per_step"],
-                     "parallel_efficiency": t1 / r["ms_per_step"] / world,
-                     "result_digest": d1, "digest_equals_n_gpu_result": d1 == r["digest"]}
+            c4["same_genome_on_1_gpu"] = {"ms_per_step": t1, "value": a["total"] / 1e6 / (t1 / 1e3),
+                                          "speedup_of_n_gpus": t1 / a["ms_per_step"], "result_digest": d1,
+                                          "digest_equals_n_gpu_result": d1 == a["digest"]}
         barrier()
-    alt = None
-    if world > 1 and not args.no_alt:
-        from sibelia_b200 import synth
-        a = measure([synth.random_genome(int(args.mbases * 1_000_000), 12345 + c) for c in range(world)], False)
-        alt = {"workload": "%d random-ACGT contigs x %g MB (default_rng(12345+c)): round 1's multi-GPU workload" % (world, args.mbases),
-               "value": a["value"], "ms_per_step": a["ms_per_step"], "e2e_value": a["e2e_value"], "e2e_ms_per_step": a["e2e_ms"],
-               "vertices": a["count"], "result_digest": a["digest"]}
 
     if rank != 0:
         if world > 1:
@@ -449,10 +457,8 @@ def main():
         "roofline": roofline,
         "cpu_baseline": cpu,
     }
-    if same1:
-        line["same_workload_1gpu"] = same1
-    if alt:
-        line["alt"] = alt
+    if c4:
+        line["c4"] = c4
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -3,7 +3,11 @@ strain recipe at 4 x 12.5 Mb (p_sub = 0.002) through the four `-s loose`-like st
 (5000,15000) of BlockFinder::PerformGraphSimplifications, maxIterations = 4.  The states are far too large to commit,
 so every stage is pinned by sha256 digests of rawSeq_ / originalPos_ per chromosome plus the bulge count; the input is
 regenerated from the seeds (sibelia_b200.synth.strains) and pinned by its own digest.  Authoring container only
-(about 15 minutes of CPU)."""
+(about 15 minutes of CPU).
+
+    python make_golden_simplify_large.py c3 [nstages]   BASELINE configs[2] itself: 4 x 125 Mb -> simplify_c3_digests.json
+                                                        (hours of CPU and ~30 GB of RAM; the JSON is rewritten after
+                                                        every stage, so a partial run still pins the stages it finished)"""
 import hashlib
 import json
 import os
@@ -20,6 +24,13 @@ from sibelia_b200 import synth  # noqa: E402
 OUT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "simplify_large_digests.json")
 CASE = {"n_strains": 4, "base_len": 12_500_000, "p_sub": 0.002, "base_seed": 1000, "strain_seed": 2000,
         "stages": [[25, 150], [100, 1000], [1000, 5000], [5000, 15000]], "iters": 4}
+
+
+if len(sys.argv) > 1 and sys.argv[1] == "c3":
+    OUT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "simplify_c3_digests.json")
+    CASE["base_len"] = 125_000_000
+    if len(sys.argv) > 2:
+        CASE["stages"] = CASE["stages"][:int(sys.argv[2])]
 
 
 def sha(a):
