@@ -144,6 +144,7 @@ int sibgpu_create(int device, sibgpu_ctx **out)
 	if(const char *e = getenv("SIBGPU_STREAMS")) c->n_streams = atoi(e);
 	if(const char *e = getenv("SIBGPU_GROUP_SMEM")) c->group_smem = atoi(e);
 	if(const char *e = getenv("SIBGPU_SPLIT_STAGES")) c->split_stages = atoi(e) == 1 ? 1 : 2;
+	if(const char *e = getenv("SIBGPU_PIECEWISE")) c->piecewise_split = atoi(e) != 0;
 	if(const char *e = getenv("SIBGPU_CKEYS_INIT")) c->ckeys_init = strtoull(e, nullptr, 10);
 	if(const char *e = getenv("SIBGPU_TABLE_FACTOR"))
 	{

@@ -94,6 +94,7 @@ struct sibgpu_ctx {
 	// 0 = one L2-resident table per hash partition (k_insert + k_table_scan; also the fallback when a bucket overflows)
 	int group_smem = 1;                                // env SIBGPU_GROUP_SMEM
 	bool split_attr_done[2] = {false, false}, group_attr_done[4] = {false, false, false, false};
+	int piecewise_split = 1;                           // host source: split every text piece behind its scatter (env SIBGPU_PIECEWISE, dev)
 	int split_stages = 2;                              // input tiles in flight per CTA of k_split (env SIBGPU_SPLIT_STAGES, dev)
 	uint64_t ckeys_init = 1u << 20;                    // initial capacity of the vertex-key list (env SIBGPU_CKEYS_INIT, tests)
 	uint64_t smem_fallbacks = 0;                       // times a bucket overflowed and the L2-table path took over

@@ -1352,18 +1352,52 @@ static int enumerate_mode(sibgpu_ctx *ctx, uint32_t k, uint64_t nrec, const Host
 		if(!ctx->exact_hist)
 		{
 			const uint64_t mean = (nrec + P - 1) / P;
-			const uint64_t cap = ((P == 1 ? nrec : mean + mean / 8 + ctx->part_slack) + 1) & ~1ull;   // even: 16-byte aligned partitions
 			uint32_t sub_bits = 0;                         // level-2 fan-out of the shared-memory grouping
 			while(((mean + ((uint64_t)1 << sub_bits) - 1) >> sub_bits) > GROUP_MEAN) sub_bits++;
 			mixed = smem_group && sub_bits <= SUB_BITS_MAX;
-			SIB_TRY(ctx->d_records.ensure(sizeof(Rec) * cap * P + 64));
+			// Pieces: with a host source the text arrives in CHUNK_TILES-tile pieces.  On the shared-memory path every piece
+			// scatters into its OWN set of partition regions and is split into the (global) buckets right away, so that
+			// when the last byte has landed only the last piece's scatter + split, the grouping and the second scan are
+			// left; otherwise all pieces share one set of regions.
+			const uint32_t nchunks = src ? (ntiles + CHUNK_TILES - 1) / CHUNK_TILES : 1;
+			const bool piecewise = mixed && nchunks > 1 && ctx->piecewise_split;
+			const uint32_t nreg = piecewise ? nchunks : 1;     // sets of partition regions
+			const uint64_t piece_mean = ((uint64_t)(CHUNK_TILES + 2) * TILE_POS + P - 1) / P;
+			const uint64_t cap = piecewise ? ((piece_mean + piece_mean / 8 + ctx->part_slack) + 1) & ~1ull
+				: ((P == 1 ? nrec : mean + mean / 8 + ctx->part_slack) + 1) & ~1ull;   // even: 16-byte aligned partitions
+			SIB_TRY(ctx->d_records.ensure(sizeof(Rec) * cap * P * nreg + 64));
+			SIB_TRY(ctx->d_cursor.ensure(sizeof(uint64_t) * (size_t)P * CURSOR_STRIDE * nreg));
 			for(uint32_t p = 0; p <= P; p++) part_base[p] = (uint64_t)p * cap;
-			std::vector<uint64_t> cur((size_t)P * CURSOR_STRIDE, 0);
-			for(uint32_t p = 0; p < P; p++) cur[(size_t)p * CURSOR_STRIDE] = part_base[p];
+			// cursors are relative to the base of their set of regions
+			std::vector<uint64_t> cur((size_t)P * CURSOR_STRIDE * nreg, 0);
+			for(uint32_t r = 0; r < nreg; r++)
+			{
+				for(uint32_t p = 0; p < P; p++) cur[((size_t)r * P + p) * CURSOR_STRIDE] = part_base[p];
+			}
 			SIB_CUDA(cudaMemcpyAsync(ctx->d_cursor.p, cur.data(), sizeof(uint64_t) * cur.size(), cudaMemcpyHostToDevice, st));
 			SIB_CUDA(cudaMemcpyAsync(ctx->d_partoff.p, part_base.data(), sizeof(uint64_t) * (P + 1), cudaMemcpyHostToDevice, st));
 			uint32_t *d_overflow = reinterpret_cast<uint32_t*>(ds + 10);
-			const uint32_t nchunks = src ? (ntiles + CHUNK_TILES - 1) / CHUNK_TILES : 1;
+			uint32_t *d_grp_flags = reinterpret_cast<uint32_t*>(ds + 11);
+			uint32_t nbuckets = 0;
+			uint32_t ckeys_cap = 0;
+			const uint32_t tiles_per_seg = (uint32_t)((cap + RecOps<SR>::TILE - 1) / RecOps<SR>::TILE);
+			if(mixed)
+			{
+				nbuckets = P << sub_bits;
+				SIB_TRY(ctx->d_records2.ensure(sizeof(SR) * (size_t)nbuckets * GROUP_CAP + 64));
+				SIB_TRY(ctx->d_cnt2.ensure(sizeof(uint32_t) * (size_t)nbuckets));
+				SIB_TRY(ctx->d_ckeys.ensure(sizeof(Key) * (ctx->ckeys_init ? ctx->ckeys_init : 1)));
+				ckeys_cap = (uint32_t)std::min<size_t>(ctx->d_ckeys.cap / sizeof(Key), 0xFFFFFFF0u);
+				SIB_CUDA(cudaMemsetAsync(ctx->d_cnt2.p, 0, sizeof(uint32_t) * (size_t)nbuckets, st));
+			}
+			auto split_regions = [&](uint32_t r, uint64_t nrec_here) -> int {
+				SplitSrc ssrc = {};
+				ssrc.seg[0] = ctx->d_records.as<Rec>() + (size_t)r * P * cap;
+				ssrc.cursor[0] = ctx->d_cursor.as<unsigned long long>() + (size_t)r * P * CURSOR_STRIDE;
+				ssrc.seg_cap = cap;
+				ssrc.W = 1;
+				return launch_split<SR>(ctx, ssrc, P, tiles_per_seg, sub_bits, nrec_here, d_grp_flags);
+			};
 			if(src)
 			{
 				SIB_TRY(ctx->ensure_copy_stream(nchunks));
@@ -1394,38 +1428,28 @@ static int enumerate_mode(sibgpu_ctx *ctx, uint32_t k, uint64_t nrec, const Host
 				{
 					const uint32_t nt = tile_hi - tiles_done;
 					const uint32_t g = nt < (uint32_t)sms * 4 ? nt : (uint32_t)sms * 4;
+					const uint32_t r = piecewise ? c : 0;
 					TextDesc tc = t;
 					tc.tile0 = tiles_done;
-					ProfScope ps(ctx, "k_scatter", (FP ? (uint64_t)nt * TILE_POS / 2 + (uint64_t)nt * TILE_POS * 2 : (uint64_t)nt * TILE_POS / 4)
-						+ nrec * sizeof(Rec) * nt / ntiles);
-					if(mixed) k_scatter<MODE, true><<<g, TILE_THREADS, scatter_smem, st>>>(tc, fp, k, nt, P,
-						ctx->d_cursor.as<unsigned long long>(), ctx->d_records.as<Rec>(), cap, d_overflow);
-					else k_scatter<MODE, false><<<g, TILE_THREADS, scatter_smem, st>>>(tc, fp, k, nt, P, ctx->d_cursor.as<unsigned long long>(),
-						ctx->d_records.as<Rec>(), cap, d_overflow);
+					{
+						ProfScope ps(ctx, "k_scatter", (FP ? (uint64_t)nt * TILE_POS / 2 + (uint64_t)nt * TILE_POS * 2 : (uint64_t)nt * TILE_POS / 4)
+							+ nrec * sizeof(Rec) * nt / ntiles);
+						unsigned long long *cursor_r = ctx->d_cursor.as<unsigned long long>() + (size_t)r * P * CURSOR_STRIDE;
+						Rec *out_r = ctx->d_records.as<Rec>() + (size_t)r * P * cap;
+						if(mixed) k_scatter<MODE, true><<<g, TILE_THREADS, scatter_smem, st>>>(tc, fp, k, nt, P, cursor_r, out_r, cap, d_overflow);
+						else k_scatter<MODE, false><<<g, TILE_THREADS, scatter_smem, st>>>(tc, fp, k, nt, P, cursor_r, out_r, cap, d_overflow);
+					}
+					if(piecewise) SIB_TRY(split_regions(r, nrec * nt / ntiles));
 					tiles_done = tile_hi;
 				}
 			}
 			// ---- shared-memory grouping, launched behind the scatter without a host round trip: the level-1 fill counts
 			// are read on the device; the flags (input error, level-1 / level-2 overflow) are checked once, below
 			bool smem_launched = false;
-			uint32_t nbuckets = 0;
-			uint32_t ckeys_cap = 0;
 			if(mixed)
 			{
-				nbuckets = P << sub_bits;
-				SIB_TRY(ctx->d_records2.ensure(sizeof(SR) * (size_t)nbuckets * GROUP_CAP + 64));
-				SIB_TRY(ctx->d_cnt2.ensure(sizeof(uint32_t) * (size_t)nbuckets));
-				SIB_TRY(ctx->d_ckeys.ensure(sizeof(Key) * (ctx->ckeys_init ? ctx->ckeys_init : 1)));
-				ckeys_cap = (uint32_t)std::min<size_t>(ctx->d_ckeys.cap / sizeof(Key), 0xFFFFFFF0u);
-				SIB_CUDA(cudaMemsetAsync(ctx->d_cnt2.p, 0, sizeof(uint32_t) * (size_t)nbuckets, st));
-				const uint32_t tiles_per_seg = (uint32_t)((cap + RecOps<SR>::TILE - 1) / RecOps<SR>::TILE);
-				SplitSrc ssrc = {};
-				ssrc.seg[0] = ctx->d_records.p;
-				ssrc.cursor[0] = ctx->d_cursor.as<unsigned long long>();
-				ssrc.seg_cap = cap;
-				ssrc.W = 1;
-				SIB_TRY(launch_split<SR>(ctx, ssrc, P, tiles_per_seg, sub_bits, nrec, reinterpret_cast<uint32_t*>(ds + 11)));
-				SIB_TRY((launch_group<SR, FP>(ctx, nbuckets, sub_bits, nrec, reinterpret_cast<uint32_t*>(ds + 11), ctx->d_ckeys.as<typename GroupKey<SR, FP>::type>(), ckeys_cap,
+				if(!piecewise) SIB_TRY(split_regions(0, nrec));
+				SIB_TRY((launch_group<SR, FP>(ctx, nbuckets, sub_bits, nrec, d_grp_flags, ctx->d_ckeys.as<typename GroupKey<SR, FP>::type>(), ckeys_cap,
 					reinterpret_cast<uint32_t*>(ds + 2))));
 				smem_launched = true;
 			}
@@ -1447,7 +1471,8 @@ static int enumerate_mode(sibgpu_ctx *ctx, uint32_t k, uint64_t nrec, const Host
 				uint64_t total = 0;
 				for(uint32_t p = 0; p < P; p++)
 				{
-					part_cnt[p] = cur[(size_t)p * CURSOR_STRIDE] - part_base[p];
+					part_cnt[p] = 0;
+					for(uint32_t r = 0; r < nreg; r++) part_cnt[p] += cur[((size_t)r * P + p) * CURSOR_STRIDE] - part_base[p];
 					total += part_cnt[p];
 					if(part_cnt[p] > maxpart) maxpart = part_cnt[p];
 				}
@@ -1456,16 +1481,17 @@ static int enumerate_mode(sibgpu_ctx *ctx, uint32_t k, uint64_t nrec, const Host
 					set_error("internal: scatter kernel wrote " + std::to_string(total) + " k-mers, expected " + std::to_string(nrec));
 					return SIBGPU_ERR_INTERNAL;
 				}
-				have_records = true;
+				have_records = !piecewise;                 // one contiguous region per partition (what the L2-table path reads)
 				if(smem_launched)
 				{
 					if(hs[11] & 0xFFFFFFFFull)
 					{
 						// a bucket outgrew its fixed region (one k-mer repeated hundreds of times): the L2-table path below
-						// regroups the intact level-1 partitions
+						// regroups the intact level-1 partitions (scattered again, exactly sized, when they lie in pieces)
 						SIB_CUDA(cudaMemsetAsync(ds + 11, 0, sizeof(uint64_t), st));
 						SIB_CUDA(cudaMemsetAsync(ds + 2, 0, sizeof(uint64_t), st));
 						ctx->smem_fallbacks++;
+						if(piecewise) mixed = false;
 					}
 					else
 					{
@@ -1475,7 +1501,7 @@ static int enumerate_mode(sibgpu_ctx *ctx, uint32_t k, uint64_t nrec, const Host
 							// the key list was too small (k_group kept counting): regrow, group again -- the buckets are intact
 							SIB_TRY(ctx->d_ckeys.ensure(sizeof(Key) * Vc));
 							SIB_CUDA(cudaMemsetAsync(ds + 2, 0, sizeof(uint64_t), st));
-							SIB_TRY((launch_group<SR, FP>(ctx, nbuckets, sub_bits, nrec, reinterpret_cast<uint32_t*>(ds + 11), ctx->d_ckeys.as<typename GroupKey<SR, FP>::type>(),
+							SIB_TRY((launch_group<SR, FP>(ctx, nbuckets, sub_bits, nrec, d_grp_flags, ctx->d_ckeys.as<typename GroupKey<SR, FP>::type>(),
 								(uint32_t)Vc, reinterpret_cast<uint32_t*>(ds + 2))));
 							SIB_CUDA(cudaStreamSynchronize(st));
 						}
@@ -1495,7 +1521,7 @@ static int enumerate_mode(sibgpu_ctx *ctx, uint32_t k, uint64_t nrec, const Host
 		}
 
 		// ---- exact path: histogram pass, prefix sums, scatter into exactly sized partitions
-		if(!have_records)
+		if(!have_records && !grouped)
 		{
 			SIB_TRY(ctx->d_records.ensure(sizeof(Rec) * nrec));
 			SIB_CUDA(cudaMemsetAsync(ctx->d_hist.p, 0, sizeof(uint32_t) * MAX_PARTS, st));
