@@ -21,6 +21,7 @@ SYMBOLS = [
     "sibgpu_dist_scatter_local", "sibgpu_dist_upload_scatter", "sibgpu_dist_export_send", "sibgpu_dist_import_peers", "sibgpu_dist_group_peer",
     "sibgpu_fasta_parse", "sibgpu_fasta_free",
     "sibgpu_fused_plan", "sibgpu_fused_release_peers", "sibgpu_fused_alloc", "sibgpu_fused_import", "sibgpu_fused_run",
+    "sibgpu_fused_run_fp", "sibgpu_fused_finish_fp",
 ]
 
 
