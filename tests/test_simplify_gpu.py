@@ -71,14 +71,11 @@ def test_max_iterations_and_tiny_inputs(ctx):
         assert_state_equal(got, want, "tiny %d (k=%d D=%d iters=%d)" % (it, k, D, iters))
 
 
-def test_large_strain_set_against_reference_digests(ctx):
-    """SURVEY 8(d) strain recipe at 4 x 12.5 Mb through the four loose stages: 143 410 collapses in stage 1 (Boost
-    rehashes past 16 buckets, multi-group vertices, the overlap guard and the double accumulation en masse).  The
-    reference's states are pinned by sha256 digests (tests/golden/make_golden_simplify_large.py, ~4 min of CPU)."""
+def _run_digest_fixture(ctx, name):
     import hashlib
     import json
     from sibelia_b200 import synth
-    z = json.load(open(os.path.join(GOLD, "simplify_large_digests.json")))
+    z = json.load(open(os.path.join(GOLD, name)))
     chrs = [c.tobytes() for c in synth.strains(z["n_strains"], z["base_len"], base_seed=z["base_seed"],
                                                strain_seed=z["strain_seed"], p_sub=z["p_sub"])]
     assert [hashlib.sha256(c).hexdigest() for c in chrs] == z["input"]["seq_sha256"], "generator drifted"
@@ -91,3 +88,17 @@ def test_large_strain_set_against_reference_digests(ctx):
         assert [hashlib.sha256(bytes(c)).hexdigest() for c in chrs] == st["seq_sha256"], what + " sequences differ"
         assert [hashlib.sha256(np.ascontiguousarray(o, dtype=np.uint32).tobytes()).hexdigest() for o in op] == st["origpos_sha256"], \
             what + " original positions differ"
+
+
+def test_large_strain_set_against_reference_digests(ctx):
+    """SURVEY 8(d) strain recipe at 4 x 12.5 Mb through the four loose stages: 143 410 collapses in stage 1 (Boost
+    rehashes past 16 buckets, multi-group vertices, the overlap guard and the double accumulation en masse).  The
+    reference's states are pinned by sha256 digests (tests/golden/make_golden_simplify_large.py, ~4 min of CPU)."""
+    _run_digest_fixture(ctx, "simplify_large_digests.json")
+
+
+def test_c3_500mb_pipeline_against_reference_digests(ctx):
+    """BASELINE configs[2] itself: the 500 MB 4-strain set through the `-s loose` stages, 1 434 694 collapses in stage 1.
+    The unmodified reference ran once in the authoring container (`make_golden_simplify_large.py c3`: 22 min for stage
+    1, 11 min per later stage, ~30 GB of RAM); its states are pinned by sha256 digests per chromosome."""
+    _run_digest_fixture(ctx, "simplify_c3_digests.json")
