@@ -88,3 +88,34 @@ def test_c3_partition_size_independence(strains500, built):
         c.close()
     assert res[0][0] == res[1][0]
     assert np.array_equal(res[0][1], res[1][1]) and np.array_equal(res[0][2], res[1][2])
+
+
+def _reference_digest_case(ctx, name, chrs):
+    """the whole index against the unmodified reference, through sha256(count || pos || neg) (tests/golden/
+    make_golden_scale_index.py ran the reference once in the authoring container)"""
+    import hashlib
+    import json
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "scale_index_digests.json")
+    cases = json.load(open(path)) if os.path.exists(path) else {}
+    if name not in cases:
+        pytest.skip("no reference digest for %s committed" % name)
+    z = cases[name]
+    assert sum(len(c) for c in chrs) == z["bases"], "generator drifted"
+    count, pos, neg = ctx.enumerate(chrs, z["k"])
+    assert count == z["vertices"] and len(pos) == z["instances_per_strand"]
+    h = hashlib.sha256()
+    h.update(np.uint64(count).tobytes())
+    h.update(np.ascontiguousarray(pos).tobytes())
+    h.update(np.ascontiguousarray(neg).tobytes())
+    assert h.hexdigest() == z["result_digest"]
+
+
+def test_c3_index_equals_reference_digest(ctx, strains500):
+    """BASELINE configs[2]/[4] input, k = 25: bit-exact against the reference's IndexedSequence at full size"""
+    _reference_digest_case(ctx, "c3", strains500)
+
+
+def test_c4_index_equals_reference_digest(ctx):
+    """BASELINE configs[3] input (8 strains x 125 Mb = 10^9 bases), k = 25, on ONE GPU; bench.py shows that 8 GPUs produce
+    the same digest (c4.same_genome_on_1_gpu.digest_equals_n_gpu_result)"""
+    _reference_digest_case(ctx, "c4", synth.strains(8, 125_000_000))
