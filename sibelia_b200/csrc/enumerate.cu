@@ -36,9 +36,10 @@ namespace sibgpu {
 __global__ void __launch_bounds__(256) k_pack(const uint4 *__restrict__ text, uint32_t *__restrict__ packed,
 	uint32_t nwords, uint32_t *__restrict__ err)
 {
-	// PACK_ILP independent 128-bit loads in flight per thread (a 100 MB text is only ~40 us of HBM time: latency, not
-	// issue, is what has to be hidden); streaming loads, the ASCII text is read exactly once
-	constexpr int PACK_ILP = 4;
+	// PACK_ILP independent 128-bit loads in flight per thread at 16 CTAs per SM; streaming loads, the ASCII text is read
+	// exactly once.  A 100 MB text is ~20 us of HBM time inside a ~37 us kernel: launch ramp and tail dominate, and
+	// 2 / 4 / 8 loads in flight at 4 / 8 / 16 CTAs per SM all land within 37-42 us (profiles/r2_k_pack_variants.txt)
+	constexpr int PACK_ILP = 2;
 	uint32_t bad = 0;
 	const uint32_t stride = gridDim.x * blockDim.x;
 	for(uint32_t i0 = blockIdx.x * blockDim.x + threadIdx.x; i0 < nwords; i0 += stride * PACK_ILP)
@@ -1234,7 +1235,7 @@ static int launch_pack(sibgpu_ctx *ctx, uint64_t w0, uint64_t w1)
 {
 	uint32_t *d_err = reinterpret_cast<uint32_t*>(ctx->d_scalars.as<uint64_t>() + 8);
 	ProfScope ps(ctx, "k_pack", (w1 - w0) * 20);
-	k_pack<<<grid_for(w1 - w0, 256, ctx->sm_count, 8), 256, 0, ctx->stream>>>(ctx->d_text.as<uint4>() + w0,
+	k_pack<<<grid_for(w1 - w0, 256, ctx->sm_count, 16), 256, 0, ctx->stream>>>(ctx->d_text.as<uint4>() + w0,
 		ctx->d_packed.as<uint32_t>() + w0, (uint32_t)(w1 - w0), d_err);
 	return SIBGPU_OK;
 }
