@@ -2,7 +2,11 @@
 // logic restated on flat arrays (pure C++, no CUDA) -- see simplify.cu for how the GPU detection kernel and this exact
 // in-order committer share the work.
 #pragma once
+#ifdef SIBGPU_COMMIT_PROF
+#include <x86intrin.h>
+#endif
 #include <algorithm>
+#include <atomic>
 #include <cstdint>
 #include <cstring>
 #include <iterator>
@@ -17,6 +21,20 @@
 
 namespace sibgpu {
 namespace simp {
+
+// Dev only (-DSIBGPU_COMMIT_PROF): time-stamp-counter split of the ordered commit, printed by sibgpu_simplify's trace.
+#ifdef SIBGPU_COMMIT_PROF
+struct CommitProf { unsigned long long t[12] = {}; };
+inline CommitProf &commit_prof() { static CommitProf p; return p; }
+struct ProfSection {
+	int i; unsigned long long t0;
+	explicit ProfSection(int idx) : i(idx), t0(__rdtsc()) {}
+	~ProfSection() { commit_prof().t[i] += __rdtsc() - t0; }
+};
+#define SIB_PROF(i) ProfSection prof_section_##i(i)
+#else
+#define SIB_PROF(i)
+#endif
 
 const uint32_t NO_BIF = 0xFFFFFFFFu;                   // BifurcationStorage::NO_BIFURCATION, bifurcationstorage.cpp:12
 const char SEP = '$';                                  // DNASequence::SEPARATION_CHAR, dnasequence.cpp:33
@@ -453,20 +471,24 @@ public:
 	// AnyBulges, :158-218.  The visit map is boost::unordered_map<size_t, BranchData>: lookups through `slot_of`,
 	// iteration order through BoostUnorderedOrder.
 	std::vector<int32_t> slot_of;                        // vertex id -> index into `branches` (-1 = absent), kept sparse
-	std::vector<BranchData> branches;
+	std::vector<BranchData> branches;                    // pooled: entries [0, n_branches) are live, the rest keep their capacity
+	size_t n_branches = 0;
 	std::vector<uint32_t> touched;
 	BoostUnorderedOrder order;
 
 	std::vector<char> first_char;                        // scratch of the existence pass
 
+	// expect_bulge: the caller has just seen a conflict for this vertex (parallel screen): the existence pass, which
+	// only exists to leave early, is skipped -- the full pass alone gives the same answer.
 	bool any_bulges(const std::vector<int32_t> &start_kmer, const std::vector<char> &end_char,
-		std::vector<std::vector<size_t> > &bulges)
+		std::vector<std::vector<size_t> > &bulges, bool expect_bulge = false)
 	{
 		bulges.clear();
 		// Existence pass.  Most calls (94 % on the reference's example genome) find nothing; the same walks without the
 		// BranchData / Boost-order bookkeeping decide that: both loops perform the same insertions up to the first
 		// conflict (a vertex reached again with another end character), so a conflict exists here iff the full pass
 		// below produces a branch with two ids.
+		if(!expect_bulge)
 		{
 			touched.clear();
 			first_char.clear();
@@ -501,7 +523,7 @@ public:
 			for(size_t i = 0; i < touched.size(); i++) slot_of[touched[i]] = -1;
 			if(!conflict) return false;
 		}
-		branches.clear();
+		n_branches = 0;
 		touched.clear();
 		order.clear();
 		for(size_t i = 0; i < start_kmer.size(); i++)
@@ -519,13 +541,14 @@ public:
 					const int32_t s = slot_of[b];
 					if(s < 0)
 					{
-						slot_of[b] = (int32_t)branches.size();
+						slot_of[b] = (int32_t)n_branches;
 						touched.push_back(b);
-						order.insert_new(b, (int)branches.size());
-						BranchData bd;
+						order.insert_new(b, (int)n_branches);
+						if(n_branches == branches.size()) branches.emplace_back();
+						BranchData &bd = branches[n_branches++];
 						bd.end_char = end_char[i];
+						bd.branch_ids.clear();
 						bd.branch_ids.push_back(i);
-						branches.push_back(bd);
 					}
 					else if(branches[s].end_char != end_char[i])
 					{
@@ -550,6 +573,8 @@ public:
 		std::vector<int32_t> slot_of, start_kmer;
 		std::vector<uint32_t> touched;
 		std::vector<char> first_char, end_char;
+		std::vector<uint32_t> surv_id, surv_off;           // vertices that kept their flag + where their instances start below
+		std::vector<int32_t> surv_elem;                    // element of every instance of those vertices
 	};
 
 	// Would RemoveBulges(id) find a bulge in the CURRENT state?  Same walks as the existence pass of any_bulges, on
@@ -620,6 +645,9 @@ public:
 		auto work = [this, &ids, flag, nt](size_t t) {
 			ScreenScratch &sc = screen_scratch[t];
 			if(sc.slot_of.size() != dirty.size()) sc.slot_of.assign(dirty.size(), -1);
+			sc.surv_id.clear();
+			sc.surv_off.clear();
+			sc.surv_elem.clear();
 			// interleaved blocks: ids are lexicographic ranks, not positions; the split only has to balance the work
 			const size_t block = 256;
 			for(size_t b = t * block; b < ids.size(); b += nt * block)
@@ -632,14 +660,108 @@ public:
 						dirty[ids[i]] = 0;
 						if(flag) flag[ids[i]] = 0;
 					}
+					else
+					{
+						sc.surv_id.push_back(ids[i]);
+						sc.surv_off.push_back((uint32_t)sc.surv_elem.size());
+						for(size_t j = 0; j < sc.start_kmer.size(); j++) sc.surv_elem.push_back(n_elem[sc.start_kmer[j]]);
+					}
 				}
 			}
+			sc.surv_off.push_back((uint32_t)sc.surv_elem.size());
 		};
 		std::vector<std::thread> th;
 		for(size_t t = 1; t < nt; t++) th.emplace_back(work, t);
 		work(0);
 		for(std::thread &x : th) x.join();
+		// the survivors in id order, for the run-ahead prefetchers of the ordered part
+		ahead_id.clear();
+		ahead_off.clear();
+		ahead_elem.clear();
+		std::vector<std::pair<uint32_t, std::pair<uint32_t, uint32_t> > > order;      // id -> (thread, index)
+		for(size_t t = 0; t < nt; t++)
+		{
+			for(size_t i = 0; i < screen_scratch[t].surv_id.size(); i++)
+			{
+				order.push_back(std::make_pair(screen_scratch[t].surv_id[i], std::make_pair((uint32_t)t, (uint32_t)i)));
+			}
+		}
+		std::sort(order.begin(), order.end());
+		for(size_t i = 0; i < order.size(); i++)
+		{
+			const ScreenScratch &sc = screen_scratch[order[i].second.first];
+			const uint32_t j = order[i].second.second;
+			ahead_id.push_back(order[i].first);
+			ahead_off.push_back((uint32_t)ahead_elem.size());
+			ahead_elem.insert(ahead_elem.end(), sc.surv_elem.begin() + sc.surv_off[j], sc.surv_elem.begin() + sc.surv_off[j + 1]);
+		}
+		ahead_off.push_back((uint32_t)ahead_elem.size());
 		return ids.size();
+	}
+
+	// ---- run-ahead prefetchers of the ordered part.  The exact calls of a chunk jump between loci of a working set far
+	// beyond the last-level cache (29 B per element), and what the screen touched is long evicted when the ordered loop
+	// gets there.  While the loop works on vertex i, helper threads issue prefetches for the neighbourhoods of the
+	// instances of the survivors a few vertices ahead.  They execute nothing but prefetch instructions on addresses
+	// computed from the survivor list (immutable during the loop) and the array bases as of ahead_start(): no load from a
+	// structure the ordered loop mutates, and a prefetch of a stale address cannot fault.  Results do not depend on them.
+	std::vector<uint32_t> ahead_id, ahead_off;
+	std::vector<int32_t> ahead_elem;
+	std::atomic<uint32_t> ahead_pos{0};                  // vertex id the ordered loop has reached
+	std::atomic<bool> ahead_quit{false};
+	std::vector<std::thread> ahead_threads;
+	size_t ahead_helpers = 3, ahead_lead = 24;
+
+	void ahead_start()
+	{
+		ahead_stop();
+		if(ahead_id.size() < 64 || ahead_helpers == 0) return;
+		ahead_quit.store(false);
+		ahead_pos.store(ahead_id[0]);
+		const char *b_ch = ch.data();
+		const char *b4[7] = {reinterpret_cast<const char*>(opos.data()), reinterpret_cast<const char*>(nxt.data()),
+			reinterpret_cast<const char*>(prv.data()), reinterpret_cast<const char*>(mark[0].data()),
+			reinterpret_cast<const char*>(mark[1].data()), reinterpret_cast<const char*>(node_of[0].data()),
+			reinterpret_cast<const char*>(node_of[1].data())};
+		const int64_t n_el = (int64_t)ch.size();
+		const int64_t reach = (int64_t)(D + 2 * k + 16);
+		const size_t H = ahead_helpers, lead = ahead_lead;
+		for(size_t h = 0; h < H; h++)
+		{
+			ahead_threads.emplace_back([this, h, H, lead, b_ch, b4, n_el, reach]() {
+				const char *base4[7];
+				for(int a = 0; a < 7; a++) base4[a] = b4[a];
+				for(size_t j = h; j < ahead_id.size(); j += H)
+				{
+					if(j >= lead)
+					{
+						const uint32_t gate = ahead_id[j - lead];
+						while(ahead_pos.load(std::memory_order_relaxed) < gate)
+						{
+							if(ahead_quit.load(std::memory_order_relaxed)) return;
+							std::this_thread::yield();
+						}
+					}
+					for(uint32_t x = ahead_off[j]; x < ahead_off[j + 1]; x++)
+					{
+						const int64_t e = ahead_elem[x];
+						const int64_t lo = e - reach < 0 ? 0 : e - reach, hi = e + reach + 1 > n_el ? n_el : e + reach + 1;
+						for(int64_t a = lo & ~int64_t(63); a < hi; a += 64) __builtin_prefetch(b_ch + a, 0, 2);
+						for(int arr = 0; arr < 7; arr++)
+						{
+							for(int64_t a = (lo * 4) & ~int64_t(63); a < hi * 4; a += 64) __builtin_prefetch(base4[arr] + a, 0, 2);
+						}
+					}
+				}
+			});
+		}
+	}
+	~Simplifier() { ahead_stop(); }
+	void ahead_stop()
+	{
+		ahead_quit.store(true);
+		for(std::thread &x : ahead_threads) x.join();
+		ahead_threads.clear();
 	}
 
 	void update_bifurcations(const std::vector<int32_t> &start_kmer, VisitData source, VisitData target,
@@ -673,55 +795,75 @@ public:
 	void mark_dirty_around(It t0, size_t new_distance)
 	{
 		const size_t reach = std::max(D, k + 1) + 1;
-		// the region spans offsets [0, new_distance + 2k) from the target's start in its strand direction
-		It lo = t0, hi = t0;
+		const uint32_t *m0 = mark[0].data(), *m1 = mark[1].data();
+		const int32_t *nx = nxt.data(), *pv = prv.data();
+		uint8_t *dr = dirty.data();
+		// marks are sparse: one test decides the common element that carries none (NO_BIF is all ones)
+		auto both = [&](int32_t e) {
+			const uint32_t v0 = m0[e], v1 = m1[e];
+			if((v0 & v1) != NO_BIF)
+			{
+				if(v0 != NO_BIF) dr[v0] = 1;
+				if(v1 != NO_BIF) dr[v1] = 1;
+			}
+		};
+		// The region spans offsets [0, new_distance + 2k) from the target's start in its strand direction (towards smaller
+		// positive positions for a negative-strand target); [lo, hi] are its end points in positive order.  One walk finds
+		// them and flags the marks of both strands on the way.
+		int32_t lo = t0.e, hi = t0.e;
+		both(t0.e);
 		if(t0.d == 1)
 		{
-			// walk in positive order: the region lies towards smaller positive positions for a negative-strand target
-			It x = t0;
-			for(size_t i = 0; i < new_distance + 2 * k; i++)
+			for(size_t i = 0; i < new_distance + 2 * k && pv[lo] >= 0; i++)
 			{
-				if(prv[x.e] < 0) break;
-				x.e = prv[x.e];
+				lo = pv[lo];
+				both(lo);
 			}
-			lo = x;
-			hi = t0;
 		}
 		else
 		{
-			It x = t0;
-			for(size_t i = 0; i < new_distance + 2 * k; i++)
+			for(size_t i = 0; i < new_distance + 2 * k && nx[hi] >= 0; i++)
 			{
-				if(nxt[x.e] < 0) break;
-				x.e = nxt[x.e];
+				hi = nx[hi];
+				both(hi);
 			}
-			lo = t0;
-			hi = x;
 		}
-		// A positive-strand instance at x reads the elements [x, x + reach], a negative-strand one [x - reach, x]: only
-		// positive marks at or before the region's end and negative marks at or after its start can see it.
-		int32_t a = lo.e, b = hi.e;
-		for(size_t i = 0; i < reach && prv[a] >= 0; i++) a = prv[a];
-		for(size_t i = 0; i < reach && nxt[b] >= 0; i++) b = nxt[b];
-		int zone = a == lo.e ? 1 : 0;                    // 0 before the region, 1 inside, 2 after
-		for(int32_t e = a; ; e = nxt[e])
+		// A positive-strand instance at x reads the elements [x, x + reach], a negative-strand one [x - reach, x]: outside
+		// the region only positive marks before it and negative marks after it can see it.
+		int32_t e = lo;
+		for(size_t i = 0; i < reach && pv[e] >= 0; i++)
 		{
-			if(zone == 0 && e == lo.e) zone = 1;
-			if(zone != 2 && mark[0][e] != NO_BIF) dirty[mark[0][e]] = 1;
-			if(zone != 0 && mark[1][e] != NO_BIF) dirty[mark[1][e]] = 1;
-			if(e == b) break;
-			if(zone == 1 && e == hi.e) zone = 2;
+			e = pv[e];
+			const uint32_t v = m0[e];
+			if(v != NO_BIF) dr[v] = 1;
+		}
+		e = hi;
+		for(size_t i = 0; i < reach && nx[e] >= 0; i++)
+		{
+			e = nx[e];
+			const uint32_t v = m1[e];
+			if(v != NO_BIF) dr[v] = 1;
 		}
 	}
 
+	std::vector<std::pair<size_t, size_t> > look_forward, look_back;   // scratch of collapse_bulge_greedily()
 	void collapse_bulge_greedily(std::vector<int32_t> &start_kmer, VisitData source, VisitData target)   // :284-327
 	{
-		std::vector<std::pair<size_t, size_t> > look_forward, look_back;
 		const It t0 = node_it(start_kmer[target.kmerId]);
-		erase_bifurcations(start_kmer, target, look_forward, look_back);
+		{
+			SIB_PROF(5);
+			erase_bifurcations(start_kmer, target, look_forward, look_back);
+		}
 		const It source_it = node_it(start_kmer[source.kmerId]);
-		replace(advance(source_it, k), source.distance, advance(t0, k), target.distance);
-		update_bifurcations(start_kmer, source, target, look_forward, look_back);
+		{
+			SIB_PROF(6);
+			replace(advance(source_it, k), source.distance, advance(t0, k), target.distance);
+		}
+		{
+			SIB_PROF(7);
+			update_bifurcations(start_kmer, source, target, look_forward, look_back);
+		}
+		SIB_PROF(8);                                     // mark_dirty_around
 		// Vertices whose walks can see the rewritten region: marks that sat INSIDE the region were erased or re-added
 		// above (erase_point / add_point flag their vertices); everything else within reach still carries its mark and
 		// is found by one pass over the region's surroundings (the region's end points are elements that did not move).
@@ -738,9 +880,10 @@ public:
 	std::vector<int> ord;
 
 	static const int PREFETCH_LINES = 10;                // 10 x 16 elements ~ the 150-element reach of the first stage
-	size_t remove_bulges(size_t bif_id)                  // RemoveBulges, :330-430
+	size_t remove_bulges(size_t bif_id, bool expect_bulge = false)   // RemoveBulges, :330-430
 	{
 		size_t ret = 0;
+		SIB_PROF(0);                                     // whole call
 		list_positions(bif_id, start_kmer);
 		if(start_kmer.size() < 2) return ret;
 		// The instances of a vertex lie far apart (different strains): start all their cache misses at once.  The walks
@@ -766,14 +909,20 @@ public:
 			const It it = node_it(start_kmer[i]);
 			if(proper_kmer(it, k + 1)) end_char[i] = deref(advance(it, k));
 		}
-		if(!any_bulges(start_kmer, end_char, bulges)) return ret;
+		{
+			SIB_PROF(1);
+			if(!any_bulges(start_kmer, end_char, bulges, expect_bulge)) return ret;
+		}
 		for(size_t num_bulge = 0; num_bulge < bulges.size(); ++num_bulge)
 		{
 			for(size_t id_i = 0; id_i < bulges[num_bulge].size(); ++id_i)
 			{
 				const size_t kmer_i = bulges[num_bulge][id_i];
 				if(!n_valid[start_kmer[kmer_i]]) continue;
-				fill_visit(node_it(start_kmer[kmer_i]), visit);
+				{
+					SIB_PROF(2);
+					fill_visit(node_it(start_kmer[kmer_i]), visit);
+				}
 				for(size_t id_j = id_i + 1; id_j < bulges[num_bulge].size(); ++id_j)
 				{
 					const size_t kmer_j = bulges[num_bulge][id_j];
@@ -796,10 +945,17 @@ public:
 							jdata.distance = step;
 							idata.kmerId = kmer_i;
 							idata.distance = vt->distance;
-							if(overlap(start_kmer, idata, jdata) || now_bif == bif_id) break;
+							{
+								SIB_PROF(3);
+								if(overlap(start_kmer, idata, jdata) || now_bif == bif_id) break;
+							}
 							++ret;
-							const size_t imlp = max_bifurcation_multiplicity(node_it(start_kmer[kmer_i]), idata.distance);
-							const size_t jmlp = max_bifurcation_multiplicity(node_it(start_kmer[kmer_j]), jdata.distance);
+							size_t imlp, jmlp;
+							{
+								SIB_PROF(4);
+								imlp = max_bifurcation_multiplicity(node_it(start_kmer[kmer_i]), idata.distance);
+								jmlp = max_bifurcation_multiplicity(node_it(start_kmer[kmer_j]), jdata.distance);
+							}
 							const bool iless = imlp > jmlp || (imlp == jmlp && idata.kmerId < jdata.kmerId);
 							if(iless)
 							{
@@ -818,7 +974,10 @@ public:
 				}
 			}
 		}
-		cleanup();
+		{
+			SIB_PROF(9);
+			cleanup();
+		}
 		return ret;
 	}
 };

@@ -303,6 +303,8 @@ extern "C" int sibgpu_simplify(sibgpu_ctx *ctx, char **seq, uint32_t **origpos, 
 	sibgpu_free(pos);
 	sibgpu_free(neg);
 	S.slot_of.assign((size_t)count + 1, -1);
+	if(const char *e = getenv("SIBGPU_AHEAD_HELPERS")) S.ahead_helpers = (size_t)atoi(e);   // dev: 0 = no run-ahead prefetchers
+	if(const char *e = getenv("SIBGPU_AHEAD_LEAD")) S.ahead_lead = (size_t)std::max(1, atoi(e));
 	lap("build host state");
 
 	// ---- SimplifyGraph, blockfinder.cpp:16-51
@@ -328,15 +330,26 @@ extern "C" int sibgpu_simplify(sibgpu_ctx *ctx, char **seq, uint32_t **origpos, 
 		{
 			const size_t chunk_hi = std::min(max_id + 1, chunk_lo + CHUNK);
 			for(size_t id = chunk_lo; id < chunk_hi; id++) n_flag += flag[id];
-			n_screened += S.screen_range(chunk_lo, chunk_hi, flag.data());
+			const size_t screened_here = S.screen_range(chunk_lo, chunk_hi, flag.data());
+			n_screened += screened_here;
+			if(screened_here) S.ahead_start();              // helper threads prefetch the loci of the vertices ahead
+			size_t survivor = 0;                            // cursor into the screen's survivors (ascending ids)
 			// ---- the reference's sweep, skipping the vertices whose negative outcome is already known
 			for(size_t id = chunk_lo; id < chunk_hi; id++)
 			{
 				if(flag[id] || S.dirty[id])
 				{
+					S.ahead_pos.store((uint32_t)id, std::memory_order_relaxed);
 					n_calls++;
 					S.dirty[id] = 0;                        // clean as of this visit; the call itself may dirty it again
-					total_bulges += S.remove_bulges(id);
+					// a vertex the screen has just seen a bulge for: its exact call skips the early-out existence pass
+					bool expect = false;
+					if(screened_here)
+					{
+						while(survivor < S.ahead_id.size() && S.ahead_id[survivor] < id) survivor++;
+						expect = survivor < S.ahead_id.size() && S.ahead_id[survivor] == id;
+					}
+					total_bulges += S.remove_bulges(id, expect);
 				}
 				if(++cnt >= threshold && progress)
 				{
@@ -345,6 +358,7 @@ extern "C" int sibgpu_simplify(sibgpu_ctx *ctx, char **seq, uint32_t **origpos, 
 					progress(total_progress, 1, user);
 				}
 			}
+			S.ahead_stop();
 		}
 		if(trace)
 		{
@@ -352,6 +366,14 @@ extern "C" int sibgpu_simplify(sibgpu_ctx *ctx, char **seq, uint32_t **origpos, 
 				"%zu exact calls, %zu collapses\n", iterations, max_id + 1, n_flag, n_screened, n_calls, S.collapses - collapses_before);
 		}
 		lap("ordered host commit");
+#ifdef SIBGPU_COMMIT_PROF
+		if(trace)
+		{
+			static const char *names[10] = {"remove_bulges (whole)", "any_bulges", "fill_visit", "overlap", "max_multiplicity",
+				"erase_bifurcations", "replace", "update_bifurcations", "mark_dirty_around", "cleanup"};
+			for(int i = 0; i < 10; i++) fprintf(stderr, "[commit prof] %-24s %10.1f Mcycles\n", names[i], commit_prof().t[i] / 1e6);
+		}
+#endif
 		if(S.collapses == collapses_before)
 		{
 			// Nothing changed in this sweep, so every further sweep of the reference (it keeps sweeping while the

@@ -124,7 +124,9 @@ extern "C" int host_simplify(uint32_t nchr, char **seq, uint32_t **origpos, uint
 			// superset of the vertices with bulges), afterwards only the vertices dirtied since their last visit
 			if(dirty_mode == 2 ? !S.dirty[id] : (dirty_mode && iterations > 1 && !S.dirty[id])) continue;
 			S.dirty[id] = 0;
-			total_bulges += S.remove_bulges(id);
+			// as in the product: survivors of the screen skip the existence pass of any_bulges
+			const bool expect = dirty_mode == 2 && std::binary_search(S.ahead_id.begin(), S.ahead_id.end(), (uint32_t)id);
+			total_bulges += S.remove_bulges(id, expect);
 			calls++;
 		}
 	}
