@@ -742,6 +742,7 @@ int dist2_run(sibgpu_ctx *ctx, const HostSrc *src, int *status)
 	ssrc.epoch = epoch;
 	ssrc.W = W;
 	ssrc.p0 = rank * PL;
+	ssrc.rot = rank;
 	const uint32_t tiles_per_seg = (uint32_t)((ctx->x_seg_cap + RecOps<uint64_t>::TILE - 1) / RecOps<uint64_t>::TILE);
 	uint32_t *d_flags = reinterpret_cast<uint32_t*>(ds + 11);
 	SIB_TRY(launch_split<uint64_t>(ctx, ssrc, PL, tiles_per_seg, sub_bits, ctx->x_nrec / W, d_flags));
@@ -953,6 +954,7 @@ int dist2_run_fp(sibgpu_ctx *ctx, const HostSrc *src, uint32_t attempt, int *sta
 	ssrc.epoch = epoch;
 	ssrc.W = W;
 	ssrc.p0 = rank * PL;
+	ssrc.rot = rank;
 	const uint32_t tiles_per_seg = (uint32_t)((ctx->x_seg_cap + RecOps<uint64_t>::TILE - 1) / RecOps<uint64_t>::TILE);
 	SIB_TRY(launch_split<uint64_t>(ctx, ssrc, PL, tiles_per_seg, sub_bits, ctx->x_nrec / W, d_flags));
 	SIB_TRY((launch_group<uint64_t, true>(ctx, nbuckets, sub_bits, ctx->x_nrec / W, d_flags, keys, key_cap,

@@ -145,6 +145,8 @@ struct SplitSrc {
 	unsigned long long seg_cap;
 	unsigned long long epoch;
 	uint32_t W, p0;                                    // number of sources, first owned partition
+	uint32_t rot;                                      // source visited first (sharded: the own rank, so that the ranks
+	                                                   // pull from different peers at any one time)
 };
 
 __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p)
@@ -204,12 +206,12 @@ __global__ void __launch_bounds__(SPLIT_THREADS, STAGES == 1 ? 3 : (sizeof(R) ==
 	}
 	__syncthreads();
 	// elected thread: first non-empty tile at or after t (stride gridDim.x); starts its bulk copy into stage st and
-	// publishes (n, p) there; n = 0: no tile left.  Tile t = (partition t % P1, source (t / P1) % W, chunk t / P1 / W).
+	// publishes (n, p) there; n = 0: no tile left.  Tile t = (partition t % P1, source (t / P1 + rot) % W, chunk t / P1 / W).
 	uint32_t seen = 0;                                 // sources whose step flag this CTA has already observed
 	auto fetch = [&](uint32_t t, int st) -> uint32_t {
 		for(; t < ntiles; t += gridDim.x)
 		{
-			const uint32_t p = t % P1, x = t / P1, sidx = x % src.W, chunk = x / src.W;
+			const uint32_t p = t % P1, x = t / P1, sidx = (x + src.rot) % src.W, chunk = x / src.W;
 			if(src.header[sidx] && !((seen >> sidx) & 1u))
 			{
 				if(!wait_epoch(&src.header[sidx]->epoch_scatter, src.epoch))
