@@ -100,6 +100,7 @@ def test_sharded_enumeration_matches_oracle(built, world, k, seed, big, part):
 
 @pytest.mark.parametrize("world,k,seed,big,part", [
     (2, 33, 11, False, 0), (3, 100, 12, False, 0), (2, 64, 13, True, 65536), (4, 500, 14, True, 0), (2, 5000, 15, True, 0),
+    (8, 40, 18, False, 0),                               # 7 text tiles over 8 ranks: one rank owns partitions but no text
 ])
 def test_sharded_fingerprint_k(built, world, k, seed, big, part):
     """k > 32 (the later -s loose stages) through the fused path: packed text replicated by peer pulls, fingerprint
