@@ -3,16 +3,17 @@
 // (libdivsufsort + Kasai LCP) to find the classes of equal k-mers; here the classes are found by hashing:
 //
 //   K0 k_pack         ASCII text -> 2-bit packed words (+ legality check)                 1 B/base read, .25 written
-//   K1 k_scan_hist    rolling canonical k-mer keys of every position -> histogram over P hash partitions
-//   K2 k_scatter      same scan, records (key, context) counting-sorted per CTA in shared memory and written to
-//                     their partition in coalesced runs
-//   K3 k_insert       one partition at a time (sized so its open-addressing table stays resident in the 126 MB L2):
-//                     claim the slot of the key (CAS), OR the occurrence's predecessor/successor symbols into it
-//   K4 k_table_scan   apply the reference's predicate (vertexenumeration.cpp:67-70,330,348) to every class,
-//                     append the bifurcation k-mers, reset the table
+//   K1 k_scatter      rolling canonical k-mer keys of every position; records (mixed key, context) counting-sorted per
+//                     CTA in shared memory and written to fixed-capacity hash partitions in coalesced runs
+//   K2 k_split        (group_smem.cuh) every partition split once more into buckets of ~1 Ki records; tiles arrive by TMA
+//   K3 k_group        (group_smem.cuh) one bucket at a time per CTA in shared memory: open-addressing table, shared
+//                     atomics, the reference's predicate (vertexenumeration.cpp:67-70,330,348), warp-ballot key append
+//      fallbacks      k_scan_hist + k_part_offsets (exactly sized partitions when a fixed-capacity region overflows);
+//                     k_insert + k_table_scan (one L2-resident table per partition when a bucket overflows)
 //   K5 k_expand / cub sort / k_build_map    vertex id = lexicographic rank among {w, revcomp(w)} (:350)
 //   K6 k_mark, K7 k_emit   second scan of the packed text: positions whose canonical key is a vertex, compacted in
 //                     text order -> the two (chr,pos)-sorted instance tables (:361-362)
+//   k > 32            fingerprint.cu (k_fp_ckpt) + scan16_fp below: rolling fingerprints fused into K1 / K6
 //
 // Both strands are handled with ONE record per text position: the record carries the canonical key
 // min(w, revcomp(w)) and the neighbour symbols re-expressed in the canonical orientation, so the class of w and the

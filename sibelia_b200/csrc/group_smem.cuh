@@ -1,6 +1,7 @@
-// Shared-memory grouping of the k-mer records (included by enumerate.cu; 8-byte records, k <= 28).
+// Shared-memory grouping of the k-mer records (included by enumerate.cu; 8-byte records for k <= 28 and for the
+// fingerprints of k > 32, 16-byte records for k = 29..32).
 //
-// The hash partitions written by k_scatter (level 1, ~512 Ki records each) are split once more into buckets of ~1 Ki
+// The hash partitions written by k_scatter (level 1, ~256 Ki records each) are split once more into buckets of ~1 Ki
 // records (k_split: one coalesced read + one coalesced write of every record), and each bucket is then grouped
 // entirely inside one SM (k_group): a TMA bulk copy (cp.async.bulk + mbarrier) brings the bucket's records into shared
 // memory, every record claims the slot of its key in a shared-memory open-addressing table of 32-bit entries
