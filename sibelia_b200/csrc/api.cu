@@ -47,6 +47,17 @@ int sibgpu_ctx::ensure_copy_stream(uint32_t nchunks)
 	return SIBGPU_OK;
 }
 
+int sibgpu_ctx::ensure_stage(size_t piece_bytes)
+{
+	if(h_stage && stage_piece >= piece_bytes) return SIBGPU_OK;
+	if(h_stage) cudaFreeHost(h_stage);
+	h_stage = nullptr;
+	stage_piece = 0;
+	SIB_CUDA(cudaMallocHost(&h_stage, piece_bytes * STAGE_SLOTS));
+	stage_piece = piece_bytes;
+	return SIBGPU_OK;
+}
+
 cudaEvent_t sibgpu_ctx::get_event()
 {
 	if(events_used == event_pool.size())
@@ -145,6 +156,7 @@ int sibgpu_create(int device, sibgpu_ctx **out)
 	if(const char *e = getenv("SIBGPU_GROUP_SMEM")) c->group_smem = atoi(e);
 	if(const char *e = getenv("SIBGPU_SPLIT_STAGES")) c->split_stages = atoi(e) == 1 ? 1 : 2;
 	if(const char *e = getenv("SIBGPU_PIECEWISE")) c->piecewise_split = atoi(e) != 0;
+	if(const char *e = getenv("SIBGPU_STAGE_THREADS")) c->stage_threads = atoi(e);
 	if(const char *e = getenv("SIBGPU_CKEYS_INIT")) c->ckeys_init = strtoull(e, nullptr, 10);
 	if(const char *e = getenv("SIBGPU_TABLE_FACTOR"))
 	{
@@ -177,6 +189,7 @@ void sibgpu_destroy(sibgpu_ctx *c)
 	for(DevBuf *b : bufs) b->release();
 	for(cudaEvent_t e : c->event_pool) cudaEventDestroy(e);
 	if(c->h_scalars) cudaFreeHost(c->h_scalars);
+	if(c->h_stage) cudaFreeHost(c->h_stage);
 	if(c->ev_begin) cudaEventDestroy(c->ev_begin);
 	if(c->ev_end) cudaEventDestroy(c->ev_end);
 	for(int i = 0; i < 8; i++)

@@ -85,6 +85,13 @@ struct sibgpu_ctx {
 	cudaEvent_t ev_fork_copy = nullptr;
 	std::vector<cudaEvent_t> ev_chunk;
 	int ensure_copy_stream(uint32_t nchunks);
+	// pageable host sources (std::string::data() of the reference's facade): the pieces are copied by host threads into a
+	// ring of pinned staging buffers and go to the device from there (env SIBGPU_STAGE_THREADS, 0 = let the driver stage)
+	void *h_stage = nullptr;
+	size_t stage_piece = 0;                            // bytes per ring slot
+	static constexpr uint32_t STAGE_SLOTS = 4;
+	int stage_threads = 4;                             // 4: 4.5 ms per 100 MB end to end, 8: 4.8, 16: 5.7 (driver staging: 10.9)
+	int ensure_stage(size_t piece_bytes);
 	int insert_variant = 1;                            // 1 = CAS first, one record per thread (env SIBGPU_INSERT_VARIANT, dev)
 	int n_streams = 4;                                 // overlapped partition streams (env SIBGPU_STREAMS)
 	cudaStream_t aux_stream[8] = {};

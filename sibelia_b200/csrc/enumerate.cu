@@ -19,6 +19,9 @@
 // min(w, revcomp(w)) and the neighbour symbols re-expressed in the canonical orientation, so the class of w and the
 // class of revcomp(w) (which the reference enumerates separately and symmetrically) are decided once.
 #include <algorithm>
+#include <atomic>
+#include <memory>
+#include <thread>
 #include <type_traits>
 #include <cub/cub.cuh>
 
@@ -1232,6 +1235,100 @@ int copy_text_range(sibgpu_ctx *ctx, const HostSrc &src, uint64_t lo, uint64_t h
 	return SIBGPU_OK;
 }
 
+// Pageable host sources.  cudaMemcpyAsync from pageable memory is staged by the driver on the calling thread at
+// ~9 GB/s; here `nthreads` host threads copy the pieces of text piece c into slot c % STAGE_SLOTS of a pinned ring while
+// the earlier pieces are on their way to the device, and the copies to the device start from the ring.
+struct HostStager {
+	struct Piece { uint64_t text_off; const char *src; uint64_t bytes; };
+	sibgpu_ctx *ctx;
+	std::vector<std::vector<Piece> > pieces;           // per text piece: the chromosome stretches it consists of
+	std::vector<uint64_t> lo;                          // first text byte of every piece
+	std::unique_ptr<std::atomic<uint32_t>[]> done;     // threads that have staged piece c
+	std::atomic<uint32_t> free_upto{0};                // pieces [0, free_upto) may be written into their ring slots
+	std::atomic<bool> quit{false};
+	std::vector<std::thread> th;
+	uint32_t nthreads = 0;
+
+	static bool pageable(const void *p)
+	{
+		cudaPointerAttributes a;
+		if(cudaPointerGetAttributes(&a, p) != cudaSuccess)
+		{
+			cudaGetLastError();
+			return true;
+		}
+		return a.type == cudaMemoryTypeUnregistered;
+	}
+	int start(sibgpu_ctx *c, const HostSrc &src, uint32_t nchunks, uint64_t chunk_bytes)
+	{
+		ctx = c;
+		nthreads = (uint32_t)std::max(1, std::min<int>(c->stage_threads, (int)std::thread::hardware_concurrency()));
+		SIB_TRY(c->ensure_stage(chunk_bytes));
+		pieces.resize(nchunks);
+		lo.resize(nchunks);
+		const std::vector<uint32_t> &cs = c->h_chr_start;
+		for(uint32_t k = 0; k < nchunks; k++)
+		{
+			const uint64_t a0 = (uint64_t)k * chunk_bytes, a1 = k + 1 == nchunks ? c->M : a0 + chunk_bytes;
+			lo[k] = a0;
+			size_t ch = std::upper_bound(cs.begin(), cs.end(), (uint32_t)a0) - cs.begin();
+			if(ch > 0) ch--;
+			for(; ch < c->nchr && cs[ch] < a1; ch++)
+			{
+				const uint64_t s = cs[ch], e = s + c->h_chr_len[ch];
+				const uint64_t a = s > a0 ? s : a0, b = e < a1 ? e : a1;
+				if(b > a) pieces[k].push_back(Piece{a, src.chr[ch] + (a - s), b - a});
+			}
+		}
+		done.reset(new std::atomic<uint32_t>[nchunks]);
+		for(uint32_t k = 0; k < nchunks; k++) done[k].store(0);
+		free_upto.store(std::min<uint32_t>(nchunks, sibgpu_ctx::STAGE_SLOTS));
+		for(uint32_t t = 0; t < nthreads; t++)
+		{
+			th.emplace_back([this, t, nchunks]() {
+				for(uint32_t k = 0; k < nchunks; k++)
+				{
+					while(free_upto.load(std::memory_order_acquire) <= k) std::this_thread::yield();
+					if(quit.load(std::memory_order_relaxed)) return;
+					char *slot = static_cast<char*>(ctx->h_stage) + (size_t)(k % sibgpu_ctx::STAGE_SLOTS) * ctx->stage_piece;
+					for(const Piece &p : pieces[k])
+					{
+						// stripes of whole cache lines
+						const uint64_t lines = (p.bytes + 63) / 64;
+						const uint64_t b = lines * t / nthreads * 64, e = std::min<uint64_t>(p.bytes, lines * (t + 1) / nthreads * 64);
+						if(e > b) memcpy(slot + (p.text_off - lo[k]) + b, p.src + b, e - b);
+					}
+					done[k].fetch_add(1, std::memory_order_release);
+				}
+			});
+		}
+		return SIBGPU_OK;
+	}
+	// waits for piece k to be staged, starts its copies to the device on `st`; ev[k] must be recorded on `st` by the caller
+	// afterwards.  Before that, the slot of piece k + 1 is released once its previous occupant has left for the device.
+	int issue(uint32_t k, cudaStream_t st, const std::vector<cudaEvent_t> &ev)
+	{
+		if(k + 1 >= sibgpu_ctx::STAGE_SLOTS)
+		{
+			SIB_CUDA(cudaEventSynchronize(ev[k + 1 - sibgpu_ctx::STAGE_SLOTS]));
+			free_upto.store(k + 2, std::memory_order_release);
+		}
+		while(done[k].load(std::memory_order_acquire) < nthreads) std::this_thread::yield();
+		const char *slot = static_cast<const char*>(ctx->h_stage) + (size_t)(k % sibgpu_ctx::STAGE_SLOTS) * ctx->stage_piece;
+		for(const Piece &p : pieces[k])
+		{
+			SIB_CUDA(cudaMemcpyAsync(ctx->d_text.as<char>() + p.text_off, slot + (p.text_off - lo[k]), p.bytes, cudaMemcpyHostToDevice, st));
+		}
+		return SIBGPU_OK;
+	}
+	~HostStager()
+	{
+		quit.store(true);
+		free_upto.store(0xFFFFFFFFu, std::memory_order_release);   // nobody waits any more (error paths)
+		for(std::thread &x : th) x.join();
+	}
+};
+
 static int launch_pack(sibgpu_ctx *ctx, uint64_t w0, uint64_t w1)
 {
 	uint32_t *d_err = reinterpret_cast<uint32_t*>(ctx->d_scalars.as<uint64_t>() + 8);
@@ -1400,12 +1497,18 @@ static int enumerate_mode(sibgpu_ctx *ctx, uint32_t k, uint64_t nrec, const Host
 				ssrc.W = 1;
 				return launch_split<SR>(ctx, ssrc, P, tiles_per_seg, sub_bits, nrec_here, d_grp_flags);
 			};
+			HostStager stager;
+			bool staged = false;
 			if(src)
 			{
 				SIB_TRY(ctx->ensure_copy_stream(nchunks));
 				SIB_CUDA(cudaEventRecord(ctx->ev_fork_copy, st));              // the '$' fill and the tables precede the copies
 				SIB_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_fork_copy, 0));
-				for(uint32_t c = 0; c < nchunks; c++)
+				const char *first = nullptr;
+				for(uint32_t c = 0; c < ctx->nchr && !first; c++) first = ctx->h_chr_len[c] ? src->chr[c] : nullptr;
+				staged = ctx->stage_threads > 0 && nchunks > 1 && first && HostStager::pageable(first);
+				if(staged) SIB_TRY(stager.start(ctx, *src, nchunks, (uint64_t)CHUNK_TILES * TILE_POS));
+				for(uint32_t c = 0; c < nchunks && !staged; c++)
 				{
 					const uint64_t lo = (uint64_t)c * CHUNK_TILES * TILE_POS;
 					const uint64_t hi = c + 1 == nchunks ? ctx->M : lo + (uint64_t)CHUNK_TILES * TILE_POS;
@@ -1417,6 +1520,11 @@ static int enumerate_mode(sibgpu_ctx *ctx, uint32_t k, uint64_t nrec, const Host
 			for(uint32_t c = 0; c < nchunks; c++)
 			{
 				uint32_t tile_hi = ntiles;
+				if(staged)
+				{
+					SIB_TRY(stager.issue(c, ctx->copy_stream, ctx->ev_chunk));
+					SIB_CUDA(cudaEventRecord(ctx->ev_chunk[c], ctx->copy_stream));
+				}
 				if(src)
 				{
 					// pack the words of this piece; scatter the tiles whose staged words (one behind, 260 ahead) are packed
@@ -1691,7 +1799,25 @@ int enumerate_resident(sibgpu_ctx *ctx, uint32_t k, const HostSrc *src)
 	const bool pipelined = src && nrec > 0 && k <= 32;
 	if(!pipelined)
 	{
-		if(src) SIB_TRY(copy_text_range(ctx, *src, 0, ctx->M, st));
+		if(src)
+		{
+			const uint64_t chunk_bytes = (uint64_t)CHUNK_TILES * TILE_POS;
+			const uint32_t nchunks = (uint32_t)((ctx->M + chunk_bytes - 1) / chunk_bytes);
+			const char *first = nullptr;
+			for(uint32_t c = 0; c < ctx->nchr && !first; c++) first = ctx->h_chr_len[c] ? src->chr[c] : nullptr;
+			if(ctx->stage_threads > 0 && nchunks > 1 && first && HostStager::pageable(first))
+			{
+				HostStager stager;
+				SIB_TRY(ctx->ensure_copy_stream(nchunks));
+				SIB_TRY(stager.start(ctx, *src, nchunks, chunk_bytes));
+				for(uint32_t c = 0; c < nchunks; c++)
+				{
+					SIB_TRY(stager.issue(c, st, ctx->ev_chunk));
+					SIB_CUDA(cudaEventRecord(ctx->ev_chunk[c], st));
+				}
+			}
+			else SIB_TRY(copy_text_range(ctx, *src, 0, ctx->M, st));
+		}
 		src = nullptr;
 		SIB_TRY(launch_pack(ctx, 0, nwords));
 		SIB_CUDA(cudaMemcpyAsync(hs + 8, ctx->d_scalars.as<uint64_t>() + 8, 8, cudaMemcpyDeviceToHost, st));
