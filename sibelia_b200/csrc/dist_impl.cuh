@@ -47,7 +47,7 @@ static int dist_scatter_mode(sibgpu_ctx *ctx, uint32_t k, void *send_dev)
 	ctx->total_launches++;
 	if(ntiles)
 	{
-		size_t smem = sizeof(ScatterSmem<MODE>);
+		size_t smem = scatter_smem_bytes<MODE, false>();
 		SIB_CUDA(cudaFuncSetAttribute(k_scatter<MODE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 		const uint32_t g = ntiles < (uint32_t)ctx->sm_count * 4 ? ntiles : (uint32_t)ctx->sm_count * 4;
 		ProfScope ps(ctx, "k_scatter", (uint64_t)ntiles * TILE_POS / 4 + ctx->dist_nrec_local * sizeof(Rec));
@@ -248,7 +248,7 @@ static int dist_scatter_core(sibgpu_ctx *ctx, uint32_t k, uint32_t PT, uint64_t 
 	TextDesc t = ctx->dist_text;
 	const uint32_t ntiles = ctx->dist_tile_hi - ctx->dist_tile_lo;
 	if(!ntiles) return SIBGPU_OK;
-	size_t smem = sizeof(ScatterSmem<MODE>);
+	size_t smem = scatter_smem_bytes<MODE, MIXED>();
 	SIB_CUDA(cudaFuncSetAttribute(k_scatter<MODE, MIXED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 	// src: the own byte range is still on the host -- stream it in pieces of CHUNK_TILES tiles on the copy stream and
 	// pack + scatter every piece as it lands (same pipeline as sibgpu_enumerate, enumerate.cu)
@@ -283,7 +283,8 @@ static int dist_scatter_core(sibgpu_ctx *ctx, uint32_t k, uint32_t PT, uint64_t 
 		if(tile_end > tiles_done)
 		{
 			const uint32_t nt = tile_end - tiles_done;
-			const uint32_t g = nt < (uint32_t)ctx->sm_count * 4 ? nt : (uint32_t)ctx->sm_count * 4;
+			const uint32_t occ = MIXED && MODE == 0 ? SIBGPU_SCATTER_OCC : 4;
+			const uint32_t g = nt < (uint32_t)ctx->sm_count * occ ? nt : (uint32_t)ctx->sm_count * occ;
 			TextDesc tc = t;
 			tc.tile0 = tiles_done;
 			ProfScope ps(ctx, "k_scatter", (uint64_t)nt * TILE_POS / 4 * (MODE == 2 ? 10 : 1) + (uint64_t)nt * TILE_POS * sizeof(Rec));

@@ -284,7 +284,7 @@ __global__ void __launch_bounds__(MAX_PARTS) k_part_offsets(const uint32_t *__re
 template<int MODE> struct ScatterSmem {
 	uint32_t sw[TILE_THREADS + 5];
 	uint32_t cnt[MAX_PARTS];           // per-bin count of this tile, then exclusive local offset
-	unsigned long long gbase[MAX_PARTS]; // global index of the bin's run minus its local offset
+	uint32_t gbase[MAX_PARTS];         // index of the bin's run in `out` minus its local offset (mod 2^32: + local index >= offset)
 	uint32_t dropmask[MAX_PARTS / 32]; // bins whose run did not fit its fixed-capacity region
 	uint32_t total, anydrop;
 	uint64_t a[TILE_POS];
@@ -292,6 +292,15 @@ template<int MODE> struct ScatterSmem {
 };
 template<> struct ScatterSmem<1> : ScatterSmem<0> { uint64_t b[TILE_POS]; };
 template<> struct ScatterSmem<2> : ScatterSmem<0> { uint64_t sD[FP_SMEM_WORDS]; };
+// dynamic shared memory of k_scatter<MODE, MIXED>: mixed 8-byte records read their partition back from the record, their
+// kernel never touches bin_of (the last member of the MODE 0 layout)
+template<int MODE, bool MIXED> constexpr size_t scatter_smem_bytes()
+{
+	return MODE == 0 && MIXED ? offsetof(ScatterSmem<0>, bin_of) : sizeof(ScatterSmem<MODE>);
+}
+#ifndef SIBGPU_SCATTER_OCC
+#define SIBGPU_SCATTER_OCC 4
+#endif
 
 // cap != 0: partition b owns the fixed region [b * cap, (b + 1) * cap) of `out` and cursor[b] starts at b * cap (no
 // histogram pass needed); a run that does not fit raises *overflow and is dropped -- the host then redoes the
@@ -300,7 +309,7 @@ template<> struct ScatterSmem<2> : ScatterSmem<0> { uint64_t sD[FP_SMEM_WORDS]; 
 // partition is a bit field of it (group_smem.cuh); fingerprint records (MODE 2) are mixed the same way but take their
 // partition from the second hash
 template<int MODE, bool MIXED>
-__global__ void __launch_bounds__(TILE_THREADS, MODE == 0 ? 4 : (MODE == 1 ? 2 : 3)) k_scatter(TextDesc t, const FpView fv, uint32_t k,
+__global__ void __launch_bounds__(TILE_THREADS, MODE == 0 ? (MIXED ? SIBGPU_SCATTER_OCC : 4) : (MODE == 1 ? 2 : 3)) k_scatter(TextDesc t, const FpView fv, uint32_t k,
 	uint32_t ntiles, uint32_t P, unsigned long long *__restrict__ cursor, typename RecT<MODE>::type *__restrict__ out,
 	unsigned long long cap, uint32_t *__restrict__ overflow)
 {
@@ -382,7 +391,7 @@ __global__ void __launch_bounds__(TILE_THREADS, MODE == 0 ? 4 : (MODE == 1 ? 2 :
 			uint32_t b = threadIdx.x * BINS_PER_THREAD + j;
 			if(b < P)
 			{
-				s.gbase[b] = g[j] - o[j];
+				s.gbase[b] = (uint32_t)g[j] - o[j];
 				if(cap && c[j] && g[j] + c[j] > (b + 1ull) * cap)
 				{
 					*overflow = 1u;
@@ -401,7 +410,7 @@ __global__ void __launch_bounds__(TILE_THREADS, MODE == 0 ? 4 : (MODE == 1 ? 2 :
 			const uint64_t a = s.a[l];
 			const uint32_t bin = KEEP_BIN ? s.bin_of[l] : (MODE == 0 ? mixed_part(a >> 7, P) : __umulhi((uint32_t)(a >> 32), P));
 			if(drops && ((s.dropmask[bin >> 5] >> (bin & 31u)) & 1u)) continue;
-			unsigned long long gi = s.gbase[bin] + l;
+			const uint32_t gi = s.gbase[bin] + l;
 			if constexpr(NARROW) { reinterpret_cast<uint64_t*>(out)[gi] = a; }
 			else reinterpret_cast<ulonglong2*>(out)[gi] = make_ulonglong2(a, s.b[l]);
 		}
@@ -1416,9 +1425,9 @@ static int enumerate_mode(sibgpu_ctx *ctx, uint32_t k, uint64_t nrec, const Host
 	typedef typename std::conditional<MODE != 1, uint64_t, ulonglong2>::type SR;   // record type of the shared-memory path
 	typedef typename KeyT<MODE>::type Key;                 // entry of the vertex-key list
 	constexpr bool FP = MODE == 2;
-	const size_t scatter_smem = sizeof(ScatterSmem<MODE>);
+	const size_t scatter_smem = scatter_smem_bytes<MODE, false>(), scatter_smem_mixed = scatter_smem_bytes<MODE, true>();
 	SIB_CUDA(cudaFuncSetAttribute(k_scatter<MODE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scatter_smem));
-	SIB_CUDA(cudaFuncSetAttribute(k_scatter<MODE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scatter_smem));
+	SIB_CUDA(cudaFuncSetAttribute(k_scatter<MODE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scatter_smem_mixed));
 
 	for(uint32_t attempt = 0; ; attempt++)
 	{
@@ -1537,7 +1546,8 @@ static int enumerate_mode(sibgpu_ctx *ctx, uint32_t k, uint64_t nrec, const Host
 				if(tile_hi > tiles_done)
 				{
 					const uint32_t nt = tile_hi - tiles_done;
-					const uint32_t g = nt < (uint32_t)sms * 4 ? nt : (uint32_t)sms * 4;
+					const uint32_t occ = mixed && MODE == 0 ? SIBGPU_SCATTER_OCC : 4;
+					const uint32_t g = nt < (uint32_t)sms * occ ? nt : (uint32_t)sms * occ;
 					const uint32_t r = piecewise ? c : 0;
 					TextDesc tc = t;
 					tc.tile0 = tiles_done;
@@ -1546,7 +1556,7 @@ static int enumerate_mode(sibgpu_ctx *ctx, uint32_t k, uint64_t nrec, const Host
 							+ nrec * sizeof(Rec) * nt / ntiles);
 						unsigned long long *cursor_r = ctx->d_cursor.as<unsigned long long>() + (size_t)r * P * CURSOR_STRIDE;
 						Rec *out_r = ctx->d_records.as<Rec>() + (size_t)r * P * cap;
-						if(mixed) k_scatter<MODE, true><<<g, TILE_THREADS, scatter_smem, st>>>(tc, fp, k, nt, P, cursor_r, out_r, cap, d_overflow);
+						if(mixed) k_scatter<MODE, true><<<g, TILE_THREADS, scatter_smem_mixed, st>>>(tc, fp, k, nt, P, cursor_r, out_r, cap, d_overflow);
 						else k_scatter<MODE, false><<<g, TILE_THREADS, scatter_smem, st>>>(tc, fp, k, nt, P, cursor_r, out_r, cap, d_overflow);
 					}
 					if(piecewise) SIB_TRY(split_regions(r, nrec * nt / ntiles));
