@@ -190,6 +190,9 @@ void sibgpu_destroy(sibgpu_ctx *c)
 	for(cudaEvent_t e : c->event_pool) cudaEventDestroy(e);
 	if(c->h_scalars) cudaFreeHost(c->h_scalars);
 	if(c->h_stage) cudaFreeHost(c->h_stage);
+	c->d_sendbuf.release();
+	for(void *q : c->send_retired_old) cudaFree(q);
+	for(void *q : c->send_retired_new) cudaFree(q);
 	if(c->ev_begin) cudaEventDestroy(c->ev_begin);
 	if(c->ev_end) cudaEventDestroy(c->ev_end);
 	for(int i = 0; i < 8; i++)
@@ -739,7 +742,7 @@ int sibgpu_dist_scatter_local(sibgpu_ctx *c, uint32_t k, uint32_t *nparts_total,
 
 int sibgpu_dist_export_send(sibgpu_ctx *c, void *handle64)
 {
-	if(!c || !handle64 || !c->d_records.p)
+	if(!c || !handle64 || !c->d_sendbuf.p)
 	{
 		set_error("invalid: NULL argument or no send buffer yet (sibgpu_dist_scatter_local comes first)");
 		return SIBGPU_ERR_INVALID;
@@ -747,7 +750,7 @@ int sibgpu_dist_export_send(sibgpu_ctx *c, void *handle64)
 	static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
 	SIB_CUDA(cudaSetDevice(c->device));
 	cudaIpcMemHandle_t h;
-	SIB_CUDA(cudaIpcGetMemHandle(&h, c->d_records.p));
+	SIB_CUDA(cudaIpcGetMemHandle(&h, c->d_sendbuf.p));
 	memcpy(handle64, &h, 64);
 	return SIBGPU_OK;
 }

@@ -54,6 +54,10 @@ struct sibgpu_ctx {
 	std::vector<void*> peer_ptr;                       // [world], nullptr for the own rank / not mapped
 	std::vector<std::vector<unsigned char>> peer_handle;
 	sibgpu::DevBuf d_keystage;                         // vertex keys of the owned partitions
+	// the send buffer the peers map: never shared with another path, and a buffer that had to grow is freed two steps
+	// later (by then every peer has closed its mapping of it: it re-imports the handles at every step)
+	sibgpu::DevBuf d_sendbuf;
+	std::vector<void*> send_retired_old, send_retired_new;
 	// fused path (sibgpu_fused_*): ONE exported buffer per rank [header | cursors | vertex keys | segments]
 	sibgpu::DevBuf d_xbuf;
 	std::vector<void*> peer_x;                         // [world] mappings of the peers' exported buffers

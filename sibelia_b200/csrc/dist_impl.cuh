@@ -309,12 +309,22 @@ static int dist_scatter_local_mode(sibgpu_ctx *ctx, uint32_t k, uint64_t *counts
 	const uint64_t mean = ((uint64_t)ntiles * TILE_POS + PT - 1) / PT;
 	const uint64_t cap = (mean + mean / 8 + ctx->part_slack + 31) / 32 * 32;   // segments start 16-byte aligned (TMA)
 	ctx->dist_seg_cap = cap;
-	SIB_TRY(ctx->d_records.ensure(sizeof(Rec) * cap * PT + 256));
+	for(void *q : ctx->send_retired_old) cudaFree(q);
+	ctx->send_retired_old.swap(ctx->send_retired_new);
+	ctx->send_retired_new.clear();
+	const size_t send_bytes = sizeof(Rec) * cap * PT + 256;
+	if(ctx->d_sendbuf.cap < send_bytes && ctx->d_sendbuf.p)
+	{
+		ctx->send_retired_new.push_back(ctx->d_sendbuf.p);         // peers may still have it mapped
+		ctx->d_sendbuf.p = nullptr;
+		ctx->d_sendbuf.cap = 0;
+	}
+	SIB_TRY(ctx->d_sendbuf.ensure(send_bytes));
 	SIB_TRY(ctx->d_cursor.ensure(sizeof(uint64_t) * MAX_PARTS * CURSOR_STRIDE));
 	std::vector<uint64_t> base(PT), cur((size_t)PT * CURSOR_STRIDE, 0);
 	for(uint32_t p = 0; p < PT; p++) cur[(size_t)p * CURSOR_STRIDE] = base[p] = (uint64_t)p * cap;
 	SIB_CUDA(cudaMemcpyAsync(ctx->d_cursor.p, cur.data(), sizeof(uint64_t) * cur.size(), cudaMemcpyHostToDevice, st));
-	SIB_TRY((dist_scatter_core<MODE, false>(ctx, k, PT, cap, ctx->d_cursor.as<unsigned long long>(), ctx->d_records.as<Rec>(), src)));
+	SIB_TRY((dist_scatter_core<MODE, false>(ctx, k, PT, cap, ctx->d_cursor.as<unsigned long long>(), ctx->d_sendbuf.as<Rec>(), src)));
 	SIB_CUDA(cudaMemcpyAsync(cur.data(), ctx->d_cursor.p, sizeof(uint64_t) * cur.size(), cudaMemcpyDeviceToHost, st));
 	SIB_CUDA(cudaMemcpyAsync(hs + 8, ds + 8, sizeof(uint64_t) * 3, cudaMemcpyDeviceToHost, st));
 	SIB_CUDA(cudaStreamSynchronize(st));
@@ -407,7 +417,7 @@ static int dist_group_peer_mode(sibgpu_ctx *ctx, uint32_t k, const uint64_t *cou
 		{
 			const uint64_t c = counts[(size_t)s * PT + b0 + p];
 			if(c == 0) continue;
-			if(s == ctx->dist_rank) segs.ptr[nseg] = ctx->d_records.as<Rec>() + (uint64_t)(b0 + p) * seg_caps[s];
+			if(s == ctx->dist_rank) segs.ptr[nseg] = ctx->d_sendbuf.as<Rec>() + (uint64_t)(b0 + p) * seg_caps[s];
 			else segs.ptr[nseg] = static_cast<const Rec*>(ctx->peer_ptr[s]) + (uint64_t)(b0 + p) * seg_caps[s];
 			segs.cnt[nseg] = (uint32_t)c;
 			seg_tiles += (uint32_t)((c + tile_rec - 1) / tile_rec);
