@@ -89,6 +89,10 @@ class GpuShard:
                 return None
         raise RuntimeError("sibelia_b200.distributed: the vertex key regions kept overflowing")
 
+    def _rep_tensor(self, ptr, n):
+        """the library's array of class representatives as a tensor (zero copy)"""
+        return torch.as_tensor(_DeviceArray(ptr, n), device=self.device)
+
     def _fused_fp(self, chrs, group, download):
         """k > 32: the two halves of the fingerprint step with the min-reduction of the class representatives between
         them and the max-reduction of the verification flag behind them (include/sibgpu.h, sibgpu_fused_run_fp)."""
@@ -99,14 +103,15 @@ class GpuShard:
             if status == 1:
                 return None
             if ncls:
-                rep = torch.as_tensor(_DeviceArray(rep_ptr, ncls), device=self.device)
+                rep = self._rep_tensor(rep_ptr, ncls)
                 if dist.get_backend(group) == "nccl":
                     dist.all_reduce(rep, op=dist.ReduceOp.MIN, group=group)
                 else:
                     h = rep.cpu()
                     dist.all_reduce(h, op=dist.ReduceOp.MIN, group=group)
                     rep.copy_(h)
-                torch.cuda.synchronize(self.device)
+                if rep.is_cuda:
+                    torch.cuda.synchronize(self.device)
             count, ninst, collision = self.ctx.dist2_finish_fp()
             flag = _comm(torch.tensor([collision], dtype=torch.int64, device=self.device), group)
             dist.all_reduce(flag, op=dist.ReduceOp.MAX, group=group)

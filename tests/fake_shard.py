@@ -189,3 +189,91 @@ class NumpyPeerShard(NumpyShard):
                 segs.append(np.asarray(buf[p * cap:p * cap + n]))
         rec = np.concatenate(segs) if segs else np.zeros(0, dtype=np.uint64)
         return self.group(torch.from_numpy(rec.view(np.int64).copy()), None)
+
+
+class FakeFusedFpContext:
+    """Stand-in for the library behind GpuShard's fused k > 32 path (sibgpu_fused_plan / _alloc / _import / _run_fp /
+    _finish_fp), so that the orchestration of sibelia_b200.distributed -- collective (re)allocation of the exported
+    buffers, the min-reduction of the class representatives between the two halves of a step, the max-reduction of the
+    verification flag and the repeat with other hash bases -- runs under gloo on CPU.  The tables come from the oracle;
+    a "class" is a vertex id and its representative the smallest text position of its positive-strand instances.
+    script: regrow = the first run reports a key region too small (status 2); collide_rank = that rank reports a
+    verification failure on attempt 0."""
+    SENTINEL = 0x7F7F7F7F7F7F7F7F
+
+    def __init__(self, rank, world, regrow=False, collide_rank=None):
+        self.rank, self.world = rank, world
+        self.regrow_pending, self.collide_rank = regrow, collide_rank
+        self.alloc_needed = True
+        self.log = []
+
+    def dist2_plan(self, chrs, rank, world, k, resident):
+        assert (rank, world) == (self.rank, self.world) and k > 32
+        self.chrs, self.k = [np.asarray(c, dtype=np.uint8) for c in chrs], k
+        self.log.append("plan")
+        return 1 if self.alloc_needed else 0
+
+    def dist2_release_peers(self):
+        self.log.append("release")
+
+    def dist2_alloc(self):
+        self.alloc_needed = False
+        self.log.append("alloc")
+        return np.full(64, self.rank, dtype=np.uint8)
+
+    def dist2_import(self, handles):
+        assert handles.shape == (self.world, 64) and all((handles[s] == s).all() for s in range(self.world))
+        self.log.append("import")
+
+    def _tables(self):
+        from oracle import restate
+        count, pos, neg = restate.enumerate_bifurcations(self.chrs, self.k)
+        lens = np.array([len(c) for c in self.chrs], dtype=np.int64)
+        start = 1 + np.concatenate([[0], np.cumsum(lens + 1)[:-1]])
+        M = int(lens.sum() + len(lens) + 1)
+        ntiles = (M + TILE - 1) // TILE
+        lo, hi = ntiles * self.rank // self.world * TILE, ntiles * (self.rank + 1) // self.world * TILE
+        tp = start[pos["chr"]] + pos["pos"]
+        tn = start[neg["chr"]] + (lens[neg["chr"]] - neg["pos"] - self.k)
+        keep_n = np.flatnonzero((tn >= lo) & (tn < hi))
+        keep_n = keep_n[np.argsort(tn[keep_n], kind="stable")]
+        own = (tp >= lo) & (tp < hi)
+        glob = np.full(count, self.SENTINEL, dtype=np.int64)
+        np.minimum.at(glob, pos["bifId"].astype(np.int64), tp)
+        mine = np.full(count, self.SENTINEL, dtype=np.int64)
+        np.minimum.at(mine, pos["bifId"][own].astype(np.int64), tp[own])
+        return count, pos[own], neg[keep_n], mine, glob
+
+    def dist2_run_fp(self, chrs, resident, attempt):
+        self.log.append("run%d" % attempt)
+        if self.regrow_pending:
+            self.regrow_pending = False
+            self.alloc_needed = True                     # the next plan asks for the collective reallocation
+            return 2, 0, 0
+        self.attempt = attempt
+        self.count, self.pos, self.negtext, self.rep, self.want_rep = self._tables()
+        return 0, len(self.rep), 1
+
+    def dist2_finish_fp(self):
+        assert np.array_equal(self.rep, self.want_rep), "the representatives were not min-reduced over the ranks"
+        self.log.append("finish%d" % self.attempt)
+        collision = 1 if (self.attempt == 0 and self.collide_rank == self.rank) else 0
+        return self.count, len(self.pos), collision
+
+    def download(self):
+        return self.pos, self.negtext
+
+
+def fake_fused_fp_shard(rank, world, **script):
+    """a GpuShard whose context is the fake above and whose representative array lives in host memory"""
+    from sibelia_b200.distributed import GpuShard
+
+    class Shard(GpuShard):
+        def __init__(self):
+            self.ctx = FakeFusedFpContext(rank, world, **script)
+            self.device = torch.device("cpu")
+            self.fused = True
+
+        def _rep_tensor(self, ptr, n):
+            return torch.from_numpy(self.ctx.rep)        # shares memory: the all-reduce lands in the fake's array
+    return Shard()

@@ -74,3 +74,50 @@ def test_peer_orchestration_matches_oracle(tmp_path, world, k, seed):
 def test_peer_overflow_takes_the_staged_path_on_every_rank(tmp_path):
     fallbacks, _ = _run(2, 25, 5, str(tmp_path), seg_cap=16)       # far too small: every rank reports overflow
     assert fallbacks == 1
+
+
+def _worker_fp(rank, world, port, k, seed, q, script):
+    sys.path.insert(0, HERE)
+    sys.path.insert(0, os.path.dirname(HERE))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from sibelia_b200 import distributed as D
+    from fake_shard import fake_fused_fp_shard
+    chrs = helpers.strain_case(3, 9_000, p_sub=0.02, inv_len=700, seed=seed)
+    shard = fake_fused_fp_shard(rank, world, **script)
+    count, pos_part, neg_part = D.enumerate_sharded(shard, chrs, k)
+    count, pos, neg = D.gather_tables(count, pos_part, neg_part)
+    logs = [None] * world if rank == 0 else None
+    dist.gather_object(shard.ctx.log, logs, dst=0)
+    if rank == 0:
+        q.put((count, pos, neg, logs, shard.last_strategy.split()[0]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,k,script", [
+    (2, 40, {}), (3, 64, {"collide_rank": 1}), (2, 100, {"regrow": True}), (3, 33, {"regrow": True, "collide_rank": 2}),
+])
+def test_fused_fingerprint_orchestration(world, k, script):
+    """k > 32 fused strategy (sibgpu_fused_run_fp / _finish_fp): collective allocation of the exported buffers, the class
+    representatives min-reduced between the two halves, a verification failure on ONE rank repeats the step with other
+    hash bases on ALL ranks, a key region that is too small is regrown collectively"""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_fp, args=(r, world, port, k, 7, q, script)) for r in range(world)]
+    for p in procs:
+        p.start()
+    count, pos, neg, logs, strategy = q.get(timeout=240)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    chrs = helpers.strain_case(3, 9_000, p_sub=0.02, inv_len=700, seed=7)
+    helpers.assert_tables_equal((count, pos, neg), restate.enumerate_bifurcations(chrs, k), "world=%d k=%d" % (world, k))
+    assert strategy == "fused"
+    want = ["plan", "release", "alloc", "import"]
+    if script.get("regrow"):
+        want += ["run0", "plan", "release", "alloc", "import"]
+    want += ["run0", "finish0"] + (["run1", "finish1"] if "collide_rank" in script else [])
+    assert all(log == want for log in logs), logs
