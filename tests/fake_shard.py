@@ -208,7 +208,7 @@ class FakeFusedFpContext:
         self.log = []
 
     def dist2_plan(self, chrs, rank, world, k, resident):
-        assert (rank, world) == (self.rank, self.world) and k > 32
+        assert (rank, world) == (self.rank, self.world)
         self.chrs, self.k = [np.asarray(c, dtype=np.uint8) for c in chrs], k
         self.log.append("plan")
         return 1 if self.alloc_needed else 0
@@ -253,6 +253,16 @@ class FakeFusedFpContext:
         self.attempt = attempt
         self.count, self.pos, self.negtext, self.rep, self.want_rep = self._tables()
         return 0, len(self.rep), 1
+
+    def dist2_run(self, chrs, resident):
+        """k <= 28: the whole step is one call (sibgpu_fused_run)"""
+        self.log.append("run")
+        if self.regrow_pending:
+            self.regrow_pending = False
+            self.alloc_needed = True
+            return 2, 0, 0
+        self.count, self.pos, self.negtext, _, _ = self._tables()
+        return 0, self.count, len(self.pos)
 
     def dist2_finish_fp(self):
         assert np.array_equal(self.rep, self.want_rep), "the representatives were not min-reduced over the ranks"

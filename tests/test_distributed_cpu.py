@@ -98,9 +98,10 @@ def _worker_fp(rank, world, port, k, seed, q, script):
 
 @pytest.mark.parametrize("world,k,script", [
     (2, 40, {}), (3, 64, {"collide_rank": 1}), (2, 100, {"regrow": True}), (3, 33, {"regrow": True, "collide_rank": 2}),
+    (2, 25, {}), (3, 17, {"regrow": True}),              # k <= 28: sibgpu_fused_run, one call per step
 ])
-def test_fused_fingerprint_orchestration(world, k, script):
-    """k > 32 fused strategy (sibgpu_fused_run_fp / _finish_fp): collective allocation of the exported buffers, the class
+def test_fused_orchestration(world, k, script):
+    """fused strategy, k > 32 (sibgpu_fused_run_fp / _finish_fp) and k <= 28 (sibgpu_fused_run): collective allocation of the exported buffers, the class
     representatives min-reduced between the two halves, a verification failure on ONE rank repeats the step with other
     hash bases on ALL ranks, a key region that is too small is regrown collectively"""
     ctx = mp.get_context("spawn")
@@ -117,7 +118,9 @@ def test_fused_fingerprint_orchestration(world, k, script):
     helpers.assert_tables_equal((count, pos, neg), restate.enumerate_bifurcations(chrs, k), "world=%d k=%d" % (world, k))
     assert strategy == "fused"
     want = ["plan", "release", "alloc", "import"]
+    first = "run0" if k > 32 else "run"
     if script.get("regrow"):
-        want += ["run0", "plan", "release", "alloc", "import"]
-    want += ["run0", "finish0"] + (["run1", "finish1"] if "collide_rank" in script else [])
+        want += [first, "plan", "release", "alloc", "import"]
+    want += [first, "finish0"] if k > 32 else [first]
+    want += ["run1", "finish1"] if "collide_rank" in script else []
     assert all(log == want for log in logs), logs
