@@ -1,9 +1,13 @@
 /* sibgpu.h -- C ABI of the B200-native de Bruijn-graph hot path of Sibelia.
  *
  * This is the drop-in boundary: plain pointers and sizes, no C++/torch types.  Every entry point names the
- * reference interface it replaces (paths relative to the reference tree, /root/reference).  The C++ facade in
- * sibelia_b200/csrc/facade/ (namespace SyntenyFinder, same class and method names as the reference) sits on top of
- * this header; INTEGRATION.md shows the binding a maintainer of the reference would add.
+ * reference interface it replaces (paths relative to the reference tree, /root/reference).  The reference binds through
+ * sibelia_b200/csrc/facade/: translation units that DEFINE the reference's own members (IndexedSequence::
+ * EnumerateBifurcationsSArray{,InRAM}, BlockFinder::PerformGraphSimplifications, FASTAReader::GetSequences) on top of
+ * this header and are linked instead of the reference's, plus generated edits of the index-building sites of
+ * synteny.cpp / serialization.cpp; INTEGRATION.md shows the binding a maintainer of the reference would add.  (No
+ * array-backed re-implementation of the IndexedSequence / BifurcationStorage / DNASequence classes exists: every
+ * production site that built those objects around the hot path calls this ABI instead.)
  *
  * Conventions
  *   - every function returns 0 on success, a sibgpu_status otherwise; sibgpu_last_error() gives the message
